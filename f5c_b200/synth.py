@@ -1,0 +1,120 @@
+"""Seeded synthetic read batches for the BASELINE.json configurations (recipe: SURVEY.md §8d).
+
+Per read: target events E* ~ LogNormal(ln(mean) - sigma^2/2, sigma); L = floor(E*/epk) + k (min 200);
+sequence iid uniform over ACGT; per k-mer: with p=0.03 no event (skip) else Geometric so the mean number of
+events per k-mer is epk; event mean = scale_r*level_mean[rank] + shift_r + level_stdv[rank]*N(0,1) with
+shift_r ~ N(0,10), scale_r ~ N(1,0.05); start cumulative, length 3..22, stdv 1.0 (unused by ABEA).
+Scalings are a method-of-moments estimate (same formula as reference src/align.c:58-106, numpy float64).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .batch import EVENT_DTYPE, SCALINGS_DTYPE, ReadBatch
+from .models import load_model
+
+# BASELINE.json configs -> generator parameters
+CONFIGS = {
+    "cfg2": dict(model="r9", n_reads=4096, mean_events=4000, sigma=0.5, epk=1.8),
+    "cfg3": dict(model="r10", n_reads=4096, mean_events=8000, sigma=1.0, epk=1.9),
+    "cfg4": dict(model="rna004", n_reads=2048, mean_events=20000, sigma=0.5, epk=2.5),
+    "cfg5": dict(model="r10", n_reads=32768, mean_events=4000, sigma=0.5, epk=1.9),
+}
+
+
+def kmer_ranks_flat(bases: np.ndarray, k: int) -> np.ndarray:
+    """rank[i] of the k-mer starting at flat position i (first base most significant; reference
+    src/align.c:36-47). Positions within k-1 of the end are garbage and must be masked by the caller."""
+    n = bases.shape[0]
+    r = np.zeros(n, dtype=np.int64)
+    for j in range(k):
+        shifted = np.zeros(n, dtype=np.int64)
+        shifted[:n - j] = bases[j:]
+        r = (r << 2) | shifted
+    return r
+
+
+def mom_scalings(ev_mean: np.ndarray, levels: np.ndarray):
+    """estimate_scalings_using_mom for one read (reference src/align.c:58-106), float64 accumulators."""
+    ev = ev_mean.astype(np.float64)
+    lv = levels.astype(np.float64)
+    shift = ev.sum() / ev.size - lv.sum() / lv.size
+    scale = (((ev - shift) ** 2).sum() / ev.size) / ((lv * lv).sum() / lv.size)
+    return np.float32(scale), np.float32(shift)
+
+
+def make_batch(model: str = "r9", n_reads: int = 64, mean_events: float = 4000.0, sigma: float = 0.5,
+               epk: float = 1.8, seed: int = 42, model_table=None, min_len: int = 200) -> ReadBatch:
+    """Generate a ragged batch. model_table=(k, MODEL_DTYPE array) overrides the named built-in table."""
+    k, mt = model_table if model_table is not None else load_model(model)
+    rng = np.random.default_rng(seed)
+    mu = np.log(mean_events) - 0.5 * sigma * sigma
+    e_star = rng.lognormal(mu, sigma, n_reads)
+    L = np.maximum((e_star / epk).astype(np.int64) + k, min_len)
+    K = L - k + 1
+
+    # sequences (flat, NUL after each read)
+    seq_ptr = np.zeros(n_reads, dtype=np.int64)
+    np.cumsum(L[:-1] + 1, out=seq_ptr[1:])
+    total_seq = int((L + 1).sum())
+    base_idx = rng.integers(0, 4, total_seq, dtype=np.int64)
+    seq = np.frombuffer(b"ACGT", dtype=np.uint8)[base_idx].copy()
+    seq[seq_ptr + L] = 0
+    ranks_flat = kmer_ranks_flat(base_idx, k)
+
+    # flat k-mer index -> (read, position)
+    kptr = np.zeros(n_reads + 1, dtype=np.int64)
+    np.cumsum(K, out=kptr[1:])
+    total_k = int(kptr[-1])
+    read_of_kmer = np.repeat(np.arange(n_reads, dtype=np.int64), K)
+    pos_in_read = np.arange(total_k, dtype=np.int64) - kptr[read_of_kmer]
+    rank = ranks_flat[seq_ptr[read_of_kmer] + pos_in_read]
+
+    # events per k-mer: 3% skips, otherwise Geometric (>=1) with overall mean epk
+    cnt = rng.geometric(min(1.0, 0.97 / epk), total_k).astype(np.int64)
+    cnt[rng.random(total_k) < 0.03] = 0
+    # every read needs at least one event on its first and last k-mer so it can span
+    cnt[kptr[:-1]] = np.maximum(cnt[kptr[:-1]], 1)
+    cnt[kptr[1:] - 1] = np.maximum(cnt[kptr[1:] - 1], 1)
+
+    ev_rank = np.repeat(rank, cnt)
+    ev_read = np.repeat(read_of_kmer, cnt)
+    n_ev_total = int(ev_rank.shape[0])
+    n_events = np.bincount(ev_read, minlength=n_reads).astype(np.int32)
+    event_ptr = np.zeros(n_reads, dtype=np.int64)
+    np.cumsum(n_events[:-1].astype(np.int64), out=event_ptr[1:])
+
+    shift_r = rng.normal(0.0, 10.0, n_reads)
+    scale_r = rng.normal(1.0, 0.05, n_reads)
+    lm = mt["level_mean"].astype(np.float64)
+    ls = mt["level_stdv"].astype(np.float64)
+    mean = scale_r[ev_read] * lm[ev_rank] + shift_r[ev_read] + ls[ev_rank] * rng.standard_normal(n_ev_total)
+
+    events = np.zeros(n_ev_total, dtype=EVENT_DTYPE)
+    events["mean"] = mean.astype(np.float32)
+    length = rng.integers(3, 23, n_ev_total)
+    events["length"] = length.astype(np.float32)
+    cs = np.cumsum(length) - length
+    events["start"] = (cs - cs[event_ptr][ev_read]).astype(np.uint64)
+    events["stdv"] = 1.0
+
+    scalings = np.zeros(n_reads, dtype=SCALINGS_DTYPE)
+    for i in range(n_reads):
+        ep, en = int(event_ptr[i]), int(n_events[i])
+        s, sh = mom_scalings(events["mean"][ep:ep + en], mt["level_mean"][rank[kptr[i]:kptr[i + 1]]])
+        scalings[i]["scale"] = s
+        scalings[i]["shift"] = sh
+
+    return ReadBatch(seq, seq_ptr, L.astype(np.int32), events, event_ptr, n_events, scalings,
+                     np.ones(n_reads, dtype=np.uint8), k,
+                     meta=dict(model=model, n_reads=n_reads, mean_events=mean_events, sigma=sigma, epk=epk,
+                               seed=seed))
+
+
+def make_config(name: str, seed: int = 42, n_reads: int | None = None) -> ReadBatch:
+    p = dict(CONFIGS[name])
+    if n_reads is not None:
+        p["n_reads"] = n_reads
+    b = make_batch(seed=seed, **p)
+    b.meta["config"] = name
+    return b

@@ -1,0 +1,85 @@
+/* abea_types.h — plain-C mirror of the POD types on f5c's ABEA boundary.
+ *
+ * Each struct is layout-identical to the reference type it names (sizes probed in SURVEY.md §8:
+ * event_t 24 B, model_t 12 B with CACHED_LOG, scalings_t 16 B, AlignedPair 8 B), so a pointer to
+ * the reference's array can be passed straight through the C ABI in abea_b200.h without repacking.
+ * The drop-in shim (f5c_b200/csrc/f5c_dropin.cu) static_asserts the equivalence against the
+ * reference's own f5c.h when it is compiled inside the f5c tree.
+ */
+#ifndef ABEA_TYPES_H
+#define ABEA_TYPES_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference: event_t, src/f5c.h:129-136 (only .mean is read by ABEA, src/align.c:131) */
+typedef struct {
+    uint64_t start;
+    float length;
+    float mean;
+    float stdv;
+} abea_event_t;
+
+/* reference: model_t with CACHED_LOG, src/f5c.h:147-155 */
+typedef struct {
+    float level_mean;
+    float level_stdv;
+    float level_log_stdv; /* log(level_stdv) evaluated on the HOST (glibc), src/model.c:179 */
+} abea_model_t;
+
+/* reference: scalings_t with CACHED_LOG, src/f5c.h:158-172 (ABEA reads .scale and .shift only) */
+typedef struct {
+    float scale;
+    float shift;
+    float var;
+    float log_var;
+} abea_scalings_t;
+
+/* reference: AlignedPair, src/f5c.h:181-184. ref_pos = k-mer index, read_pos = event index */
+typedef struct {
+    int32_t ref_pos;
+    int32_t read_pos;
+} abea_pair_t;
+
+/* reference constants: src/f5c.h:30-34, src/f5cmisc.h:18 */
+#define ABEA_BANDWIDTH 100
+#define ABEA_MAX_KMER_SIZE 9
+#define ABEA_MAX_NUM_KMER 262144
+#define ABEA_AVG_EVENTS_PER_KMER_MAX 15.0f
+
+/* reference model ids: src/f5cmisc.h:24-30 */
+#define ABEA_MODEL_ID_DNA_R9 1
+#define ABEA_MODEL_ID_RNA_R9 3
+#define ABEA_MODEL_ID_DNA_R10 4
+#define ABEA_MODEL_ID_RNA_RNA004 6
+
+/* A ragged batch of reads in flat (CSR-style) form: what the reference's align_cuda packs db_t into
+ * (src/f5c.cu:744-800) and what every implementation in this repo (CUDA path, oracle, _ref shim)
+ * consumes. All pointers are host pointers unless a function says otherwise.
+ *
+ *   seq      : concatenated read sequences, read i at seq[seq_ptr[i] .. seq_ptr[i]+read_len[i]) followed
+ *              by one NUL (so seq_ptr advances by read_len+1, like the reference's read_ptr)
+ *   events   : concatenated event tables, read i at events[event_ptr[i] .. +n_events[i])
+ *   scalings : per read (from estimate_scalings_using_mom)
+ *   good     : per read, non-zero iff db->sig[i]->nsample > 0 (src/f5c.c:811); NULL = all good
+ */
+typedef struct {
+    int32_t n_reads;
+    const char* seq;
+    const int64_t* seq_ptr;
+    const int32_t* read_len;
+    const abea_event_t* events;
+    const int64_t* event_ptr;
+    const int32_t* n_events;
+    const abea_scalings_t* scalings;
+    const uint8_t* good;
+} abea_batch_t;
+
+#ifdef __cplusplus
+}
+#endif
+#endif

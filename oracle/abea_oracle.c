@@ -1,0 +1,321 @@
+/* abea_oracle.c — TEST INFRASTRUCTURE: CPU restatement of f5c's adaptive banded event alignment.
+ *
+ * Parity status: PINNED. This restatement is checked (tests/test_oracle.py) against
+ *   (1) the reference's golden vectors test/ecoli_2kb_region/single_read/adaptive.exp and
+ *       test/ecoli_2kb_region/adaptive.exp (n_aligned_events exact, sum_emission to print precision),
+ *   (2) the unmodified reference align() compiled in place (oracle/_ref/libf5c_ref.so): identical pair
+ *       lists on real reads and on seeded synthetic R9 / R10 / RNA004 batches,
+ *   (3) committed fixtures under tests/golden/ generated from (2) by tests/golden/make_golden.py.
+ *
+ * It is written from the algorithm, not from the reference's text; every function cites the reference
+ * lines whose behaviour it must reproduce (paths relative to /root/reference/). Arithmetic notes that
+ * matter for bit-exactness: emissions are float; the three transition sums are evaluated in double and
+ * rounded once to float (lp_* are double in the reference, src/align.c:207-216, 382-384); build with
+ * -ffp-contract=off so no FMA is formed.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * this library. The product path (f5c_b200/) never does.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "../include/abea_types.h"
+
+#define W ABEA_BANDWIDTH
+
+enum { FROM_D = 0, FROM_U = 1, FROM_L = 2 }; /* src/align.c:194-196 */
+
+typedef struct {
+    double sum_emission;   /* double sum of float emissions in traceback order (src/align.c:476) */
+    float end_score;       /* best last-column score incl. trailing trim (src/align.c:438-443) */
+    int32_t n_aligned;     /* pairs emitted before QC (src/align.c:480) */
+    int32_t max_gap;       /* longest run of FROM_L (src/align.c:495-497) */
+    int32_t end_event;     /* event index the traceback starts from */
+    int32_t spanned;       /* first.ref_pos==0 && last.ref_pos==K-1 (src/align.c:529-530) */
+    int64_t n_bands;
+    int64_t n_fills;       /* cells filled by the inner loop (src/align.c:408) */
+} abea_oracle_stats_t;
+
+/* src/align.c:19-32: A,C,G,T -> 0..3, anything else -> 0 (the reference also prints a WARNING) */
+static inline uint32_t base_rank(char b) {
+    switch (b) {
+        case 'C': return 1;
+        case 'G': return 2;
+        case 'T': return 3;
+        default: return 0;
+    }
+}
+
+/* src/align.c:36-47: first base is the most significant 2-bit digit */
+static inline uint32_t kmer_rank(const char* s, uint32_t k) {
+    uint32_t r = 0;
+    for (uint32_t i = 0; i < k; i++) r = (r << 2) | base_rank(s[i]);
+    return r;
+}
+
+/* src/align.c:108-115 + 117-154 (CACHED_LOG): all float, no FMA, left-to-right association */
+static inline float emission(float x, float scale, float shift, const abea_model_t* m) {
+    float gp_mean = scale * m->level_mean + shift;
+    float a = (x - gp_mean) / m->level_stdv;
+    float lead = -0.918938f - m->level_log_stdv;
+    float quad = -0.5f * a;
+    quad = quad * a;
+    return lead + quad;
+}
+
+/* src/align.c:207-216. n_events and n_kmers are size_t in the reference; the quotient is double. */
+void abea_oracle_transitions(int64_t n_events, int64_t n_kmers, double* lp_skip, double* lp_stay,
+                             double* lp_step, double* lp_trim) {
+    double events_per_kmer = (double)(size_t)n_events / (size_t)n_kmers;
+    double p_stay = 1 - (1 / (events_per_kmer + 1));
+    *lp_skip = log(1e-10);
+    *lp_stay = log(p_stay);
+    *lp_step = log(1.0 - exp(*lp_skip) - exp(*lp_stay));
+    *lp_trim = log(0.01);
+}
+
+/* src/model.c:93,179: level_log_stdv = log(level_stdv). The reference is compiled as C++ (Makefile:6), where
+ * log(float) binds to the float overload, i.e. glibc logf — NOT a double log rounded to float (probed: the two
+ * differ in 250 of the 262144 R10 entries). */
+void abea_oracle_fill_log_stdv(abea_model_t* model, int64_t n) {
+    for (int64_t i = 0; i < n; i++) model[i].level_log_stdv = logf(model[i].level_stdv);
+}
+
+/* The whole of align() (src/align.c:180-559) for one read.
+ * out must hold n_events + seq_len pairs (src/f5c.c:724-726). Returns the pair count after QC
+ * (0 when QC fails, src/align.c:534-543); stats (optional) reports the pre-QC quantities. */
+int32_t abea_oracle_align(abea_pair_t* out, const char* seq, int32_t seq_len, const abea_event_t* ev,
+                          int64_t n_events_i, const abea_model_t* model, uint32_t k, float scale,
+                          float shift, abea_oracle_stats_t* stats) {
+    const int64_t E = n_events_i;
+    const int64_t K = (int64_t)seq_len - (int64_t)k + 1;
+    const int64_t NB = (E + 1) + (K + 1); /* src/align.c:219-221 */
+
+    double lp_skip, lp_stay, lp_step, lp_trim;
+    abea_oracle_transitions(E, K, &lp_skip, &lp_stay, &lp_step, &lp_trim);
+
+    uint32_t* ranks = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(K > 0 ? K : 1));
+    for (int64_t i = 0; i < K; i++) ranks[i] = kmer_rank(seq + i, k);
+
+    /* full score and trace matrices, band-major (src/align.c:242-259) */
+    float* score = (float*)malloc(sizeof(float) * (size_t)NB * W);
+    uint8_t* trace = (uint8_t*)malloc((size_t)NB * W);
+    int32_t* ll_e = (int32_t*)malloc(sizeof(int32_t) * (size_t)NB); /* event index of offset 0 */
+    int32_t* ll_k = (int32_t*)malloc(sizeof(int32_t) * (size_t)NB); /* k-mer index of offset 0 */
+    for (int64_t i = 0; i < NB * W; i++) score[i] = -INFINITY;
+    memset(trace, 0, (size_t)NB * W);
+
+    /* bands 0 and 1 (src/align.c:277-291): cell (event -1, kmer -1) scores 0; trimming event 0 costs lp_trim */
+    ll_e[0] = W / 2 - 1;
+    ll_k[0] = -1 - W / 2;
+    ll_e[1] = ll_e[0] + 1;
+    ll_k[1] = ll_k[0];
+    score[0 * W + (-1 - ll_k[0])] = 0.0f;
+    score[1 * W + (ll_e[1] - 0)] = (float)lp_trim;
+    trace[1 * W + (ll_e[1] - 0)] = FROM_U;
+
+    int64_t fills = 0;
+    for (int64_t b = 2; b < NB; b++) {
+        const float* p1 = score + (b - 1) * W;
+        const float* p2 = score + (b - 2) * W;
+        float* cur = score + b * W;
+        uint8_t* tr = trace + b * W;
+
+        /* Suzuki's rule (src/align.c:304-322) */
+        float ll = p1[0], ur = p1[W - 1];
+        int right;
+        if (ll == -INFINITY && ur == -INFINITY) right = (b % 2 == 1);
+        else right = ll < ur;
+        ll_e[b] = ll_e[b - 1] + (right ? 0 : 1);
+        ll_k[b] = ll_k[b - 1] + (right ? 1 : 0);
+        const int32_t eb = ll_e[b], kb = ll_k[b];
+
+        /* trim column, k-mer -1 (src/align.c:324-333) */
+        int32_t to = -1 - kb;
+        if (to >= 0 && to < W) {
+            int64_t te = (int64_t)eb - to;
+            if (te >= 0 && te < E) {
+                cur[to] = (float)(lp_trim * (double)(te + 1));
+                tr[to] = FROM_U;
+            } else {
+                cur[to] = -INFINITY;
+            }
+        }
+
+        /* offsets whose event and k-mer both exist (src/align.c:337-346) */
+        int64_t lo = -(int64_t)kb;                    /* kmer >= 0       */
+        if ((int64_t)eb - (E - 1) > lo) lo = (int64_t)eb - (E - 1); /* event <= E-1 */
+        if (lo < 0) lo = 0;
+        int64_t hi = K - (int64_t)kb;                 /* kmer <= K-1     */
+        if ((int64_t)eb + 1 < hi) hi = (int64_t)eb + 1; /* event >= 0    */
+        if (hi > W) hi = W;
+
+        /* neighbour offsets relative to this band's offset o (src/align.c:354-356) */
+        const int32_t d_up = ll_e[b - 1] - eb + 1;   /* o_up   = o + d_up   */
+        const int32_t d_left = -1 - ll_k[b - 1] + kb; /* o_left = o + d_left */
+        const int32_t d_diag = -1 - ll_k[b - 2] + kb; /* o_diag = o + d_diag */
+
+        for (int64_t o = lo; o < hi; o++) {
+            int32_t e = eb - (int32_t)o, km = kb + (int32_t)o;
+            int64_t ou = o + d_up, ol = o + d_left, od = o + d_diag;
+            float up = (ou >= 0 && ou < W) ? p1[ou] : -INFINITY;
+            float left = (ol >= 0 && ol < W) ? p1[ol] : -INFINITY;
+            float diag = (od >= 0 && od < W) ? p2[od] : -INFINITY;
+            float lp = emission(ev[e].mean, scale, shift, &model[ranks[km]]);
+            /* double sums rounded once (src/align.c:382-384) */
+            float sd = (float)(((double)diag + lp_step) + (double)lp);
+            float su = (float)(((double)up + lp_stay) + (double)lp);
+            float sl = (float)((double)left + lp_skip);
+            /* ties resolve L over U over D (src/align.c:386-392) */
+            float best = sd;
+            uint8_t from = FROM_D;
+            best = su > best ? su : best;
+            from = best == su ? FROM_U : from;
+            best = sl > best ? sl : best;
+            from = best == sl ? FROM_L : from;
+            cur[o] = best;
+            tr[o] = from;
+            fills++;
+        }
+    }
+
+    /* best end cell on the last k-mer column, trailing events trimmed (src/align.c:424-445) */
+    float best_score = -INFINITY;
+    int32_t ce = 0, ck = (int32_t)(K - 1);
+    for (int64_t e = 0; e < E; e++) {
+        int64_t b = (e + 1) + ((int64_t)ck + 1);
+        int64_t o = (int64_t)ll_e[b] - e;
+        if (o >= 0 && o < W) {
+            float s = (float)((double)score[b * W + o] + (double)(size_t)(E - e) * lp_trim);
+            if (s > best_score) {
+                best_score = s;
+                ce = (int32_t)e;
+            }
+        }
+    }
+    const int32_t end_event = ce;
+
+    /* traceback (src/align.c:452-499) */
+    int32_t n = 0, gap = 0, max_gap = 0;
+    double sum_emission = 0;
+    while (ck >= 0 && ce >= 0) {
+        out[n].ref_pos = ck;
+        out[n].read_pos = ce;
+        n++;
+        sum_emission += emission(ev[ce].mean, scale, shift, &model[kmer_rank(seq + ck, k)]);
+        int64_t b = ((int64_t)ce + 1) + ((int64_t)ck + 1);
+        int64_t o = (int64_t)ll_e[b] - ce;
+        uint8_t from = trace[b * W + o];
+        if (from == FROM_D) { ck--; ce--; gap = 0; }
+        else if (from == FROM_U) { ce--; gap = 0; }
+        else { ck--; gap++; if (gap > max_gap) max_gap = gap; }
+    }
+
+    /* ascending order (src/align.c:503-513) */
+    for (int32_t i = 0, j = n - 1; i < j; i++, j--) {
+        abea_pair_t t = out[i];
+        out[i] = out[j];
+        out[j] = t;
+    }
+
+    /* QC (src/align.c:526-543) */
+    double avg = sum_emission / (double)n;
+    int spanned = n > 0 && out[0].ref_pos == 0 && out[n - 1].ref_pos == (int32_t)(K - 1);
+    if (stats) {
+        stats->sum_emission = sum_emission;
+        stats->end_score = best_score;
+        stats->n_aligned = n;
+        stats->max_gap = max_gap;
+        stats->end_event = end_event;
+        stats->spanned = spanned;
+        stats->n_bands = NB;
+        stats->n_fills = fills;
+    }
+    int32_t ret = n;
+    if (avg < -5.0 || !spanned || max_gap > 50) ret = 0;
+
+    free(ranks);
+    free(score);
+    free(trace);
+    free(ll_e);
+    free(ll_k);
+    return ret;
+}
+
+/* estimate_scalings_using_mom (src/align.c:58-106): method-of-moments shift/scale, double accumulators */
+void abea_oracle_estimate_scalings(const char* seq, int32_t seq_len, const abea_model_t* model, uint32_t k,
+                                   const abea_event_t* ev, int64_t n_events, abea_scalings_t* out) {
+    int32_t n_kmers = seq_len - (int32_t)k + 1;
+    double ev_sum = 0.0;
+    for (int64_t i = 0; i < n_events; i++) ev_sum += ev[i].mean;
+    double km_sum = 0.0, km_sq = 0.0;
+    for (int32_t i = 0; i < n_kmers; i++) {
+        double l = model[kmer_rank(seq + i, k)].level_mean;
+        km_sum += l;
+        km_sq += l * l;
+    }
+    double shift = ev_sum / (size_t)n_events - km_sum / n_kmers;
+    double ev_sq = 0.0;
+    for (int64_t i = 0; i < n_events; i++) ev_sq += (ev[i].mean - shift) * (ev[i].mean - shift);
+    double scale = (ev_sq / (size_t)n_events) / (km_sq / n_kmers);
+    out->shift = (float)shift;
+    out->scale = (float)scale;
+    out->var = 0;
+    out->log_var = 0;
+}
+
+/* ---- batch driver: CPU branch of align_db (src/f5c.c:811-845) over a flat batch ------------------- */
+
+typedef struct {
+    const abea_batch_t* b;
+    const abea_model_t* model;
+    uint32_t k;
+    abea_pair_t* pairs;
+    const int64_t* pair_ptr;
+    int32_t* n_pairs;
+    abea_oracle_stats_t* stats;
+    volatile int32_t* next;
+} pool_t;
+
+static void* worker(void* p) {
+    pool_t* a = (pool_t*)p;
+    const abea_batch_t* b = a->b;
+    for (;;) {
+        int32_t i = __sync_fetch_and_add(a->next, 1);
+        if (i >= b->n_reads) break;
+        int good = b->good ? b->good[i] : 1;
+        if (a->stats) memset(&a->stats[i], 0, sizeof(abea_oracle_stats_t));
+        /* align_single's filter: good read and events/base < 15 in float (src/f5c.c:813-814) */
+        if (good && (size_t)b->n_events[i] / (float)b->read_len[i] < ABEA_AVG_EVENTS_PER_KMER_MAX) {
+            a->n_pairs[i] = abea_oracle_align(a->pairs + a->pair_ptr[i], b->seq + b->seq_ptr[i], b->read_len[i],
+                                              b->events + b->event_ptr[i], b->n_events[i], a->model, a->k,
+                                              b->scalings[i].scale, b->scalings[i].shift,
+                                              a->stats ? &a->stats[i] : NULL);
+        } else {
+            a->n_pairs[i] = 0;
+        }
+    }
+    return NULL;
+}
+
+/* Returns wall-clock seconds spent aligning. stats may be NULL. */
+double abea_oracle_align_batch(const abea_batch_t* b, const abea_model_t* model, uint32_t k, abea_pair_t* pairs,
+                               const int64_t* pair_ptr, int32_t* n_pairs, abea_oracle_stats_t* stats,
+                               int32_t n_threads) {
+    volatile int32_t next = 0;
+    pool_t a = {b, model, k, pairs, pair_ptr, n_pairs, stats, &next};
+    if (n_threads < 1) n_threads = 1;
+    pthread_t* tid = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 1; t < n_threads; t++) pthread_create(&tid[t], NULL, worker, &a);
+    worker(&a);
+    for (int t = 1; t < n_threads; t++) pthread_join(tid[t], NULL);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    free(tid);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
