@@ -1,0 +1,219 @@
+"""ctypes binding of libabea_b200.so (include/abea_b200.h) and the host-side mirror of the reference call surface.
+
+``AbeaContext`` plays the role of ``core_t``'s CUDA half (reference ``init_cuda``/``free_cuda``, src/f5c.cu:23-234):
+it owns the device, the uploaded pore model and all device memory. ``align_db(ctx, batch)`` is the batch call the
+reference spells ``align_db(core, db)`` -> ``align_cuda(core, db)`` (src/f5c.c:833-845, src/f5c.cu:647): it fills
+``n_event_align_pairs`` and ``event_align_pairs`` for every read of the batch.
+
+There is no CPU path: if the CUDA library is missing or no GPU is visible this module raises, loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from .batch import MODEL_DTYPE, PAIR_DTYPE, CBatch, ReadBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libabea_b200.so")
+
+
+class AbeaError(RuntimeError):
+    pass
+
+
+class Timing(ctypes.Structure):
+    """abea_timing_t"""
+    _fields_ = [("pack_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("kmer_ms", ctypes.c_double),
+                ("fill_ms", ctypes.c_double), ("trace_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double),
+                ("d2h_ms", ctypes.c_double), ("unpack_ms", ctypes.c_double), ("h2d_bytes", ctypes.c_int64),
+                ("d2h_bytes", ctypes.c_int64), ("kernel_launches", ctypes.c_int32),
+                ("n_scheduled", ctypes.c_int32), ("n_bands", ctypes.c_int64), ("n_events", ctypes.c_int64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def _bind(path: str):
+    if not os.path.exists(path):
+        raise AbeaError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a). f5c_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    lib.abea_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+    lib.abea_destroy.argtypes = [vp]
+    lib.abea_destroy.restype = None
+    lib.abea_last_error.argtypes = [vp]
+    lib.abea_last_error.restype = ctypes.c_char_p
+    lib.abea_set_model.argtypes = [vp, vp, ctypes.c_uint32]
+    lib.abea_model_fill_log_stdv.argtypes = [vp, i64]
+    lib.abea_model_fill_log_stdv.restype = None
+    lib.abea_align_batch.argtypes = [vp, ctypes.POINTER(CBatch), vp, vp, vp, ctypes.POINTER(Timing)]
+    lib.abea_upload_batch.argtypes = [vp, ctypes.POINTER(CBatch), ctypes.POINTER(Timing)]
+    lib.abea_run.argtypes = [vp, ctypes.POINTER(Timing)]
+    lib.abea_download.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Timing)]
+    lib.abea_read_stats.argtypes = [vp, vp, vp, vp, vp]
+    lib.abea_host_alloc.argtypes = [ctypes.c_size_t]
+    lib.abea_host_alloc.restype = vp
+    lib.abea_host_free.argtypes = [vp]
+    lib.abea_host_free.restype = None
+    lib.abea_device_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p]
+    lib.abea_version.restype = ctypes.c_char_p
+    return lib
+
+
+_LIBS = {}
+
+
+def load_library(path: str | None = None):
+    path = path or LIB_PATH
+    if path not in _LIBS:
+        _LIBS[path] = _bind(path)
+    return _LIBS[path]
+
+
+@dataclass
+class Alignment:
+    """Output of align_db: the reference's db->event_align_pairs / db->n_event_align_pairs, flat."""
+    pairs: np.ndarray      # PAIR_DTYPE, capacity layout (pair_ptr = prefix sum of E+L)
+    pair_ptr: np.ndarray   # int64 [n]
+    n_pairs: np.ndarray    # int32 [n]
+    timing: dict
+
+    def read_pairs(self, i: int) -> np.ndarray:
+        p = int(self.pair_ptr[i])
+        return self.pairs[p:p + int(self.n_pairs[i])]
+
+
+class AbeaContext:
+    """One GPU's ABEA state (reference: init_cuda(core) ... free_cuda(core))."""
+
+    def __init__(self, device: int = 0, lib_path: str | None = None):
+        self.lib = load_library(lib_path)
+        self._h = ctypes.c_void_p()
+        rc = self.lib.abea_create(ctypes.byref(self._h), device)
+        if rc != 0:
+            raise AbeaError(f"abea_create(device={device}) failed with {rc}: no usable CUDA device; "
+                            "f5c_b200 has no CPU fallback")
+        self.device = device
+        self.kmer_size = None
+        self._pinned = []
+
+    # -- lifecycle ---------------------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            for p in self._pinned:
+                self.lib.abea_host_free(p)
+            self._pinned = []
+            self.lib.abea_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise AbeaError(f"{what} failed ({rc}): {self.lib.abea_last_error(self._h).decode()}")
+
+    # -- model ---------------------------------------------------------------------------------------------
+    def set_model(self, model: np.ndarray, kmer_size: int):
+        """Upload a MODEL_DTYPE table of 4^k entries; level_log_stdv is (re)computed by the C library."""
+        m = np.ascontiguousarray(model.copy())
+        assert m.dtype == MODEL_DTYPE and m.shape[0] == 4 ** kmer_size
+        self.lib.abea_model_fill_log_stdv(m.ctypes.data, m.shape[0])
+        self._check(self.lib.abea_set_model(self._h, m.ctypes.data, kmer_size), "abea_set_model")
+        self.kmer_size = kmer_size
+        self.model = m
+        return m
+
+    def device_info(self):
+        n = ctypes.c_int()
+        name = ctypes.create_string_buffer(256)
+        self.lib.abea_device_info(self._h, ctypes.byref(n), name)
+        return n.value, name.value.decode()
+
+    # -- pinned host memory ----------------------------------------------------------------------------
+    def pinned_empty(self, shape, dtype) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = self.lib.abea_host_alloc(max(n, 1))
+        if not p:
+            raise AbeaError("abea_host_alloc failed")
+        self._pinned.append(p)
+        buf = (ctypes.c_char * max(n, 1)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def pin_batch(self, b: ReadBatch) -> ReadBatch:
+        """Copy a batch's flat arrays into pinned host memory (so H2D runs at PCIe rate)."""
+        def pin(a):
+            out = self.pinned_empty(a.shape, a.dtype)
+            out[...] = a
+            return out
+        return ReadBatch(pin(b.seq), pin(b.seq_ptr), pin(b.read_len), pin(b.events), pin(b.event_ptr),
+                         pin(b.n_events), pin(b.scalings), pin(b.good), b.kmer_size, dict(b.meta))
+
+    # -- the path ------------------------------------------------------------------------------------------
+    def alloc_output(self, batch: ReadBatch, pinned: bool = False):
+        cap = int(batch.pair_capacity().sum())
+        if pinned:
+            pairs = self.pinned_empty((cap,), PAIR_DTYPE)
+            n_pairs = self.pinned_empty((batch.n_reads,), np.int32)
+        else:
+            pairs = np.empty(cap, dtype=PAIR_DTYPE)
+            n_pairs = np.empty(batch.n_reads, dtype=np.int32)
+        return pairs, batch.pair_ptr(), n_pairs
+
+    def align_batch(self, batch: ReadBatch, out=None) -> Alignment:
+        """abea_align_batch: host buffers in, host buffers out (the e2e path)."""
+        assert batch.kmer_size == self.kmer_size, "batch k-mer size does not match the uploaded model"
+        pairs, pair_ptr, n_pairs = out if out is not None else self.alloc_output(batch)
+        t = Timing()
+        cb = batch.as_c()
+        self._check(self.lib.abea_align_batch(self._h, ctypes.byref(cb), pairs.ctypes.data, pair_ptr.ctypes.data,
+                                              n_pairs.ctypes.data, ctypes.byref(t)), "abea_align_batch")
+        return Alignment(pairs, pair_ptr, n_pairs, t.as_dict())
+
+    def upload(self, batch: ReadBatch) -> dict:
+        assert batch.kmer_size == self.kmer_size
+        t = Timing()
+        cb = batch.as_c()
+        self._check(self.lib.abea_upload_batch(self._h, ctypes.byref(cb), ctypes.byref(t)), "abea_upload_batch")
+        return t.as_dict()
+
+    def run(self) -> dict:
+        t = Timing()
+        self._check(self.lib.abea_run(self._h, ctypes.byref(t)), "abea_run")
+        return t.as_dict()
+
+    def download(self, batch: ReadBatch, out=None) -> Alignment:
+        pairs, pair_ptr, n_pairs = out if out is not None else self.alloc_output(batch)
+        t = Timing()
+        self._check(self.lib.abea_download(self._h, pairs.ctypes.data, pair_ptr.ctypes.data, n_pairs.ctypes.data,
+                                           ctypes.byref(t)), "abea_download")
+        return Alignment(pairs, pair_ptr, n_pairs, t.as_dict())
+
+    def read_stats(self, n_reads: int) -> dict:
+        se = np.zeros(n_reads, dtype=np.float64)
+        na = np.zeros(n_reads, dtype=np.int32)
+        ee = np.zeros(n_reads, dtype=np.int32)
+        mg = np.zeros(n_reads, dtype=np.int32)
+        self._check(self.lib.abea_read_stats(self._h, se.ctypes.data, na.ctypes.data, ee.ctypes.data, mg.ctypes.data),
+                    "abea_read_stats")
+        return dict(sum_emission=se, n_aligned=na, end_event=ee, max_gap=mg)
+
+
+def align_db(ctx: AbeaContext, batch: ReadBatch) -> Alignment:
+    """The reference's align_db(core, db) for the GPU build (src/f5c.c:833-845): ABEA for a data batch."""
+    return ctx.align_batch(batch)

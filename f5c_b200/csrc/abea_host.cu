@@ -1,0 +1,449 @@
+/* abea_host.cu — host side of libabea_b200.so: context, device memory, batch packer, launches, unpacker.
+ *
+ * Replaces the GPU dispatch of the reference (src/f5c.cu: init_cuda :23-202, free_cuda :204-234, align_cuda
+ * :647-1061) behind the C ABI in include/abea_b200.h. What is deliberately NOT reproduced: the CPU side-pool for
+ * long / over-segmented reads (src/f5c.cu:243-452) and the load/memory advisors (:457-644) — every eligible read is
+ * aligned on the GPU, scheduled longest-first onto persistent warps.
+ *
+ * There is no CPU implementation of the alignment in this library: without a CUDA device every entry point fails
+ * with ABEA_ERR_NODEVICE.
+ */
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <vector>
+
+#ifndef ABEA_SIMT_EMU
+#include <cuda_runtime.h>
+#define ABEA_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#else /* tests/simt: CPU lock-step emulation of the same sources (test infrastructure) */
+#define ABEA_LAUNCH(kern, grid, block, stream, ...) SIMT_LAUNCH(kern, grid, block, __VA_ARGS__)
+#endif
+
+#include "../../include/abea_b200.h"
+#include "abea_kernels.cuh"
+
+#define ABEA_VERSION_STR "abea-b200 0.1 (sm_100a)"
+
+namespace {
+
+double now_ms() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+enum { EV_H2D0, EV_H2D1, EV_K0, EV_K1, EV_K2, EV_K3, EV_D2H0, EV_D2H1, EV_COUNT };
+
+} // namespace
+
+struct abea_devbuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+struct abea_hostbuf { /* pinned */
+    void* p = nullptr;
+    size_t cap = 0;
+};
+typedef abea_devbuf DevBuf;
+typedef abea_hostbuf HostBuf;
+
+struct abea_ctx {
+    int device = 0;
+    int sm_count = 0;
+    char dev_name[256] = {0};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[EV_COUNT] = {};
+    char err[1024] = {0};
+
+    /* model */
+    DevBuf d_model;
+    uint32_t kmer_size = 0;
+    bool have_model = false;
+
+    /* resident batch */
+    DevBuf d_seq, d_events, d_reads, d_kparams, d_trace, d_pairs, d_results, d_queue;
+    HostBuf h_results, h_pairs;
+    std::vector<abea_read_t> reads;   /* scheduled reads, longest first */
+    int32_t n_batch_reads = 0;        /* reads in the caller's batch */
+    int64_t total_kmers = 0, total_trace_words = 0, total_pair_cap = 0, total_bands = 0, total_events = 0;
+    bool uploaded = false, ran = false;
+    abea_consts_t cst;
+    abea_timing_t last = {};
+};
+
+namespace {
+
+int fail(abea_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU(call)                                                                                            \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess)                                                                              \
+            return fail(c, ABEA_ERR_CUDA, "Cuda error: %s (%s) at %s:%d", cudaGetErrorString(e_), #call,    \
+                        __FILE__, __LINE__);                                                                \
+    } while (0)
+
+int dev_reserve(abea_ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256; /* head-room so that similar batches do not reallocate */
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+int host_reserve(abea_ctx* c, HostBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CU(cudaFreeHost(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CU(cudaMallocHost(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+
+float ev_ms(abea_ctx* c, int a, int b) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) return 0.f;
+    return ms;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* abea_version(void) { return ABEA_VERSION_STR; }
+
+const char* abea_last_error(const abea_ctx_t* ctx) { return ctx ? ctx->err : "null context"; }
+
+void abea_model_fill_log_stdv(abea_model_t* model, int64_t n) {
+    /* the reference is C++: log(float) is the float overload == logf (src/model.c:93,179) */
+    for (int64_t i = 0; i < n; i++) model[i].level_log_stdv = logf(model[i].level_stdv);
+}
+
+void* abea_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void abea_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int abea_create(abea_ctx_t** out, int device) {
+    if (!out) return ABEA_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        fprintf(stderr, "[abea_create::ERROR] no usable CUDA device (requested %d of %d); this library has no CPU path\n",
+                device, n);
+        return ABEA_ERR_NODEVICE;
+    }
+    abea_ctx* c = new abea_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete c;
+        return ABEA_ERR_CUDA;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    snprintf(c->dev_name, sizeof(c->dev_name), "%s", prop.name);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return ABEA_ERR_CUDA;
+    }
+    for (int i = 0; i < EV_COUNT; i++) {
+        if (cudaEventCreate(&c->ev[i]) != cudaSuccess) {
+            delete c;
+            return ABEA_ERR_CUDA;
+        }
+    }
+    /* transition constants shared by all reads, host double (reference src/align.c:212-216) */
+    c->cst.lp_skip = log(1e-10);
+    c->cst.lp_trim = log(0.01);
+    *out = c;
+    return ABEA_OK;
+}
+
+void abea_destroy(abea_ctx_t* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_reads, &c->d_kparams,
+                      &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (c->h_results.p) cudaFreeHost(c->h_results.p);
+    if (c->h_pairs.p) cudaFreeHost(c->h_pairs.p);
+    for (int i = 0; i < EV_COUNT; i++)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int abea_device_info(abea_ctx_t* c, int* sm_count, char* name) {
+    if (!c) return ABEA_ERR_ARG;
+    if (sm_count) *sm_count = c->sm_count;
+    if (name) snprintf(name, 256, "%s", c->dev_name);
+    return ABEA_OK;
+}
+
+int abea_set_model(abea_ctx_t* c, const abea_model_t* model, uint32_t kmer_size) {
+    if (!c || !model || kmer_size < 1 || kmer_size > ABEA_MAX_KMER_SIZE) return fail(c, ABEA_ERR_ARG, "bad model");
+    CU(cudaSetDevice(c->device));
+    size_t n = (size_t)1 << (2 * kmer_size);
+    if (dev_reserve(c, c->d_model, n * sizeof(abea_model_t))) return ABEA_ERR_CUDA;
+    CU(cudaMemcpyAsync(c->d_model.p, model, n * sizeof(abea_model_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->kmer_size = kmer_size;
+    c->have_model = true;
+    return ABEA_OK;
+}
+
+int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timing) {
+    if (!c || !b || b->n_reads < 0) return fail(c, ABEA_ERR_ARG, "bad batch");
+    if (!c->have_model) return fail(c, ABEA_ERR_NOMODEL, "abea_set_model has not been called");
+    CU(cudaSetDevice(c->device));
+    double t0 = now_ms();
+    c->uploaded = false;
+    c->ran = false;
+    c->n_batch_reads = b->n_reads;
+    c->reads.clear();
+    c->reads.reserve(b->n_reads);
+
+    /* total sizes of the caller's flat arrays */
+    int64_t seq_bytes = 0, n_ev_total = 0;
+    for (int32_t i = 0; i < b->n_reads; i++) {
+        int64_t se = b->seq_ptr[i] + b->read_len[i] + 1;
+        if (se > seq_bytes) seq_bytes = se;
+        int64_t ee = b->event_ptr[i] + b->n_events[i];
+        if (ee > n_ev_total) n_ev_total = ee;
+    }
+
+    /* eligibility: align_single's filter (reference src/f5c.c:811-830). Reads with no events or fewer bases than
+     * k are undefined in the reference; they get 0 pairs here. */
+    const int32_t k = (int32_t)c->kmer_size;
+    for (int32_t i = 0; i < b->n_reads; i++) {
+        const int32_t E = b->n_events[i], L = b->read_len[i];
+        const bool good = b->good ? (b->good[i] != 0) : true;
+        if (!good || E < 1 || L < k) continue;
+        if (!((float)(size_t)E / (float)L < ABEA_AVG_EVENTS_PER_KMER_MAX)) continue;
+        abea_read_t r;
+        memset(&r, 0, sizeof(r));
+        r.seq_off = b->seq_ptr[i];
+        r.ev_off = b->event_ptr[i];
+        r.n_events = E;
+        r.n_kmers = L - k + 1;
+        r.pair_cap = E + L;
+        r.orig_index = i;
+        r.scale = b->scalings[i].scale;
+        r.shift = b->scalings[i].shift;
+        /* per-read transition penalties in host double (reference src/align.c:207-215) */
+        double events_per_kmer = (double)(size_t)E / (size_t)r.n_kmers;
+        double p_stay = 1 - (1 / (events_per_kmer + 1));
+        r.lp_stay = log(p_stay);
+        r.lp_step = log(1.0 - exp(c->cst.lp_skip) - exp(r.lp_stay));
+        c->reads.push_back(r);
+    }
+    /* longest-first schedule: a read is a serial chain of NB = E+K+2 bands */
+    std::stable_sort(c->reads.begin(), c->reads.end(), [](const abea_read_t& x, const abea_read_t& y) {
+        return (int64_t)x.n_events + x.n_kmers > (int64_t)y.n_events + y.n_kmers;
+    });
+    int64_t kp = 0, tw = 0, pc = 0, nb = 0, ne = 0;
+    for (abea_read_t& r : c->reads) {
+        const int64_t NB = (int64_t)r.n_events + r.n_kmers + 2;
+        r.kp_off = kp;
+        r.trace_off = tw;
+        r.pair_off = pc;
+        kp += r.n_kmers;
+        tw += ((NB + 3) / 4) * ABEA_TRACE_GROUP_WORDS;
+        pc += r.pair_cap;
+        nb += NB;
+        ne += r.n_events;
+    }
+    c->total_kmers = kp;
+    c->total_trace_words = tw;
+    c->total_pair_cap = pc;
+    c->total_bands = nb;
+    c->total_events = ne;
+    const size_t n_sched = c->reads.size();
+    double t1 = now_ms();
+
+    if (dev_reserve(c, c->d_seq, (size_t)seq_bytes + 16)) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_events, (size_t)n_ev_total * sizeof(abea_event_t) + 16)) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_reads, (n_sched + 1) * sizeof(abea_read_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_kparams, (size_t)(kp + 1) * sizeof(float4))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_trace, (size_t)(tw + 32) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_pairs, (size_t)(pc + 1) * sizeof(abea_pair_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_results, (n_sched + 1) * sizeof(abea_result_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_queue, 64)) return ABEA_ERR_CUDA;
+
+    CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
+    if (seq_bytes) CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (n_ev_total)
+        CU(cudaMemcpyAsync(c->d_events.p, b->events, (size_t)n_ev_total * sizeof(abea_event_t),
+                           cudaMemcpyHostToDevice, c->stream));
+    if (n_sched)
+        CU(cudaMemcpyAsync(c->d_reads.p, c->reads.data(), n_sched * sizeof(abea_read_t), cudaMemcpyHostToDevice,
+                           c->stream));
+    CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = true;
+
+    c->last = abea_timing_t();
+    c->last.pack_ms = t1 - t0;
+    c->last.h2d_ms = ev_ms(c, EV_H2D0, EV_H2D1);
+    c->last.h2d_bytes = seq_bytes + n_ev_total * (int64_t)sizeof(abea_event_t) + (int64_t)(n_sched * sizeof(abea_read_t));
+    c->last.n_scheduled = (int32_t)n_sched;
+    c->last.n_bands = nb;
+    c->last.n_events = ne;
+    if (timing) *timing = c->last;
+    return ABEA_OK;
+}
+
+int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
+    if (!c) return ABEA_ERR_ARG;
+    if (!c->uploaded) return fail(c, ABEA_ERR_STATE, "abea_run before abea_upload_batch");
+    CU(cudaSetDevice(c->device));
+    const int32_t n = (int32_t)c->reads.size();
+    int launches = 0;
+    CU(cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
+    CU(cudaEventRecord(c->ev[EV_K0], c->stream));
+    if (n > 0) {
+        {
+            int threads = 256;
+            int64_t blocks64 = (c->total_kmers + threads - 1) / threads;
+            int blocks = (int)std::min<int64_t>(blocks64, (int64_t)c->sm_count * 16);
+            if (blocks < 1) blocks = 1;
+            ABEA_LAUNCH(abea_kmer_params_kernel, blocks, threads, c->stream,
+                (const abea_read_t*)c->d_reads.p, n, (const uint8_t*)c->d_seq.p, (const abea_model_t*)c->d_model.p,
+                c->kmer_size, (float4*)c->d_kparams.p, c->total_kmers);
+            launches++;
+        }
+        CU(cudaEventRecord(c->ev[EV_K1], c->stream));
+        {
+            /* persistent warps: 4 CTAs of 4 warps per SM, each warp pulls reads longest-first */
+            int warps_needed = n;
+            int blocks = std::min(c->sm_count * 4, (warps_needed + 3) / 4);
+            if (blocks < 1) blocks = 1;
+            ABEA_LAUNCH(abea_fill_kernel, blocks, 128, c->stream,
+                (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, (int32_t*)c->d_queue.p);
+            launches++;
+        }
+        CU(cudaEventRecord(c->ev[EV_K2], c->stream));
+        {
+            int blocks = std::min(c->sm_count * 4, (n + 3) / 4);
+            if (blocks < 1) blocks = 1;
+            ABEA_LAUNCH(abea_traceback_kernel, blocks, 128, c->stream,
+                (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                (const uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p, (abea_result_t*)c->d_results.p,
+                (int32_t*)c->d_queue.p + 1);
+            launches++;
+        }
+    } else {
+        CU(cudaEventRecord(c->ev[EV_K1], c->stream));
+        CU(cudaEventRecord(c->ev[EV_K2], c->stream));
+    }
+    CU(cudaEventRecord(c->ev[EV_K3], c->stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->ran = true;
+    c->last.kmer_ms = ev_ms(c, EV_K0, EV_K1);
+    c->last.fill_ms = ev_ms(c, EV_K1, EV_K2);
+    c->last.trace_ms = ev_ms(c, EV_K2, EV_K3);
+    c->last.kernel_ms = ev_ms(c, EV_K0, EV_K3);
+    c->last.kernel_launches = launches;
+    if (timing) *timing = c->last;
+    return ABEA_OK;
+}
+
+int abea_download(abea_ctx_t* c, abea_pair_t* pairs, const int64_t* pair_ptr, int32_t* n_pairs,
+                  abea_timing_t* timing) {
+    if (!c || !n_pairs || (!pairs && c->total_pair_cap > 0) || !pair_ptr) return fail(c, ABEA_ERR_ARG, "bad output");
+    if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_download before abea_run");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->reads.size();
+    if (host_reserve(c, c->h_results, (n + 1) * sizeof(abea_result_t))) return ABEA_ERR_CUDA;
+    if (host_reserve(c, c->h_pairs, (size_t)(c->total_pair_cap + 1) * sizeof(abea_pair_t))) return ABEA_ERR_CUDA;
+    CU(cudaEventRecord(c->ev[EV_D2H0], c->stream));
+    if (n) {
+        CU(cudaMemcpyAsync(c->h_results.p, c->d_results.p, n * sizeof(abea_result_t), cudaMemcpyDeviceToHost,
+                           c->stream));
+        CU(cudaMemcpyAsync(c->h_pairs.p, c->d_pairs.p, (size_t)c->total_pair_cap * sizeof(abea_pair_t),
+                           cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    double t0 = now_ms();
+    for (int32_t i = 0; i < c->n_batch_reads; i++) n_pairs[i] = 0;
+    const abea_result_t* res = (const abea_result_t*)c->h_results.p;
+    const abea_pair_t* hp = (const abea_pair_t*)c->h_pairs.p;
+    for (size_t j = 0; j < n; j++) {
+        const abea_read_t& r = c->reads[j];
+        const int32_t np = res[j].n_pairs;
+        n_pairs[r.orig_index] = np;
+        if (np > 0)
+            memcpy(pairs + pair_ptr[r.orig_index], hp + r.pair_off + res[j].pair_start, (size_t)np * sizeof(abea_pair_t));
+    }
+    double t1 = now_ms();
+    c->last.d2h_ms = ev_ms(c, EV_D2H0, EV_D2H1);
+    c->last.unpack_ms = t1 - t0;
+    c->last.d2h_bytes = (int64_t)(n * sizeof(abea_result_t)) + c->total_pair_cap * (int64_t)sizeof(abea_pair_t);
+    if (timing) *timing = c->last;
+    return ABEA_OK;
+}
+
+int abea_read_stats(abea_ctx_t* c, double* sum_emission, int32_t* n_aligned, int32_t* end_event, int32_t* max_gap) {
+    if (!c) return ABEA_ERR_ARG;
+    if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_read_stats before abea_run");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->reads.size();
+    std::vector<abea_result_t> res(n);
+    if (n) CU(cudaMemcpy(res.data(), c->d_results.p, n * sizeof(abea_result_t), cudaMemcpyDeviceToHost));
+    for (int32_t i = 0; i < c->n_batch_reads; i++) {
+        if (sum_emission) sum_emission[i] = 0;
+        if (n_aligned) n_aligned[i] = 0;
+        if (end_event) end_event[i] = 0;
+        if (max_gap) max_gap[i] = 0;
+    }
+    for (size_t j = 0; j < n; j++) {
+        int32_t i = c->reads[j].orig_index;
+        if (sum_emission) sum_emission[i] = res[j].sum_emission;
+        if (n_aligned) n_aligned[i] = res[j].n_aligned;
+        if (end_event) end_event[i] = res[j].end_event;
+        if (max_gap) max_gap[i] = res[j].max_gap;
+    }
+    return ABEA_OK;
+}
+
+int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pairs, const int64_t* pair_ptr,
+                     int32_t* n_pairs, abea_timing_t* timing) {
+    int rc = abea_upload_batch(c, batch, nullptr);
+    if (rc) return rc;
+    rc = abea_run(c, nullptr);
+    if (rc) return rc;
+    rc = abea_download(c, pairs, pair_ptr, n_pairs, nullptr);
+    if (rc) return rc;
+    if (timing) *timing = c->last;
+    return ABEA_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,107 @@
+/* abea_b200.h — C ABI of libabea_b200.so: f5c's adaptive banded event alignment (ABEA) on B200 (sm_100a).
+ *
+ * This is the boundary a host program binds. Plain pointers and sizes only; no C++ or torch types.
+ * Each entry point names the reference interface it replaces (paths relative to the f5c tree):
+ *
+ *   abea_create / abea_destroy      init_cuda / free_cuda            src/f5c.h:575-581, src/f5c.cu:23-234
+ *   abea_set_model                  the model H2D inside init_cuda   src/f5c.cu:96-103 (core->model, src/f5c.c:286-337)
+ *   abea_align_batch                align_cuda(core_t*, db_t*)       src/f5cmisc.h:122-125, src/f5c.cu:647-1061
+ *                                   == the GPU branch of align_db    src/f5c.c:833-845
+ *   abea_upload_batch / abea_run /  the three phases of align_cuda   src/f5c.cu:744-899 (pack + H2D),
+ *   abea_download                   kept separable for measurement   :910-960 (kernels), :979-1030 (D2H + unpack)
+ *   abea_model_fill_log_stdv        set_model's CACHED_LOG fill      src/model.c:179
+ *
+ * The drop-in with the reference's own C++-linkage symbols (align_cuda/init_cuda/free_cuda over core_t/db_t) is
+ * f5c_b200/csrc/f5c_dropin.cu, a thin packer over this ABI that is compiled inside the f5c tree.
+ *
+ * Semantics of abea_align_batch (identical to the reference CPU path, align_single src/f5c.c:811-830 + align
+ * src/align.c:180-559): for every read i, n_pairs[i] is the number of aligned pairs after QC (0 for bad reads,
+ * over-segmented reads with events/base >= 15, and QC failures) and pairs[pair_ptr[i] .. +n_pairs[i]) holds them in
+ * ascending order, bit-identical to the reference. The caller sizes read i's region to n_events[i]+read_len[i]
+ * pairs (src/f5c.c:724-726). No read is ever sent to a CPU fallback (the reference's if_on_gpu heuristic,
+ * src/f5c.cu:440-452, has no counterpart).
+ *
+ * Errors: functions return 0 on success or a negative abea_status; abea_last_error() gives the message. The
+ * reference convention (print and exit(-1), src/f5cmisc.cuh:54-97) is applied by the drop-in shim, not here.
+ * Threading: one context per host thread / GPU; a context is not re-entrant.
+ */
+#ifndef ABEA_B200_H
+#define ABEA_B200_H
+
+#include "abea_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct abea_ctx abea_ctx_t;
+
+enum abea_status {
+    ABEA_OK = 0,
+    ABEA_ERR_CUDA = -1,     /* a CUDA runtime call failed */
+    ABEA_ERR_ARG = -2,      /* invalid argument */
+    ABEA_ERR_NOMODEL = -3,  /* abea_set_model not called */
+    ABEA_ERR_NODEVICE = -4, /* no usable CUDA device (the library has no CPU path) */
+    ABEA_ERR_STATE = -5     /* call order violated (e.g. abea_run before abea_upload_batch) */
+};
+
+/* Device-side time of each phase in milliseconds (CUDA events on the context's stream), plus host-side packing.
+ * Mirrors the reference's timer split (core->align_cuda_preprocess/memcpy/kernel/postprocess, src/f5c.h:457-466). */
+typedef struct {
+    double pack_ms;        /* host: descriptors, scheduling order */
+    double h2d_ms;         /* device: sequence + event + descriptor copies */
+    double kmer_ms;        /* device: abea_kmer_params_kernel */
+    double fill_ms;        /* device: band fill (narrow + wide kernels, concurrent) */
+    double trace_ms;       /* device: abea_traceback_kernel */
+    double kernel_ms;      /* device: first kernel start to last kernel end */
+    double d2h_ms;         /* device: result copies */
+    double unpack_ms;      /* host: scatter into the caller's buffers */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+    int32_t kernel_launches; /* kernels of this library launched by the call */
+    int32_t n_scheduled;     /* reads that passed the eligibility filter */
+    int64_t n_bands;         /* sum of NB over scheduled reads */
+    int64_t n_events;        /* sum of E over scheduled reads (the metric's numerator) */
+} abea_timing_t;
+
+/* Create a context on CUDA device `device` (cudaSetDevice is applied on every call). */
+int abea_create(abea_ctx_t** ctx, int device);
+void abea_destroy(abea_ctx_t* ctx);
+const char* abea_last_error(const abea_ctx_t* ctx);
+
+/* Upload the pore-model table: 4^kmer_size entries with level_log_stdv already filled. */
+int abea_set_model(abea_ctx_t* ctx, const abea_model_t* model, uint32_t kmer_size);
+
+/* level_log_stdv = logf(level_stdv) on the host, exactly as the reference's set_model/read_model do. */
+void abea_model_fill_log_stdv(abea_model_t* model, int64_t n);
+
+/* The whole path with HOST buffers in and out (pack + H2D + kernels + D2H + unpack). timing may be NULL. */
+int abea_align_batch(abea_ctx_t* ctx, const abea_batch_t* batch, abea_pair_t* pairs, const int64_t* pair_ptr,
+                     int32_t* n_pairs, abea_timing_t* timing);
+
+/* The same path in three separable phases. abea_run may be repeated on a resident batch (it re-zeroes its queues). */
+int abea_upload_batch(abea_ctx_t* ctx, const abea_batch_t* batch, abea_timing_t* timing);
+int abea_run(abea_ctx_t* ctx, abea_timing_t* timing);
+int abea_download(abea_ctx_t* ctx, abea_pair_t* pairs, const int64_t* pair_ptr, int32_t* n_pairs,
+                  abea_timing_t* timing);
+
+/* Per-read diagnostics of the last run, indexed like the batch (any pointer may be NULL):
+ * sum of emissions along the traceback (the quantity in the reference's adaptive.exp debug dumps), pairs before
+ * QC, the event the traceback started from and the longest skip run. Reads that were not scheduled report 0. */
+int abea_read_stats(abea_ctx_t* ctx, double* sum_emission, int32_t* n_aligned, int32_t* end_event,
+                    int32_t* max_gap);
+
+/* Pinned host memory for callers that want the H2D/D2H copies to run at full PCIe rate. */
+void* abea_host_alloc(size_t bytes);
+void abea_host_free(void* p);
+
+/* Device properties of the context's GPU (for reports): SM count and name (buffer of >= 256 bytes). */
+int abea_device_info(abea_ctx_t* ctx, int* sm_count, char* name);
+
+/* Library version string. */
+const char* abea_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
