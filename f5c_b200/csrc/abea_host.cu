@@ -67,7 +67,7 @@ struct abea_ctx {
     bool have_model = false;
 
     /* resident batch */
-    DevBuf d_seq, d_events, d_reads, d_kparams, d_trace, d_pairs, d_results, d_queue;
+    DevBuf d_seq, d_events, d_reads, d_kparams, d_trace, d_pairs, d_results, d_queue, d_flags;
     HostBuf h_results, h_pairs;
     std::vector<abea_read_t> reads;   /* scheduled reads, longest first */
     int32_t n_batch_reads = 0;        /* reads in the caller's batch */
@@ -187,7 +187,7 @@ void abea_destroy(abea_ctx_t* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_reads, &c->d_kparams,
-                      &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue};
+                      &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_results.p) cudaFreeHost(c->h_results.p);
@@ -270,6 +270,7 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
     for (abea_read_t& r : c->reads) {
         const int64_t NB = (int64_t)r.n_events + r.n_kmers + 2;
         r.kp_off = kp;
+        r.evs_off = ne;
         r.trace_off = tw;
         r.pair_off = pc;
         kp += r.n_kmers;
@@ -294,6 +295,7 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
     if (dev_reserve(c, c->d_pairs, (size_t)(pc + 1) * sizeof(abea_pair_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_results, (n_sched + 1) * sizeof(abea_result_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_queue, 64)) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_flags, (n_sched + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
 
     CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
     if (seq_bytes) CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -327,26 +329,33 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
     CU(cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
     CU(cudaEventRecord(c->ev[EV_K0], c->stream));
     if (n > 0) {
+        int32_t* queue = (int32_t*)c->d_queue.p;
         {
+            /* every read starts as "fast"; abea_prepare_kernel clears the flag of reads with out-of-range inputs */
+            CU(cudaMemsetAsync(c->d_flags.p, 0x01, (size_t)n * sizeof(uint32_t), c->stream));
             int threads = 256;
-            int64_t blocks64 = (c->total_kmers + threads - 1) / threads;
-            int blocks = (int)std::min<int64_t>(blocks64, (int64_t)c->sm_count * 16);
+            int64_t work = std::max(c->total_kmers, c->total_events);
+            int blocks = (int)std::min<int64_t>((work + threads - 1) / threads, (int64_t)c->sm_count * 16);
             if (blocks < 1) blocks = 1;
-            ABEA_LAUNCH(abea_kmer_params_kernel, blocks, threads, c->stream,
+            ABEA_LAUNCH(abea_prepare_kernel, blocks, threads, c->stream,
                 (const abea_read_t*)c->d_reads.p, n, (const uint8_t*)c->d_seq.p, (const abea_model_t*)c->d_model.p,
-                c->kmer_size, (float4*)c->d_kparams.p, c->total_kmers);
+                c->kmer_size, (const abea_event_t*)c->d_events.p, (float4*)c->d_kparams.p, (uint32_t*)c->d_flags.p,
+                c->total_kmers, c->total_events);
             launches++;
         }
         CU(cudaEventRecord(c->ev[EV_K1], c->stream));
         {
-            /* persistent warps: 4 CTAs of 4 warps per SM, each warp pulls reads longest-first */
-            int warps_needed = n;
-            int blocks = std::min(c->sm_count * 4, (warps_needed + 3) / 4);
+            /* persistent warps: 4 CTAs of 4 warps per SM, each warp pulls reads longest-first. The FAST
+             * instantiation takes the reads whose inputs passed validation, the EXACT one the rest (normally none). */
+            int blocks = std::min(c->sm_count * 4, (n + 3) / 4);
             if (blocks < 1) blocks = 1;
-            ABEA_LAUNCH(abea_fill_kernel, blocks, 128, c->stream,
+            ABEA_LAUNCH(abea_fill_kernel<true>, blocks, 128, c->stream,
                 (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
-                (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, (int32_t*)c->d_queue.p);
-            launches++;
+                (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue);
+            ABEA_LAUNCH(abea_fill_kernel<false>, blocks, 128, c->stream,
+                (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue + 1);
+            launches += 2;
         }
         CU(cudaEventRecord(c->ev[EV_K2], c->stream));
         {
@@ -354,8 +363,7 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
             if (blocks < 1) blocks = 1;
             ABEA_LAUNCH(abea_traceback_kernel, blocks, 128, c->stream,
                 (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
-                (const uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p, (abea_result_t*)c->d_results.p,
-                (int32_t*)c->d_queue.p + 1);
+                (const uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p, (abea_result_t*)c->d_results.p, queue + 2);
             launches++;
         }
     } else {

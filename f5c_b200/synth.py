@@ -43,13 +43,36 @@ def mom_scalings(ev_mean: np.ndarray, levels: np.ndarray):
     return np.float32(scale), np.float32(shift)
 
 
+def draw_lengths(n_reads: int, mean_events: float, sigma: float, rng) -> np.ndarray:
+    """Target events per read: LogNormal(ln(mean) - sigma^2/2, sigma)."""
+    return rng.lognormal(np.log(mean_events) - 0.5 * sigma * sigma, sigma, n_reads)
+
+
+def lpt_shards(weights: np.ndarray, n_shards: int):
+    """Longest-processing-time-first partition: reads sorted by weight descending, each to the lightest shard
+    (balance the sum of band counts, not the read count). Returns a list of index arrays."""
+    order = np.argsort(-np.asarray(weights, dtype=np.float64), kind="stable")
+    load = np.zeros(n_shards)
+    bins = [[] for _ in range(n_shards)]
+    for i in order:
+        j = int(np.argmin(load))
+        bins[j].append(int(i))
+        load[j] += weights[i]
+    return [np.array(sorted(b), dtype=np.int64) for b in bins]
+
+
 def make_batch(model: str = "r9", n_reads: int = 64, mean_events: float = 4000.0, sigma: float = 0.5,
-               epk: float = 1.8, seed: int = 42, model_table=None, min_len: int = 200) -> ReadBatch:
-    """Generate a ragged batch. model_table=(k, MODEL_DTYPE array) overrides the named built-in table."""
+               epk: float = 1.8, seed: int = 42, model_table=None, min_len: int = 200,
+               e_star: np.ndarray | None = None) -> ReadBatch:
+    """Generate a ragged batch. model_table=(k, MODEL_DTYPE array) overrides the named built-in table;
+    e_star (target event counts per read) overrides the log-normal draw (used for read-wise sharding)."""
     k, mt = model_table if model_table is not None else load_model(model)
     rng = np.random.default_rng(seed)
-    mu = np.log(mean_events) - 0.5 * sigma * sigma
-    e_star = rng.lognormal(mu, sigma, n_reads)
+    if e_star is None:
+        e_star = draw_lengths(n_reads, mean_events, sigma, rng)
+    else:
+        e_star = np.asarray(e_star, dtype=np.float64)
+        n_reads = int(e_star.shape[0])
     L = np.maximum((e_star / epk).astype(np.int64) + k, min_len)
     K = L - k + 1
 
@@ -117,4 +140,23 @@ def make_config(name: str, seed: int = 42, n_reads: int | None = None) -> ReadBa
         p["n_reads"] = n_reads
     b = make_batch(seed=seed, **p)
     b.meta["config"] = name
+    return b
+
+
+def make_config_shard(name: str, rank: int, world: int, seed: int = 42, reads_per_gpu: int | None = None) -> ReadBatch:
+    """Rank `rank`'s shard of a global batch of world*reads_per_gpu reads, partitioned read-wise.
+
+    Every rank draws the same global list of target lengths (one cheap log-normal draw), the list is split
+    longest-first by estimated band count E*(1+1/epk), and the rank materialises only its own reads. With world == 1
+    this is exactly make_config(name, seed)."""
+    p = dict(CONFIGS[name])
+    per = reads_per_gpu if reads_per_gpu is not None else p["n_reads"]
+    if world == 1:
+        return make_config(name, seed=seed, n_reads=per)
+    rng = np.random.default_rng(seed)
+    e_star = draw_lengths(per * world, p["mean_events"], p["sigma"], rng)
+    shards = lpt_shards(e_star * (1.0 + 1.0 / p["epk"]), world)
+    p.pop("n_reads")
+    b = make_batch(seed=seed * 1000003 + rank + 1, e_star=e_star[shards[rank]], **p)
+    b.meta.update(config=name, rank=rank, world=world, global_reads=per * world)
     return b

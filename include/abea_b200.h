@@ -50,7 +50,7 @@ enum abea_status {
 typedef struct {
     double pack_ms;        /* host: descriptors, scheduling order */
     double h2d_ms;         /* device: sequence + event + descriptor copies */
-    double kmer_ms;        /* device: abea_kmer_params_kernel */
+    double kmer_ms;        /* device: abea_prepare_kernel (k-mer parameter cache + input validation) */
     double fill_ms;        /* device: band fill (narrow + wide kernels, concurrent) */
     double trace_ms;       /* device: abea_traceback_kernel */
     double kernel_ms;      /* device: first kernel start to last kernel end */

@@ -1,0 +1,170 @@
+"""Parity tests proper (run on the B200 with -m gpu): the CUDA path, called through the C ABI (ctypes ->
+libabea_b200.so), against the oracle on the same seeded inputs; the committed golden fixtures; and, at BASELINE.json's
+full sizes, size-independent properties of the alignment."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from edge_cases import edge_batch
+from f5c_b200 import models, synth
+from f5c_b200.abea import AbeaContext, align_db
+from f5c_b200.batch import ReadBatch
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = AbeaContext(0)
+    yield c
+    c.close()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def run_and_check(ctx, batch, model_name, what):
+    k, m = models.load_model(model_name)
+    m = ctx.set_model(m, k)
+    got = align_db(ctx, batch)
+    st = ctx.read_stats(batch.n_reads)
+    want = ol.port_align(batch, m)
+    ol.assert_same_alignment(got, want, what)     # integer outputs: bit-exact
+    sched = want.stats["n_bands"] > 0
+    # emission log-probabilities: north_star allows 1e-4 relative; we get bit equality
+    np.testing.assert_allclose(st["sum_emission"][sched], want.stats["sum_emission"][sched], rtol=1e-4)
+    assert np.array_equal(st["sum_emission"][sched], want.stats["sum_emission"][sched])
+    assert np.array_equal(st["end_event"][sched], want.stats["end_event"][sched])
+    assert got.timing["kernel_launches"] >= 3
+    return got, want
+
+
+@pytest.mark.parametrize("cfg,n", [("cfg2", 192), ("cfg3", 96), ("cfg4", 24)])
+def test_parity_synthetic_configs(ctx, cfg, n):
+    b = synth.make_config(cfg, seed=77, n_reads=n)
+    got, _ = run_and_check(ctx, b, b.meta["model"], cfg)
+    assert (got.n_pairs > 0).mean() > 0.9
+
+
+def test_parity_rna_r9_5mer(ctx):
+    b = synth.make_batch("rna_r9", n_reads=32, mean_events=2500, sigma=0.5, epk=2.2, seed=31)
+    run_and_check(ctx, b, "rna_r9", "rna_r9")
+
+
+def test_parity_short_reads(ctx):
+    """Reads shorter than the band: every band is an edge band (validity window, trim column, end column)."""
+    b = synth.make_batch("r9", n_reads=256, mean_events=120, sigma=0.9, epk=1.8, seed=32, min_len=12)
+    run_and_check(ctx, b, "r9", "short")
+
+
+def test_parity_edge_cases(ctx):
+    b = edge_batch()
+    got, _ = run_and_check(ctx, b, "r9", "edge")
+    assert got.n_pairs[1] == 0 and got.n_pairs[3] == 0 and got.n_pairs[4] == 0
+
+
+def test_golden_fixtures(ctx):
+    """Committed vectors generated from the reference (tests/golden/make_golden.py): single_read/adaptive.exp and
+    a spread of test/ecoli_2kb_region reads."""
+    gold = json.load(open(os.path.join(HERE, "golden", "abea_golden.json")))
+    npz = np.load(os.path.join(HERE, "golden", "abea_golden.npz"))
+    k, m = models.load_model("r9")
+    ctx.set_model(m, k)
+    b1 = ReadBatch.from_reads([npz["single_seq"].tobytes()], [npz["single_events"]], npz["single_scalings"], k)
+    a1 = align_db(ctx, b1)
+    assert a1.n_pairs[0] == 7206 and sha(a1.read_pairs(0)) == gold["single_read"]["pairs_sha256"]
+    st = ctx.read_stats(1)
+    assert abs(st["sum_emission"][0] - gold["single_read"]["golden_sum_emission"]) < 2e-2
+    be = ReadBatch(npz["ecoli_seq"], npz["ecoli_seq_ptr"], npz["ecoli_read_len"], npz["ecoli_events"],
+                   npz["ecoli_event_ptr"], npz["ecoli_n_events"], npz["ecoli_scalings"],
+                   np.ones(len(npz["ecoli_read_len"]), dtype=np.uint8), k)
+    ae = align_db(ctx, be)
+    assert [int(x) for x in ae.n_pairs] == gold["ecoli"]["n_pairs"]
+    assert [sha(ae.read_pairs(i)) for i in range(be.n_reads)] == gold["ecoli"]["pairs_sha256"]
+    st = ctx.read_stats(be.n_reads)
+    for i, g in enumerate(gold["ecoli"]["golden_sum_emission"]):
+        if g is not None:
+            assert abs(st["sum_emission"][i] - g) < 5e-2
+
+
+def test_long_read_no_cpu_fallback(ctx):
+    """A read 30x longer than the batch mean (the reference would send it to the CPU, src/f5c.cu:440-452)."""
+    short = synth.make_batch("r9", n_reads=31, mean_events=1000, sigma=0.2, epk=1.8, seed=41)
+    long_ = synth.make_batch("r9", n_reads=1, mean_events=30000, sigma=0.01, epk=1.8, seed=42)
+    seqs = [short.read_seq(i) for i in range(31)] + [long_.read_seq(0)]
+    evs = [short.read_events(i) for i in range(31)] + [long_.read_events(0)]
+    sc = np.concatenate([short.scalings, long_.scalings])
+    b = ReadBatch.from_reads(seqs, evs, sc, short.kmer_size)
+    got, _ = run_and_check(ctx, b, "r9", "long")
+    assert got.n_pairs[31] > 25000
+
+
+def check_alignment_properties(batch, aln):
+    """Size-independent invariants of a passing alignment (reference src/align.c:452-543)."""
+    K = batch.n_kmers
+    for i in range(batch.n_reads):
+        n = int(aln.n_pairs[i])
+        if n == 0:
+            continue
+        p = aln.read_pairs(i)
+        k, e = p["ref_pos"].astype(np.int64), p["read_pos"].astype(np.int64)
+        assert k[0] == 0 and k[-1] == K[i] - 1                       # spanned
+        assert e.min() >= 0 and e.max() < batch.n_events[i]
+        dk, de = np.diff(k), np.diff(e)
+        assert np.all((dk >= 0) & (dk <= 1) & (de >= 0) & (de <= 1) & (dk + de >= 1))   # D / U / L steps only
+        skip = (de == 0)                                             # runs of FROM_L are bounded by max_gap 50
+        if skip.any():
+            runs = np.diff(np.flatnonzero(np.diff(np.concatenate(([0], skip.astype(np.int8), [0])))))[::2]
+            assert runs.max() <= 50
+
+
+def test_full_size_cfg2_properties(ctx):
+    """BASELINE configs[1] at full size: invariants on all 4096 reads, oracle parity on a random sample, batch
+    composition independence, idempotence."""
+    b = synth.make_config("cfg2", seed=42)
+    k, m = models.load_model("r9")
+    m = ctx.set_model(m, k)
+    a = align_db(ctx, b)
+    assert (a.n_pairs > 0).mean() > 0.98
+    check_alignment_properties(b, a)
+    a2 = align_db(ctx, b)
+    assert np.array_equal(a.n_pairs, a2.n_pairs) and sha(a.pairs[: 1 << 20]) == sha(a2.pairs[: 1 << 20])
+    rng = np.random.default_rng(5)
+    longest = np.argsort(b.n_events)[-8:]
+    idx = np.concatenate([rng.choice(b.n_reads, 56, replace=False), longest])
+    sub = b.subset(idx)
+    want = ol.port_align(sub, m)
+    alone = align_db(ctx, sub)
+    ol.assert_same_alignment(alone, want, "cfg2 sample")
+    for j, i in enumerate(idx):
+        assert np.array_equal(a.read_pairs(int(i)), want.read_pairs(j))
+
+
+def test_full_size_cfg4_long_read_stress(ctx):
+    """BASELINE configs[3] (RNA004, mean 20k events/read) at reduced read count but full read lengths."""
+    b = synth.make_config("cfg4", seed=43, n_reads=256)
+    k, m = models.load_model("rna004")
+    m = ctx.set_model(m, k)
+    a = align_db(ctx, b)
+    check_alignment_properties(b, a)
+    idx = np.argsort(b.n_events)[-4:]
+    sub = b.subset(idx)
+    want = ol.port_align(sub, m)
+    for j, i in enumerate(idx):
+        assert np.array_equal(a.read_pairs(int(i)), want.read_pairs(j))
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not shipped")
+def test_parity_against_reference_object_code(ctx):
+    """Same comparison with the unmodified reference align() (oracle/_ref, built from /root/reference)."""
+    b = synth.make_config("cfg3", seed=91, n_reads=48)
+    k, m = models.load_model("r10")
+    m = ctx.set_model(m, k)
+    ol.assert_same_alignment(align_db(ctx, b), ol.ref_align(b, m), "cfg3 vs reference")

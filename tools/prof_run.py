@@ -1,0 +1,17 @@
+#!/usr/bin/env python3
+"""Workload for ncu captures: one config resident on the GPU, run the three kernels a few times."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from f5c_b200 import synth, models
+from f5c_b200.abea import AbeaContext
+cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+n = int(sys.argv[2]) if len(sys.argv) > 2 else None
+runs = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+b = synth.make_config(cfg, seed=42, n_reads=n)
+k, m = models.load_model(b.meta["model"])
+ctx = AbeaContext(0); ctx.set_model(m, k)
+ctx.upload(b)
+for i in range(runs):
+    t = ctx.run()
+    print({x: round(t[x], 3) for x in ("kmer_ms", "fill_ms", "trace_ms", "kernel_ms")}, "Mev/s %.1f" % (t["n_events"] / t["kernel_ms"] / 1e3))
