@@ -67,7 +67,8 @@ struct abea_ctx {
     bool have_model = false;
 
     /* resident batch */
-    DevBuf d_seq, d_events, d_reads, d_kparams, d_trace, d_pairs, d_results, d_queue, d_flags;
+    DevBuf d_seq, d_events, d_reads, d_kparams, d_trace, d_pairs, d_results, d_queue, d_flags, d_npairs;
+    std::vector<int64_t> cap_ptr;     /* canonical pair_ptr of the caller's batch: prefix sum of E+L over ALL reads */
     HostBuf h_results, h_pairs;
     std::vector<abea_read_t> reads;   /* scheduled reads, longest first */
     int32_t n_batch_reads = 0;        /* reads in the caller's batch */
@@ -187,7 +188,7 @@ void abea_destroy(abea_ctx_t* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_reads, &c->d_kparams,
-                      &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags};
+                      &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags, &c->d_npairs};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_results.p) cudaFreeHost(c->h_results.p);
@@ -237,6 +238,11 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
         if (ee > n_ev_total) n_ev_total = ee;
     }
 
+    /* canonical output layout: read i owns pairs [cap_ptr[i], cap_ptr[i] + E_i + L_i) (reference src/f5c.c:724-726) */
+    c->cap_ptr.assign((size_t)b->n_reads + 1, 0);
+    for (int32_t i = 0; i < b->n_reads; i++)
+        c->cap_ptr[i + 1] = c->cap_ptr[i] + (int64_t)b->n_events[i] + (int64_t)b->read_len[i];
+
     /* eligibility: align_single's filter (reference src/f5c.c:811-830). Reads with no events or fewer bases than
      * k are undefined in the reference; they get 0 pairs here. */
     const int32_t k = (int32_t)c->kmer_size;
@@ -244,6 +250,7 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
         const int32_t E = b->n_events[i], L = b->read_len[i];
         const bool good = b->good ? (b->good[i] != 0) : true;
         if (!good || E < 1 || L < k) continue;
+        if ((int64_t)E + (int64_t)L + 2 >= (int64_t)0x7fffffff) continue; /* band counters are 32-bit */
         if (!((float)(size_t)E / (float)L < ABEA_AVG_EVENTS_PER_KMER_MAX)) continue;
         abea_read_t r;
         memset(&r, 0, sizeof(r));
@@ -272,7 +279,7 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
         r.kp_off = kp;
         r.evs_off = ne;
         r.trace_off = tw;
-        r.pair_off = pc;
+        r.pair_off = c->cap_ptr[r.orig_index];
         kp += r.n_kmers;
         tw += ((NB + 3) / 4) * ABEA_TRACE_GROUP_WORDS;
         pc += r.pair_cap;
@@ -281,7 +288,8 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
     }
     c->total_kmers = kp;
     c->total_trace_words = tw;
-    c->total_pair_cap = pc;
+    c->total_pair_cap = c->cap_ptr[b->n_reads];
+    (void)pc;
     c->total_bands = nb;
     c->total_events = ne;
     const size_t n_sched = c->reads.size();
@@ -291,8 +299,10 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
     if (dev_reserve(c, c->d_events, (size_t)n_ev_total * sizeof(abea_event_t) + 16)) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_reads, (n_sched + 1) * sizeof(abea_read_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_kparams, (size_t)(kp + 1) * sizeof(float4))) return ABEA_ERR_CUDA;
-    if (dev_reserve(c, c->d_trace, (size_t)(tw + 32) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
-    if (dev_reserve(c, c->d_pairs, (size_t)(pc + 1) * sizeof(abea_pair_t))) return ABEA_ERR_CUDA;
+    /* + one traceback chunk of slack: the prefetcher copies whole 16-group chunks */
+    if (dev_reserve(c, c->d_trace, (size_t)(tw + (ABEA_TB_CHUNK_GROUPS + 1) * ABEA_TRACE_GROUP_WORDS) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_pairs, (size_t)(c->total_pair_cap + 1) * sizeof(abea_pair_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_npairs, ((size_t)b->n_reads + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_results, (n_sched + 1) * sizeof(abea_result_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_queue, 64)) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_flags, (n_sched + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
@@ -327,6 +337,7 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
     const int32_t n = (int32_t)c->reads.size();
     int launches = 0;
     CU(cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
+    CU(cudaMemsetAsync(c->d_npairs.p, 0, ((size_t)c->n_batch_reads + 1) * sizeof(int32_t), c->stream));
     CU(cudaEventRecord(c->ev[EV_K0], c->stream));
     if (n > 0) {
         int32_t* queue = (int32_t*)c->d_queue.p;
@@ -363,7 +374,8 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
             if (blocks < 1) blocks = 1;
             ABEA_LAUNCH(abea_traceback_kernel, blocks, 128, c->stream,
                 (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
-                (const uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p, (abea_result_t*)c->d_results.p, queue + 2);
+                (const uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p, (abea_result_t*)c->d_results.p,
+                (int32_t*)c->d_npairs.p, queue + 2);
             launches++;
         }
     } else {
@@ -388,33 +400,46 @@ int abea_download(abea_ctx_t* c, abea_pair_t* pairs, const int64_t* pair_ptr, in
     if (!c || !n_pairs || (!pairs && c->total_pair_cap > 0) || !pair_ptr) return fail(c, ABEA_ERR_ARG, "bad output");
     if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_download before abea_run");
     CU(cudaSetDevice(c->device));
-    const size_t n = c->reads.size();
-    if (host_reserve(c, c->h_results, (n + 1) * sizeof(abea_result_t))) return ABEA_ERR_CUDA;
-    if (host_reserve(c, c->h_pairs, (size_t)(c->total_pair_cap + 1) * sizeof(abea_pair_t))) return ABEA_ERR_CUDA;
+    const int32_t nb = c->n_batch_reads;
+    /* The device holds the pairs in the canonical capacity layout (read i at prefix-sum(E+L)); when the caller's
+     * pair_ptr is that layout — it is what align_cuda's packer and ReadBatch.pair_ptr() produce — both results are
+     * copied straight into the caller's buffers. Any other layout goes through pinned staging and a scatter. */
+    bool canonical = true;
+    for (int32_t i = 0; i < nb && canonical; i++) canonical = (pair_ptr[i] == c->cap_ptr[i]);
+    double unpack_ms = 0.0;
+    int64_t d2h = 0;
     CU(cudaEventRecord(c->ev[EV_D2H0], c->stream));
-    if (n) {
-        CU(cudaMemcpyAsync(c->h_results.p, c->d_results.p, n * sizeof(abea_result_t), cudaMemcpyDeviceToHost,
-                           c->stream));
-        CU(cudaMemcpyAsync(c->h_pairs.p, c->d_pairs.p, (size_t)c->total_pair_cap * sizeof(abea_pair_t),
-                           cudaMemcpyDeviceToHost, c->stream));
+    if (nb > 0) {
+        CU(cudaMemcpyAsync(n_pairs, c->d_npairs.p, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        d2h += (int64_t)nb * (int64_t)sizeof(int32_t);
     }
-    CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    double t0 = now_ms();
-    for (int32_t i = 0; i < c->n_batch_reads; i++) n_pairs[i] = 0;
-    const abea_result_t* res = (const abea_result_t*)c->h_results.p;
-    const abea_pair_t* hp = (const abea_pair_t*)c->h_pairs.p;
-    for (size_t j = 0; j < n; j++) {
-        const abea_read_t& r = c->reads[j];
-        const int32_t np = res[j].n_pairs;
-        n_pairs[r.orig_index] = np;
-        if (np > 0)
-            memcpy(pairs + pair_ptr[r.orig_index], hp + r.pair_off + res[j].pair_start, (size_t)np * sizeof(abea_pair_t));
+    if (canonical) {
+        if (c->total_pair_cap > 0) {
+            CU(cudaMemcpyAsync(pairs, c->d_pairs.p, (size_t)c->total_pair_cap * sizeof(abea_pair_t),
+                               cudaMemcpyDeviceToHost, c->stream));
+            d2h += c->total_pair_cap * (int64_t)sizeof(abea_pair_t);
+        }
+        CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    } else {
+        if (host_reserve(c, c->h_pairs, (size_t)(c->total_pair_cap + 1) * sizeof(abea_pair_t))) return ABEA_ERR_CUDA;
+        if (c->total_pair_cap > 0) {
+            CU(cudaMemcpyAsync(c->h_pairs.p, c->d_pairs.p, (size_t)c->total_pair_cap * sizeof(abea_pair_t),
+                               cudaMemcpyDeviceToHost, c->stream));
+            d2h += c->total_pair_cap * (int64_t)sizeof(abea_pair_t);
+        }
+        CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        double t0 = now_ms();
+        const abea_pair_t* hp = (const abea_pair_t*)c->h_pairs.p;
+        for (int32_t i = 0; i < nb; i++)
+            if (n_pairs[i] > 0)
+                memcpy(pairs + pair_ptr[i], hp + c->cap_ptr[i], (size_t)n_pairs[i] * sizeof(abea_pair_t));
+        unpack_ms = now_ms() - t0;
     }
-    double t1 = now_ms();
     c->last.d2h_ms = ev_ms(c, EV_D2H0, EV_D2H1);
-    c->last.unpack_ms = t1 - t0;
-    c->last.d2h_bytes = (int64_t)(n * sizeof(abea_result_t)) + c->total_pair_cap * (int64_t)sizeof(abea_pair_t);
+    c->last.unpack_ms = unpack_ms;
+    c->last.d2h_bytes = d2h;
     if (timing) *timing = c->last;
     return ABEA_OK;
 }

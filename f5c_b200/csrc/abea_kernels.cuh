@@ -47,7 +47,7 @@ struct abea_read_t {
     int64_t evs_off;    /* running sum of n_events over the schedule (flat index space of abea_prepare_kernel) */
     int64_t kp_off;     /* first k-mer in d_kparams */
     int64_t trace_off;  /* first 32-bit word of this read's trace in d_trace */
-    int64_t pair_off;   /* first pair slot in d_pairs (capacity pair_cap) */
+    int64_t pair_off;   /* first pair slot of the read in d_pairs == in the caller's canonical layout (capacity pair_cap) */
     double lp_stay;     /* log(p_stay), host double (reference src/align.c:214) */
     double lp_step;     /* log(1 - exp(lp_skip) - exp(lp_stay)) (src/align.c:215) */
     float scale;
@@ -65,7 +65,7 @@ struct abea_result_t {
     int32_t end_event;   /* event the traceback starts from */
     int32_t n_aligned;   /* pairs before QC */
     int32_t n_pairs;     /* pairs after QC (0 = failed) */
-    int32_t pair_start;  /* pairs live at d_pairs[pair_off + pair_start .. + n_aligned), ascending */
+    int32_t pair_start;  /* always 0: pairs live at d_pairs[pair_off .. pair_off + n_pairs), ascending */
     int32_t max_gap;
 };
 
@@ -235,46 +235,222 @@ __device__ __forceinline__ void abea_cell_d(float lp, double up, double left, do
     from = isL ? ABEA_FROM_L : (isU ? ABEA_FROM_U : ABEA_FROM_D);
 }
 
-struct abea_band_state {
-    float x[ABEA_CPL];        /* event means of the lane's cells */
-    float4 kp[ABEA_CPL];      /* k-mer parameters of the lane's cells */
-    double R1[ABEA_CPL];      /* scores of band b-1 */
-    double R2[ABEA_CPL];      /* scores of band b-2 */
-    double halo_prev;         /* neighbour-lane score of band b-2 fetched one band earlier */
+/* cp.async helpers (LDGSTS on sm_100a); the CPU emulator copies synchronously */
+__device__ __forceinline__ void abea_cp_async4(void* dst_smem, const void* src_gmem) {
+#ifdef ABEA_SIMT_EMU
+    *(uint32_t*)dst_smem = *(const uint32_t*)src_gmem;
+#else
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src_gmem) : "memory");
+#endif
+}
+__device__ __forceinline__ void abea_cp_async16(void* dst_smem, const void* src_gmem) {
+#ifdef ABEA_SIMT_EMU
+    for (int i = 0; i < 4; i++) ((uint32_t*)dst_smem)[i] = ((const uint32_t*)src_gmem)[i];
+#else
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src_gmem) : "memory");
+#endif
+}
+__device__ __forceinline__ void abea_cp_async_wait_all() {
+#ifndef ABEA_SIMT_EMU
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+
+/* One band of scores as held by a lane, with the two neighbour-lane cells next to its four ("halos"). */
+struct abea_band_t {
+    double R[ABEA_CPL];
+    double lo; /* lane-1's R[3]  (offset 4*lane-1), -inf for lane 0  */
+    double hi; /* lane+1's R[0]  (offset 4*lane+4), -inf for lane 24 */
 };
+
+#define ABEA_RING 64 /* entries of the per-warp shared-memory rings (two chunks of 32) */
+
+struct abea_fill_smem_t {
+    float ev[ABEA_RING];   /* event means, slot = event index & 63 */
+    float4 kp[ABEA_RING];  /* k-mer parameters, slot = k-mer index & 63 */
+};
+
+/* asynchronously stage chunk `chunk` (indices 32*chunk .. +31, clamped into the read) of the event means / k-mer
+ * parameters into the warp's ring: the "TMA/async-copy staging of the active band window" of the design */
+__device__ __forceinline__ void abea_stage_events(abea_fill_smem_t* sm, const abea_event_t* __restrict__ ev, int32_t chunk,
+                                                  int32_t E, int lane) {
+    int32_t e = chunk * 32 + lane;
+    int32_t ec = e < 0 ? 0 : (e >= E ? E - 1 : e);
+    abea_cp_async4(&sm->ev[e & (ABEA_RING - 1)], &ev[ec].mean);
+}
+__device__ __forceinline__ void abea_stage_kparams(abea_fill_smem_t* sm, const float4* __restrict__ kpr, int32_t chunk,
+                                                   int32_t K, int lane) {
+    int32_t k = chunk * 32 + lane;
+    int32_t kc = k < 0 ? 0 : (k >= K ? K - 1 : k);
+    abea_cp_async16(&sm->kp[k & (ABEA_RING - 1)], &kpr[kc]);
+}
 
 /* The four (previous move, this move) geometries, each fully specialised so that every neighbour is a fixed
  * register: RIGHT: up = b-1[o+1], left = b-1[o]; DOWN: up = b-1[o], left = b-1[o-1];
- * diag = b-2[o+1] (right,right), b-2[o-1] (down,down), else b-2[o]. */
+ * diag = b-2[o+1] (right,right), b-2[o-1] (down,down), else b-2[o]. A = band b-1, B = band b-2. */
 template <bool FAST, bool RIGHT, bool PREV_RIGHT>
-__device__ __forceinline__ void abea_band_cells(abea_band_state& st, int lane, double lp_step, double lp_stay,
-                                                double lp_skip, double* Rn, uint32_t* fr) {
-    const double NEG = abea_neg_inf_d();
-    double halo;
-    if (RIGHT) {
-        halo = __shfl_down_sync(ABEA_FULL, st.R1[0], 1);
-        if (lane >= ABEA_LANES - 1) halo = NEG;
-    } else {
-        halo = __shfl_up_sync(ABEA_FULL, st.R1[ABEA_CPL - 1], 1);
-        if (lane == 0) halo = NEG;
-    }
+__device__ __forceinline__ void abea_band_cells(const float* x, const float4* kp, const abea_band_t& A,
+                                                const abea_band_t& B, double lp_step, double lp_stay, double lp_skip,
+                                                double* Rn, uint32_t* fr) {
 #pragma unroll
     for (int c = 0; c < ABEA_CPL; c++) {
         double up, left, diag;
         if (RIGHT) {
-            up = (c < ABEA_CPL - 1) ? st.R1[c + 1 < ABEA_CPL ? c + 1 : c] : halo;
-            left = st.R1[c];
+            up = (c < ABEA_CPL - 1) ? A.R[c + 1 < ABEA_CPL ? c + 1 : c] : A.hi;
+            left = A.R[c];
         } else {
-            up = st.R1[c];
-            left = (c > 0) ? st.R1[c > 0 ? c - 1 : 0] : halo;
+            up = A.R[c];
+            left = (c > 0) ? A.R[c > 0 ? c - 1 : 0] : A.lo;
         }
-        if (RIGHT && PREV_RIGHT) diag = (c < ABEA_CPL - 1) ? st.R2[c + 1 < ABEA_CPL ? c + 1 : c] : st.halo_prev;
-        else if (!RIGHT && !PREV_RIGHT) diag = (c > 0) ? st.R2[c > 0 ? c - 1 : 0] : st.halo_prev;
-        else diag = st.R2[c];
-        float lp = abea_emission_t<FAST>(st.x[c], st.kp[c]);
+        if (RIGHT && PREV_RIGHT) diag = (c < ABEA_CPL - 1) ? B.R[c + 1 < ABEA_CPL ? c + 1 : c] : B.hi;
+        else if (!RIGHT && !PREV_RIGHT) diag = (c > 0) ? B.R[c > 0 ? c - 1 : 0] : B.lo;
+        else diag = B.R[c];
+        float lp = abea_emission_t<FAST>(x[c], kp[c]);
         abea_cell_d<FAST>(lp, up, left, diag, lp_step, lp_stay, lp_skip, Rn[c], fr[c]);
     }
-    st.halo_prev = halo;
+}
+
+/* Per-read constants and cursors of the fill, warp-uniform. */
+struct abea_fill_ctx_t {
+    const abea_event_t* ev;
+    const float4* kpr;
+    uint32_t* tr;
+    double lp_stay, lp_step, lp_skip, lp_trim;
+    int32_t E, K;
+    int32_t NB;
+    int32_t eb, kb;       /* lower-left of the current band */
+    int32_t b;            /* band being filled */
+    int32_t safe;         /* further bands guaranteed to be interior */
+    uint32_t tword;       /* this lane's trace bytes of the current 4-band group */
+    int32_t eb_keep;      /* lanes 25..28: event index of the group's bands */
+    double best_s;        /* best end cell seen by this lane */
+    int32_t best_e;
+    float x_next;         /* mean of event eb+1 (enters at offset 0 on the next down move) */
+    float4 kp_next;       /* parameters of k-mer kb+100 (enters at offset 99 on the next right move) */
+    bool prev_right;
+};
+
+/* One band: A holds band b-1, B holds band b-2 and receives band b. `right` is this band's move; returns the next
+ * band's move (Suzuki's rule, reference src/align.c:304-322), decided as soon as this band's scores exist so that its
+ * shuffle/vote latency overlaps the trace bookkeeping. */
+template <bool FAST>
+__device__ __forceinline__ bool abea_fill_step(abea_fill_ctx_t& cx, float* x, float4* kp, const abea_band_t& A,
+                                               abea_band_t& B, abea_fill_smem_t* sm, bool right, int lane) {
+    const double NEG = abea_neg_inf_d();
+    double Rn[ABEA_CPL];
+    uint32_t fr[ABEA_CPL];
+    if (right) {
+        cx.kb += 1;
+        /* k-mer window slides towards lower offsets; k-mer kb+99 enters at offset 99 */
+        float4 nb;
+        nb.x = __shfl_down_sync(ABEA_FULL, kp[0].x, 1);
+        nb.y = __shfl_down_sync(ABEA_FULL, kp[0].y, 1);
+        nb.z = __shfl_down_sync(ABEA_FULL, kp[0].z, 1);
+        nb.w = __shfl_down_sync(ABEA_FULL, kp[0].w, 1);
+#pragma unroll
+        for (int c = 0; c < ABEA_CPL - 1; c++) kp[c] = kp[c + 1];
+        kp[ABEA_CPL - 1] = (lane == ABEA_LANES - 1) ? cx.kp_next : nb;
+        const int32_t kn = cx.kb + ABEA_W; /* next k-mer to enter */
+        if ((kn & 31) == 0) {              /* first use of a chunk that was in flight: land it, start the next one */
+            abea_cp_async_wait_all();
+            __syncwarp();
+            abea_stage_kparams(sm, cx.kpr, (kn >> 5) + 1, cx.K, lane);
+        }
+        cx.kp_next = sm->kp[kn & (ABEA_RING - 1)];
+        if (cx.prev_right) abea_band_cells<FAST, true, true>(x, kp, A, B, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+        else abea_band_cells<FAST, true, false>(x, kp, A, B, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+    } else {
+        cx.eb += 1;
+        /* event window slides towards higher offsets; event eb enters at offset 0 */
+        float nb = __shfl_up_sync(ABEA_FULL, x[ABEA_CPL - 1], 1);
+#pragma unroll
+        for (int c = ABEA_CPL - 1; c > 0; c--) x[c] = x[c - 1];
+        x[0] = (lane == 0) ? cx.x_next : nb;
+        const int32_t en = cx.eb + 1;
+        if ((en & 31) == 0) {
+            abea_cp_async_wait_all();
+            __syncwarp();
+            abea_stage_events(sm, cx.ev, (en >> 5) + 1, cx.E, lane);
+        }
+        cx.x_next = sm->ev[en & (ABEA_RING - 1)];
+        if (cx.prev_right) abea_band_cells<FAST, false, true>(x, kp, A, B, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+        else abea_band_cells<FAST, false, false>(x, kp, A, B, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+    }
+    cx.prev_right = right;
+
+    /* --- band edges: validity window, trim column, end column. Interior bands (all 100 cells valid, trim and end
+     * columns outside the band) skip this; `safe` counts how many more bands are certainly interior. --- */
+    if (cx.safe > 0) {
+        cx.safe -= 1;
+    } else {
+        const int32_t kb = cx.kb, eb = cx.eb, E = cx.E, K = cx.K;
+        const bool interior = (kb >= 0) && (kb + ABEA_W < K) && (eb >= ABEA_W - 1) && (eb <= E - 1);
+        if (interior) {
+            /* each band advances exactly one of kb, eb by one */
+            int32_t s1 = K - ABEA_W - 1 - kb, s2 = E - 1 - eb;
+            cx.safe = s1 < s2 ? s1 : s2;
+        } else {
+            /* offsets whose event and k-mer exist (reference src/align.c:337-346) */
+            int32_t lo = -kb;
+            if (eb - (E - 1) > lo) lo = eb - (E - 1);
+            if (lo < 0) lo = 0;
+            int32_t hi = K - kb;
+            if (eb + 1 < hi) hi = eb + 1;
+            if (hi > ABEA_W) hi = ABEA_W;
+            /* trim column: k-mer -1 (reference src/align.c:324-333) */
+            const int32_t to = -1 - kb;
+            const int32_t te = eb - to;
+            const bool trim_in = (to >= 0) && (to < ABEA_W) && (te >= 0) && (te < E);
+            const double trim_s = (double)__double2float_rn(__dmul_rn(cx.lp_trim, (double)(te + 1)));
+            /* end column: k-mer K-1 (reference src/align.c:429-445) */
+            const int32_t oe = (K - 1) - kb;
+#pragma unroll
+            for (int c = 0; c < ABEA_CPL; c++) {
+                int32_t o = ABEA_CPL * lane + c;
+                bool valid = (o >= lo) && (o < hi);
+                Rn[c] = valid ? Rn[c] : NEG;
+                fr[c] = valid ? fr[c] : 0u;
+                if (o == to && trim_in) {
+                    Rn[c] = trim_s;
+                    fr[c] = ABEA_FROM_U;
+                }
+                if (o == oe && valid) {
+                    int32_t e = eb - o;
+                    double s = (double)__double2float_rn(__dadd_rn(Rn[c], __dmul_rn((double)(E - e), cx.lp_trim)));
+                    if (s > cx.best_s) {
+                        cx.best_s = s;
+                        cx.best_e = e;
+                    }
+                }
+            }
+        }
+    }
+
+    /* --- the new band replaces band b-2; its halos and the next move are requested right away --- */
+#pragma unroll
+    for (int c = 0; c < ABEA_CPL; c++) B.R[c] = Rn[c];
+    double hi = __shfl_down_sync(ABEA_FULL, Rn[0], 1);
+    double lo = __shfl_up_sync(ABEA_FULL, Rn[ABEA_CPL - 1], 1);
+    double ll = __shfl_sync(ABEA_FULL, Rn[0], 0);
+    B.hi = (lane >= ABEA_LANES - 1) ? NEG : hi;
+    B.lo = (lane == 0) ? NEG : lo;
+    const double ur = Rn[ABEA_CPL - 1]; /* meaningful on lane 24 */
+    bool my_right = (ll == NEG && ur == NEG) ? (((cx.b + 1) & 1) == 1) : (ll < ur);
+    const bool next_right = __any_sync(ABEA_FULL, (lane == ABEA_LANES - 1) && my_right) != 0;
+
+    /* --- trace: 2 bits per cell, one byte per lane per band, one 128-B line per 4 bands --- */
+    const uint32_t byte = fr[0] | (fr[1] << 2) | (fr[2] << 4) | (fr[3] << 6);
+    const int q = cx.b & 3;
+    cx.tword |= byte << (8 * q);
+    if (lane == ABEA_LANES + q) cx.eb_keep = cx.eb;
+    if (q == 3 || cx.b == cx.NB - 1) {
+        cx.tr[(int64_t)(cx.b >> 2) * ABEA_TRACE_GROUP_WORDS + lane] = (lane < ABEA_LANES) ? cx.tword : (uint32_t)cx.eb_keep;
+        cx.tword = 0u;
+    }
+    cx.b += 1;
+    return next_right;
 }
 
 template <bool FAST>
@@ -283,7 +459,9 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
                  const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                  uint32_t* __restrict__ trace, abea_result_t* __restrict__ results, abea_consts_t cst,
                  int32_t* __restrict__ queue) {
+    __shared__ __align__(16) abea_fill_smem_t smem_all[4];
     const int lane = threadIdx.x & 31;
+    abea_fill_smem_t* sm = &smem_all[threadIdx.x >> 5];
     const double NEG = abea_neg_inf_d();
 
     for (;;) {
@@ -295,148 +473,67 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
         if (((read_flags[ridx] & ABEA_READ_FAST) != 0u) != FAST) continue;
 
         const abea_read_t rd = reads[ridx];
-        const int32_t E = rd.n_events, K = rd.n_kmers;
-        const int64_t NB = (int64_t)E + (int64_t)K + 2;
-        const abea_event_t* __restrict__ ev = events + rd.ev_off;
-        const float4* __restrict__ kpr = kparams + rd.kp_off;
-        uint32_t* __restrict__ tr = trace + rd.trace_off;
-        const double lp_stay = rd.lp_stay, lp_step = rd.lp_step, lp_skip = cst.lp_skip, lp_trim = cst.lp_trim;
-
+        abea_fill_ctx_t cx;
+        cx.E = rd.n_events;
+        cx.K = rd.n_kmers;
+        cx.NB = cx.E + cx.K + 2; /* the host rejects reads with E + K + 2 >= 2^31 */
+        cx.ev = events + rd.ev_off;
+        cx.kpr = kparams + rd.kp_off;
+        cx.tr = trace + rd.trace_off;
+        cx.lp_stay = rd.lp_stay;
+        cx.lp_step = rd.lp_step;
+        cx.lp_skip = cst.lp_skip;
+        cx.lp_trim = cst.lp_trim;
         /* band 1 geometry (reference src/align.c:277-279): e0=49,k0=-51 ; band 1 = move_down(band 0) */
-        int32_t eb = ABEA_W / 2, kb = -1 - ABEA_W / 2;
+        cx.eb = ABEA_W / 2;
+        cx.kb = -1 - ABEA_W / 2;
+        cx.b = 2;
+        cx.safe = 0;
+        cx.prev_right = false; /* band 1 was a down move */
+        cx.best_s = NEG;
+        cx.best_e = 0x7fffffff;
+        cx.tword = (lane == (ABEA_W / 2) / ABEA_CPL) ? (ABEA_FROM_U << (8 + 2 * ((ABEA_W / 2) % ABEA_CPL))) : 0u;
+        cx.eb_keep = (lane == 25) ? (ABEA_W / 2 - 1) : ((lane == 26) ? ABEA_W / 2 : 0);
 
-        abea_band_state st;
+        /* stage the chunks holding the first entering event (eb+1) and k-mer (kb+100), prefetch the ones after */
+        __syncwarp();
+        const int32_t ec0 = (cx.eb + 1) >> 5, kc0 = (cx.kb + ABEA_W) >> 5;
+        abea_stage_events(sm, cx.ev, ec0, cx.E, lane);
+        abea_stage_kparams(sm, cx.kpr, kc0, cx.K, lane);
+        abea_cp_async_wait_all();
+        __syncwarp();
+        abea_stage_events(sm, cx.ev, ec0 + 1, cx.E, lane);
+        abea_stage_kparams(sm, cx.kpr, kc0 + 1, cx.K, lane);
+        cx.x_next = sm->ev[(cx.eb + 1) & (ABEA_RING - 1)];
+        cx.kp_next = sm->kp[(cx.kb + ABEA_W) & (ABEA_RING - 1)];
+
+        /* sliding windows for band 1: x[c] = mean of event eb-o ; kp[c] = params of k-mer kb+o, o = 4*lane+c */
+        float x[ABEA_CPL];
+        float4 kp[ABEA_CPL];
+        abea_band_t P, Q; /* P = band 1, Q = band 0 */
 #pragma unroll
         for (int c = 0; c < ABEA_CPL; c++) {
             int o = ABEA_CPL * lane + c;
-            st.x[c] = abea_load_event_mean(ev, eb - o, E);
-            st.kp[c] = abea_load_kparam(kpr, kb + o, K);
-            st.R2[c] = (o == ABEA_W / 2) ? 0.0 : NEG;                                        /* src/align.c:284 */
-            st.R1[c] = (o == ABEA_W / 2) ? (double)__double2float_rn(lp_trim) : NEG;          /* src/align.c:290 */
+            x[c] = abea_load_event_mean(cx.ev, cx.eb - o, cx.E);
+            kp[c] = abea_load_kparam(cx.kpr, cx.kb + o, cx.K);
+            Q.R[c] = (o == ABEA_W / 2) ? 0.0 : NEG;                                        /* src/align.c:284 */
+            P.R[c] = (o == ABEA_W / 2) ? (double)__double2float_rn(cx.lp_trim) : NEG;       /* src/align.c:290 */
         }
-        st.halo_prev = NEG;
-        /* register chunk buffers for the elements that enter the window: lane i holds event (ebase+i) and
-         * k-mer (kbase+i); the element needed next is fetched with a shuffle, a chunk is refilled every 32 moves */
-        int32_t ebase = eb + 1;
-        int32_t kbase = kb + ABEA_W;
-        float evbuf = abea_load_event_mean(ev, ebase + lane, E);
-        float evnext = abea_load_event_mean(ev, ebase + 32 + lane, E);
-        float4 kbuf = abea_load_kparam(kpr, kbase + lane, K);
-        float4 knext = abea_load_kparam(kpr, kbase + 32 + lane, K);
-        bool prev_right = false; /* band 1 was a down move */
+        /* the only finite cells of bands 0 and 1 sit at offset 50 (lane 12, c = 2): every halo is -inf */
+        P.lo = P.hi = Q.lo = Q.hi = NEG;
 
-        uint32_t tword = (lane == (ABEA_W / 2) / ABEA_CPL) ? (ABEA_FROM_U << (8 + 2 * ((ABEA_W / 2) % ABEA_CPL))) : 0u;
-        int32_t eb_keep = (lane == 25) ? (ABEA_W / 2 - 1) : ((lane == 26) ? ABEA_W / 2 : 0);
-
-        double best_s = NEG;
-        int32_t best_e = 0x7fffffff;
-
-        for (int64_t b = 2; b < NB; b++) {
-            /* --- Suzuki's rule (reference src/align.c:304-322): lane 24 owns ur, fetches ll, votes --- */
-            double ll = __shfl_sync(ABEA_FULL, st.R1[0], 0);
-            bool my_right = (ll == NEG && st.R1[ABEA_CPL - 1] == NEG) ? ((b & 1) == 1) : (ll < st.R1[ABEA_CPL - 1]);
-            const bool right = __any_sync(ABEA_FULL, (lane == ABEA_LANES - 1) && my_right) != 0;
-
-            double Rn[ABEA_CPL];
-            uint32_t fr[ABEA_CPL];
-            if (right) {
-                kb += 1;
-                /* k-mer window slides towards lower offsets; the new k-mer kb+99 enters at offset 99 */
-                const int src = (kb + ABEA_W - 1) - kbase;
-                float4 in, nb;
-                in.x = __shfl_sync(ABEA_FULL, kbuf.x, src);
-                in.y = __shfl_sync(ABEA_FULL, kbuf.y, src);
-                in.z = __shfl_sync(ABEA_FULL, kbuf.z, src);
-                in.w = __shfl_sync(ABEA_FULL, kbuf.w, src);
-                nb.x = __shfl_down_sync(ABEA_FULL, st.kp[0].x, 1);
-                nb.y = __shfl_down_sync(ABEA_FULL, st.kp[0].y, 1);
-                nb.z = __shfl_down_sync(ABEA_FULL, st.kp[0].z, 1);
-                nb.w = __shfl_down_sync(ABEA_FULL, st.kp[0].w, 1);
-#pragma unroll
-                for (int c = 0; c < ABEA_CPL - 1; c++) st.kp[c] = st.kp[c + 1];
-                st.kp[ABEA_CPL - 1] = (lane == ABEA_LANES - 1) ? in : nb;
-                if ((kb + ABEA_W) - kbase == 32) { /* chunk exhausted */
-                    kbase += 32;
-                    kbuf = knext;
-                    knext = abea_load_kparam(kpr, kbase + 32 + lane, K);
-                }
-                if (prev_right) abea_band_cells<FAST, true, true>(st, lane, lp_step, lp_stay, lp_skip, Rn, fr);
-                else abea_band_cells<FAST, true, false>(st, lane, lp_step, lp_stay, lp_skip, Rn, fr);
-            } else {
-                eb += 1;
-                /* event window slides towards higher offsets; the new event eb enters at offset 0 */
-                float in = __shfl_sync(ABEA_FULL, evbuf, eb - ebase);
-                float nb = __shfl_up_sync(ABEA_FULL, st.x[ABEA_CPL - 1], 1);
-#pragma unroll
-                for (int c = ABEA_CPL - 1; c > 0; c--) st.x[c] = st.x[c - 1];
-                st.x[0] = (lane == 0) ? in : nb;
-                if ((eb + 1) - ebase == 32) {
-                    ebase += 32;
-                    evbuf = evnext;
-                    evnext = abea_load_event_mean(ev, ebase + 32 + lane, E);
-                }
-                if (prev_right) abea_band_cells<FAST, false, true>(st, lane, lp_step, lp_stay, lp_skip, Rn, fr);
-                else abea_band_cells<FAST, false, false>(st, lane, lp_step, lp_stay, lp_skip, Rn, fr);
-            }
-
-            /* --- band edges: validity window, trim column, end column (interior bands skip all of this) --- */
-            const bool interior = (kb >= 0) && (kb + ABEA_W < K) && (eb >= ABEA_W - 1) && (eb <= E - 1);
-            if (!interior) {
-                /* offsets whose event and k-mer exist (reference src/align.c:337-346) */
-                int32_t lo = -kb;
-                if (eb - (E - 1) > lo) lo = eb - (E - 1);
-                if (lo < 0) lo = 0;
-                int32_t hi = K - kb;
-                if (eb + 1 < hi) hi = eb + 1;
-                if (hi > ABEA_W) hi = ABEA_W;
-                /* trim column: k-mer -1 (reference src/align.c:324-333) */
-                const int32_t to = -1 - kb;
-                const int32_t te = eb - to;
-                const bool trim_in = (to >= 0) && (to < ABEA_W) && (te >= 0) && (te < E);
-                const double trim_s = (double)__double2float_rn(__dmul_rn(lp_trim, (double)(te + 1)));
-                /* end column: k-mer K-1 (reference src/align.c:429-445) */
-                const int32_t oe = (K - 1) - kb;
-#pragma unroll
-                for (int c = 0; c < ABEA_CPL; c++) {
-                    int32_t o = ABEA_CPL * lane + c;
-                    bool valid = (o >= lo) && (o < hi);
-                    Rn[c] = valid ? Rn[c] : NEG;
-                    fr[c] = valid ? fr[c] : 0u;
-                    if (o == to && trim_in) {
-                        Rn[c] = trim_s;
-                        fr[c] = ABEA_FROM_U;
-                    }
-                    if (o == oe && valid) {
-                        int32_t e = eb - o;
-                        double s = (double)__double2float_rn(__dadd_rn(Rn[c], __dmul_rn((double)(E - e), lp_trim)));
-                        if (s > best_s) {
-                            best_s = s;
-                            best_e = e;
-                        }
-                    }
-                }
-            }
-
-            /* --- trace: 2 bits per cell, one byte per lane per band, one 128-B line per 4 bands --- */
-            uint32_t byte = fr[0] | (fr[1] << 2) | (fr[2] << 4) | (fr[3] << 6);
-            const int q = (int)(b & 3);
-            tword |= byte << (8 * q);
-            if (lane == ABEA_LANES + q) eb_keep = eb;
-            if (q == 3 || b == NB - 1) {
-                tr[(b >> 2) * ABEA_TRACE_GROUP_WORDS + lane] = (lane < ABEA_LANES) ? tword : (uint32_t)eb_keep;
-                tword = 0u;
-            }
-
-            /* rotate */
-#pragma unroll
-            for (int c = 0; c < ABEA_CPL; c++) {
-                st.R2[c] = st.R1[c];
-                st.R1[c] = Rn[c];
-            }
-            prev_right = right;
+        /* move of band 2: both extreme cells of band 1 are -inf, so it alternates: band 2 is even -> down */
+        bool right = false;
+        while (cx.b < cx.NB) {
+            right = abea_fill_step<FAST>(cx, x, kp, P, Q, sm, right, lane); /* Q <- band b */
+            if (cx.b >= cx.NB) break;
+            right = abea_fill_step<FAST>(cx, x, kp, Q, P, sm, right, lane); /* P <- band b */
         }
+        abea_cp_async_wait_all(); /* nothing may still be landing in the ring when the next read reuses it */
 
         /* merge per-lane best end cells: max score, ties to the smaller event (first strict max in event order) */
+        double best_s = cx.best_s;
+        int32_t best_e = cx.best_e;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             double os = __shfl_xor_sync(ABEA_FULL, best_s, d);
@@ -454,15 +551,55 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */
-/* Traceback + QC (reference src/align.c:452-543). One warp per read, all lanes walk in lock-step over the 128-B
- * trace line of the current 4-band group held one word per lane; pairs are written from the END of the read's
- * capacity region backwards, so they come out ascending (no reversal pass).                                      */
+/* Traceback + QC (reference src/align.c:452-543). One warp per read. The walk is a pointer chase through the packed
+ * trace, strictly downwards in band index, so the trace lines it will need are known in advance: they are streamed
+ * with cp.async into a per-warp shared-memory ring of 32 lines (two chunks of 16 groups = 64 bands each; the next
+ * chunk is in flight while the current one is walked), which takes HBM latency off the dependent chain. All lanes
+ * walk in lock-step (the state is warp-uniform); step n's pair is parked in lane n%32 and every 32 steps the warp
+ * (i) stores 32 pairs with one coalesced 256-B store, from the END of the read's capacity region backwards so the
+ * list comes out ascending with no reversal pass, (ii) evaluates the 32 emissions in parallel and (iii) adds them
+ * to the QC sum strictly in traceback order (the reference's summation order, src/align.c:476).                    */
 
-__global__ void __launch_bounds__(128)
+#define ABEA_TB_CHUNK_GROUPS 16
+#define ABEA_TB_RING_GROUPS 32
+#define ABEA_TB_WARPS 4
+
+/* start the asynchronous copy of trace chunk `chunk` (groups 16*chunk .. 16*chunk+15) into the ring */
+__device__ __forceinline__ void abea_tb_prefetch(uint32_t* ring, const uint32_t* __restrict__ tr, int64_t chunk, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int idx = i * 32 + lane;                       /* 128 pieces of 16 B = 16 lines of 128 B */
+        int64_t g = chunk * ABEA_TB_CHUNK_GROUPS + (idx >> 3);
+        abea_cp_async16(ring + (g & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + (idx & 7) * 4,
+                        tr + g * ABEA_TRACE_GROUP_WORDS + (idx & 7) * 4);
+    }
+}
+
+/* emissions of the pairs parked in the lanes (first `cnt` lanes valid), added to `sum` in lane order */
+__device__ __forceinline__ double abea_tb_flush(double sum, int cnt, int lane, int32_t pk, int32_t pe, int32_t n_before,
+                                                const abea_event_t* __restrict__ ev, const float4* __restrict__ kpr,
+                                                abea_pair_t* __restrict__ out, int32_t pair_cap) {
+    double lpd = 0.0;
+    if (lane < cnt) {
+        abea_pair_t p;
+        p.ref_pos = pk;
+        p.read_pos = pe;
+        out[pair_cap - 1 - (n_before + lane)] = p;
+        float4 kp = kpr[pk];
+        lpd = (double)abea_emission(ev[pe].mean, kp.x, kp.y, kp.z);
+    }
+    for (int j = 0; j < cnt; j++) sum = __dadd_rn(sum, __shfl_sync(ABEA_FULL, lpd, j));
+    return sum;
+}
+
+__global__ void __launch_bounds__(32 * ABEA_TB_WARPS)
 abea_traceback_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const abea_event_t* __restrict__ events,
                       const float4* __restrict__ kparams, const uint32_t* __restrict__ trace,
-                      abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results, int32_t* __restrict__ queue) {
+                      abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
+                      int32_t* __restrict__ n_pairs_out, int32_t* __restrict__ queue) {
+    __shared__ __align__(16) uint32_t ring_all[ABEA_TB_WARPS][ABEA_TB_RING_GROUPS * ABEA_TRACE_GROUP_WORDS];
     const int lane = threadIdx.x & 31;
+    uint32_t* ring = ring_all[threadIdx.x >> 5];
     for (;;) {
         int32_t ridx = 0;
         if (lane == 0) ridx = atomicAdd(queue, 1);
@@ -481,33 +618,41 @@ abea_traceback_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, co
         int32_t n = 0, gap = 0, max_gap = 0;
         int32_t last_k = ck;
         double sum = 0.0;
-        int64_t cur_group = -1;
-        uint32_t w = 0;
+        int32_t pk = 0, pe = 0; /* the pair parked in this lane */
+
+        __syncwarp();           /* the previous read's ring is no longer being read by any lane */
+        int64_t cur_chunk = (((int64_t)ce + (int64_t)ck + 2) >> 2) / ABEA_TB_CHUNK_GROUPS;
+        abea_tb_prefetch(ring, tr, cur_chunk, lane);
+        abea_cp_async_wait_all();
+        __syncwarp();
+        if (cur_chunk > 0) abea_tb_prefetch(ring, tr, cur_chunk - 1, lane);
+
         while (ck >= 0 && ce >= 0) {
-            /* emit (reference src/align.c:458-460) */
-            if (lane == 0) {
-                abea_pair_t p;
-                p.ref_pos = ck;
-                p.read_pos = ce;
-                out[rd.pair_cap - 1 - n] = p;
+            /* emit (reference src/align.c:458-460): park the pair in lane n%32 */
+            if (lane == (n & 31)) {
+                pk = ck;
+                pe = ce;
             }
             n++;
             last_k = ck;
-            float4 kp = kpr[ck];
-            sum = __dadd_rn(sum, (double)abea_emission(ev[ce].mean, kp.x, kp.y, kp.z));
+            if ((n & 31) == 0) sum = abea_tb_flush(sum, 32, lane, pk, pe, n - 32, ev, kpr, out, rd.pair_cap);
 
-            int64_t b = (int64_t)ce + (int64_t)ck + 2;
-            int64_t g = b >> 2;
-            if (g != cur_group) {
-                w = tr[g * ABEA_TRACE_GROUP_WORDS + lane];
-                cur_group = g;
+            const int64_t b = (int64_t)ce + (int64_t)ck + 2;
+            const int64_t g = b >> 2;
+            const int64_t chunk = g / ABEA_TB_CHUNK_GROUPS;
+            if (chunk != cur_chunk) { /* walked down into the chunk that was in flight */
+                abea_cp_async_wait_all();
+                __syncwarp();
+                cur_chunk = chunk;
+                if (chunk > 0) abea_tb_prefetch(ring, tr, chunk - 1, lane);
             }
-            int q = (int)(b & 3);
-            int32_t ebb = (int32_t)__shfl_sync(ABEA_FULL, w, ABEA_LANES + q);
-            int32_t o = ebb - ce;
+            const uint32_t* line = ring + (g & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS;
+            const int q = (int)(b & 3);
+            const int32_t ebb = (int32_t)line[ABEA_LANES + q];
+            const int32_t o = ebb - ce;
             /* an out-of-band start cell is undefined behaviour in the reference; stay in bounds */
-            uint32_t tw = __shfl_sync(ABEA_FULL, w, (o >> 2) & 31);
-            uint32_t from = (o >= 0 && o < ABEA_W) ? ((tw >> (8 * q + 2 * (o & 3))) & 3u) : ABEA_FROM_D;
+            const uint32_t tw = line[(o >> 2) & 31];
+            const uint32_t from = (o >= 0 && o < ABEA_W) ? ((tw >> (8 * q + 2 * (o & 3))) & 3u) : ABEA_FROM_D;
             if (from == ABEA_FROM_D) {
                 ck--; ce--; gap = 0;
             } else if (from == ABEA_FROM_U) {
@@ -517,6 +662,9 @@ abea_traceback_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, co
                 max_gap = gap > max_gap ? gap : max_gap;
             }
         }
+        abea_cp_async_wait_all(); /* drain the chunk still in flight before the ring is reused */
+        if ((n & 31) != 0) sum = abea_tb_flush(sum, n & 31, lane, pk, pe, n & ~31, ev, kpr, out, rd.pair_cap);
+
         /* QC (reference src/align.c:526-543) */
         double avg = sum / (double)n;
         bool spanned = (n > 0) && (last_k == 0);
@@ -525,8 +673,25 @@ abea_traceback_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, co
             results[ridx].sum_emission = sum;
             results[ridx].n_aligned = n;
             results[ridx].n_pairs = fail ? 0 : n;
-            results[ridx].pair_start = rd.pair_cap - n;
+            results[ridx].pair_start = 0;
             results[ridx].max_gap = max_gap;
+            n_pairs_out[rd.orig_index] = fail ? 0 : n; /* db->n_event_align_pairs[i] */
+        }
+        /* slide the list to the front of the read's capacity region (the layout the caller's buffer has), in place:
+         * destination index t <= source index cap-n+t, batches of 32 are loaded before they are stored */
+        __syncwarp();
+        const int32_t src0 = rd.pair_cap - n;
+        if (!fail && src0 > 0) {
+            for (int32_t t0 = 0; t0 < n; t0 += 32) {
+                const int32_t t = t0 + lane;
+                abea_pair_t p;
+                p.ref_pos = 0;
+                p.read_pos = 0;
+                if (t < n) p = out[src0 + t];
+                __syncwarp();
+                if (t < n) out[t] = p;
+                __syncwarp();
+            }
         }
     }
 }

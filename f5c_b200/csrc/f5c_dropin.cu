@@ -1,0 +1,202 @@
+/* f5c_dropin.cu — the reference-facing entry points, to be compiled INSIDE the f5c tree in place of
+ * src/f5c.cu + src/align.cu:
+ *
+ *     void init_cuda(core_t* core);              reference src/f5c.h:575-581, src/f5c.cu:23-202
+ *     void free_cuda(core_t* core);              reference src/f5c.cu:204-234
+ *     void align_cuda(core_t* core, db_t* db);   reference src/f5cmisc.h:122-125, src/f5c.cu:647-1061
+ *
+ * with the reference's own C++ linkage, structs (core_t/db_t from the reference's f5c.h, -DHAVE_CUDA=1) and error
+ * convention (message on stderr + exit, src/f5cmisc.cuh:54-118). It is a thin packer over the C ABI in
+ * include/abea_b200.h: ragged db_t -> flat pinned staging -> abea_align_batch -> db->event_align_pairs[i] /
+ * db->n_event_align_pairs[i]. It needs the reference headers, so it is built only where the f5c tree is available
+ * (__graft_entry__.build_dropin); nothing in it is copied from the reference.
+ *
+ * Differences from the reference's align_cuda, all deliberate: no read is diverted to CPU threads (src/f5c.cu:440-452,
+ * 701-735 have no counterpart), no load/memory "advisor" messages (:457-644), device memory grows on demand instead of
+ * being pre-sized from cuda_mem_frac (:121-146).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "f5c.h"
+#include "f5cmisc.h"
+
+#include "../../include/abea_b200.h"
+
+static_assert(sizeof(abea_event_t) == sizeof(event_t), "event_t layout differs from abea_event_t");
+static_assert(sizeof(abea_model_t) == sizeof(model_t), "model_t layout differs (CACHED_LOG must be defined)");
+static_assert(sizeof(abea_scalings_t) == sizeof(scalings_t), "scalings_t layout differs");
+static_assert(sizeof(abea_pair_t) == sizeof(AlignedPair), "AlignedPair layout differs");
+static_assert(ABEA_BANDWIDTH == ALN_BANDWIDTH, "band width differs");
+
+namespace {
+
+/* what core->cuda points to: the reference's own struct first (so the pointer type is honoured), ours after it */
+struct dropin_data {
+    cuda_data_t base;
+    abea_ctx_t* ctx;
+    /* pinned staging, grown on demand */
+    char* seq; size_t seq_cap;
+    abea_event_t* events; size_t ev_cap;
+    abea_pair_t* pairs; size_t pair_cap;
+    int64_t* seq_ptr; int64_t* event_ptr; int64_t* pair_ptr;
+    int32_t* read_len; int32_t* n_events; int32_t* n_pairs;
+    abea_scalings_t* scalings; uint8_t* good;
+    size_t read_cap;
+};
+
+void die(const char* func, const char* what, abea_ctx_t* ctx) {
+    fprintf(stderr, "[%s::ERROR]\033[1;31m %s: %s\033[0m\n", func, what, ctx ? abea_last_error(ctx) : "");
+    exit(-1);
+}
+
+template <typename T> void grow(T*& p, size_t& cap, size_t need) {
+    if (need <= cap) return;
+    if (p) abea_host_free(p);
+    cap = need + need / 4 + 64;
+    p = (T*)abea_host_alloc(cap * sizeof(T));
+    if (!p) { fprintf(stderr, "[align_cuda::ERROR] pinned allocation of %zu bytes failed\n", cap * sizeof(T)); exit(EXIT_FAILURE); }
+}
+
+} // namespace
+
+void init_cuda(core_t* core) {
+    dropin_data* d = (dropin_data*)calloc(1, sizeof(dropin_data));
+    if (!d) { fprintf(stderr, "[init_cuda::ERROR] out of memory\n"); exit(EXIT_FAILURE); }
+    int rc = abea_create(&d->ctx, core->opt.cuda_dev_id);
+    if (rc == ABEA_ERR_NODEVICE) { fprintf(stderr, "[init_cuda::ERROR] no CUDA capable device %d\n", core->opt.cuda_dev_id); exit(1); }
+    if (rc) die("init_cuda", "abea_create failed", NULL);
+    if (abea_set_model(d->ctx, (const abea_model_t*)core->model, core->kmer_size)) die("init_cuda", "model upload", d->ctx);
+    if (core->opt.verbosity > 1) {
+        int sms = 0; char name[256];
+        abea_device_info(d->ctx, &sms, name);
+        fprintf(stderr, "[init_cuda] %s on %s (%d SMs), k=%u\n", abea_version(), name, sms, core->kmer_size);
+    }
+    core->cuda = &d->base;
+    core->align_kernel_time = core->align_pre_kernel_time = core->align_core_kernel_time = 0;
+    core->align_post_kernel_time = core->align_cuda_malloc = core->align_cuda_memcpy = 0;
+    core->align_cuda_postprocess = core->align_cuda_preprocess = core->align_cuda_total_kernel = 0;
+    core->extra_load_cpu = 0;
+}
+
+void free_cuda(core_t* core) {
+    dropin_data* d = (dropin_data*)core->cuda;
+    if (!d) return;
+    abea_destroy(d->ctx);
+    void* bufs[] = {d->seq, d->events, d->pairs, d->seq_ptr, d->event_ptr, d->pair_ptr, d->read_len, d->n_events,
+                    d->n_pairs, d->scalings, d->good};
+    for (void* b : bufs) abea_host_free(b);
+    free(d);
+    core->cuda = NULL;
+}
+
+void align_cuda(core_t* core, db_t* db) {
+    dropin_data* d = (dropin_data*)core->cuda;
+    const int32_t n = db->n_bam_rec;
+    double t0 = realtime();
+
+    /* flatten the ragged batch (what the reference does at src/f5c.cu:744-800) into pinned staging */
+    if ((size_t)n > d->read_cap) {
+        size_t c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;
+        grow(d->seq_ptr, c1, (size_t)n); grow(d->event_ptr, c2, (size_t)n); grow(d->pair_ptr, c3, (size_t)n);
+        grow(d->read_len, c4, (size_t)n); grow(d->n_events, c5, (size_t)n); grow(d->n_pairs, c6, (size_t)n);
+        grow(d->scalings, c7, (size_t)n); grow(d->good, c8, (size_t)n);
+        d->read_cap = c1;
+    }
+    int64_t sp = 0, ep = 0, pp = 0;
+    for (int32_t i = 0; i < n; i++) {
+        d->seq_ptr[i] = sp; d->event_ptr[i] = ep; d->pair_ptr[i] = pp;
+        d->read_len[i] = db->read_len[i];
+        d->n_events[i] = (int32_t)db->et[i].n;
+        d->good[i] = (db->sig[i] && db->sig[i]->nsample > 0) ? 1 : 0;   /* align_single, src/f5c.c:811 */
+        d->scalings[i].scale = db->scalings[i].scale; d->scalings[i].shift = db->scalings[i].shift;
+        d->scalings[i].var = db->scalings[i].var; d->scalings[i].log_var = db->scalings[i].log_var;
+        sp += db->read_len[i] + 1; ep += (int64_t)db->et[i].n; pp += (int64_t)db->et[i].n + db->read_len[i];
+    }
+    grow(d->seq, d->seq_cap, (size_t)sp + 1);
+    grow(d->events, d->ev_cap, (size_t)ep + 1);
+    grow(d->pairs, d->pair_cap, (size_t)pp + 1);
+    for (int32_t i = 0; i < n; i++) {
+        memcpy(d->seq + d->seq_ptr[i], db->read[i], (size_t)db->read_len[i]);
+        d->seq[d->seq_ptr[i] + db->read_len[i]] = 0;
+        if (db->et[i].n) memcpy(d->events + d->event_ptr[i], db->et[i].event, db->et[i].n * sizeof(event_t));
+    }
+    abea_batch_t b;
+    b.n_reads = n; b.seq = d->seq; b.seq_ptr = d->seq_ptr; b.read_len = d->read_len; b.events = d->events;
+    b.event_ptr = d->event_ptr; b.n_events = d->n_events; b.scalings = d->scalings; b.good = d->good;
+    double t1 = realtime();
+
+    abea_timing_t tm;
+    if (abea_align_batch(d->ctx, &b, d->pairs, d->pair_ptr, d->n_pairs, &tm)) die("align_cuda", "Cuda error", d->ctx);
+    double t2 = realtime();
+
+    /* un-flatten (src/f5c.cu:1005-1030): pairs already ascending, no host-side reversal */
+    for (int32_t i = 0; i < n; i++) {
+        db->n_event_align_pairs[i] = d->n_pairs[i];
+        if (d->n_pairs[i] > 0) memcpy(db->event_align_pairs[i], d->pairs + d->pair_ptr[i], (size_t)d->n_pairs[i] * sizeof(AlignedPair));
+    }
+    double t3 = realtime();
+
+    /* the reference's timer split (src/f5c.h:457-466), printed by meth_main (src/meth_main.c:767-788) */
+    core->align_cuda_preprocess += (t1 - t0) + tm.pack_ms * 1e-3;
+    core->align_cuda_memcpy += (tm.h2d_ms + tm.d2h_ms) * 1e-3;
+    core->align_kernel_time += tm.kernel_ms * 1e-3;
+    core->align_pre_kernel_time += tm.kmer_ms * 1e-3;
+    core->align_core_kernel_time += tm.fill_ms * 1e-3;
+    core->align_post_kernel_time += tm.trace_ms * 1e-3;
+    core->align_cuda_total_kernel += tm.kernel_ms * 1e-3;
+    core->align_cuda_postprocess += (t3 - t2) + tm.unpack_ms * 1e-3;
+    if (core->opt.verbosity > 1)
+        fprintf(stderr, "[align_cuda] Load : GPU %d entries (%.1fM events), CPU 0 entries; kernels %.3f ms\n",
+                tm.n_scheduled, tm.n_events / 1e6, tm.kernel_ms);
+}
+
+/* ---- self-test door (used by tests/test_dropin.py): builds core_t/db_t from a flat batch, calls the three entry
+ * points exactly as init_core/align_db/free_core would, and hands the per-read outputs back. ------------------- */
+extern "C" int f5c_dropin_selftest(const abea_batch_t* b, const abea_model_t* model, uint32_t kmer_size, int device,
+                                   abea_pair_t* pairs, const int64_t* pair_ptr, int32_t* n_pairs) {
+    core_t* core = (core_t*)calloc(1, sizeof(core_t));
+    db_t* db = (db_t*)calloc(1, sizeof(db_t));
+    core->model = (model_t*)model;
+    core->kmer_size = kmer_size;
+    core->opt.cuda_dev_id = device;
+    core->opt.verbosity = 0;
+    const int32_t n = b->n_reads;
+    db->n_bam_rec = n;
+    db->capacity_bam_rec = n;
+    db->read = (char**)calloc(n, sizeof(char*));
+    db->read_len = (int32_t*)calloc(n, sizeof(int32_t));
+    db->et = (event_table*)calloc(n, sizeof(event_table));
+    db->scalings = (scalings_t*)calloc(n, sizeof(scalings_t));
+    db->sig = (signal_t**)calloc(n, sizeof(signal_t*));
+    db->event_align_pairs = (AlignedPair**)calloc(n, sizeof(AlignedPair*));
+    db->n_event_align_pairs = (int32_t*)calloc(n, sizeof(int32_t));
+    for (int32_t i = 0; i < n; i++) {
+        db->read[i] = (char*)(b->seq + b->seq_ptr[i]);
+        db->read_len[i] = b->read_len[i];
+        db->et[i].n = (size_t)b->n_events[i];
+        db->et[i].end = (size_t)b->n_events[i];
+        db->et[i].event = (event_t*)(b->events + b->event_ptr[i]);
+        memcpy(&db->scalings[i], &b->scalings[i], sizeof(scalings_t));
+        db->sig[i] = (signal_t*)calloc(1, sizeof(signal_t));
+        db->sig[i]->nsample = (b->good && !b->good[i]) ? 0 : 1;
+        /* event_single allocates E+L pairs per good read (src/f5c.c:724-731) */
+        db->event_align_pairs[i] = db->sig[i]->nsample ? (AlignedPair*)malloc(sizeof(AlignedPair) * ((size_t)b->n_events[i] + b->read_len[i])) : NULL;
+        db->sum_bases += b->read_len[i];
+    }
+    init_cuda(core);
+    align_cuda(core, db);
+    align_cuda(core, db); /* a second batch through the same core: buffers are reused */
+    for (int32_t i = 0; i < n; i++) {
+        n_pairs[i] = db->n_event_align_pairs[i];
+        if (n_pairs[i] > 0) memcpy(pairs + pair_ptr[i], db->event_align_pairs[i], (size_t)n_pairs[i] * sizeof(AlignedPair));
+        free(db->event_align_pairs[i]);
+        free(db->sig[i]);
+    }
+    free_cuda(core);
+    free(db->read); free(db->read_len); free(db->et); free(db->scalings); free(db->sig);
+    free(db->event_align_pairs); free(db->n_event_align_pairs);
+    free(db); free(core);
+    return 0;
+}

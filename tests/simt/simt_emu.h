@@ -32,6 +32,7 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n)
 
 struct float4 { float x, y, z, w; };
 struct float2 { float x, y; };
