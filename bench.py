@@ -125,6 +125,7 @@ def main():
     import torch.distributed as dist
     from f5c_b200 import models, synth
     from f5c_b200.abea import AbeaContext
+    from f5c_b200.dist import compact_pairs, gather_results
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; f5c_b200 has no CPU path (use --impl reference for the CPU arm)")
@@ -175,19 +176,7 @@ def main():
         g_ms = 0.0
         if world > 1:
             g0 = time.perf_counter()
-            counts = torch.from_numpy(r.n_pairs).cuda()
-            total = int(r.n_pairs.sum())
-            flat = np.concatenate([r.read_pairs(i) for i in range(batch.n_reads)]) if total else r.pairs[:0]
-            pairs_dev = torch.from_numpy(flat.view(np.int32).reshape(-1, 2)).cuda()
-            sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-            dist.all_gather(sizes, torch.tensor([total], dtype=torch.int64, device="cuda"))
-            mx = int(max(int(s.item()) for s in sizes))
-            pad = torch.zeros((mx, 2), dtype=torch.int32, device="cuda")
-            pad[:total] = pairs_dev
-            gl = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-            dist.gather(pad, gl, dst=0)
-            cl = [torch.empty_like(counts) for _ in range(world)] if rank == 0 else None
-            dist.gather(counts, cl, dst=0)
+            gather_results(r.n_pairs, compact_pairs(r.pairs, r.pair_ptr, r.n_pairs), rank, world, f"cuda:{local_rank}")
             torch.cuda.synchronize()
             g_ms = (time.perf_counter() - g0) * 1e3
         return r, g_ms

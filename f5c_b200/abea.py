@@ -31,7 +31,8 @@ class Timing(ctypes.Structure):
                 ("fill_ms", ctypes.c_double), ("trace_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double),
                 ("d2h_ms", ctypes.c_double), ("unpack_ms", ctypes.c_double), ("h2d_bytes", ctypes.c_int64),
                 ("d2h_bytes", ctypes.c_int64), ("kernel_launches", ctypes.c_int32),
-                ("n_scheduled", ctypes.c_int32), ("n_bands", ctypes.c_int64), ("n_events", ctypes.c_int64)]
+                ("n_scheduled", ctypes.c_int32), ("n_wide", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+                ("n_bands", ctypes.c_int64), ("n_events", ctypes.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -76,6 +76,14 @@ struct abea_ctx {
     bool uploaded = false, ran = false;
     abea_consts_t cst;
     abea_timing_t last = {};
+    int32_t n_wide = 0;               /* the first n_wide scheduled reads (the longest) are filled by the wide kernel */
+    cudaStream_t wide_stream = nullptr; /* the wide fill runs beside the narrow one */
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int wide_mode = 1;                /* ABEA_WIDE=0 disables the wide kernel */
+    double wide_alpha = 1.0;          /* ABEA_WIDE_ALPHA scales the wide/narrow threshold */
+    double wide_min_bands = 1024.0;   /* ABEA_WIDE_MIN_BANDS: reads shorter than this are never wide */
+    int fill_ctas_per_sm = 4;  /* persistent fill grid = sm_count * this (tuning knob: ABEA_FILL_CTAS_PER_SM) */
+    int trace_ctas_per_sm = 4; /* ABEA_TRACE_CTAS_PER_SM */
 };
 
 namespace {
@@ -178,6 +186,16 @@ int abea_create(abea_ctx_t** out, int device) {
         }
     }
     /* transition constants shared by all reads, host double (reference src/align.c:212-216) */
+    if (const char* e = getenv("ABEA_WIDE")) c->wide_mode = atoi(e);
+    if (const char* e = getenv("ABEA_WIDE_ALPHA")) c->wide_alpha = atof(e);
+    if (const char* e = getenv("ABEA_WIDE_MIN_BANDS")) c->wide_min_bands = atof(e);
+    if (cudaStreamCreateWithFlags(&c->wide_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev_fork) != cudaSuccess || cudaEventCreate(&c->ev_join) != cudaSuccess) {
+        delete c;
+        return ABEA_ERR_CUDA;
+    }
+    if (const char* e = getenv("ABEA_FILL_CTAS_PER_SM")) c->fill_ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("ABEA_TRACE_CTAS_PER_SM")) c->trace_ctas_per_sm = std::max(1, atoi(e));
     c->cst.lp_skip = log(1e-10);
     c->cst.lp_trim = log(0.01);
     *out = c;
@@ -195,6 +213,9 @@ void abea_destroy(abea_ctx_t* c) {
     if (c->h_pairs.p) cudaFreeHost(c->h_pairs.p);
     for (int i = 0; i < EV_COUNT; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->wide_stream) cudaStreamDestroy(c->wide_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -286,6 +307,20 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
         nb += NB;
         ne += r.n_events;
     }
+    /* Long reads go to the wide kernel (4 warps per read). A narrow warp shares its SM sub-partition with three
+     * others and advances ~5x slower per band than a wide CTA; a read is "long" when, at that rate, it alone would
+     * outlast the time the whole batch needs at full throughput (or the time the longest read needs in wide form).
+     * Constants are per-band cycle counts measured on B200 (profiles/README.md). */
+    c->n_wide = 0;
+    if (c->wide_mode && !c->reads.empty()) {
+        const double cyc_batch = (double)nb * 360.0 / ((double)c->sm_count * 4.0);
+        const double cyc_longest_wide = ((double)c->reads[0].n_events + c->reads[0].n_kmers + 2) * 260.0;
+        const double target = std::max(cyc_batch, cyc_longest_wide);
+        const double thr = std::max(c->wide_min_bands, c->wide_alpha * target / 1400.0);
+        while (c->n_wide < (int32_t)c->reads.size() &&
+               (double)c->reads[c->n_wide].n_events + c->reads[c->n_wide].n_kmers + 2 > thr)
+            c->n_wide++;
+    }
     c->total_kmers = kp;
     c->total_trace_words = tw;
     c->total_pair_cap = c->cap_ptr[b->n_reads];
@@ -324,6 +359,7 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
     c->last.h2d_ms = ev_ms(c, EV_H2D0, EV_H2D1);
     c->last.h2d_bytes = seq_bytes + n_ev_total * (int64_t)sizeof(abea_event_t) + (int64_t)(n_sched * sizeof(abea_read_t));
     c->last.n_scheduled = (int32_t)n_sched;
+    c->last.n_wide = c->n_wide;
     c->last.n_bands = nb;
     c->last.n_events = ne;
     if (timing) *timing = c->last;
@@ -356,21 +392,39 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
         }
         CU(cudaEventRecord(c->ev[EV_K1], c->stream));
         {
-            /* persistent warps: 4 CTAs of 4 warps per SM, each warp pulls reads longest-first. The FAST
-             * instantiation takes the reads whose inputs passed validation, the EXACT one the rest (normally none). */
-            int blocks = std::min(c->sm_count * 4, (n + 3) / 4);
-            if (blocks < 1) blocks = 1;
-            ABEA_LAUNCH(abea_fill_kernel<true>, blocks, 128, c->stream,
-                (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
-                (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue);
-            ABEA_LAUNCH(abea_fill_kernel<false>, blocks, 128, c->stream,
-                (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
-                (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue + 1);
-            launches += 2;
+            /* The longest n_wide reads: one CTA of 4 warps each (wide kernel) on a second stream, beside the persistent
+             * narrow warps (4 CTAs of 4 warps per SM, each warp pulls reads longest-first). The FAST instantiations
+             * take the reads whose inputs passed validation, the EXACT ones the rest (normally none). */
+            const int32_t nw = c->n_wide;
+            if (nw > 0) {
+                CU(cudaEventRecord(c->ev_fork, c->stream));
+                CU(cudaStreamWaitEvent(c->wide_stream, c->ev_fork, 0));
+                int wblocks = std::min(c->sm_count * 4, (int)nw);
+                ABEA_LAUNCH(abea_fill_wide_kernel<true>, wblocks, 128, c->wide_stream,
+                    (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue + 3);
+                ABEA_LAUNCH(abea_fill_wide_kernel<false>, wblocks, 128, c->wide_stream,
+                    (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue + 4);
+                CU(cudaEventRecord(c->ev_join, c->wide_stream));
+                launches += 2;
+            }
+            if (n > nw) {
+                int blocks = std::min(c->sm_count * c->fill_ctas_per_sm, (n - nw + 3) / 4);
+                if (blocks < 1) blocks = 1;
+                ABEA_LAUNCH(abea_fill_kernel<true>, blocks, 128, c->stream,
+                    (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue, nw);
+                ABEA_LAUNCH(abea_fill_kernel<false>, blocks, 128, c->stream,
+                    (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue + 1, nw);
+                launches += 2;
+            }
+            if (nw > 0) CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         }
         CU(cudaEventRecord(c->ev[EV_K2], c->stream));
         {
-            int blocks = std::min(c->sm_count * 4, (n + 3) / 4);
+            int blocks = std::min(c->sm_count * c->trace_ctas_per_sm, (n + 3) / 4);
             if (blocks < 1) blocks = 1;
             ABEA_LAUNCH(abea_traceback_kernel, blocks, 128, c->stream,
                 (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,

@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(128)
 abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const abea_event_t* __restrict__ events,
                  const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                  uint32_t* __restrict__ trace, abea_result_t* __restrict__ results, abea_consts_t cst,
-                 int32_t* __restrict__ queue) {
+                 int32_t* __restrict__ queue, int32_t first) {
     __shared__ __align__(16) abea_fill_smem_t smem_all[4];
     const int lane = threadIdx.x & 31;
     abea_fill_smem_t* sm = &smem_all[threadIdx.x >> 5];
@@ -466,7 +466,7 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
 
     for (;;) {
         int32_t ridx = 0;
-        if (lane == 0) ridx = atomicAdd(queue, 1);
+        if (lane == 0) ridx = first + atomicAdd(queue, 1); /* reads [0, first) are filled by the wide kernel */
         ridx = __shfl_sync(ABEA_FULL, ridx, 0);
         if (ridx >= n_reads) break;
         /* each instantiation takes only the reads validated for its arithmetic */
@@ -544,6 +544,222 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
             }
         }
         if (lane == 0) {
+            results[ridx].end_score = __double2float_rn(best_s);
+            results[ridx].end_event = (best_e == 0x7fffffff) ? 0 : best_e;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Band fill, WIDE form: one CTA (4 warps) per read, ONE band cell per lane. A read is a serial chain of NB bands, so
+ * the longest reads of a batch set the makespan; the reference sends them to CPU threads (src/f5c.cu:440-452), here
+ * they get four warps instead of one, which cuts the per-band critical path (one cell instead of four per lane, no
+ * register windows to slide). Warp w owns offsets 28w..28w+27 (warp 3: 84..99), so that four lanes form one word of
+ * the same 128-B trace line layout the narrow kernel writes. Events and k-mer parameters of the whole band window live
+ * in shared-memory rings (256 entries, 64-entry chunks staged by cp.async) and are simply re-addressed every band.
+ * Warps exchange their two boundary cells and the two cells of Suzuki's rule through shared memory, one
+ * __syncthreads per band, double-buffered by band parity. Arithmetic is the same templates as the narrow kernel.   */
+
+#define ABEA_WIDE_WARPS 4
+#define ABEA_WIDE_SPAN 28   /* offsets per warp */
+#define ABEA_WRING 256      /* ring entries (window of 100 + chunks in flight) */
+#define ABEA_WCHUNK 64
+
+struct abea_wide_smem_t {
+    float ev[ABEA_WRING];
+    float4 kp[ABEA_WRING];
+    double edge[2][ABEA_WIDE_WARPS][2]; /* [band parity][warp][0 = first cell, 1 = last cell] */
+    double red_s[ABEA_WIDE_WARPS];
+    int32_t red_e[ABEA_WIDE_WARPS];
+    int32_t ridx;
+};
+
+__device__ __forceinline__ void abea_wide_stage(abea_wide_smem_t* sm, const abea_event_t* __restrict__ ev,
+                                                const float4* __restrict__ kpr, int32_t echunk, int32_t kchunk,
+                                                int32_t E, int32_t K, int tid) {
+    if (tid < ABEA_WCHUNK) {
+        if (echunk >= 0) {
+            int32_t e = echunk * ABEA_WCHUNK + tid;
+            int32_t ec = e >= E ? E - 1 : e;
+            abea_cp_async4(&sm->ev[e & (ABEA_WRING - 1)], &ev[ec].mean);
+        }
+        if (kchunk >= 0) {
+            int32_t k = kchunk * ABEA_WCHUNK + tid;
+            int32_t kc = k >= K ? K - 1 : k;
+            abea_cp_async16(&sm->kp[k & (ABEA_WRING - 1)], &kpr[kc]);
+        }
+    }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(32 * ABEA_WIDE_WARPS)
+abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, const abea_event_t* __restrict__ events,
+                      const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
+                      uint32_t* __restrict__ trace, abea_result_t* __restrict__ results, abea_consts_t cst,
+                      int32_t* __restrict__ queue) {
+    __shared__ __align__(16) abea_wide_smem_t sm;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int w = tid >> 5;
+    const int o = ABEA_WIDE_SPAN * w + lane;                       /* this lane's band offset */
+    const bool active = (lane < ABEA_WIDE_SPAN) && (o < ABEA_W);
+    const int last_lane = (w == ABEA_WIDE_WARPS - 1) ? (ABEA_W - 1 - ABEA_WIDE_SPAN * (ABEA_WIDE_WARPS - 1)) : (ABEA_WIDE_SPAN - 1);
+    const double NEG = abea_neg_inf_d();
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sm.ridx = atomicAdd(queue, 1);
+        __syncthreads();
+        const int32_t ridx = sm.ridx;
+        if (ridx >= n_wide) break;
+        if (((read_flags[ridx] & ABEA_READ_FAST) != 0u) != FAST) continue;
+
+        const abea_read_t rd = reads[ridx];
+        const int32_t E = rd.n_events, K = rd.n_kmers;
+        const int32_t NB = E + K + 2;
+        const abea_event_t* __restrict__ ev = events + rd.ev_off;
+        const float4* __restrict__ kpr = kparams + rd.kp_off;
+        uint32_t* __restrict__ tr = trace + rd.trace_off;
+        const double lp_stay = rd.lp_stay, lp_step = rd.lp_step, lp_skip = cst.lp_skip, lp_trim = cst.lp_trim;
+
+        int32_t eb = ABEA_W / 2, kb = -1 - ABEA_W / 2; /* band 1 (reference src/align.c:277-279) */
+        /* stage the chunks covering events [0, eb+64) and k-mers [0, kb+99+64): chunk 0 and 1 of each (indices < 0 are
+         * never valid cells; the ring slots they alias hold clamped garbage that the validity mask discards) */
+        abea_wide_stage(&sm, ev, kpr, 0, 0, E, K, tid);
+        abea_wide_stage(&sm, ev, kpr, 1, 1, E, K, tid);
+        abea_cp_async_wait_all();
+        __syncthreads();
+        abea_wide_stage(&sm, ev, kpr, 2, 2, E, K, tid); /* in flight while chunks 0 and 1 are consumed */
+        int32_t echunk_hi = 2, kchunk_hi = 2;           /* highest chunk staged; it may still be in flight */
+
+        double R1 = (o == ABEA_W / 2) ? (double)__double2float_rn(lp_trim) : NEG; /* band 1, src/align.c:290 */
+        double R2 = (o == ABEA_W / 2) ? 0.0 : NEG;                                 /* band 0, src/align.c:284 */
+        if (!active) { R1 = NEG; R2 = NEG; }
+        double lo1 = __shfl_up_sync(ABEA_FULL, R1, 1), hi1 = __shfl_down_sync(ABEA_FULL, R1, 1);
+        double lo2 = __shfl_up_sync(ABEA_FULL, R2, 1), hi2 = __shfl_down_sync(ABEA_FULL, R2, 1);
+        /* the only finite cells of bands 0 and 1 sit at offset 50 = warp 1 lane 22: no warp boundary is involved */
+        if (lane == 0) { lo1 = NEG; lo2 = NEG; }
+        if (lane >= last_lane) { hi1 = NEG; hi2 = NEG; }
+
+        uint32_t acc = (o == ABEA_W / 2) ? (ABEA_FROM_U << (8 + 2 * (o & 3))) : 0u; /* band 1's trim cell */
+        int32_t eb_keep = (w == 3 && lane == 28) ? (ABEA_W / 2 - 1) : ((w == 3 && lane == 29) ? ABEA_W / 2 : 0);
+        double best_s = NEG;
+        int32_t best_e = 0x7fffffff;
+        bool right = false, prev_right = false; /* band 2 moves down (both extreme cells of band 1 are -inf, b even) */
+        int32_t safe = 0;
+
+        for (int32_t b = 2; b < NB; b++) {
+            if (right) kb += 1; else eb += 1;
+            /* keep the rings ahead of the window (top event eb, top k-mer kb+99): when the window reaches the first
+             * index of the chunk that is in flight, land it and start the next one. Chunk c+1 reuses the ring slots of
+             * chunk c-3, whose last index left the 100-wide window 29 moves earlier. */
+            {
+                const int32_t top_k = kb + ABEA_W - 1;
+                const bool need_e = !right && ((eb & (ABEA_WCHUNK - 1)) == 0) && ((eb >> 6) == echunk_hi);
+                const bool need_k = right && ((top_k & (ABEA_WCHUNK - 1)) == 0) && ((top_k >> 6) == kchunk_hi);
+                if (need_e || need_k) {
+                    abea_cp_async_wait_all();
+                    __syncthreads();
+                    if (need_e) { echunk_hi += 1; abea_wide_stage(&sm, ev, kpr, echunk_hi, -1, E, K, tid); }
+                    if (need_k) { kchunk_hi += 1; abea_wide_stage(&sm, ev, kpr, -1, kchunk_hi, E, K, tid); }
+                }
+            }
+            const int32_t e = eb - o, km = kb + o;
+            const float x = sm.ev[e & (ABEA_WRING - 1)];
+            const float4 kp = sm.kp[km & (ABEA_WRING - 1)];
+            const float lp = abea_emission_t<FAST>(x, kp);
+            const double up = right ? hi1 : R1;
+            const double left = right ? R1 : lo1;
+            const double diag = (right == prev_right) ? (right ? hi2 : lo2) : R2;
+            double Rn;
+            uint32_t fr;
+            abea_cell_d<FAST>(lp, up, left, diag, lp_step, lp_stay, lp_skip, Rn, fr);
+            if (!active) { Rn = NEG; fr = 0u; }
+
+            if (safe > 0) {
+                safe -= 1;
+            } else {
+                const bool interior = (kb >= 0) && (kb + ABEA_W < K) && (eb >= ABEA_W - 1) && (eb <= E - 1);
+                if (interior) {
+                    int32_t s1 = K - ABEA_W - 1 - kb, s2 = E - 1 - eb;
+                    safe = s1 < s2 ? s1 : s2;
+                } else {
+                    int32_t lo = -kb;
+                    if (eb - (E - 1) > lo) lo = eb - (E - 1);
+                    if (lo < 0) lo = 0;
+                    int32_t hi = K - kb;
+                    if (eb + 1 < hi) hi = eb + 1;
+                    if (hi > ABEA_W) hi = ABEA_W;
+                    const int32_t to = -1 - kb;
+                    const int32_t te = eb - to;
+                    const bool trim_in = (to >= 0) && (to < ABEA_W) && (te >= 0) && (te < E);
+                    const double trim_s = (double)__double2float_rn(__dmul_rn(lp_trim, (double)(te + 1)));
+                    const int32_t oe = (K - 1) - kb;
+                    const bool valid = active && (o >= lo) && (o < hi);
+                    Rn = valid ? Rn : NEG;
+                    fr = valid ? fr : 0u;
+                    if (active && o == to && trim_in) {
+                        Rn = trim_s;
+                        fr = ABEA_FROM_U;
+                    }
+                    if (o == oe && valid) {
+                        double s = (double)__double2float_rn(__dadd_rn(Rn, __dmul_rn((double)(E - e), lp_trim)));
+                        if (s > best_s) {
+                            best_s = s;
+                            best_e = e;
+                        }
+                    }
+                }
+            }
+
+            /* publish this warp's boundary cells, then everybody learns its halos and the next move */
+            const int par = b & 1;
+            if (lane == 0) sm.edge[par][w][0] = Rn;
+            if (lane == last_lane) sm.edge[par][w][1] = Rn;
+            double lo_n = __shfl_up_sync(ABEA_FULL, Rn, 1);
+            double hi_n = __shfl_down_sync(ABEA_FULL, Rn, 1);
+            __syncthreads();
+            if (lane == 0) lo_n = (w > 0) ? sm.edge[par][w - 1][1] : NEG;
+            if (lane >= last_lane) hi_n = (w < ABEA_WIDE_WARPS - 1 && lane == last_lane) ? sm.edge[par][w + 1][0] : NEG;
+            const double ll = sm.edge[par][0][0], ur = sm.edge[par][ABEA_WIDE_WARPS - 1][1];
+            const bool next_right = (ll == NEG && ur == NEG) ? (((b + 1) & 1) == 1) : (ll < ur);
+
+            /* trace: this lane's 2 bits go to bit 8q + 2(o&3) of word o>>2 of the 128-B line of the 4-band group */
+            const int q = b & 3;
+            acc |= fr << (8 * q + 2 * (o & 3));
+            if (w == 3 && lane == 28 + q) eb_keep = eb;
+            if (q == 3 || b == NB - 1) {
+                uint32_t word = acc | __shfl_xor_sync(ABEA_FULL, acc, 1);
+                word |= __shfl_xor_sync(ABEA_FULL, word, 2);
+                uint32_t* line = tr + (int64_t)(b >> 2) * ABEA_TRACE_GROUP_WORDS;
+                if (active && (lane & 3) == 0) line[o >> 2] = word;
+                if (w == 3 && lane >= 28) line[ABEA_LANES + (lane - 28)] = (uint32_t)eb_keep;
+                acc = 0u;
+            }
+
+            R2 = R1; R1 = Rn;
+            lo2 = lo1; hi2 = hi1;
+            lo1 = lo_n; hi1 = hi_n;
+            prev_right = right;
+            right = next_right;
+        }
+        abea_cp_async_wait_all();
+
+        /* best end cell over the CTA: max score, ties to the smaller event */
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            double os = __shfl_xor_sync(ABEA_FULL, best_s, d);
+            int32_t oe2 = __shfl_xor_sync(ABEA_FULL, best_e, d);
+            if (os > best_s || (os == best_s && oe2 < best_e)) { best_s = os; best_e = oe2; }
+        }
+        if (lane == 0) { sm.red_s[w] = best_s; sm.red_e[w] = best_e; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 1; i < ABEA_WIDE_WARPS; i++) {
+                double os = sm.red_s[i];
+                int32_t oe2 = sm.red_e[i];
+                if (os > best_s || (os == best_s && oe2 < best_e)) { best_s = os; best_e = oe2; }
+            }
             results[ridx].end_score = __double2float_rn(best_s);
             results[ridx].end_event = (best_e == 0x7fffffff) ? 0 : best_e;
         }

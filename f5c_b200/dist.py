@@ -1,0 +1,61 @@
+"""Multi-GPU host logic: reads are independent, so a batch is partitioned read-wise (one process per GPU, no
+collective on the data path) and only the RESULTS are gathered to rank 0 (north_star: "NCCL over NVLink only for the
+final result gather"). The reference has no counterpart (multi-GPU = run several processes by hand, docs/f5c.1:271).
+
+The same functions run over NCCL (CUDA tensors, bench.py) and over gloo (CPU tensors, tests/test_sharding_gloo.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .batch import PAIR_DTYPE
+
+
+def compact_pairs(pairs: np.ndarray, pair_ptr: np.ndarray, n_pairs: np.ndarray) -> np.ndarray:
+    """Concatenate the per-read pair lists (capacity layout -> dense)."""
+    total = int(n_pairs.astype(np.int64).sum())
+    out = np.empty(total, dtype=PAIR_DTYPE)
+    pos = 0
+    for i in range(n_pairs.shape[0]):
+        n = int(n_pairs[i])
+        if n:
+            p = int(pair_ptr[i])
+            out[pos:pos + n] = pairs[p:p + n]
+            pos += n
+    return out
+
+
+def gather_results(n_pairs: np.ndarray, dense_pairs: np.ndarray, rank: int, world: int, device: str = "cpu"):
+    """Gather every rank's (n_pairs, dense pair list) to rank 0.
+
+    Returns on rank 0 a list of (n_pairs, pairs) per rank (rank order); None elsewhere. Two collectives: an
+    all_gather of the shard sizes (so every rank can pad to a common length) and a gather of the padded payloads.
+    """
+    dev = torch.device(device)
+    counts = torch.from_numpy(np.ascontiguousarray(n_pairs.astype(np.int32))).to(dev)
+    flat = torch.from_numpy(np.ascontiguousarray(dense_pairs).view(np.int32).reshape(-1, 2)).to(dev)
+    sizes = torch.tensor([counts.numel(), flat.shape[0]], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [s.cpu().numpy() for s in all_sizes]
+    max_reads = int(max(s[0] for s in all_sizes))
+    max_pairs = int(max(s[1] for s in all_sizes))
+    cpad = torch.zeros(max_reads, dtype=torch.int32, device=dev)
+    cpad[:counts.numel()] = counts
+    ppad = torch.zeros((max(max_pairs, 1), 2), dtype=torch.int32, device=dev)
+    ppad[:flat.shape[0]] = flat
+    cl = [torch.empty_like(cpad) for _ in range(world)] if rank == 0 else None
+    pl = [torch.empty_like(ppad) for _ in range(world)] if rank == 0 else None
+    dist.gather(cpad, cl, dst=0)
+    dist.gather(ppad, pl, dst=0)
+    if rank != 0:
+        return None
+    out = []
+    for r in range(world):
+        nr, npz = int(all_sizes[r][0]), int(all_sizes[r][1])
+        c = cl[r][:nr].cpu().numpy()
+        p = pl[r][:npz].cpu().numpy().reshape(-1).view(PAIR_DTYPE)
+        out.append((c, p))
+    return out

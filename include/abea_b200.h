@@ -60,6 +60,8 @@ typedef struct {
     int64_t d2h_bytes;
     int32_t kernel_launches; /* kernels of this library launched by the call */
     int32_t n_scheduled;     /* reads that passed the eligibility filter */
+    int32_t n_wide;          /* of those, reads filled by the wide (4 warps per read) kernel */
+    int32_t reserved_;
     int64_t n_bands;         /* sum of NB over scheduled reads */
     int64_t n_events;        /* sum of E over scheduled reads (the metric's numerator) */
 } abea_timing_t;

@@ -70,3 +70,24 @@ def test_emulated_resident_phases(emu):
         assert t["kernel_launches"] == 4
         two = ctx.download(b)
     ol.assert_same_alignment(one, two, "resident")
+
+
+def test_emulated_wide_kernel_all_reads(emu, monkeypatch):
+    """Force every read through the wide (4 warps per read) fill kernel, including the edge cases."""
+    monkeypatch.setenv("ABEA_WIDE_MIN_BANDS", "1")
+    monkeypatch.setenv("ABEA_WIDE_ALPHA", "0.00001")
+    b = synth.make_batch("r10", n_reads=3, mean_events=800, sigma=0.8, epk=1.9, seed=15)
+    k, m = models.load_model("r10")
+    with AbeaContext(0, lib_path=emu) as ctx:
+        m = ctx.set_model(m, k)
+        got = ctx.align_batch(b)
+    assert got.timing["n_wide"] == 3
+    ol.assert_same_alignment(got, ol.port_align(b, m), "wide")
+    check(emu, edge_batch(), "r9", "wide edge")
+
+
+def test_emulated_narrow_only(emu, monkeypatch):
+    monkeypatch.setenv("ABEA_WIDE", "0")
+    b = synth.make_batch("r9", n_reads=4, mean_events=1500, sigma=0.5, epk=1.8, seed=16)
+    got = check(emu, b, "r9", "narrow only")
+    assert got.timing["n_wide"] == 0
