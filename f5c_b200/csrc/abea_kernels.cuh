@@ -627,6 +627,7 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
          * never valid cells; the ring slots they alias hold clamped garbage that the validity mask discards) */
         abea_wide_stage(&sm, ev, kpr, 0, 0, E, K, tid);
         abea_wide_stage(&sm, ev, kpr, 1, 1, E, K, tid);
+        if (tid < 2 * ABEA_WIDE_WARPS) sm.edge[1][tid >> 1][tid & 1] = NEG; /* band 1's boundary cells are all -inf */
         abea_cp_async_wait_all();
         __syncthreads();
         abea_wide_stage(&sm, ev, kpr, 2, 2, E, K, tid); /* in flight while chunks 0 and 1 are consumed */
@@ -635,28 +636,46 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
         double R1 = (o == ABEA_W / 2) ? (double)__double2float_rn(lp_trim) : NEG; /* band 1, src/align.c:290 */
         double R2 = (o == ABEA_W / 2) ? 0.0 : NEG;                                 /* band 0, src/align.c:284 */
         if (!active) { R1 = NEG; R2 = NEG; }
+        /* neighbour cells inside the warp; the two warp-boundary lanes are patched from shared memory each band.
+         * The only finite cells of bands 0 and 1 sit at offset 50 = warp 1 lane 22: no warp boundary is involved. */
         double lo1 = __shfl_up_sync(ABEA_FULL, R1, 1), hi1 = __shfl_down_sync(ABEA_FULL, R1, 1);
         double lo2 = __shfl_up_sync(ABEA_FULL, R2, 1), hi2 = __shfl_down_sync(ABEA_FULL, R2, 1);
-        /* the only finite cells of bands 0 and 1 sit at offset 50 = warp 1 lane 22: no warp boundary is involved */
-        if (lane == 0) { lo1 = NEG; lo2 = NEG; }
-        if (lane >= last_lane) { hi1 = NEG; hi2 = NEG; }
+        if (lane == 0) lo2 = NEG;
+        if (lane >= last_lane) hi2 = NEG;
 
         uint32_t acc = (o == ABEA_W / 2) ? (ABEA_FROM_U << (8 + 2 * (o & 3))) : 0u; /* band 1's trim cell */
         int32_t eb_keep = (w == 3 && lane == 28) ? (ABEA_W / 2 - 1) : ((w == 3 && lane == 29) ? ABEA_W / 2 : 0);
         double best_s = NEG;
         int32_t best_e = 0x7fffffff;
-        bool right = false, prev_right = false; /* band 2 moves down (both extreme cells of band 1 are -inf, b even) */
+        bool prev_right = false; /* band 1 was a down move */
         int32_t safe = 0;
 
+        /* the lane's event / k-mer of band b-1 and, speculatively, what it would hold after either move:
+         * a right move keeps the event and takes k-mer kb+1+o, a down move keeps the k-mer and takes event eb+1-o */
+        float x_cur = sm.ev[(eb - o) & (ABEA_WRING - 1)];
+        float4 kp_cur = sm.kp[(kb + o) & (ABEA_WRING - 1)];
+        float x_dn = sm.ev[(eb + 1 - o) & (ABEA_WRING - 1)];
+        float4 kp_rt = sm.kp[(kb + 1 + o) & (ABEA_WRING - 1)];
+        double lpd_rt = (double)abea_emission_t<FAST>(x_cur, kp_rt);
+        double lpd_dn = (double)abea_emission_t<FAST>(x_dn, kp_cur);
+
         for (int32_t b = 2; b < NB; b++) {
-            if (right) kb += 1; else eb += 1;
-            /* keep the rings ahead of the window (top event eb, top k-mer kb+99): when the window reaches the first
-             * index of the chunk that is in flight, land it and start the next one. Chunk c+1 reuses the ring slots of
-             * chunk c-3, whose last index left the 100-wide window 29 moves earlier. */
+            /* ---- band b-1 is complete and published: halos across warp boundaries and this band's move ---- */
+            const int pp = (b - 1) & 1;
+            if (lane == 0) lo1 = (w > 0) ? sm.edge[pp][w - 1][1] : NEG;
+            if (lane >= last_lane) hi1 = (w < ABEA_WIDE_WARPS - 1 && lane == last_lane) ? sm.edge[pp][w + 1][0] : NEG;
+            const double ll = sm.edge[pp][0][0], ur = sm.edge[pp][ABEA_WIDE_WARPS - 1][1];
+            const bool right = (ll == NEG && ur == NEG) ? ((b & 1) == 1) : (ll < ur); /* src/align.c:304-314 */
+            double lpd;
+            if (right) { kb += 1; kp_cur = kp_rt; lpd = lpd_rt; }
+            else { eb += 1; x_cur = x_dn; lpd = lpd_dn; }
+
+            /* keep the rings ahead of what the next band may touch (event eb+1, k-mer kb+100): when that index is the
+             * first of the chunk in flight, land it and start the next one. Chunk c+1 reuses the ring slots of chunk
+             * c-3, which left the 100-wide window long before. */
             {
-                const int32_t top_k = kb + ABEA_W - 1;
-                const bool need_e = !right && ((eb & (ABEA_WCHUNK - 1)) == 0) && ((eb >> 6) == echunk_hi);
-                const bool need_k = right && ((top_k & (ABEA_WCHUNK - 1)) == 0) && ((top_k >> 6) == kchunk_hi);
+                const bool need_e = (((eb + 1) & (ABEA_WCHUNK - 1)) == 0) && (((eb + 1) >> 6) == echunk_hi);
+                const bool need_k = (((kb + ABEA_W) & (ABEA_WCHUNK - 1)) == 0) && (((kb + ABEA_W) >> 6) == kchunk_hi);
                 if (need_e || need_k) {
                     abea_cp_async_wait_all();
                     __syncthreads();
@@ -664,16 +683,23 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                     if (need_k) { kchunk_hi += 1; abea_wide_stage(&sm, ev, kpr, -1, kchunk_hi, E, K, tid); }
                 }
             }
-            const int32_t e = eb - o, km = kb + o;
-            const float x = sm.ev[e & (ABEA_WRING - 1)];
-            const float4 kp = sm.kp[km & (ABEA_WRING - 1)];
-            const float lp = abea_emission_t<FAST>(x, kp);
+
+            /* ---- the cell (same templates as the narrow kernel) ---- */
             const double up = right ? hi1 : R1;
             const double left = right ? R1 : lo1;
             const double diag = (right == prev_right) ? (right ? hi2 : lo2) : R2;
             double Rn;
             uint32_t fr;
-            abea_cell_d<FAST>(lp, up, left, diag, lp_step, lp_stay, lp_skip, Rn, fr);
+            {
+                double rd = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(diag, lp_step), lpd));
+                double ru = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(up, lp_stay), lpd));
+                double rl = abea_round_f32<FAST>(__dadd_rn(left, lp_skip));
+                bool isU = ru >= rd;
+                double m = isU ? ru : rd;
+                bool isL = rl >= m;
+                Rn = isL ? rl : m;
+                fr = isL ? ABEA_FROM_L : (isU ? ABEA_FROM_U : ABEA_FROM_D);
+            }
             if (!active) { Rn = NEG; fr = 0u; }
 
             if (safe > 0) {
@@ -703,6 +729,7 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                         fr = ABEA_FROM_U;
                     }
                     if (o == oe && valid) {
+                        const int32_t e = eb - o;
                         double s = (double)__double2float_rn(__dadd_rn(Rn, __dmul_rn((double)(E - e), lp_trim)));
                         if (s > best_s) {
                             best_s = s;
@@ -712,17 +739,22 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                 }
             }
 
-            /* publish this warp's boundary cells, then everybody learns its halos and the next move */
+            /* ---- publish this warp's boundary cells; everything below is independent of the other warps and
+             * overlaps their arrival at the barrier ---- */
             const int par = b & 1;
             if (lane == 0) sm.edge[par][w][0] = Rn;
             if (lane == last_lane) sm.edge[par][w][1] = Rn;
-            double lo_n = __shfl_up_sync(ABEA_FULL, Rn, 1);
-            double hi_n = __shfl_down_sync(ABEA_FULL, Rn, 1);
-            __syncthreads();
-            if (lane == 0) lo_n = (w > 0) ? sm.edge[par][w - 1][1] : NEG;
-            if (lane >= last_lane) hi_n = (w < ABEA_WIDE_WARPS - 1 && lane == last_lane) ? sm.edge[par][w + 1][0] : NEG;
-            const double ll = sm.edge[par][0][0], ur = sm.edge[par][ABEA_WIDE_WARPS - 1][1];
-            const bool next_right = (ll == NEG && ur == NEG) ? (((b + 1) & 1) == 1) : (ll < ur);
+            lo2 = lo1; hi2 = hi1;
+            lo1 = __shfl_up_sync(ABEA_FULL, Rn, 1);
+            hi1 = __shfl_down_sync(ABEA_FULL, Rn, 1);
+            R2 = R1; R1 = Rn;
+            prev_right = right;
+
+            /* speculative emissions of band b+1 for both moves */
+            x_dn = sm.ev[(eb + 1 - o) & (ABEA_WRING - 1)];
+            kp_rt = sm.kp[(kb + 1 + o) & (ABEA_WRING - 1)];
+            lpd_rt = (double)abea_emission_t<FAST>(x_cur, kp_rt);
+            lpd_dn = (double)abea_emission_t<FAST>(x_dn, kp_cur);
 
             /* trace: this lane's 2 bits go to bit 8q + 2(o&3) of word o>>2 of the 128-B line of the 4-band group */
             const int q = b & 3;
@@ -736,12 +768,7 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                 if (w == 3 && lane >= 28) line[ABEA_LANES + (lane - 28)] = (uint32_t)eb_keep;
                 acc = 0u;
             }
-
-            R2 = R1; R1 = Rn;
-            lo2 = lo1; hi2 = hi1;
-            lo1 = lo_n; hi1 = hi_n;
-            prev_right = right;
-            right = next_right;
+            __syncthreads();
         }
         abea_cp_async_wait_all();
 
@@ -776,18 +803,18 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
  * list comes out ascending with no reversal pass, (ii) evaluates the 32 emissions in parallel and (iii) adds them
  * to the QC sum strictly in traceback order (the reference's summation order, src/align.c:476).                    */
 
-#define ABEA_TB_CHUNK_GROUPS 16
+#define ABEA_TB_CHUNK_GROUPS 8
 #define ABEA_TB_RING_GROUPS 32
 #define ABEA_TB_WARPS 4
 
-/* start the asynchronous copy of trace chunk `chunk` (groups 16*chunk .. 16*chunk+15) into the ring */
-__device__ __forceinline__ void abea_tb_prefetch(uint32_t* ring, const uint32_t* __restrict__ tr, int64_t chunk, int lane) {
+/* start the asynchronous copy of trace chunk `chunk` (groups 8*chunk .. 8*chunk+7 = 32 bands) into the ring */
+__device__ __forceinline__ void abea_tb_prefetch(uint32_t* ring, const uint32_t* __restrict__ tr, int32_t chunk, int lane) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        int idx = i * 32 + lane;                       /* 128 pieces of 16 B = 16 lines of 128 B */
-        int64_t g = chunk * ABEA_TB_CHUNK_GROUPS + (idx >> 3);
+    for (int i = 0; i < 2; i++) {
+        int idx = i * 32 + lane;                       /* 64 pieces of 16 B = 8 lines of 128 B */
+        int32_t g = chunk * ABEA_TB_CHUNK_GROUPS + (idx >> 3);
         abea_cp_async16(ring + (g & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + (idx & 7) * 4,
-                        tr + g * ABEA_TRACE_GROUP_WORDS + (idx & 7) * 4);
+                        tr + (int64_t)g * ABEA_TRACE_GROUP_WORDS + (idx & 7) * 4);
     }
 }
 
@@ -837,11 +864,18 @@ abea_traceback_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, co
         int32_t pk = 0, pe = 0; /* the pair parked in this lane */
 
         __syncwarp();           /* the previous read's ring is no longer being read by any lane */
-        int64_t cur_chunk = (((int64_t)ce + (int64_t)ck + 2) >> 2) / ABEA_TB_CHUNK_GROUPS;
-        abea_tb_prefetch(ring, tr, cur_chunk, lane);
+        /* The ring holds 4 chunks of 32 bands. Before a step at band b the chunks of b, b-1 and b-2 must have
+         * landed (the step reads the trace word of b and the lower-left event index of whichever of b-1 / b-2 comes
+         * next); c_ready is the lowest landed chunk, c_ready-1 is in flight. */
+        int32_t b = ce + ck + 2;
+        int32_t c_ready = b >> 5;
+        abea_tb_prefetch(ring, tr, c_ready, lane);
+        if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
         abea_cp_async_wait_all();
         __syncwarp();
-        if (cur_chunk > 0) abea_tb_prefetch(ring, tr, cur_chunk - 1, lane);
+        if (c_ready > 0) c_ready -= 1;
+        if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
+        int32_t eb_cur = (int32_t)ring[((b >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b & 3)];
 
         while (ck >= 0 && ce >= 0) {
             /* emit (reference src/align.c:458-460): park the pair in lane n%32 */
@@ -853,30 +887,30 @@ abea_traceback_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, co
             last_k = ck;
             if ((n & 31) == 0) sum = abea_tb_flush(sum, 32, lane, pk, pe, n - 32, ev, kpr, out, rd.pair_cap);
 
-            const int64_t b = (int64_t)ce + (int64_t)ck + 2;
-            const int64_t g = b >> 2;
-            const int64_t chunk = g / ABEA_TB_CHUNK_GROUPS;
-            if (chunk != cur_chunk) { /* walked down into the chunk that was in flight */
+            const int32_t b2 = b >= 2 ? b - 2 : 0;
+            if ((b2 >> 5) < c_ready) { /* the walk is about to need the chunk that was in flight */
                 abea_cp_async_wait_all();
                 __syncwarp();
-                cur_chunk = chunk;
-                if (chunk > 0) abea_tb_prefetch(ring, tr, chunk - 1, lane);
+                c_ready -= 1;
+                if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
             }
-            const uint32_t* line = ring + (g & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS;
-            const int q = (int)(b & 3);
-            const int32_t ebb = (int32_t)line[ABEA_LANES + q];
-            const int32_t o = ebb - ce;
+            /* lower-left event index of the two bands the walk can move to (off the dependent chain) */
+            const int32_t b1 = b >= 1 ? b - 1 : 0;
+            const int32_t eb1 = (int32_t)ring[((b1 >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b1 & 3)];
+            const int32_t eb2 = (int32_t)ring[((b2 >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b2 & 3)];
+            /* the trace bits of cell (band b, offset o) */
+            const int32_t o = eb_cur - ce;
+            const uint32_t tw = ring[((b >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ((o >> 2) & 31)];
             /* an out-of-band start cell is undefined behaviour in the reference; stay in bounds */
-            const uint32_t tw = line[(o >> 2) & 31];
-            const uint32_t from = (o >= 0 && o < ABEA_W) ? ((tw >> (8 * q + 2 * (o & 3))) & 3u) : ABEA_FROM_D;
-            if (from == ABEA_FROM_D) {
-                ck--; ce--; gap = 0;
-            } else if (from == ABEA_FROM_U) {
-                ce--; gap = 0;
-            } else {
-                ck--; gap++;
-                max_gap = gap > max_gap ? gap : max_gap;
-            }
+            const uint32_t from = (o >= 0 && o < ABEA_W) ? ((tw >> (8 * (b & 3) + 2 * (o & 3))) & 3u) : ABEA_FROM_D;
+            const bool isD = (from == ABEA_FROM_D), isU = (from == ABEA_FROM_U);
+            const bool isL = !(isD || isU);
+            ce -= (isD || isU) ? 1 : 0;
+            ck -= (isD || isL) ? 1 : 0;
+            b = isD ? b2 : b1;
+            eb_cur = isD ? eb2 : eb1;
+            gap = isL ? gap + 1 : 0;
+            max_gap = gap > max_gap ? gap : max_gap;
         }
         abea_cp_async_wait_all(); /* drain the chunk still in flight before the ring is reused */
         if ((n & 31) != 0) sum = abea_tb_flush(sum, n & 31, lane, pk, pe, n & ~31, ev, kpr, out, rd.pair_cap);
