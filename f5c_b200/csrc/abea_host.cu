@@ -79,10 +79,10 @@ struct abea_ctx {
     int32_t n_wide = 0;               /* the first n_wide scheduled reads (the longest) are filled by the wide kernel */
     cudaStream_t wide_stream = nullptr; /* the wide fill runs beside the narrow one */
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int wide_mode = 1;                /* ABEA_WIDE=0 disables the wide kernel */
+    int wide_mode = 0;                /* ABEA_WIDE=1 enables the wide kernel (off by default: DESIGN.md §3.2b) */
     double wide_alpha = 1.0;          /* ABEA_WIDE_ALPHA scales the wide/narrow threshold */
     double wide_min_bands = 1024.0;   /* ABEA_WIDE_MIN_BANDS: reads shorter than this are never wide */
-    int fill_ctas_per_sm = 4;  /* persistent fill grid = sm_count * this (tuning knob: ABEA_FILL_CTAS_PER_SM) */
+    int fill_ctas_per_sm = 2;  /* persistent fill grid = sm_count * this (ABEA_FILL_CTAS_PER_SM; 2 measured best, profiles/) */
     int trace_ctas_per_sm = 4; /* ABEA_TRACE_CTAS_PER_SM */
 };
 
@@ -314,9 +314,9 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
     c->n_wide = 0;
     if (c->wide_mode && !c->reads.empty()) {
         const double cyc_batch = (double)nb * 360.0 / ((double)c->sm_count * 4.0);
-        const double cyc_longest_wide = ((double)c->reads[0].n_events + c->reads[0].n_kmers + 2) * 260.0;
+        const double cyc_longest_wide = ((double)c->reads[0].n_events + c->reads[0].n_kmers + 2) * 500.0;
         const double target = std::max(cyc_batch, cyc_longest_wide);
-        const double thr = std::max(c->wide_min_bands, c->wide_alpha * target / 1400.0);
+        const double thr = std::max(c->wide_min_bands, c->wide_alpha * target / 800.0);
         while (c->n_wide < (int32_t)c->reads.size() &&
                (double)c->reads[c->n_wide].n_events + c->reads[c->n_wide].n_kmers + 2 > thr)
             c->n_wide++;
@@ -402,10 +402,12 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
                 int wblocks = std::min(c->sm_count * 4, (int)nw);
                 ABEA_LAUNCH(abea_fill_wide_kernel<true>, wblocks, 128, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
-                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue + 3);
+                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
+                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 3);
                 ABEA_LAUNCH(abea_fill_wide_kernel<false>, wblocks, 128, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
-                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue + 4);
+                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
+                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 4);
                 CU(cudaEventRecord(c->ev_join, c->wide_stream));
                 launches += 2;
             }
@@ -414,24 +416,17 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
                 if (blocks < 1) blocks = 1;
                 ABEA_LAUNCH(abea_fill_kernel<true>, blocks, 128, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
-                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue, nw);
+                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
+                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue, nw);
                 ABEA_LAUNCH(abea_fill_kernel<false>, blocks, 128, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
-                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_result_t*)c->d_results.p, c->cst, queue + 1, nw);
+                    (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
+                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 1, nw);
                 launches += 2;
             }
             if (nw > 0) CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         }
-        CU(cudaEventRecord(c->ev[EV_K2], c->stream));
-        {
-            int blocks = std::min(c->sm_count * c->trace_ctas_per_sm, (n + 3) / 4);
-            if (blocks < 1) blocks = 1;
-            ABEA_LAUNCH(abea_traceback_kernel, blocks, 128, c->stream,
-                (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
-                (const uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p, (abea_result_t*)c->d_results.p,
-                (int32_t*)c->d_npairs.p, queue + 2);
-            launches++;
-        }
+        CU(cudaEventRecord(c->ev[EV_K2], c->stream)); /* traceback + QC are fused into the fill kernels */
     } else {
         CU(cudaEventRecord(c->ev[EV_K1], c->stream));
         CU(cudaEventRecord(c->ev[EV_K2], c->stream));

@@ -258,6 +258,149 @@ __device__ __forceinline__ void abea_cp_async_wait_all() {
 #endif
 }
 
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Traceback + QC (reference src/align.c:452-543). One warp per read. The walk is a pointer chase through the packed
+ * trace, strictly downwards in band index, so the trace lines it will need are known in advance: they are streamed
+ * with cp.async into a per-warp shared-memory ring of 32 lines (two chunks of 16 groups = 64 bands each; the next
+ * chunk is in flight while the current one is walked), which takes HBM latency off the dependent chain. All lanes
+ * walk in lock-step (the state is warp-uniform); step n's pair is parked in lane n%32 and every 32 steps the warp
+ * (i) stores 32 pairs with one coalesced 256-B store, from the END of the read's capacity region backwards so the
+ * list comes out ascending with no reversal pass, (ii) evaluates the 32 emissions in parallel and (iii) adds them
+ * to the QC sum strictly in traceback order (the reference's summation order, src/align.c:476).                    */
+
+#define ABEA_TB_CHUNK_GROUPS 8
+#define ABEA_TB_RING_GROUPS 32
+
+/* start the asynchronous copy of trace chunk `chunk` (groups 8*chunk .. 8*chunk+7 = 32 bands) into the ring */
+__device__ __forceinline__ void abea_tb_prefetch(uint32_t* ring, const uint32_t* __restrict__ tr, int32_t chunk, int lane) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        int idx = i * 32 + lane;                       /* 64 pieces of 16 B = 8 lines of 128 B */
+        int32_t g = chunk * ABEA_TB_CHUNK_GROUPS + (idx >> 3);
+        abea_cp_async16(ring + (g & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + (idx & 7) * 4,
+                        tr + (int64_t)g * ABEA_TRACE_GROUP_WORDS + (idx & 7) * 4);
+    }
+}
+
+/* emissions of the pairs parked in the lanes (first `cnt` lanes valid), added to `sum` in lane order */
+__device__ __forceinline__ double abea_tb_flush(double sum, int cnt, int lane, int32_t pk, int32_t pe, int32_t n_before,
+                                                const abea_event_t* __restrict__ ev, const float4* __restrict__ kpr,
+                                                abea_pair_t* __restrict__ out, int32_t pair_cap) {
+    double lpd = 0.0;
+    if (lane < cnt) {
+        abea_pair_t p;
+        p.ref_pos = pk;
+        p.read_pos = pe;
+        out[pair_cap - 1 - (n_before + lane)] = p;
+        float4 kp = kpr[pk];
+        lpd = (double)abea_emission(ev[pe].mean, kp.x, kp.y, kp.z);
+    }
+    for (int j = 0; j < cnt; j++) sum = __dadd_rn(sum, __shfl_sync(ABEA_FULL, lpd, j));
+    return sum;
+}
+
+/* Traceback + QC of one read by one warp. `ring` is the warp's 4 KB shared-memory ring (32 trace lines). The trace
+ * lines were written by lanes of this warp or CTA; the caller has synchronised (__syncwarp / __syncthreads). */
+__device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32_t ridx, int32_t end_event, uint32_t* ring,
+                                                    int lane, const abea_event_t* __restrict__ events,
+                                                    const float4* __restrict__ kparams, const uint32_t* __restrict__ trace,
+                                                    abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
+                                                    int32_t* __restrict__ n_pairs_out) {
+    const int32_t K = rd.n_kmers;
+    const abea_event_t* __restrict__ ev = events + rd.ev_off;
+    const float4* __restrict__ kpr = kparams + rd.kp_off;
+    const uint32_t* __restrict__ tr = trace + rd.trace_off;
+    abea_pair_t* __restrict__ out = pairs + rd.pair_off;
+
+    int32_t ce = end_event;
+    int32_t ck = K - 1;
+    int32_t n = 0, gap = 0, max_gap = 0;
+    int32_t last_k = ck;
+    double sum = 0.0;
+    int32_t pk = 0, pe = 0; /* the pair parked in this lane */
+
+    __syncwarp();           /* the previous read's ring is no longer being read by any lane */
+    /* The ring holds 4 chunks of 32 bands. Before a step at band b the chunks of b, b-1 and b-2 must have
+     * landed (the step reads the trace word of b and the lower-left event index of whichever of b-1 / b-2 comes
+     * next); c_ready is the lowest landed chunk, c_ready-1 is in flight. */
+    int32_t b = ce + ck + 2;
+    int32_t c_ready = b >> 5;
+    abea_tb_prefetch(ring, tr, c_ready, lane);
+    if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
+    abea_cp_async_wait_all();
+    __syncwarp();
+    if (c_ready > 0) c_ready -= 1;
+    if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
+    int32_t eb_cur = (int32_t)ring[((b >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b & 3)];
+
+    while (ck >= 0 && ce >= 0) {
+        /* emit (reference src/align.c:458-460): park the pair in lane n%32 */
+        if (lane == (n & 31)) {
+            pk = ck;
+            pe = ce;
+        }
+        n++;
+        last_k = ck;
+        if ((n & 31) == 0) sum = abea_tb_flush(sum, 32, lane, pk, pe, n - 32, ev, kpr, out, rd.pair_cap);
+
+        const int32_t b2 = b >= 2 ? b - 2 : 0;
+        if ((b2 >> 5) < c_ready) { /* the walk is about to need the chunk that was in flight */
+            abea_cp_async_wait_all();
+            __syncwarp();
+            c_ready -= 1;
+            if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
+        }
+        /* lower-left event index of the two bands the walk can move to (off the dependent chain) */
+        const int32_t b1 = b >= 1 ? b - 1 : 0;
+        const int32_t eb1 = (int32_t)ring[((b1 >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b1 & 3)];
+        const int32_t eb2 = (int32_t)ring[((b2 >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b2 & 3)];
+        /* the trace bits of cell (band b, offset o) */
+        const int32_t o = eb_cur - ce;
+        const uint32_t tw = ring[((b >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ((o >> 2) & 31)];
+        /* an out-of-band start cell is undefined behaviour in the reference; stay in bounds */
+        const uint32_t from = (o >= 0 && o < ABEA_W) ? ((tw >> (8 * (b & 3) + 2 * (o & 3))) & 3u) : ABEA_FROM_D;
+        const bool isD = (from == ABEA_FROM_D), isU = (from == ABEA_FROM_U);
+        const bool isL = !(isD || isU);
+        ce -= (isD || isU) ? 1 : 0;
+        ck -= (isD || isL) ? 1 : 0;
+        b = isD ? b2 : b1;
+        eb_cur = isD ? eb2 : eb1;
+        gap = isL ? gap + 1 : 0;
+        max_gap = gap > max_gap ? gap : max_gap;
+    }
+    abea_cp_async_wait_all(); /* drain the chunk still in flight before the ring is reused */
+    if ((n & 31) != 0) sum = abea_tb_flush(sum, n & 31, lane, pk, pe, n & ~31, ev, kpr, out, rd.pair_cap);
+
+    /* QC (reference src/align.c:526-543) */
+    double avg = sum / (double)n;
+    bool spanned = (n > 0) && (last_k == 0);
+    bool fail = (avg < -5.0) || !spanned || (max_gap > 50);
+    if (lane == 0) {
+        results[ridx].sum_emission = sum;
+        results[ridx].n_aligned = n;
+        results[ridx].n_pairs = fail ? 0 : n;
+        results[ridx].pair_start = 0;
+        results[ridx].max_gap = max_gap;
+        n_pairs_out[rd.orig_index] = fail ? 0 : n; /* db->n_event_align_pairs[i] */
+    }
+    /* slide the list to the front of the read's capacity region (the layout the caller's buffer has), in place:
+     * destination index t <= source index cap-n+t, batches of 32 are loaded before they are stored */
+    __syncwarp();
+    const int32_t src0 = rd.pair_cap - n;
+    if (!fail && src0 > 0) {
+        for (int32_t t0 = 0; t0 < n; t0 += 32) {
+            const int32_t t = t0 + lane;
+            abea_pair_t p;
+            p.ref_pos = 0;
+            p.read_pos = 0;
+            if (t < n) p = out[src0 + t];
+            __syncwarp();
+            if (t < n) out[t] = p;
+            __syncwarp();
+        }
+    }
+}
+
 /* One band of scores as held by a lane, with the two neighbour-lane cells next to its four ("halos"). */
 struct abea_band_t {
     double R[ABEA_CPL];
@@ -457,9 +600,10 @@ template <bool FAST>
 __global__ void __launch_bounds__(128)
 abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const abea_event_t* __restrict__ events,
                  const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
-                 uint32_t* __restrict__ trace, abea_result_t* __restrict__ results, abea_consts_t cst,
-                 int32_t* __restrict__ queue, int32_t first) {
+                 uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
+                 int32_t* __restrict__ n_pairs_out, abea_consts_t cst, int32_t* __restrict__ queue, int32_t first) {
     __shared__ __align__(16) abea_fill_smem_t smem_all[4];
+    __shared__ __align__(16) uint32_t tb_ring_all[4][ABEA_TB_RING_GROUPS * ABEA_TRACE_GROUP_WORDS];
     const int lane = threadIdx.x & 31;
     abea_fill_smem_t* sm = &smem_all[threadIdx.x >> 5];
     const double NEG = abea_neg_inf_d();
@@ -543,10 +687,16 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
                 best_e = oe2;
             }
         }
+        const int32_t end_event = (best_e == 0x7fffffff) ? 0 : best_e;
         if (lane == 0) {
             results[ridx].end_score = __double2float_rn(best_s);
-            results[ridx].end_event = (best_e == 0x7fffffff) ? 0 : best_e;
+            results[ridx].end_event = end_event;
         }
+        /* traceback + QC of this read by the same warp, while the other warps keep filling: the walk of a long read
+         * is a serial chain too, and fusing it here takes it off the tail of the batch */
+        __syncwarp();
+        abea_traceback_read(rd, ridx, end_event, tb_ring_all[threadIdx.x >> 5], lane, events, kparams, trace, pairs,
+                            results, n_pairs_out);
     }
 }
 
@@ -595,8 +745,8 @@ template <bool FAST>
 __global__ void __launch_bounds__(32 * ABEA_WIDE_WARPS)
 abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, const abea_event_t* __restrict__ events,
                       const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
-                      uint32_t* __restrict__ trace, abea_result_t* __restrict__ results, abea_consts_t cst,
-                      int32_t* __restrict__ queue) {
+                      uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
+                      int32_t* __restrict__ n_pairs_out, abea_consts_t cst, int32_t* __restrict__ queue) {
     __shared__ __align__(16) abea_wide_smem_t sm;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -781,167 +931,20 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
         }
         if (lane == 0) { sm.red_s[w] = best_s; sm.red_e[w] = best_e; }
         __syncthreads();
-        if (tid == 0) {
+        if (w == 0) { /* warp 0 merges and then walks the trace; the k-mer ring (4 KB) becomes its trace ring */
             for (int i = 1; i < ABEA_WIDE_WARPS; i++) {
                 double os = sm.red_s[i];
                 int32_t oe2 = sm.red_e[i];
                 if (os > best_s || (os == best_s && oe2 < best_e)) { best_s = os; best_e = oe2; }
             }
-            results[ridx].end_score = __double2float_rn(best_s);
-            results[ridx].end_event = (best_e == 0x7fffffff) ? 0 : best_e;
-        }
-    }
-}
-
-/* ------------------------------------------------------------------------------------------------------------ */
-/* Traceback + QC (reference src/align.c:452-543). One warp per read. The walk is a pointer chase through the packed
- * trace, strictly downwards in band index, so the trace lines it will need are known in advance: they are streamed
- * with cp.async into a per-warp shared-memory ring of 32 lines (two chunks of 16 groups = 64 bands each; the next
- * chunk is in flight while the current one is walked), which takes HBM latency off the dependent chain. All lanes
- * walk in lock-step (the state is warp-uniform); step n's pair is parked in lane n%32 and every 32 steps the warp
- * (i) stores 32 pairs with one coalesced 256-B store, from the END of the read's capacity region backwards so the
- * list comes out ascending with no reversal pass, (ii) evaluates the 32 emissions in parallel and (iii) adds them
- * to the QC sum strictly in traceback order (the reference's summation order, src/align.c:476).                    */
-
-#define ABEA_TB_CHUNK_GROUPS 8
-#define ABEA_TB_RING_GROUPS 32
-#define ABEA_TB_WARPS 4
-
-/* start the asynchronous copy of trace chunk `chunk` (groups 8*chunk .. 8*chunk+7 = 32 bands) into the ring */
-__device__ __forceinline__ void abea_tb_prefetch(uint32_t* ring, const uint32_t* __restrict__ tr, int32_t chunk, int lane) {
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        int idx = i * 32 + lane;                       /* 64 pieces of 16 B = 8 lines of 128 B */
-        int32_t g = chunk * ABEA_TB_CHUNK_GROUPS + (idx >> 3);
-        abea_cp_async16(ring + (g & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + (idx & 7) * 4,
-                        tr + (int64_t)g * ABEA_TRACE_GROUP_WORDS + (idx & 7) * 4);
-    }
-}
-
-/* emissions of the pairs parked in the lanes (first `cnt` lanes valid), added to `sum` in lane order */
-__device__ __forceinline__ double abea_tb_flush(double sum, int cnt, int lane, int32_t pk, int32_t pe, int32_t n_before,
-                                                const abea_event_t* __restrict__ ev, const float4* __restrict__ kpr,
-                                                abea_pair_t* __restrict__ out, int32_t pair_cap) {
-    double lpd = 0.0;
-    if (lane < cnt) {
-        abea_pair_t p;
-        p.ref_pos = pk;
-        p.read_pos = pe;
-        out[pair_cap - 1 - (n_before + lane)] = p;
-        float4 kp = kpr[pk];
-        lpd = (double)abea_emission(ev[pe].mean, kp.x, kp.y, kp.z);
-    }
-    for (int j = 0; j < cnt; j++) sum = __dadd_rn(sum, __shfl_sync(ABEA_FULL, lpd, j));
-    return sum;
-}
-
-__global__ void __launch_bounds__(32 * ABEA_TB_WARPS)
-abea_traceback_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const abea_event_t* __restrict__ events,
-                      const float4* __restrict__ kparams, const uint32_t* __restrict__ trace,
-                      abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
-                      int32_t* __restrict__ n_pairs_out, int32_t* __restrict__ queue) {
-    __shared__ __align__(16) uint32_t ring_all[ABEA_TB_WARPS][ABEA_TB_RING_GROUPS * ABEA_TRACE_GROUP_WORDS];
-    const int lane = threadIdx.x & 31;
-    uint32_t* ring = ring_all[threadIdx.x >> 5];
-    for (;;) {
-        int32_t ridx = 0;
-        if (lane == 0) ridx = atomicAdd(queue, 1);
-        ridx = __shfl_sync(ABEA_FULL, ridx, 0);
-        if (ridx >= n_reads) break;
-
-        const abea_read_t rd = reads[ridx];
-        const int32_t K = rd.n_kmers;
-        const abea_event_t* __restrict__ ev = events + rd.ev_off;
-        const float4* __restrict__ kpr = kparams + rd.kp_off;
-        const uint32_t* __restrict__ tr = trace + rd.trace_off;
-        abea_pair_t* __restrict__ out = pairs + rd.pair_off;
-
-        int32_t ce = results[ridx].end_event;
-        int32_t ck = K - 1;
-        int32_t n = 0, gap = 0, max_gap = 0;
-        int32_t last_k = ck;
-        double sum = 0.0;
-        int32_t pk = 0, pe = 0; /* the pair parked in this lane */
-
-        __syncwarp();           /* the previous read's ring is no longer being read by any lane */
-        /* The ring holds 4 chunks of 32 bands. Before a step at band b the chunks of b, b-1 and b-2 must have
-         * landed (the step reads the trace word of b and the lower-left event index of whichever of b-1 / b-2 comes
-         * next); c_ready is the lowest landed chunk, c_ready-1 is in flight. */
-        int32_t b = ce + ck + 2;
-        int32_t c_ready = b >> 5;
-        abea_tb_prefetch(ring, tr, c_ready, lane);
-        if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
-        abea_cp_async_wait_all();
-        __syncwarp();
-        if (c_ready > 0) c_ready -= 1;
-        if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
-        int32_t eb_cur = (int32_t)ring[((b >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b & 3)];
-
-        while (ck >= 0 && ce >= 0) {
-            /* emit (reference src/align.c:458-460): park the pair in lane n%32 */
-            if (lane == (n & 31)) {
-                pk = ck;
-                pe = ce;
+            const int32_t end_event = (best_e == 0x7fffffff) ? 0 : best_e;
+            if (lane == 0) {
+                results[ridx].end_score = __double2float_rn(best_s);
+                results[ridx].end_event = end_event;
             }
-            n++;
-            last_k = ck;
-            if ((n & 31) == 0) sum = abea_tb_flush(sum, 32, lane, pk, pe, n - 32, ev, kpr, out, rd.pair_cap);
-
-            const int32_t b2 = b >= 2 ? b - 2 : 0;
-            if ((b2 >> 5) < c_ready) { /* the walk is about to need the chunk that was in flight */
-                abea_cp_async_wait_all();
-                __syncwarp();
-                c_ready -= 1;
-                if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
-            }
-            /* lower-left event index of the two bands the walk can move to (off the dependent chain) */
-            const int32_t b1 = b >= 1 ? b - 1 : 0;
-            const int32_t eb1 = (int32_t)ring[((b1 >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b1 & 3)];
-            const int32_t eb2 = (int32_t)ring[((b2 >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b2 & 3)];
-            /* the trace bits of cell (band b, offset o) */
-            const int32_t o = eb_cur - ce;
-            const uint32_t tw = ring[((b >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ((o >> 2) & 31)];
-            /* an out-of-band start cell is undefined behaviour in the reference; stay in bounds */
-            const uint32_t from = (o >= 0 && o < ABEA_W) ? ((tw >> (8 * (b & 3) + 2 * (o & 3))) & 3u) : ABEA_FROM_D;
-            const bool isD = (from == ABEA_FROM_D), isU = (from == ABEA_FROM_U);
-            const bool isL = !(isD || isU);
-            ce -= (isD || isU) ? 1 : 0;
-            ck -= (isD || isL) ? 1 : 0;
-            b = isD ? b2 : b1;
-            eb_cur = isD ? eb2 : eb1;
-            gap = isL ? gap + 1 : 0;
-            max_gap = gap > max_gap ? gap : max_gap;
-        }
-        abea_cp_async_wait_all(); /* drain the chunk still in flight before the ring is reused */
-        if ((n & 31) != 0) sum = abea_tb_flush(sum, n & 31, lane, pk, pe, n & ~31, ev, kpr, out, rd.pair_cap);
-
-        /* QC (reference src/align.c:526-543) */
-        double avg = sum / (double)n;
-        bool spanned = (n > 0) && (last_k == 0);
-        bool fail = (avg < -5.0) || !spanned || (max_gap > 50);
-        if (lane == 0) {
-            results[ridx].sum_emission = sum;
-            results[ridx].n_aligned = n;
-            results[ridx].n_pairs = fail ? 0 : n;
-            results[ridx].pair_start = 0;
-            results[ridx].max_gap = max_gap;
-            n_pairs_out[rd.orig_index] = fail ? 0 : n; /* db->n_event_align_pairs[i] */
-        }
-        /* slide the list to the front of the read's capacity region (the layout the caller's buffer has), in place:
-         * destination index t <= source index cap-n+t, batches of 32 are loaded before they are stored */
-        __syncwarp();
-        const int32_t src0 = rd.pair_cap - n;
-        if (!fail && src0 > 0) {
-            for (int32_t t0 = 0; t0 < n; t0 += 32) {
-                const int32_t t = t0 + lane;
-                abea_pair_t p;
-                p.ref_pos = 0;
-                p.read_pos = 0;
-                if (t < n) p = out[src0 + t];
-                __syncwarp();
-                if (t < n) out[t] = p;
-                __syncwarp();
-            }
+            abea_traceback_read(rd, ridx, end_event, (uint32_t*)sm.kp, lane, events, kparams, trace, pairs, results,
+                                n_pairs_out);
         }
     }
 }
+
