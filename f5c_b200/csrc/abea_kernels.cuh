@@ -193,12 +193,22 @@ __device__ __forceinline__ float4 abea_load_kparam(const float4* __restrict__ kp
     return kp[k];
 }
 
-/* x rounded to float precision, returned as a double. FAST: FP64-pipe magic constant; else hardware conversions. */
+/* x rounded to float precision, returned as a double. FAST: FP64-pipe magic constant; else hardware conversions.
+ * `donor` is any float-valued double (or +-inf): its low word (29 zero bits below at most 3 mantissa bits) becomes the
+ * low word of C, which keeps C an even multiple of the float ulp — so C needs no register of its own zeroed. */
 template <bool FAST>
-__device__ __forceinline__ double abea_round_f32(double x) {
+__device__ __forceinline__ double abea_round_f32(double x, double donor) {
     if (FAST) {
         int hi = __double2hiint(x);
-        double C = __hiloint2double((int)(((unsigned)hi & 0xfff00000u) + 0x01d80000u), 0);
+        /* (hi & 0xfff00000) + 0x01d80000 written as shift + multiply-add: one ALU-pipe op and one FMA-pipe op
+         * instead of two ALU-pipe ops (the ALU pipe is the busiest pipe of this kernel, profiles/) */
+        unsigned chi;
+#ifdef ABEA_SIMT_EMU
+        chi = ((unsigned)hi >> 20) * 0x00100000u + 0x01d80000u;
+#else
+        asm("{\n\t.reg .u32 t;\n\tshr.u32 t, %1, 20;\n\tmad.lo.u32 %0, t, 1048576, 30932992;\n\t}" : "=r"(chi) : "r"(hi));
+#endif
+        double C = __hiloint2double((int)chi, __double2loint(donor));
         return __dadd_rn(__dadd_rn(x, C), -C);
     } else {
         return (double)__double2float_rn(x);
@@ -225,9 +235,9 @@ template <bool FAST>
 __device__ __forceinline__ void abea_cell_d(float lp, double up, double left, double diag, double lp_step,
                                             double lp_stay, double lp_skip, double& score, uint32_t& from) {
     double lpd = (double)lp;
-    double rd = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(diag, lp_step), lpd));
-    double ru = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(up, lp_stay), lpd));
-    double rl = abea_round_f32<FAST>(__dadd_rn(left, lp_skip));
+    double rd = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(diag, lp_step), lpd), diag);
+    double ru = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(up, lp_stay), lpd), up);
+    double rl = abea_round_f32<FAST>(__dadd_rn(left, lp_skip), left);
     bool isU = ru >= rd;          /* (su > max) || (max == su) */
     double m = isU ? ru : rd;
     bool isL = rl >= m;
@@ -841,9 +851,9 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
             double Rn;
             uint32_t fr;
             {
-                double rd = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(diag, lp_step), lpd));
-                double ru = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(up, lp_stay), lpd));
-                double rl = abea_round_f32<FAST>(__dadd_rn(left, lp_skip));
+                double rd = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(diag, lp_step), lpd), diag);
+                double ru = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(up, lp_stay), lpd), up);
+                double rl = abea_round_f32<FAST>(__dadd_rn(left, lp_skip), left);
                 bool isU = ru >= rd;
                 double m = isU ? ru : rd;
                 bool isL = rl >= m;
