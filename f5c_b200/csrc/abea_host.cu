@@ -79,7 +79,7 @@ struct abea_ctx {
     int32_t n_wide = 0;               /* the first n_wide scheduled reads (the longest) are filled by the wide kernel */
     cudaStream_t wide_stream = nullptr; /* the wide fill runs beside the narrow one */
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    int wide_mode = 0;                /* ABEA_WIDE=1 enables the wide kernel (off by default: DESIGN.md §3.2b) */
+    int wide_mode = 1;                /* ABEA_WIDE=0 disables the wide kernel */
     double wide_alpha = 1.0;          /* ABEA_WIDE_ALPHA scales the wide/narrow threshold */
     double wide_min_bands = 1024.0;   /* ABEA_WIDE_MIN_BANDS: reads shorter than this are never wide */
     int fill_ctas_per_sm = 2;  /* persistent fill grid = sm_count * this (ABEA_FILL_CTAS_PER_SM; 2 measured best, profiles/) */
@@ -307,17 +307,17 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
         nb += NB;
         ne += r.n_events;
     }
-    /* Long reads go to the wide kernel (4 warps per read). A narrow warp shares its SM sub-partition with three
-     * others and advances ~5x slower per band than a wide CTA; a read is "long" when, at that rate, it alone would
-     * outlast the time the whole batch needs at full throughput (or the time the longest read needs in wide form).
-     * Constants are per-band cycle counts measured on B200 (profiles/README.md). */
+    /* The longest reads go to the wide kernel (one CTA of 4 warps per read). Measured on B200 (profiles/README.md):
+     * a narrow warp alone on its SM sub-partition needs ~655 cycles per band, a wide CTA alone on its SM ~490, and
+     * when SMs are shared the wide form has no advantage. So a read is made wide only when it would outlast the whole
+     * batch even as a lone narrow warp — it is going to run (nearly) alone at the end anyway, and then the wide form
+     * finishes it sooner. cfg2 (log-normal sigma 0.5) has no such read; cfg3 (sigma 1.0) has a handful. */
     c->n_wide = 0;
     if (c->wide_mode && !c->reads.empty()) {
         const double cyc_batch = (double)nb * 360.0 / ((double)c->sm_count * 4.0);
-        const double cyc_longest_wide = ((double)c->reads[0].n_events + c->reads[0].n_kmers + 2) * 500.0;
-        const double target = std::max(cyc_batch, cyc_longest_wide);
-        const double thr = std::max(c->wide_min_bands, c->wide_alpha * target / 800.0);
-        while (c->n_wide < (int32_t)c->reads.size() &&
+        const double thr = std::max(c->wide_min_bands, c->wide_alpha * 1.25 * cyc_batch / 655.0);
+        /* at most one wide CTA per SM: co-resident wide CTAs lose their advantage */
+        while (c->n_wide < (int32_t)c->reads.size() && c->n_wide < c->sm_count &&
                (double)c->reads[c->n_wide].n_events + c->reads[c->n_wide].n_kmers + 2 > thr)
             c->n_wide++;
     }
@@ -399,7 +399,7 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
             if (nw > 0) {
                 CU(cudaEventRecord(c->ev_fork, c->stream));
                 CU(cudaStreamWaitEvent(c->wide_stream, c->ev_fork, 0));
-                int wblocks = std::min(c->sm_count * 4, (int)nw);
+                int wblocks = std::min(c->sm_count, (int)nw);
                 ABEA_LAUNCH(abea_fill_wide_kernel<true>, wblocks, 128, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,

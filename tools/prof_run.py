@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 from f5c_b200 import synth, models
 from f5c_b200.abea import AbeaContext
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-n = int(sys.argv[2]) if len(sys.argv) > 2 else None
+n = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] not in ("", "-") else None
 runs = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 b = synth.make_config(cfg, seed=42, n_reads=n)
 k, m = models.load_model(b.meta["model"])
