@@ -162,7 +162,7 @@ static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSucces
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     snprintf(p->name, sizeof(p->name), "SIMT-EMU (CPU, tests only)");
-    p->multiProcessorCount = 2;
+    p->multiProcessorCount = 8;
     return cudaSuccess;
 }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
