@@ -125,7 +125,7 @@ def main():
     import torch.distributed as dist
     from f5c_b200 import models, synth
     from f5c_b200.abea import AbeaContext
-    from f5c_b200.dist import compact_pairs, gather_results
+    from f5c_b200.dist import gather_device_results
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device visible; f5c_b200 has no CPU path (use --impl reference for the CPU arm)")
@@ -176,7 +176,7 @@ def main():
         g_ms = 0.0
         if world > 1:
             g0 = time.perf_counter()
-            gather_results(r.n_pairs, compact_pairs(r.pairs, r.pair_ptr, r.n_pairs), rank, world, f"cuda:{local_rank}")
+            gather_device_results(ctx, rank, world)   # device-resident results -> rank 0's HBM over NCCL/NVLink
             torch.cuda.synchronize()
             g_ms = (time.perf_counter() - g0) * 1e3
         return r, g_ms

@@ -57,6 +57,8 @@ def _bind(path: str):
     lib.abea_run.argtypes = [vp, ctypes.POINTER(Timing)]
     lib.abea_download.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Timing)]
     lib.abea_read_stats.argtypes = [vp, vp, vp, vp, vp]
+    lib.abea_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
+                                        ctypes.POINTER(i32)]
     lib.abea_host_alloc.argtypes = [ctypes.c_size_t]
     lib.abea_host_alloc.restype = vp
     lib.abea_host_free.argtypes = [vp]
@@ -204,6 +206,14 @@ class AbeaContext:
         self._check(self.lib.abea_download(self._h, pairs.ctypes.data, pair_ptr.ctypes.data, n_pairs.ctypes.data,
                                            ctypes.byref(t)), "abea_download")
         return Alignment(pairs, pair_ptr, n_pairs, t.as_dict())
+
+    def device_results(self):
+        """(pairs_ptr, n_pairs_ptr, total_pair_capacity, n_reads) of the last run, as raw device addresses."""
+        dp, dn = ctypes.c_void_p(), ctypes.c_void_p()
+        cap, n = ctypes.c_int64(), ctypes.c_int32()
+        self._check(self.lib.abea_device_results(self._h, ctypes.byref(dp), ctypes.byref(dn), ctypes.byref(cap),
+                                                 ctypes.byref(n)), "abea_device_results")
+        return dp.value, dn.value, cap.value, n.value
 
     def read_stats(self, n_reads: int) -> dict:
         se = np.zeros(n_reads, dtype=np.float64)

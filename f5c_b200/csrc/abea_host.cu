@@ -516,6 +516,17 @@ int abea_read_stats(abea_ctx_t* c, double* sum_emission, int32_t* n_aligned, int
     return ABEA_OK;
 }
 
+int abea_device_results(abea_ctx_t* c, const abea_pair_t** d_pairs, const int32_t** d_n_pairs,
+                        int64_t* total_pairs_capacity, int32_t* n_reads) {
+    if (!c) return ABEA_ERR_ARG;
+    if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_device_results before abea_run");
+    if (d_pairs) *d_pairs = (const abea_pair_t*)c->d_pairs.p;
+    if (d_n_pairs) *d_n_pairs = (const int32_t*)c->d_npairs.p;
+    if (total_pairs_capacity) *total_pairs_capacity = c->total_pair_cap;
+    if (n_reads) *n_reads = c->n_batch_reads;
+    return ABEA_OK;
+}
+
 int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pairs, const int64_t* pair_ptr,
                      int32_t* n_pairs, abea_timing_t* timing) {
     int rc = abea_upload_batch(c, batch, nullptr);

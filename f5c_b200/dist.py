@@ -59,3 +59,44 @@ def gather_results(n_pairs: np.ndarray, dense_pairs: np.ndarray, rank: int, worl
         p = pl[r][:npz].cpu().numpy().reshape(-1).view(PAIR_DTYPE)
         out.append((c, p))
     return out
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ holder so torch can view library-owned device memory without a copy."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def device_views(ctx):
+    """torch views (no copy) of the context's device-resident results: pairs int32 [cap, 2], n_pairs int32 [n]."""
+    dp, dn, cap, n = ctx.device_results()
+    dev = torch.device("cuda", ctx.device)
+    pairs = torch.as_tensor(_DevArray(dp, (max(cap, 1), 2), "<i4"), device=dev)[:cap]
+    counts = torch.as_tensor(_DevArray(dn, (max(n, 1),), "<i4"), device=dev)[:n]
+    return pairs, counts
+
+
+def gather_device_results(ctx, rank: int, world: int):
+    """NCCL gather of every rank's device-resident results (capacity layout) into rank 0's HBM — the only collective
+    of the path. Returns on rank 0 a list of (n_pairs, pairs) device tensors per rank; None elsewhere."""
+    pairs, counts = device_views(ctx)
+    dev = pairs.device
+    sizes = torch.tensor([counts.numel(), pairs.shape[0]], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes)
+    all_sizes = [s.cpu().numpy() for s in all_sizes]
+    max_reads = int(max(s[0] for s in all_sizes))
+    max_pairs = int(max(s[1] for s in all_sizes))
+    cpad = torch.zeros(max_reads, dtype=torch.int32, device=dev)
+    cpad[:counts.numel()] = counts
+    ppad = torch.empty((max(max_pairs, 1), 2), dtype=torch.int32, device=dev)
+    ppad[:pairs.shape[0]] = pairs
+    cl = [torch.empty_like(cpad) for _ in range(world)] if rank == 0 else None
+    pl = [torch.empty_like(ppad) for _ in range(world)] if rank == 0 else None
+    dist.gather(cpad, cl, dst=0)
+    dist.gather(ppad, pl, dst=0)
+    if rank != 0:
+        return None
+    return [(cl[r][:int(all_sizes[r][0])], pl[r][:int(all_sizes[r][1])]) for r in range(world)]

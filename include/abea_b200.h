@@ -93,6 +93,13 @@ int abea_download(abea_ctx_t* ctx, abea_pair_t* pairs, const int64_t* pair_ptr, 
 int abea_read_stats(abea_ctx_t* ctx, double* sum_emission, int32_t* n_aligned, int32_t* end_event,
                     int32_t* max_gap);
 
+/* Device-resident results of the last abea_run, for consumers that stay on the GPU (e.g. the NCCL gather of a
+ * multi-GPU driver): *d_pairs points at the pairs in the canonical capacity layout (read i of the batch at the prefix
+ * sum of n_events+read_len, *total_pairs_capacity entries in all), *d_n_pairs at n_reads int32 counts in batch order.
+ * The pointers stay valid until the next abea_upload_batch / abea_destroy on this context. */
+int abea_device_results(abea_ctx_t* ctx, const abea_pair_t** d_pairs, const int32_t** d_n_pairs,
+                        int64_t* total_pairs_capacity, int32_t* n_reads);
+
 /* Pinned host memory for callers that want the H2D/D2H copies to run at full PCIe rate. */
 void* abea_host_alloc(size_t bytes);
 void abea_host_free(void* p);
