@@ -57,6 +57,7 @@ def _bind(path: str):
     lib.abea_run.argtypes = [vp, ctypes.POINTER(Timing)]
     lib.abea_download.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Timing)]
     lib.abea_read_stats.argtypes = [vp, vp, vp, vp, vp]
+    lib.abea_read_cycles.argtypes = [vp, vp, vp, vp]
     lib.abea_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
                                         ctypes.POINTER(i32)]
     lib.abea_host_alloc.argtypes = [ctypes.c_size_t]
@@ -206,6 +207,13 @@ class AbeaContext:
         self._check(self.lib.abea_download(self._h, pairs.ctypes.data, pair_ptr.ctypes.data, n_pairs.ctypes.data,
                                            ctypes.byref(t)), "abea_download")
         return Alignment(pairs, pair_ptr, n_pairs, t.as_dict())
+
+    def read_cycles(self, n_reads: int) -> dict:
+        fc = np.zeros(n_reads, dtype=np.int64)
+        tc = np.zeros(n_reads, dtype=np.int64)
+        wd = np.zeros(n_reads, dtype=np.int32)
+        self._check(self.lib.abea_read_cycles(self._h, fc.ctypes.data, tc.ctypes.data, wd.ctypes.data), "abea_read_cycles")
+        return dict(fill_cycles=fc, trace_cycles=tc, wide=wd)
 
     def device_results(self):
         """(pairs_ptr, n_pairs_ptr, total_pair_capacity, n_reads) of the last run, as raw device addresses."""

@@ -21,8 +21,10 @@
 #ifndef ABEA_SIMT_EMU
 #include <cuda_runtime.h>
 #define ABEA_LAUNCH(kern, grid, block, stream, ...) kern<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define ABEA_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #else /* tests/simt: CPU lock-step emulation of the same sources (test infrastructure) */
 #define ABEA_LAUNCH(kern, grid, block, stream, ...) SIMT_LAUNCH(kern, grid, block, __VA_ARGS__)
+#define ABEA_LAUNCH_SMEM(kern, grid, block, smem, stream, ...) SIMT_LAUNCH_SMEM(kern, grid, block, smem, __VA_ARGS__)
 #endif
 
 #include "../../include/abea_b200.h"
@@ -82,7 +84,9 @@ struct abea_ctx {
     int wide_mode = 1;                /* ABEA_WIDE=0 disables the wide kernel */
     double wide_alpha = 1.0;          /* ABEA_WIDE_ALPHA scales the wide/narrow threshold */
     double wide_min_bands = 1024.0;   /* ABEA_WIDE_MIN_BANDS: reads shorter than this are never wide */
-    int fill_ctas_per_sm = 2;  /* persistent fill grid = sm_count * this (ABEA_FILL_CTAS_PER_SM; 2 measured best, profiles/) */
+    int fill_ctas_per_sm = 1;  /* persistent narrow grid = sm_count * this (ABEA_FILL_CTAS_PER_SM) */
+    int fill_warps_per_cta = 12; /* 4 primary + 8 secondary warps (ABEA_FILL_WARPS_PER_CTA, multiple of 4, <= 16; 12 measured best) */
+    double long_alpha = 0.8;   /* ABEA_LONG_ALPHA: a read is "long" (runs alone on its sub-partition) above this share of the batch time */
     int trace_ctas_per_sm = 4; /* ABEA_TRACE_CTAS_PER_SM */
 };
 
@@ -195,6 +199,8 @@ int abea_create(abea_ctx_t** out, int device) {
         return ABEA_ERR_CUDA;
     }
     if (const char* e = getenv("ABEA_FILL_CTAS_PER_SM")) c->fill_ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("ABEA_FILL_WARPS_PER_CTA")) c->fill_warps_per_cta = std::min(16, std::max(4, atoi(e) / 4 * 4));
+    if (const char* e = getenv("ABEA_LONG_ALPHA")) c->long_alpha = atof(e);
     if (const char* e = getenv("ABEA_TRACE_CTAS_PER_SM")) c->trace_ctas_per_sm = std::max(1, atoi(e));
     c->cst.lp_skip = log(1e-10);
     c->cst.lp_trim = log(0.01);
@@ -403,25 +409,34 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
                 ABEA_LAUNCH(abea_fill_wide_kernel<true>, wblocks, 128, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 3);
+                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 6);
                 ABEA_LAUNCH(abea_fill_wide_kernel<false>, wblocks, 128, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 4);
+                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 7);
                 CU(cudaEventRecord(c->ev_join, c->wide_stream));
                 launches += 2;
             }
             if (n > nw) {
-                int blocks = std::min(c->sm_count * c->fill_ctas_per_sm, (n - nw + 3) / 4);
+                const int wpc = c->fill_warps_per_cta;
+                int blocks = std::min(c->sm_count * c->fill_ctas_per_sm, (n - nw + wpc - 1) / wpc);
                 if (blocks < 1) blocks = 1;
-                ABEA_LAUNCH(abea_fill_kernel<true>, blocks, 128, c->stream,
+                const size_t smem = (size_t)wpc * (sizeof(abea_fill_smem_t) +
+                                                   sizeof(uint32_t) * ABEA_TB_RING_GROUPS * ABEA_TRACE_GROUP_WORDS);
+                CU(cudaFuncSetAttribute(abea_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CU(cudaFuncSetAttribute(abea_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                /* a narrow read is "long" when, sharing its sub-partition (~780 cycles/band), it would take more than
+                 * long_alpha of the time the whole batch needs at full throughput */
+                const double cyc_batch = (double)c->total_bands * 360.0 / ((double)c->sm_count * 4.0);
+                const int32_t long_thr = (int32_t)std::min(2.0e9, std::max(1.0, c->long_alpha * cyc_batch / 780.0));
+                ABEA_LAUNCH_SMEM(abea_fill_kernel<true>, blocks, 32 * wpc, smem, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue, nw);
-                ABEA_LAUNCH(abea_fill_kernel<false>, blocks, 128, c->stream,
+                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue, nw, long_thr);
+                ABEA_LAUNCH_SMEM(abea_fill_kernel<false>, blocks, 32 * wpc, smem, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 1, nw);
+                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 8, nw, long_thr);
                 launches += 2;
             }
             if (nw > 0) CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
@@ -512,6 +527,27 @@ int abea_read_stats(abea_ctx_t* c, double* sum_emission, int32_t* n_aligned, int
         if (n_aligned) n_aligned[i] = res[j].n_aligned;
         if (end_event) end_event[i] = res[j].end_event;
         if (max_gap) max_gap[i] = res[j].max_gap;
+    }
+    return ABEA_OK;
+}
+
+int abea_read_cycles(abea_ctx_t* c, int64_t* fill_cycles, int64_t* trace_cycles, int32_t* wide) {
+    if (!c) return ABEA_ERR_ARG;
+    if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_read_cycles before abea_run");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->reads.size();
+    std::vector<abea_result_t> res(n);
+    if (n) CU(cudaMemcpy(res.data(), c->d_results.p, n * sizeof(abea_result_t), cudaMemcpyDeviceToHost));
+    for (int32_t i = 0; i < c->n_batch_reads; i++) {
+        if (fill_cycles) fill_cycles[i] = 0;
+        if (trace_cycles) trace_cycles[i] = 0;
+        if (wide) wide[i] = 0;
+    }
+    for (size_t j = 0; j < n; j++) {
+        int32_t i = c->reads[j].orig_index;
+        if (fill_cycles) fill_cycles[i] = res[j].fill_cycles;
+        if (trace_cycles) trace_cycles[i] = res[j].trace_cycles;
+        if (wide) wide[i] = res[j].wide;
     }
     return ABEA_OK;
 }

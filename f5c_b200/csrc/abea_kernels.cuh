@@ -67,7 +67,18 @@ struct abea_result_t {
     int32_t n_pairs;     /* pairs after QC (0 = failed) */
     int32_t pair_start;  /* always 0: pairs live at d_pairs[pair_off .. pair_off + n_pairs), ascending */
     int32_t max_gap;
+    int32_t wide;        /* 1 if the wide kernel filled this read */
+    int64_t fill_cycles; /* SM clock cycles this read spent in the band fill ... */
+    int64_t trace_cycles;/* ... and in traceback + QC (per-read latency, for profiles/) */
 };
+
+__device__ __forceinline__ long long abea_clock() {
+#ifdef ABEA_SIMT_EMU
+    return 0;
+#else
+    return clock64();
+#endif
+}
 
 struct abea_consts_t {
     double lp_skip; /* log(1e-10) (src/align.c:212-213) */
@@ -606,27 +617,67 @@ __device__ __forceinline__ bool abea_fill_step(abea_fill_ctx_t& cx, float* x, fl
     return next_right;
 }
 
+/* Scheduling of the persistent narrow warps. A CTA has ABEA_NARROW_WARPS_MAX or fewer warps; warp w sits on SM
+ * sub-partition w%4. Warps 0..3 are PRIMARY: they pull reads from the head of the longest-first queue. The others
+ * are SECONDARY: they pull from the TAIL (shortest first) and, while the primary of their sub-partition is filling a
+ * read longer than long_thr bands, they wait between reads — so the reads that set the makespan run alone on their
+ * sub-partition (~655 instead of ~780 cycles per band, profiles/README.md) at the cost of idling a few of the 592
+ * sub-partitions' second slots. queue[0] counts pulls, queue[1] the head, queue[2] the tail. */
+#define ABEA_NARROW_WARPS_MAX 16
+
+__device__ __forceinline__ void abea_backoff() {
+#ifndef ABEA_SIMT_EMU
+    __nanosleep(2000);
+#endif
+}
+
 template <bool FAST>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * ABEA_NARROW_WARPS_MAX)
 abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const abea_event_t* __restrict__ events,
                  const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                  uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
-                 int32_t* __restrict__ n_pairs_out, abea_consts_t cst, int32_t* __restrict__ queue, int32_t first) {
-    __shared__ __align__(16) abea_fill_smem_t smem_all[4];
-    __shared__ __align__(16) uint32_t tb_ring_all[4][ABEA_TB_RING_GROUPS * ABEA_TRACE_GROUP_WORDS];
+                 int32_t* __restrict__ n_pairs_out, abea_consts_t cst, int32_t* __restrict__ queue, int32_t first,
+                 int32_t long_thr) {
+    /* dynamic shared memory: per warp one abea_fill_smem_t and one 4-KB traceback ring */
+#ifdef ABEA_SIMT_EMU
+    unsigned char* dyn = (unsigned char*)simt::g_dynsmem;
+#else
+    extern __shared__ __align__(16) unsigned char abea_dyn_smem[];
+    unsigned char* dyn = abea_dyn_smem;
+#endif
+    __shared__ volatile int long_flag[4];
     const int lane = threadIdx.x & 31;
-    abea_fill_smem_t* sm = &smem_all[threadIdx.x >> 5];
+    const int wid = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    abea_fill_smem_t* sm = (abea_fill_smem_t*)dyn + wid;
+    uint32_t* tb_ring = (uint32_t*)(dyn + (size_t)nwarps * sizeof(abea_fill_smem_t)) +
+                        (size_t)wid * (ABEA_TB_RING_GROUPS * ABEA_TRACE_GROUP_WORDS);
+    const bool primary = wid < 4;
+    const int slot = wid & 3;
+    if (threadIdx.x < 4) long_flag[threadIdx.x] = 0;
+    __syncthreads();
     const double NEG = abea_neg_inf_d();
 
     for (;;) {
-        int32_t ridx = 0;
-        if (lane == 0) ridx = first + atomicAdd(queue, 1); /* reads [0, first) are filled by the wide kernel */
+        if (!primary) { /* let the long read on this sub-partition run alone */
+            while (long_flag[slot] != 0) {
+                abea_backoff();
+                __syncwarp();
+            }
+        }
+        int32_t ridx = n_reads;
+        if (lane == 0) { /* reads [0, first) are filled by the wide kernel */
+            if (first + atomicAdd(queue, 1) < n_reads)
+                ridx = primary ? first + atomicAdd(queue + 1, 1) : n_reads - 1 - atomicAdd(queue + 2, 1);
+        }
         ridx = __shfl_sync(ABEA_FULL, ridx, 0);
         if (ridx >= n_reads) break;
         /* each instantiation takes only the reads validated for its arithmetic */
         if (((read_flags[ridx] & ABEA_READ_FAST) != 0u) != FAST) continue;
 
         const abea_read_t rd = reads[ridx];
+        if (primary && lane == 0) long_flag[slot] = (rd.n_events + rd.n_kmers + 2 > long_thr) ? 1 : 0;
+        const long long t_start = abea_clock();
         abea_fill_ctx_t cx;
         cx.E = rd.n_events;
         cx.K = rd.n_kmers;
@@ -705,8 +756,14 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
         /* traceback + QC of this read by the same warp, while the other warps keep filling: the walk of a long read
          * is a serial chain too, and fusing it here takes it off the tail of the batch */
         __syncwarp();
-        abea_traceback_read(rd, ridx, end_event, tb_ring_all[threadIdx.x >> 5], lane, events, kparams, trace, pairs,
-                            results, n_pairs_out);
+        const long long t_fill = abea_clock();
+        abea_traceback_read(rd, ridx, end_event, tb_ring, lane, events, kparams, trace, pairs, results, n_pairs_out);
+        if (lane == 0) {
+            results[ridx].wide = 0;
+            results[ridx].fill_cycles = t_fill - t_start;
+            results[ridx].trace_cycles = abea_clock() - t_fill;
+        }
+        if (primary && lane == 0) long_flag[slot] = 0;
     }
 }
 
@@ -775,6 +832,7 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
         if (((read_flags[ridx] & ABEA_READ_FAST) != 0u) != FAST) continue;
 
         const abea_read_t rd = reads[ridx];
+        const long long t_start = abea_clock();
         const int32_t E = rd.n_events, K = rd.n_kmers;
         const int32_t NB = E + K + 2;
         const abea_event_t* __restrict__ ev = events + rd.ev_off;
@@ -952,8 +1010,14 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                 results[ridx].end_score = __double2float_rn(best_s);
                 results[ridx].end_event = end_event;
             }
+            const long long t_fill = abea_clock();
             abea_traceback_read(rd, ridx, end_event, (uint32_t*)sm.kp, lane, events, kparams, trace, pairs, results,
                                 n_pairs_out);
+            if (lane == 0) {
+                results[ridx].wide = 1;
+                results[ridx].fill_cycles = t_fill - t_start;
+                results[ridx].trace_cycles = abea_clock() - t_fill;
+            }
         }
     }
 }

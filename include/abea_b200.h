@@ -93,6 +93,11 @@ int abea_download(abea_ctx_t* ctx, abea_pair_t* pairs, const int64_t* pair_ptr, 
 int abea_read_stats(abea_ctx_t* ctx, double* sum_emission, int32_t* n_aligned, int32_t* end_event,
                     int32_t* max_gap);
 
+/* Per-read latency of the last run in SM clock cycles (band fill; traceback + QC) and whether the wide kernel took
+ * the read; indexed like the batch, any pointer may be NULL. A profiling aid: it is how profiles/ shows what the
+ * longest reads cost. */
+int abea_read_cycles(abea_ctx_t* ctx, int64_t* fill_cycles, int64_t* trace_cycles, int32_t* wide);
+
 /* Device-resident results of the last abea_run, for consumers that stay on the GPU (e.g. the NCCL gather of a
  * multi-GPU driver): *d_pairs points at the pairs in the canonical capacity layout (read i of the batch at the prefix
  * sum of n_events+read_len, *total_pairs_capacity entries in all), *d_n_pairs at n_reads int32 counts in batch order.

@@ -5,6 +5,7 @@ namespace simt {
 
 Fiber* cur = nullptr;
 Dim3 g_blockIdx, g_blockDim, g_gridDim;
+void* g_dynsmem = nullptr;
 
 static ucontext_t sched_ctx;
 static const std::function<void()>* g_body = nullptr;
@@ -69,8 +70,10 @@ static void resolve_warp(Fiber** lanes, int n) {
         if (lanes[i] && lanes[i]->state == ST_WAIT_WARP) lanes[i]->state = ST_READY;
 }
 
-void launch(Dim3 grid, Dim3 block, const std::function<void()>& body) {
+void launch(Dim3 grid, Dim3 block, const std::function<void()>& body, size_t dyn_smem) {
     g_body = &body;
+    void* dyn = dyn_smem ? calloc(1, dyn_smem) : nullptr;
+    g_dynsmem = dyn;
     g_gridDim = grid;
     g_blockDim = block;
     const int nthreads = (int)(block.x * block.y * block.z);
@@ -137,6 +140,8 @@ void launch(Dim3 grid, Dim3 block, const std::function<void()>& body) {
                 }
             }
     for (int t = 0; t < nthreads; t++) free(fibers[t].stack);
+    free(dyn);
+    g_dynsmem = nullptr;
     cur = nullptr;
 }
 

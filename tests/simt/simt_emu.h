@@ -68,8 +68,9 @@ struct Fiber {
 
 extern Fiber* cur;
 extern Dim3 g_blockIdx, g_blockDim, g_gridDim;
+extern void* g_dynsmem; /* dynamic shared memory of the running block */
 
-void launch(Dim3 grid, Dim3 block, const std::function<void()>& body);
+void launch(Dim3 grid, Dim3 block, const std::function<void()>& body, size_t dyn_smem = 0);
 uint64_t collective(int op, uint64_t payload, int arg);
 void block_barrier();
 
@@ -189,3 +190,6 @@ static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 
 /* kernel launch: the product's ABEA_LAUNCH macro expands to this under ABEA_SIMT_EMU */
 #define SIMT_LAUNCH(kern, grid, block, ...) simt::launch(simt::Dim3(grid), simt::Dim3(block), [&]() { kern(__VA_ARGS__); })
+#define SIMT_LAUNCH_SMEM(kern, grid, block, smem, ...) simt::launch(simt::Dim3(grid), simt::Dim3(block), [&]() { kern(__VA_ARGS__); }, smem)
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }

@@ -15,3 +15,15 @@ ctx.upload(b)
 for i in range(runs):
     t = ctx.run()
     print({x: round(t[x], 3) for x in ("kmer_ms", "fill_ms", "trace_ms", "kernel_ms")}, "Mev/s %.1f" % (t["n_events"] / t["kernel_ms"] / 1e3))
+
+import numpy as np
+cyc = ctx.read_cycles(b.n_reads)
+nb = b.n_bands
+order = np.argsort(-nb)[:6]
+ev = b.n_events
+print("longest reads: bands", nb[order].tolist())
+print("  fill cycles/band ", np.round(cyc["fill_cycles"][order] / nb[order], 1).tolist(), " wide", cyc["wide"][order].tolist())
+print("  trace cycles/step", np.round(cyc["trace_cycles"][order] / ev[order], 1).tolist())
+sel = np.argsort(nb)[len(nb)//2 - 3: len(nb)//2 + 3]
+print("median reads: fill cycles/band", np.round(cyc["fill_cycles"][sel] / nb[sel], 1).tolist(), " trace cycles/step", np.round(cyc["trace_cycles"][sel] / ev[sel], 1).tolist())
+print("sum fill Mcycles", cyc["fill_cycles"].sum() / 1e6, "sum trace Mcycles", cyc["trace_cycles"].sum() / 1e6, "max fill+trace Mcycles", (cyc["fill_cycles"] + cyc["trace_cycles"]).max() / 1e6)
