@@ -292,6 +292,22 @@ __device__ __forceinline__ void abea_cp_async_wait_all() {
 #define ABEA_TB_CHUNK_GROUPS 8
 #define ABEA_TB_RING_GROUPS 32
 
+/* Shared-memory reads by 32-bit shared address: the traceback ring is reached through a pointer, and a generic
+ * pointer would make the compiler rebuild the shared window address (S2R + LEA) inside the dependent loop. */
+#ifdef ABEA_SIMT_EMU
+typedef uint32_t* abea_sptr_t;
+__device__ __forceinline__ abea_sptr_t abea_smem_base(uint32_t* p) { return p; }
+__device__ __forceinline__ uint32_t abea_lds_u32(abea_sptr_t base, int32_t word) { return base[word]; }
+#else
+typedef uint32_t abea_sptr_t;
+__device__ __forceinline__ abea_sptr_t abea_smem_base(uint32_t* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t abea_lds_u32(abea_sptr_t base, int32_t word) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + 4u * (uint32_t)word) : "memory");
+    return v;
+}
+#endif
+
 /* start the asynchronous copy of trace chunk `chunk` (groups 8*chunk .. 8*chunk+7 = 32 bands) into the ring */
 __device__ __forceinline__ void abea_tb_prefetch(uint32_t* ring, const uint32_t* __restrict__ tr, int32_t chunk, int lane) {
 #pragma unroll
@@ -352,9 +368,14 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
     __syncwarp();
     if (c_ready > 0) c_ready -= 1;
     if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
-    int32_t eb_cur = (int32_t)ring[((b >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b & 3)];
+    const abea_sptr_t rs = abea_smem_base(ring);
+    /* word index of band b's line in the ring: ((b>>2) & 31) * 32 == (b & 124) << 3 */
+#define ABEA_TB_LINE(bb) (((bb) & 124) << 3)
+    int32_t line = ABEA_TB_LINE(b);
+    int32_t q8 = (b & 3) << 3;
+    int32_t eb_cur = (int32_t)abea_lds_u32(rs, line + ABEA_LANES + (b & 3));
 
-    while (ck >= 0 && ce >= 0) {
+    while ((ck | ce) >= 0) {
         /* emit (reference src/align.c:458-460): park the pair in lane n%32 */
         if (lane == (n & 31)) {
             pk = ck;
@@ -364,31 +385,34 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
         last_k = ck;
         if ((n & 31) == 0) sum = abea_tb_flush(sum, 32, lane, pk, pe, n - 32, ev, kpr, out, rd.pair_cap);
 
-        const int32_t b2 = b >= 2 ? b - 2 : 0;
+        /* inside the loop b = ce + ck + 2 >= 2 */
+        const int32_t b1 = b - 1, b2 = b - 2;
         if ((b2 >> 5) < c_ready) { /* the walk is about to need the chunk that was in flight */
             abea_cp_async_wait_all();
             __syncwarp();
             c_ready -= 1;
             if (c_ready > 0) abea_tb_prefetch(ring, tr, c_ready - 1, lane);
         }
-        /* lower-left event index of the two bands the walk can move to (off the dependent chain) */
-        const int32_t b1 = b >= 1 ? b - 1 : 0;
-        const int32_t eb1 = (int32_t)ring[((b1 >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b1 & 3)];
-        const int32_t eb2 = (int32_t)ring[((b2 >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b2 & 3)];
-        /* the trace bits of cell (band b, offset o) */
+        /* everything the next step needs about bands b-1 and b-2, off the dependent chain */
+        const int32_t line1 = ABEA_TB_LINE(b1), line2 = ABEA_TB_LINE(b2);
+        const int32_t eb1 = (int32_t)abea_lds_u32(rs, line1 + ABEA_LANES + (b1 & 3));
+        const int32_t eb2 = (int32_t)abea_lds_u32(rs, line2 + ABEA_LANES + (b2 & 3));
+        /* the dependent chain: offset -> trace word -> 2 bits */
         const int32_t o = eb_cur - ce;
-        const uint32_t tw = ring[((b >> 2) & (ABEA_TB_RING_GROUPS - 1)) * ABEA_TRACE_GROUP_WORDS + ((o >> 2) & 31)];
+        const uint32_t tw = abea_lds_u32(rs, line + ((o >> 2) & 31));
         /* an out-of-band start cell is undefined behaviour in the reference; stay in bounds */
-        const uint32_t from = (o >= 0 && o < ABEA_W) ? ((tw >> (8 * (b & 3) + 2 * (o & 3))) & 3u) : ABEA_FROM_D;
+        const uint32_t from = ((uint32_t)o < (uint32_t)ABEA_W) ? ((tw >> (q8 + 2 * (o & 3))) & 3u) : ABEA_FROM_D;
         const bool isD = (from == ABEA_FROM_D), isU = (from == ABEA_FROM_U);
-        const bool isL = !(isD || isU);
-        ce -= (isD || isU) ? 1 : 0;
-        ck -= (isD || isL) ? 1 : 0;
+        ce -= (from != ABEA_FROM_L) ? 1 : 0;
+        ck -= isU ? 0 : 1;
         b = isD ? b2 : b1;
+        line = isD ? line2 : line1;
+        q8 = (b & 3) << 3;
         eb_cur = isD ? eb2 : eb1;
-        gap = isL ? gap + 1 : 0;
+        gap = (isD || isU) ? 0 : gap + 1;
         max_gap = gap > max_gap ? gap : max_gap;
     }
+#undef ABEA_TB_LINE
     abea_cp_async_wait_all(); /* drain the chunk still in flight before the ring is reused */
     if ((n & 31) != 0) sum = abea_tb_flush(sum, n & 31, lane, pk, pe, n & ~31, ev, kpr, out, rd.pair_cap);
 
