@@ -46,6 +46,15 @@ def parse():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+def measured_traffic():
+    """DRAM bytes of the dominant kernel from the committed ncu --set full capture (profiles/), per launch."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -240,8 +249,9 @@ def main():
                     "last_step_parts_ms_rank0": e2e_parts},
             "gpu_launches": int(launches + e2e_launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "kernel": "abea_fill_kernel (dominant; bytes and time cover the 3-kernel step)",
+                         "traffic": (measured_traffic() if a.config == "cfg2" and a.reads_per_gpu is None else None),
+                         "peak_source": peak_src,
+                         "kernel": "abea_fill_kernel<true> = band fill + fused traceback (dominant; bytes and time cover the whole step incl. abea_prepare_kernel)",
                          "kernel_share": fill_ms / dev_ms if dev_ms else None,
                          "algorithmic_bytes_per_step_rank0": int(alg_bytes),
                          "bytes_per_event": alg_bytes / max(1.0, float(my_events))},
