@@ -92,3 +92,22 @@ def test_emulated_narrow_only(emu, monkeypatch):
     b = synth.make_batch("r9", n_reads=4, mean_events=1500, sigma=0.5, epk=1.8, seed=16)
     got = check(emu, b, "r9", "narrow only")
     assert got.timing["n_wide"] == 0
+
+
+def test_emulated_degenerate_batches(emu):
+    """No read scheduled at all (everything filtered), and an empty batch: counts are zero, nothing crashes."""
+    import numpy as np
+    from f5c_b200.batch import ReadBatch
+    b = synth.make_batch("r9", n_reads=3, mean_events=200, sigma=0.2, epk=1.8, seed=19)
+    b.good[:] = 0
+    k, m = models.load_model("r9")
+    with AbeaContext(0, lib_path=emu) as ctx:
+        ctx.set_model(m, k)
+        got = ctx.align_batch(b)
+        assert got.n_pairs.tolist() == [0, 0, 0] and got.timing["n_scheduled"] == 0
+        empty = ReadBatch.from_reads([], [], np.zeros(0, dtype=b.scalings.dtype), k)
+        got = ctx.align_batch(empty)
+        assert got.n_pairs.shape == (0,)
+        b.good[:] = 1            # the same context keeps working afterwards
+        got = ctx.align_batch(b)
+        assert (got.n_pairs > 0).all()
