@@ -406,11 +406,17 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
                 CU(cudaEventRecord(c->ev_fork, c->stream));
                 CU(cudaStreamWaitEvent(c->wide_stream, c->ev_fork, 0));
                 int wblocks = std::min(c->sm_count, (int)nw);
-                ABEA_LAUNCH(abea_fill_wide_kernel<true>, wblocks, 128, c->wide_stream,
+                /* A wide CTA is only faster than a lone narrow warp when it has its SM to itself (measured: 495
+                 * cycles/band alone, 800 beside a narrow CTA). It therefore asks for so much dynamic shared memory
+                 * that no narrow CTA fits on the same SM. Tiny batches (every read wide) do not need the exclusion. */
+                const size_t excl = (n > nw) ? (size_t)160 * 1024 : 0;
+                CU(cudaFuncSetAttribute(abea_fill_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)excl));
+                CU(cudaFuncSetAttribute(abea_fill_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)excl));
+                ABEA_LAUNCH_SMEM(abea_fill_wide_kernel<true>, wblocks, 128, excl, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
                     (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 6);
-                ABEA_LAUNCH(abea_fill_wide_kernel<false>, wblocks, 128, c->wide_stream,
+                ABEA_LAUNCH_SMEM(abea_fill_wide_kernel<false>, wblocks, 128, excl, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
                     (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 7);
@@ -419,7 +425,10 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
             }
             if (n > nw) {
                 const int wpc = c->fill_warps_per_cta;
-                int blocks = std::min(c->sm_count * c->fill_ctas_per_sm, (n - nw + wpc - 1) / wpc);
+                /* SMs taken by SM-exclusive wide CTAs are left out of the persistent narrow grid, so that both kernels
+                 * are resident from the start whatever order the hardware dispatches them in */
+                const int wide_sms = (nw > 0) ? std::min(c->sm_count, (int)nw) : 0;
+                int blocks = std::min((c->sm_count - wide_sms) * c->fill_ctas_per_sm, (n - nw + wpc - 1) / wpc);
                 if (blocks < 1) blocks = 1;
                 const size_t smem = (size_t)wpc * (sizeof(abea_fill_smem_t) +
                                                    sizeof(uint32_t) * ABEA_TB_RING_GROUPS * ABEA_TRACE_GROUP_WORDS);

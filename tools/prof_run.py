@@ -8,7 +8,8 @@ from f5c_b200.abea import AbeaContext
 cfg = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 n = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2] not in ("", "-") else None
 runs = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-b = synth.make_config(cfg, seed=42, n_reads=n)
+world = int(os.environ.get('PROF_WORLD', '1'))
+b = synth.make_config_shard(cfg, 0, world, seed=42, reads_per_gpu=n) if world > 1 else synth.make_config(cfg, seed=42, n_reads=n)
 k, m = models.load_model(b.meta["model"])
 ctx = AbeaContext(0); ctx.set_model(m, k)
 ctx.upload(b)
