@@ -83,6 +83,7 @@ struct abea_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int wide_mode = 1;                /* ABEA_WIDE=0 disables the wide kernel */
     double wide_alpha = 1.0;          /* ABEA_WIDE_ALPHA scales the wide/narrow threshold */
+    int wide_cap = 0;                 /* ABEA_WIDE_CAP: most reads (= SMs) given to the wide kernel; default sm_count/4 */
     double wide_min_bands = 1024.0;   /* ABEA_WIDE_MIN_BANDS: reads shorter than this are never wide */
     int fill_ctas_per_sm = 1;  /* persistent narrow grid = sm_count * this (ABEA_FILL_CTAS_PER_SM) */
     int fill_warps_per_cta = 12; /* 4 primary + 8 secondary warps (ABEA_FILL_WARPS_PER_CTA, multiple of 4, <= 16; 12 measured best) */
@@ -192,6 +193,8 @@ int abea_create(abea_ctx_t** out, int device) {
     /* transition constants shared by all reads, host double (reference src/align.c:212-216) */
     if (const char* e = getenv("ABEA_WIDE")) c->wide_mode = atoi(e);
     if (const char* e = getenv("ABEA_WIDE_ALPHA")) c->wide_alpha = atof(e);
+    c->wide_cap = std::max(1, c->sm_count / 4);
+    if (const char* e = getenv("ABEA_WIDE_CAP")) c->wide_cap = std::max(0, atoi(e));
     if (const char* e = getenv("ABEA_WIDE_MIN_BANDS")) c->wide_min_bands = atof(e);
     if (cudaStreamCreateWithFlags(&c->wide_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_fork) != cudaSuccess || cudaEventCreate(&c->ev_join) != cudaSuccess) {
@@ -323,7 +326,9 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
         const double cyc_batch = (double)nb * 360.0 / ((double)c->sm_count * 4.0);
         const double thr = std::max(c->wide_min_bands, c->wide_alpha * 1.25 * cyc_batch / 655.0);
         /* at most one wide CTA per SM: co-resident wide CTAs lose their advantage */
-        while (c->n_wide < (int32_t)c->reads.size() && c->n_wide < c->sm_count &&
+        /* a batch with fewer reads than SMs may run entirely wide; a larger one gives at most wide_cap SMs away */
+        const int32_t cap = ((int32_t)c->reads.size() <= c->sm_count) ? c->sm_count : c->wide_cap;
+        while (c->n_wide < (int32_t)c->reads.size() && c->n_wide < cap &&
                (double)c->reads[c->n_wide].n_events + c->reads[c->n_wide].n_kmers + 2 > thr)
             c->n_wide++;
     }

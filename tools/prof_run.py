@@ -15,7 +15,7 @@ ctx = AbeaContext(0); ctx.set_model(m, k)
 ctx.upload(b)
 for i in range(runs):
     t = ctx.run()
-    print({x: round(t[x], 3) for x in ("kmer_ms", "fill_ms", "trace_ms", "kernel_ms")}, "Mev/s %.1f" % (t["n_events"] / t["kernel_ms"] / 1e3))
+    print({x: round(t[x], 3) for x in ("kmer_ms", "fill_ms", "trace_ms", "kernel_ms")}, "Mev/s %.1f" % (t["n_events"] / t["kernel_ms"] / 1e3), "n_wide", t["n_wide"])
 
 import numpy as np
 cyc = ctx.read_cycles(b.n_reads)
