@@ -118,6 +118,9 @@ int dev_reserve(abea_ctx* c, DevBuf& b, size_t bytes) {
     b.cap = 0;
     size_t want = bytes + bytes / 8 + 256; /* head-room so that similar batches do not reallocate */
     CU(cudaMalloc(&b.p, want));
+    /* once per growth, not per batch: the traceback stages whole 32-band chunks of trace lines, so it copies (and
+     * never looks at) the padding words of a line and the lines past a read's last band */
+    CU(cudaMemset(b.p, 0, want));
     b.cap = want;
     return 0;
 }

@@ -669,7 +669,7 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
     extern __shared__ __align__(16) unsigned char abea_dyn_smem[];
     unsigned char* dyn = abea_dyn_smem;
 #endif
-    __shared__ volatile int long_flag[4];
+    __shared__ int long_flag[4]; /* only ever touched with atomics: a flag, not data */
     const int lane = threadIdx.x & 31;
     const int wid = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
@@ -684,9 +684,11 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
 
     for (;;) {
         if (!primary) { /* let the long read on this sub-partition run alone */
-            while (long_flag[slot] != 0) {
+            for (;;) {
+                int busy = 0;
+                if (lane == 0) busy = atomicOr(&long_flag[slot], 0);
+                if (__shfl_sync(ABEA_FULL, busy, 0) == 0) break;
                 abea_backoff();
-                __syncwarp();
             }
         }
         int32_t ridx = n_reads;
@@ -700,7 +702,7 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
         if (((read_flags[ridx] & ABEA_READ_FAST) != 0u) != FAST) continue;
 
         const abea_read_t rd = reads[ridx];
-        if (primary && lane == 0) long_flag[slot] = (rd.n_events + rd.n_kmers + 2 > long_thr) ? 1 : 0;
+        if (primary && lane == 0) atomicExch(&long_flag[slot], (rd.n_events + rd.n_kmers + 2 > long_thr) ? 1 : 0);
         const long long t_start = abea_clock();
         abea_fill_ctx_t cx;
         cx.E = rd.n_events;
@@ -787,7 +789,7 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
             results[ridx].fill_cycles = t_fill - t_start;
             results[ridx].trace_cycles = abea_clock() - t_fill;
         }
-        if (primary && lane == 0) long_flag[slot] = 0;
+        if (primary && lane == 0) atomicExch(&long_flag[slot], 0);
     }
 }
 
@@ -894,10 +896,13 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
 
         /* the lane's event / k-mer of band b-1 and, speculatively, what it would hold after either move:
          * a right move keeps the event and takes k-mer kb+1+o, a down move keeps the k-mer and takes event eb+1-o */
-        float x_cur = sm.ev[(eb - o) & (ABEA_WRING - 1)];
-        float4 kp_cur = sm.kp[(kb + o) & (ABEA_WRING - 1)];
-        float x_dn = sm.ev[(eb + 1 - o) & (ABEA_WRING - 1)];
-        float4 kp_rt = sm.kp[(kb + 1 + o) & (ABEA_WRING - 1)];
+        /* lanes past offset 99 hold no cell: they read the ring at offset 99 so that they never touch a chunk that is
+         * still in flight */
+        const int oa = o < ABEA_W ? o : ABEA_W - 1;
+        float x_cur = sm.ev[(eb - oa) & (ABEA_WRING - 1)];
+        float4 kp_cur = sm.kp[(kb + oa) & (ABEA_WRING - 1)];
+        float x_dn = sm.ev[(eb + 1 - oa) & (ABEA_WRING - 1)];
+        float4 kp_rt = sm.kp[(kb + 1 + oa) & (ABEA_WRING - 1)];
         double lpd_rt = (double)abea_emission_t<FAST>(x_cur, kp_rt);
         double lpd_dn = (double)abea_emission_t<FAST>(x_dn, kp_cur);
 
@@ -993,8 +998,8 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
             prev_right = right;
 
             /* speculative emissions of band b+1 for both moves */
-            x_dn = sm.ev[(eb + 1 - o) & (ABEA_WRING - 1)];
-            kp_rt = sm.kp[(kb + 1 + o) & (ABEA_WRING - 1)];
+            x_dn = sm.ev[(eb + 1 - oa) & (ABEA_WRING - 1)];
+            kp_rt = sm.kp[(kb + 1 + oa) & (ABEA_WRING - 1)];
             lpd_rt = (double)abea_emission_t<FAST>(x_cur, kp_rt);
             lpd_dn = (double)abea_emission_t<FAST>(x_dn, kp_cur);
 

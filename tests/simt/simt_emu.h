@@ -140,6 +140,8 @@ template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline unsigned atomicAnd(unsigned* p, unsigned v) { unsigned o = *p; *p = o & v; return o; }
+static inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
+static inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
 
 /* ---- the slice of the CUDA runtime the host code uses ------------------------------------------------------- */
 typedef int cudaError_t;
