@@ -31,8 +31,8 @@ class Timing(ctypes.Structure):
                 ("fill_ms", ctypes.c_double), ("trace_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double),
                 ("d2h_ms", ctypes.c_double), ("unpack_ms", ctypes.c_double), ("h2d_bytes", ctypes.c_int64),
                 ("d2h_bytes", ctypes.c_int64), ("kernel_launches", ctypes.c_int32),
-                ("n_scheduled", ctypes.c_int32), ("n_wide", ctypes.c_int32), ("reserved_", ctypes.c_int32),
-                ("n_bands", ctypes.c_int64), ("n_events", ctypes.c_int64)]
+                ("n_scheduled", ctypes.c_int32), ("n_wide", ctypes.c_int32), ("streamed", ctypes.c_int32),
+                ("n_bands", ctypes.c_int64), ("n_events", ctypes.c_int64), ("load_ms", ctypes.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -56,6 +56,7 @@ def _bind(path: str):
     lib.abea_upload_batch.argtypes = [vp, ctypes.POINTER(CBatch), ctypes.POINTER(Timing)]
     lib.abea_run.argtypes = [vp, ctypes.POINTER(Timing)]
     lib.abea_download.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Timing)]
+    lib.abea_read_starts.argtypes = [vp, vp]
     lib.abea_read_stats.argtypes = [vp, vp, vp, vp, vp]
     lib.abea_read_cycles.argtypes = [vp, vp, vp, vp]
     lib.abea_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
@@ -214,6 +215,11 @@ class AbeaContext:
         wd = np.zeros(n_reads, dtype=np.int32)
         self._check(self.lib.abea_read_cycles(self._h, fc.ctypes.data, tc.ctypes.data, wd.ctypes.data), "abea_read_cycles")
         return dict(fill_cycles=fc, trace_cycles=tc, wide=wd)
+
+    def read_starts(self, n_reads: int) -> np.ndarray:
+        st = np.zeros(n_reads, dtype=np.int32)
+        self._check(self.lib.abea_read_starts(self._h, st.ctypes.data), "abea_read_starts")
+        return st
 
     def device_results(self):
         """(pairs_ptr, n_pairs_ptr, total_pair_capacity, n_reads) of the last run, as raw device addresses."""

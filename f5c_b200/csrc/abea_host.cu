@@ -10,6 +10,7 @@
  */
 #include <math.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -89,6 +90,18 @@ struct abea_ctx {
     int fill_warps_per_cta = 12; /* 4 primary + 8 secondary warps (ABEA_FILL_WARPS_PER_CTA, multiple of 4, <= 16; 12 measured best) */
     double long_alpha = 0.8;   /* ABEA_LONG_ALPHA: a read is "long" (runs alone on its sub-partition) above this share of the batch time */
     int trace_ctas_per_sm = 4; /* ABEA_TRACE_CTAS_PER_SM */
+
+    /* streaming (abea_align_batch with pinned host buffers): events pulled over PCIe by abea_load_kernel in the order
+     * the fill asks for them, pair lists written to the caller's mapped buffer by the traceback */
+    int stream_mode = 3;       /* ABEA_STREAM: bit 0 events in, bit 1 pair lists out; 0: always stage through the copy engine */
+    int load_ctas = 64;        /* ABEA_LOAD_CTAS */
+    DevBuf d_ready, d_items;
+    std::vector<abea_load_item_t> items;
+    cudaStream_t load_stream = nullptr;
+    cudaEvent_t ev_meta = nullptr, ev_loaded = nullptr, ev_load0 = nullptr;
+    bool streaming = false;    /* the resident batch is being streamed in: its fill must wait on d_ready */
+    bool results_on_device = false; /* d_pairs / d_npairs hold the final lists (false after a streamed-out run) */
+    int64_t event_bytes = 0;   /* size of the batch's event array */
 };
 
 namespace {
@@ -120,7 +133,7 @@ int dev_reserve(abea_ctx* c, DevBuf& b, size_t bytes) {
     CU(cudaMalloc(&b.p, want));
     /* once per growth, not per batch: the traceback stages whole 32-band chunks of trace lines, so it copies (and
      * never looks at) the padding words of a line and the lines past a read's last band */
-    CU(cudaMemset(b.p, 0, want));
+    CU(cudaMemsetAsync(b.p, 0, want, c->stream));
     b.cap = want;
     return 0;
 }
@@ -140,6 +153,22 @@ float ev_ms(abea_ctx* c, int a, int b) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev[a], c->ev[b]) != cudaSuccess) return 0.f;
     return ms;
+}
+
+/* the device-side alias of a pinned (cudaHostAlloc / cudaHostRegister) host pointer, or NULL */
+void* mapped_alias(const void* host) {
+    if (!host) return nullptr;
+#ifdef ABEA_SIMT_EMU
+    return (void*)host;
+#else
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost) return nullptr;
+    return at.devicePointer;
+#endif
 }
 
 } // namespace
@@ -208,6 +237,32 @@ int abea_create(abea_ctx_t** out, int device) {
     if (const char* e = getenv("ABEA_FILL_WARPS_PER_CTA")) c->fill_warps_per_cta = std::min(16, std::max(4, atoi(e) / 4 * 4));
     if (const char* e = getenv("ABEA_LONG_ALPHA")) c->long_alpha = atof(e);
     if (const char* e = getenv("ABEA_TRACE_CTAS_PER_SM")) c->trace_ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("ABEA_STREAM")) c->stream_mode = atoi(e);
+    if (const char* e = getenv("ABEA_LOAD_CTAS")) c->load_ctas = std::max(1, atoi(e));
+    if (cudaStreamCreateWithFlags(&c->load_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev_meta) != cudaSuccess || cudaEventCreate(&c->ev_loaded) != cudaSuccess ||
+        cudaEventCreate(&c->ev_load0) != cudaSuccess) {
+        delete c;
+        return ABEA_ERR_CUDA;
+    }
+    /* Every kernel asks for the same (largest) shared-memory carve-out. An SM cannot change its L1/shared split while
+     * CTAs are resident, so a loader or prepare CTA running with a small carve-out would keep the persistent fill
+     * CTAs (64 KB / 160 KB of shared memory) off its SM until it exits — measured: the fill started only when the
+     * loader had finished. */
+    {
+        cudaError_t e = cudaSuccess;
+        const int carve = 100; /* percent of the maximum: cudaSharedmemCarveoutMaxShared */
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_load_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_fill_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_fill_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_fill_wide_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_fill_wide_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e != cudaSuccess) {
+            delete c;
+            return ABEA_ERR_CUDA;
+        }
+    }
     c->cst.lp_skip = log(1e-10);
     c->cst.lp_trim = log(0.01);
     *out = c;
@@ -218,7 +273,8 @@ void abea_destroy(abea_ctx_t* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_reads, &c->d_kparams,
-                      &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags, &c->d_npairs};
+                      &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags, &c->d_npairs,
+                      &c->d_ready, &c->d_items};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_results.p) cudaFreeHost(c->h_results.p);
@@ -227,6 +283,10 @@ void abea_destroy(abea_ctx_t* c) {
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_meta) cudaEventDestroy(c->ev_meta);
+    if (c->ev_loaded) cudaEventDestroy(c->ev_loaded);
+    if (c->ev_load0) cudaEventDestroy(c->ev_load0);
+    if (c->load_stream) cudaStreamDestroy(c->load_stream);
     if (c->wide_stream) cudaStreamDestroy(c->wide_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -251,7 +311,9 @@ int abea_set_model(abea_ctx_t* c, const abea_model_t* model, uint32_t kmer_size)
     return ABEA_OK;
 }
 
-int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timing) {
+/* ev_alias: device-side alias of the caller's pinned event array (the batch is streamed in by abea_load_kernel while
+ * the fill runs), or NULL (the events go through the copy engine before anything starts). */
+static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alias, abea_timing_t* timing) {
     if (!c || !b || b->n_reads < 0) return fail(c, ABEA_ERR_ARG, "bad batch");
     if (!c->have_model) return fail(c, ABEA_ERR_NOMODEL, "abea_set_model has not been called");
     CU(cudaSetDevice(c->device));
@@ -356,52 +418,110 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
     if (dev_reserve(c, c->d_queue, 64)) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_flags, (n_sched + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
 
+    c->event_bytes = n_ev_total * (int64_t)sizeof(abea_event_t);
+    c->streaming = false;
+    c->results_on_device = false;
+    double t2 = t1;
     CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
-    if (seq_bytes) CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
-    if (n_ev_total)
-        CU(cudaMemcpyAsync(c->d_events.p, b->events, (size_t)n_ev_total * sizeof(abea_event_t),
-                           cudaMemcpyHostToDevice, c->stream));
     if (n_sched)
         CU(cudaMemcpyAsync(c->d_reads.p, c->reads.data(), n_sched * sizeof(abea_read_t), cudaMemcpyHostToDevice,
                            c->stream));
+    if (ev_alias && n_sched) {
+        /* Work list of the loader, in the order the fill is going to ask: the longest reads (they set the makespan:
+         * wide CTAs and the first pulls of the primary warps), then the two ends of the schedule interleaved —
+         * primary warps walk it from the head, the (twice as many) secondary warps from the tail. */
+        c->items.clear();
+        int64_t h = 0, t = (int64_t)n_sched - 1, ev_head = 0, ev_tail = 0;
+        const int64_t first = std::min<int64_t>((int64_t)n_sched, c->sm_count);
+        auto push = [&](int64_t r) {
+            const uint32_t np = abea_load_pieces(c->reads[r].ev_off, c->reads[r].n_events, c->event_bytes);
+            for (uint32_t q = 0; q < np; q++) c->items.push_back(abea_load_item_t{(int32_t)r, (int32_t)q});
+        };
+        for (; h < first; h++) push(h);
+        while (h <= t) {
+            if (ev_tail < 2 * ev_head) {
+                ev_tail += c->reads[t].n_events;
+                push(t--);
+            } else {
+                ev_head += c->reads[h].n_events;
+                push(h++);
+            }
+        }
+        if (dev_reserve(c, c->d_items, c->items.size() * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
+        if (dev_reserve(c, c->d_ready, (n_sched + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
+        t2 = now_ms();
+        CU(cudaMemcpyAsync(c->d_items.p, c->items.data(), c->items.size() * sizeof(abea_load_item_t),
+                           cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
+        CU(cudaMemsetAsync(c->d_flags.p, 0x01, n_sched * sizeof(uint32_t), c->stream));
+        CU(cudaMemsetAsync(c->d_ready.p, 0, n_sched * sizeof(uint32_t), c->stream));
+        CU(cudaEventRecord(c->ev_meta, c->stream));
+        CU(cudaStreamWaitEvent(c->load_stream, c->ev_meta, 0));
+        CU(cudaEventRecord(c->ev_load0, c->load_stream));
+        const int blocks = (int)std::min<size_t>(c->items.size(), (size_t)c->load_ctas);
+        ABEA_LAUNCH(abea_load_kernel, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
+                    (const abea_load_item_t*)c->d_items.p, (int32_t)c->items.size(), (const uint4*)ev_alias,
+                    (uint4*)c->d_events.p, c->event_bytes, (uint32_t*)c->d_flags.p, (uint32_t*)c->d_ready.p,
+                    (int32_t*)c->d_queue.p + 12);
+        CU(cudaEventRecord(c->ev_loaded, c->load_stream));
+        c->streaming = true;
+    } else if (n_ev_total) {
+        CU(cudaMemcpyAsync(c->d_events.p, b->events, (size_t)n_ev_total * sizeof(abea_event_t),
+                           cudaMemcpyHostToDevice, c->stream));
+    }
+    if (seq_bytes) CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    if (!c->streaming) CU(cudaStreamSynchronize(c->stream));
     c->uploaded = true;
 
     c->last = abea_timing_t();
-    c->last.pack_ms = t1 - t0;
-    c->last.h2d_ms = ev_ms(c, EV_H2D0, EV_H2D1);
+    c->last.pack_ms = (c->streaming ? t2 : t1) - t0;
+    c->last.h2d_ms = c->streaming ? 0.f : ev_ms(c, EV_H2D0, EV_H2D1); /* streamed: filled in after the run */
     c->last.h2d_bytes = seq_bytes + n_ev_total * (int64_t)sizeof(abea_event_t) + (int64_t)(n_sched * sizeof(abea_read_t));
     c->last.n_scheduled = (int32_t)n_sched;
     c->last.n_wide = c->n_wide;
+    c->last.streamed = c->streaming ? 1 : 0;
     c->last.n_bands = nb;
     c->last.n_events = ne;
     if (timing) *timing = c->last;
     return ABEA_OK;
 }
 
-int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
+int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timing) {
+    return upload_impl(c, b, nullptr, timing);
+}
+
+/* fin_pairs / fin_np: device-side aliases of the caller's pinned output buffers (canonical layout), or NULL: the
+ * lists stay in d_pairs / d_npairs for abea_download. */
+static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea_timing_t* timing) {
     if (!c) return ABEA_ERR_ARG;
     if (!c->uploaded) return fail(c, ABEA_ERR_STATE, "abea_run before abea_upload_batch");
     CU(cudaSetDevice(c->device));
     const int32_t n = (int32_t)c->reads.size();
     int launches = 0;
-    CU(cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
-    CU(cudaMemsetAsync(c->d_npairs.p, 0, ((size_t)c->n_batch_reads + 1) * sizeof(int32_t), c->stream));
+    const bool streaming = c->streaming; /* set by upload_impl: queue, flags and ready counters are already armed */
+    abea_stream_t io;
+    io.ready = streaming ? (const uint32_t*)c->d_ready.p : nullptr;
+    io.pairs_final = fin_pairs ? fin_pairs : (abea_pair_t*)c->d_pairs.p;
+    io.n_pairs_final = fin_np ? fin_np : (int32_t*)c->d_npairs.p;
+    if (!streaming) CU(cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
+    if (!fin_np) CU(cudaMemsetAsync(c->d_npairs.p, 0, ((size_t)c->n_batch_reads + 1) * sizeof(int32_t), c->stream));
     CU(cudaEventRecord(c->ev[EV_K0], c->stream));
     if (n > 0) {
         int32_t* queue = (int32_t*)c->d_queue.p;
         {
-            /* every read starts as "fast"; abea_prepare_kernel clears the flag of reads with out-of-range inputs */
-            CU(cudaMemsetAsync(c->d_flags.p, 0x01, (size_t)n * sizeof(uint32_t), c->stream));
+            /* every read starts as "fast"; abea_prepare_kernel clears the flag of reads with out-of-range inputs
+             * (when streaming, the loader checks the event means as they pass through it) */
+            if (!streaming) CU(cudaMemsetAsync(c->d_flags.p, 0x01, (size_t)n * sizeof(uint32_t), c->stream));
             int threads = 256;
-            int64_t work = std::max(c->total_kmers, c->total_events);
+            const int64_t check_events = streaming ? 0 : c->total_events;
+            int64_t work = std::max(c->total_kmers, check_events);
             int blocks = (int)std::min<int64_t>((work + threads - 1) / threads, (int64_t)c->sm_count * 16);
             if (blocks < 1) blocks = 1;
             ABEA_LAUNCH(abea_prepare_kernel, blocks, threads, c->stream,
                 (const abea_read_t*)c->d_reads.p, n, (const uint8_t*)c->d_seq.p, (const abea_model_t*)c->d_model.p,
                 c->kmer_size, (const abea_event_t*)c->d_events.p, (float4*)c->d_kparams.p, (uint32_t*)c->d_flags.p,
-                c->total_kmers, c->total_events);
+                c->total_kmers, check_events);
             launches++;
         }
         CU(cudaEventRecord(c->ev[EV_K1], c->stream));
@@ -423,11 +543,11 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
                 ABEA_LAUNCH_SMEM(abea_fill_wide_kernel<true>, wblocks, 128, excl, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 6);
+                    (abea_result_t*)c->d_results.p, io, c->event_bytes, c->cst, queue + 6);
                 ABEA_LAUNCH_SMEM(abea_fill_wide_kernel<false>, wblocks, 128, excl, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 7);
+                    (abea_result_t*)c->d_results.p, io, c->event_bytes, c->cst, queue + 7);
                 CU(cudaEventRecord(c->ev_join, c->wide_stream));
                 launches += 2;
             }
@@ -449,11 +569,11 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
                 ABEA_LAUNCH_SMEM(abea_fill_kernel<true>, blocks, 32 * wpc, smem, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue, nw, long_thr);
+                    (abea_result_t*)c->d_results.p, io, c->event_bytes, c->cst, queue, nw, long_thr);
                 ABEA_LAUNCH_SMEM(abea_fill_kernel<false>, blocks, 32 * wpc, smem, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, (int32_t*)c->d_npairs.p, c->cst, queue + 8, nw, long_thr);
+                    (abea_result_t*)c->d_results.p, io, c->event_bytes, c->cst, queue + 8, nw, long_thr);
                 launches += 2;
             }
             if (nw > 0) CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
@@ -463,10 +583,22 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
         CU(cudaEventRecord(c->ev[EV_K1], c->stream));
         CU(cudaEventRecord(c->ev[EV_K2], c->stream));
     }
+    if (streaming) {
+        CU(cudaStreamWaitEvent(c->stream, c->ev_loaded, 0));
+        launches++;
+    }
     CU(cudaEventRecord(c->ev[EV_K3], c->stream));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     c->ran = true;
+    c->streaming = false; /* everything has landed: a further abea_run works on the resident copy */
+    c->results_on_device = (fin_pairs == nullptr && fin_np == nullptr);
+    if (streaming) {
+        c->last.h2d_ms = ev_ms(c, EV_H2D0, EV_H2D1);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_load0, c->ev_loaded) == cudaSuccess) c->last.load_ms = ms;
+    }
+    if (fin_pairs) c->last.streamed |= 2;
     c->last.kmer_ms = ev_ms(c, EV_K0, EV_K1);
     c->last.fill_ms = ev_ms(c, EV_K1, EV_K2);
     c->last.trace_ms = ev_ms(c, EV_K2, EV_K3);
@@ -476,10 +608,13 @@ int abea_run(abea_ctx_t* c, abea_timing_t* timing) {
     return ABEA_OK;
 }
 
+int abea_run(abea_ctx_t* c, abea_timing_t* timing) { return run_impl(c, nullptr, nullptr, timing); }
+
 int abea_download(abea_ctx_t* c, abea_pair_t* pairs, const int64_t* pair_ptr, int32_t* n_pairs,
                   abea_timing_t* timing) {
     if (!c || !n_pairs || (!pairs && c->total_pair_cap > 0) || !pair_ptr) return fail(c, ABEA_ERR_ARG, "bad output");
     if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_download before abea_run");
+    if (!c->results_on_device) return fail(c, ABEA_ERR_STATE, "the last run wrote its results to the caller's buffers");
     CU(cudaSetDevice(c->device));
     const int32_t nb = c->n_batch_reads;
     /* The device holds the pairs in the canonical capacity layout (read i at prefix-sum(E+L)); when the caller's
@@ -569,10 +704,23 @@ int abea_read_cycles(abea_ctx_t* c, int64_t* fill_cycles, int64_t* trace_cycles,
     return ABEA_OK;
 }
 
+int abea_read_starts(abea_ctx_t* c, int32_t* start_us) {
+    if (!c || !start_us) return ABEA_ERR_ARG;
+    if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_read_starts before abea_run");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->reads.size();
+    std::vector<abea_result_t> res(n);
+    if (n) CU(cudaMemcpy(res.data(), c->d_results.p, n * sizeof(abea_result_t), cudaMemcpyDeviceToHost));
+    for (int32_t i = 0; i < c->n_batch_reads; i++) start_us[i] = -1;
+    for (size_t j = 0; j < n; j++) start_us[c->reads[j].orig_index] = res[j].start_us;
+    return ABEA_OK;
+}
+
 int abea_device_results(abea_ctx_t* c, const abea_pair_t** d_pairs, const int32_t** d_n_pairs,
                         int64_t* total_pairs_capacity, int32_t* n_reads) {
     if (!c) return ABEA_ERR_ARG;
     if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_device_results before abea_run");
+    if (!c->results_on_device) return fail(c, ABEA_ERR_STATE, "the last run wrote its results to the caller's buffers");
     if (d_pairs) *d_pairs = (const abea_pair_t*)c->d_pairs.p;
     if (d_n_pairs) *d_n_pairs = (const int32_t*)c->d_npairs.p;
     if (total_pairs_capacity) *total_pairs_capacity = c->total_pair_cap;
@@ -582,12 +730,38 @@ int abea_device_results(abea_ctx_t* c, const abea_pair_t** d_pairs, const int32_
 
 int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pairs, const int64_t* pair_ptr,
                      int32_t* n_pairs, abea_timing_t* timing) {
-    int rc = abea_upload_batch(c, batch, nullptr);
+    if (!c || !batch) return fail(c, ABEA_ERR_ARG, "bad batch");
+    if (!n_pairs || !pair_ptr) return fail(c, ABEA_ERR_ARG, "bad output");
+    /* Pinned (mapped) caller buffers are streamed: events in over PCIe while the fill runs, pair lists out as each
+     * read finishes. Anything else is staged through the copy engine (abea_upload_batch / abea_download). */
+    const void* ev_alias = nullptr;
+    if ((c->stream_mode & 1) && batch->n_reads > 0 && ((uintptr_t)batch->events & 15) == 0) ev_alias = mapped_alias(batch->events);
+    int rc = upload_impl(c, batch, ev_alias, nullptr);
     if (rc) return rc;
-    rc = abea_run(c, nullptr);
+    abea_pair_t* fin_pairs = nullptr;
+    int32_t* fin_np = nullptr;
+    if ((c->stream_mode & 2) && batch->n_reads > 0 && c->total_pair_cap > 0) {
+        bool canonical = true;
+        for (int32_t i = 0; i < batch->n_reads && canonical; i++) canonical = (pair_ptr[i] == c->cap_ptr[i]);
+        if (canonical) {
+            fin_pairs = (abea_pair_t*)mapped_alias(pairs);
+            fin_np = (int32_t*)mapped_alias(n_pairs);
+            if (!fin_pairs || !fin_np) fin_pairs = nullptr, fin_np = nullptr;
+        }
+    }
+    if (fin_np) memset(n_pairs, 0, (size_t)batch->n_reads * sizeof(int32_t)); /* reads that are not scheduled */
+    rc = run_impl(c, fin_pairs, fin_np, nullptr);
     if (rc) return rc;
-    rc = abea_download(c, pairs, pair_ptr, n_pairs, nullptr);
-    if (rc) return rc;
+    if (!fin_np) {
+        rc = abea_download(c, pairs, pair_ptr, n_pairs, nullptr);
+        if (rc) return rc;
+    } else {
+        int64_t np = 0;
+        for (int32_t i = 0; i < batch->n_reads; i++) np += n_pairs[i];
+        c->last.d2h_ms = 0.f;
+        c->last.unpack_ms = 0.0;
+        c->last.d2h_bytes = np * (int64_t)sizeof(abea_pair_t) + (int64_t)batch->n_reads * (int64_t)sizeof(int32_t);
+    }
     if (timing) *timing = c->last;
     return ABEA_OK;
 }

@@ -65,12 +65,22 @@ struct abea_result_t {
     int32_t end_event;   /* event the traceback starts from */
     int32_t n_aligned;   /* pairs before QC */
     int32_t n_pairs;     /* pairs after QC (0 = failed) */
-    int32_t pair_start;  /* always 0: pairs live at d_pairs[pair_off .. pair_off + n_pairs), ascending */
+    int32_t start_us;    /* %globaltimer (microseconds, low 31 bits) when the fill of this read began (for profiles/) */
     int32_t max_gap;
     int32_t wide;        /* 1 if the wide kernel filled this read */
     int64_t fill_cycles; /* SM clock cycles this read spent in the band fill ... */
     int64_t trace_cycles;/* ... and in traceback + QC (per-read latency, for profiles/) */
 };
+
+__device__ __forceinline__ int32_t abea_now_us() {
+#ifdef ABEA_SIMT_EMU
+    return 0;
+#else
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return (int32_t)((t / 1000ull) & 0x7fffffffull);
+#endif
+}
 
 __device__ __forceinline__ long long abea_clock() {
 #ifdef ABEA_SIMT_EMU
@@ -173,6 +183,124 @@ __global__ void abea_prepare_kernel(const abea_read_t* __restrict__ reads, int32
         const abea_read_t rd = reads[r];
         float x = events[rd.ev_off + (idx - rd.evs_off)].mean;
         if (!abea_sane_level(x)) atomicAnd(&read_flags[r], ~ABEA_READ_FAST);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Streaming (abea_align_batch with pinned, mapped host buffers). The copy engine would bring the events of a batch in
+ * the caller's order and the kernels could only start when the last byte has landed; instead a few CTAs of
+ * abea_load_kernel read the events straight out of the caller's pinned buffer over PCIe — in the order the fill
+ * warps are going to ask for them — and publish a per-read counter of landed pieces that a fill warp (or wide CTA)
+ * waits on before it touches the read. The results go the other way without a copy either: the last step of the
+ * traceback writes the finished pair list to the caller's mapped buffer. With ready == NULL and pairs_final ==
+ * pairs the kernels run on data that is already resident (abea_upload_batch / abea_run / abea_download). */
+struct abea_stream_t {
+    const uint32_t* ready;      /* [scheduled read] pieces of its events landed so far; NULL: everything is resident */
+    abea_pair_t* pairs_final;   /* where the finished lists go: d_pairs, or the caller's mapped host buffer */
+    int32_t* n_pairs_final;     /* [batch read] pair counts: device, or the caller's mapped host buffer */
+};
+
+#define ABEA_LOAD_PIECE_BYTES (96 * 1024) /* one work item of the loader: 768 lines of 128 B = 4096 events */
+#define ABEA_LOAD_THREADS 128
+#define ABEA_LOAD_UNROLL 8                /* 16-B loads in flight per thread */
+
+struct abea_load_item_t {
+    int32_t read;  /* scheduled index */
+    int32_t piece; /* piece of that read's line-aligned byte range */
+};
+
+/* The byte range of a read's events, widened to whole 128-B lines (clamped to the buffer): a line shared by two reads
+ * is copied for both, so whichever is published first the line is complete — no SM can cache half a line. */
+__device__ __host__ __forceinline__ void abea_load_range(int64_t ev_off, int32_t n_events, int64_t total_bytes,
+                                                         int64_t* lo, int64_t* hi) {
+    const int64_t a = ev_off * (int64_t)sizeof(abea_event_t), b = a + (int64_t)n_events * (int64_t)sizeof(abea_event_t);
+    int64_t h = (b + 127) & ~(int64_t)127;
+    *lo = a & ~(int64_t)127;
+    *hi = h < total_bytes ? h : total_bytes;
+}
+__device__ __host__ __forceinline__ uint32_t abea_load_pieces(int64_t ev_off, int32_t n_events, int64_t total_bytes) {
+    int64_t lo, hi;
+    abea_load_range(ev_off, n_events, total_bytes, &lo, &hi);
+    return (uint32_t)((hi - lo + ABEA_LOAD_PIECE_BYTES - 1) / ABEA_LOAD_PIECE_BYTES);
+}
+
+__device__ __forceinline__ uint32_t abea_ld_acquire_u32(const uint32_t* p) {
+#ifdef ABEA_SIMT_EMU
+    return *p;
+#else
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+
+/* lane 0 / thread 0 only; the caller follows with __syncwarp / __syncthreads */
+__device__ __forceinline__ void abea_wait_landed(const uint32_t* ready, int32_t ridx, const abea_read_t& rd,
+                                                 int64_t total_event_bytes) {
+    if (ready == nullptr) return;
+    const uint32_t need = abea_load_pieces(rd.ev_off, rd.n_events, total_event_bytes);
+    while (abea_ld_acquire_u32(ready + ridx) < need) {
+#ifndef ABEA_SIMT_EMU
+        __nanosleep(500);
+#else
+        break; /* the emulator runs kernels one after the other: the loader has finished */
+#endif
+    }
+}
+
+/* src: the caller's events (pinned host memory, mapped); dst: d_events; both 16-B aligned, same layout. The event
+ * means pass through here, so this is also where they are range-checked for the fast arithmetic (the resident path
+ * does that in abea_prepare_kernel). In a 16-B unit u of the AoS array the mean is .w when u % 3 == 0 and .y when
+ * u % 3 == 2 (24-B events, mean at byte 12). */
+__global__ void __launch_bounds__(ABEA_LOAD_THREADS)
+abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* __restrict__ items, int32_t n_items,
+                 const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t total_bytes,
+                 uint32_t* __restrict__ read_flags, uint32_t* __restrict__ ready, int32_t* __restrict__ counter) {
+    __shared__ int s_item;
+    const int tid = threadIdx.x;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(counter, 1);
+        __syncthreads();
+        const int it = s_item;
+        if (it >= n_items) break;
+        const abea_load_item_t item = items[it];
+        const abea_read_t rd = reads[item.read];
+        const int64_t a = rd.ev_off * (int64_t)sizeof(abea_event_t);
+        const int64_t b = a + (int64_t)rd.n_events * (int64_t)sizeof(abea_event_t);
+        int64_t lo, hi;
+        abea_load_range(rd.ev_off, rd.n_events, total_bytes, &lo, &hi);
+        const int64_t p0 = lo + (int64_t)item.piece * ABEA_LOAD_PIECE_BYTES;
+        const int64_t p1 = (p0 + ABEA_LOAD_PIECE_BYTES < hi) ? p0 + ABEA_LOAD_PIECE_BYTES : hi;
+        const int64_t u1 = p1 >> 4;
+        bool bad = false;
+        for (int64_t u = (p0 >> 4) + tid; u < u1; u += ABEA_LOAD_THREADS * ABEA_LOAD_UNROLL) {
+            uint4 v[ABEA_LOAD_UNROLL];
+#pragma unroll
+            for (int j = 0; j < ABEA_LOAD_UNROLL; j++) {
+                const int64_t uj = u + (int64_t)j * ABEA_LOAD_THREADS;
+                if (uj < u1) v[j] = src[uj];
+            }
+#pragma unroll
+            for (int j = 0; j < ABEA_LOAD_UNROLL; j++) {
+                const int64_t uj = u + (int64_t)j * ABEA_LOAD_THREADS;
+                if (uj < u1) {
+                    dst[uj] = v[j];
+                    const int m3 = (int)(uj % 3);
+                    if (m3 != 1) {
+                        const int64_t mb = (uj << 4) + (m3 == 0 ? 12 : 4);
+                        const float x = __uint_as_float(m3 == 0 ? v[j].w : v[j].y);
+                        if (mb >= a && mb < b && !abea_sane_level(x)) bad = true;
+                    }
+                }
+            }
+        }
+        if (tid == 0 && (p1 & 8)) /* the buffer ends on half a unit: {pos, state} of the last event */
+            ((uint2*)dst)[p1 / 8 - 1] = ((const uint2*)src)[p1 / 8 - 1];
+        if (bad) atomicAnd(&read_flags[item.read], ~ABEA_READ_FAST);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) atomicAdd(&ready[item.read], 1u);
     }
 }
 
@@ -342,12 +470,12 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
                                                     int lane, const abea_event_t* __restrict__ events,
                                                     const float4* __restrict__ kparams, const uint32_t* __restrict__ trace,
                                                     abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
-                                                    int32_t* __restrict__ n_pairs_out) {
+                                                    const abea_stream_t& io) {
     const int32_t K = rd.n_kmers;
     const abea_event_t* __restrict__ ev = events + rd.ev_off;
     const float4* __restrict__ kpr = kparams + rd.kp_off;
     const uint32_t* __restrict__ tr = trace + rd.trace_off;
-    abea_pair_t* __restrict__ out = pairs + rd.pair_off;
+    abea_pair_t* out = pairs + rd.pair_off;
 
     int32_t ce = end_event;
     int32_t ck = K - 1;
@@ -424,15 +552,16 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
         results[ridx].sum_emission = sum;
         results[ridx].n_aligned = n;
         results[ridx].n_pairs = fail ? 0 : n;
-        results[ridx].pair_start = 0;
         results[ridx].max_gap = max_gap;
-        n_pairs_out[rd.orig_index] = fail ? 0 : n; /* db->n_event_align_pairs[i] */
+        io.n_pairs_final[rd.orig_index] = fail ? 0 : n; /* db->n_event_align_pairs[i] */
     }
-    /* slide the list to the front of the read's capacity region (the layout the caller's buffer has), in place:
-     * destination index t <= source index cap-n+t, batches of 32 are loaded before they are stored */
+    /* move the list to the front of the read's capacity region of the destination (the layout the caller's buffer
+     * has). The destination is d_pairs itself (in place: destination index t <= source index cap-n+t, batches of 32
+     * are loaded before they are stored) or the caller's mapped host buffer (posted writes over PCIe). */
     __syncwarp();
     const int32_t src0 = rd.pair_cap - n;
-    if (!fail && src0 > 0) {
+    abea_pair_t* __restrict__ fin = io.pairs_final + rd.pair_off;
+    if (!fail && (src0 > 0 || fin != out)) {
         for (int32_t t0 = 0; t0 < n; t0 += 32) {
             const int32_t t = t0 + lane;
             abea_pair_t p;
@@ -440,7 +569,7 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
             p.read_pos = 0;
             if (t < n) p = out[src0 + t];
             __syncwarp();
-            if (t < n) out[t] = p;
+            if (t < n) fin[t] = p;
             __syncwarp();
         }
     }
@@ -660,8 +789,8 @@ __global__ void __launch_bounds__(32 * ABEA_NARROW_WARPS_MAX)
 abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const abea_event_t* __restrict__ events,
                  const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                  uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
-                 int32_t* __restrict__ n_pairs_out, abea_consts_t cst, int32_t* __restrict__ queue, int32_t first,
-                 int32_t long_thr) {
+                 abea_stream_t io, int64_t total_event_bytes, abea_consts_t cst, int32_t* __restrict__ queue,
+                 int32_t first, int32_t long_thr) {
     /* dynamic shared memory: per warp one abea_fill_smem_t and one 4-KB traceback ring */
 #ifdef ABEA_SIMT_EMU
     unsigned char* dyn = (unsigned char*)simt::g_dynsmem;
@@ -698,12 +827,15 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
         }
         ridx = __shfl_sync(ABEA_FULL, ridx, 0);
         if (ridx >= n_reads) break;
-        /* each instantiation takes only the reads validated for its arithmetic */
-        if (((read_flags[ridx] & ABEA_READ_FAST) != 0u) != FAST) continue;
-
         const abea_read_t rd = reads[ridx];
+        if (lane == 0) abea_wait_landed(io.ready, ridx, rd, total_event_bytes); /* streaming: the read's events */
+        __syncwarp();
+        /* each instantiation takes only the reads validated for its arithmetic */
+        if (((abea_ld_acquire_u32(read_flags + ridx) & ABEA_READ_FAST) != 0u) != FAST) continue;
+
         if (primary && lane == 0) atomicExch(&long_flag[slot], (rd.n_events + rd.n_kmers + 2 > long_thr) ? 1 : 0);
         const long long t_start = abea_clock();
+        if (lane == 0) results[ridx].start_us = abea_now_us();
         abea_fill_ctx_t cx;
         cx.E = rd.n_events;
         cx.K = rd.n_kmers;
@@ -783,7 +915,7 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
          * is a serial chain too, and fusing it here takes it off the tail of the batch */
         __syncwarp();
         const long long t_fill = abea_clock();
-        abea_traceback_read(rd, ridx, end_event, tb_ring, lane, events, kparams, trace, pairs, results, n_pairs_out);
+        abea_traceback_read(rd, ridx, end_event, tb_ring, lane, events, kparams, trace, pairs, results, io);
         if (lane == 0) {
             results[ridx].wide = 0;
             results[ridx].fill_cycles = t_fill - t_start;
@@ -839,7 +971,7 @@ __global__ void __launch_bounds__(32 * ABEA_WIDE_WARPS)
 abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, const abea_event_t* __restrict__ events,
                       const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                       uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
-                      int32_t* __restrict__ n_pairs_out, abea_consts_t cst, int32_t* __restrict__ queue) {
+                      abea_stream_t io, int64_t total_event_bytes, abea_consts_t cst, int32_t* __restrict__ queue) {
     __shared__ __align__(16) abea_wide_smem_t sm;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -855,10 +987,13 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
         __syncthreads();
         const int32_t ridx = sm.ridx;
         if (ridx >= n_wide) break;
-        if (((read_flags[ridx] & ABEA_READ_FAST) != 0u) != FAST) continue;
-
         const abea_read_t rd = reads[ridx];
+        if (tid == 0) abea_wait_landed(io.ready, ridx, rd, total_event_bytes); /* streaming: the read's events */
+        __syncthreads();
+        if (((abea_ld_acquire_u32(read_flags + ridx) & ABEA_READ_FAST) != 0u) != FAST) continue;
+
         const long long t_start = abea_clock();
+        if (tid == 0) results[ridx].start_us = abea_now_us();
         const int32_t E = rd.n_events, K = rd.n_kmers;
         const int32_t NB = E + K + 2;
         const abea_event_t* __restrict__ ev = events + rd.ev_off;
@@ -1040,8 +1175,7 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                 results[ridx].end_event = end_event;
             }
             const long long t_fill = abea_clock();
-            abea_traceback_read(rd, ridx, end_event, (uint32_t*)sm.kp, lane, events, kparams, trace, pairs, results,
-                                n_pairs_out);
+            abea_traceback_read(rd, ridx, end_event, (uint32_t*)sm.kp, lane, events, kparams, trace, pairs, results, io);
             if (lane == 0) {
                 results[ridx].wide = 1;
                 results[ridx].fill_cycles = t_fill - t_start;

@@ -61,9 +61,10 @@ typedef struct {
     int32_t kernel_launches; /* kernels of this library launched by the call */
     int32_t n_scheduled;     /* reads that passed the eligibility filter */
     int32_t n_wide;          /* of those, reads filled by the wide (4 warps per read) kernel */
-    int32_t reserved_;
+    int32_t streamed;        /* bit 0: events streamed in by abea_load_kernel; bit 1: pair lists written straight to the caller's buffer */
     int64_t n_bands;         /* sum of NB over scheduled reads */
     int64_t n_events;        /* sum of E over scheduled reads (the metric's numerator) */
+    double load_ms;          /* device: abea_load_kernel, first CTA start to last piece landed (streaming only) */
 } abea_timing_t;
 
 /* Create a context on CUDA device `device` (cudaSetDevice is applied on every call). */
@@ -97,6 +98,9 @@ int abea_read_stats(abea_ctx_t* ctx, double* sum_emission, int32_t* n_aligned, i
  * the read; indexed like the batch, any pointer may be NULL. A profiling aid: it is how profiles/ shows what the
  * longest reads cost. */
 int abea_read_cycles(abea_ctx_t* ctx, int64_t* fill_cycles, int64_t* trace_cycles, int32_t* wide);
+/* When the fill of each read began: %globaltimer in microseconds (low 31 bits), -1 for reads that were not scheduled.
+ * A profiling aid (how far the streaming loader is ahead of the fill). */
+int abea_read_starts(abea_ctx_t* ctx, int32_t* start_us);
 
 /* Device-resident results of the last abea_run, for consumers that stay on the GPU (e.g. the NCCL gather of a
  * multi-GPU driver): *d_pairs points at the pairs in the canonical capacity layout (read i of the batch at the prefix

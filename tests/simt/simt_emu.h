@@ -113,6 +113,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
 static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 static inline void __syncwarp(unsigned = 0xffffffffu) { simt::collective(simt::OP_SYNCWARP, 0, 0); }
 static inline void __syncthreads() { simt::block_barrier(); }
+static inline void __threadfence() {}
 
 /* ---- arithmetic intrinsics: plain IEEE (built with -ffp-contract=off) -------------------------------------- */
 static inline float __fadd_rn(float a, float b) { return a + b; }
@@ -193,5 +194,5 @@ static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 /* kernel launch: the product's ABEA_LAUNCH macro expands to this under ABEA_SIMT_EMU */
 #define SIMT_LAUNCH(kern, grid, block, ...) simt::launch(simt::Dim3(grid), simt::Dim3(block), [&]() { kern(__VA_ARGS__); })
 #define SIMT_LAUNCH_SMEM(kern, grid, block, smem, ...) simt::launch(simt::Dim3(grid), simt::Dim3(block), [&]() { kern(__VA_ARGS__); }, smem)
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }

@@ -46,6 +46,7 @@ def check(emu, batch, model_name, what):
     ("r9", dict(n_reads=9, mean_events=120, sigma=0.8, epk=1.8, seed=7, min_len=20)),
 ])
 def test_emulated_kernels_match_oracle(emu, monkeypatch, name, kw, wide):
+    monkeypatch.setenv("ABEA_STREAM", "3" if kw["seed"] % 2 else "0")
     """wide=0: everything through the narrow (warp per read) kernel; wide=1: the scheduler's own split (a batch with
     fewer reads than SMs runs wide, a larger one mixes wide, long-narrow and regular reads)."""
     monkeypatch.setenv("ABEA_WIDE", wide)
@@ -55,11 +56,18 @@ def test_emulated_kernels_match_oracle(emu, monkeypatch, name, kw, wide):
         assert got.timing["n_wide"] == 0
 
 
+@pytest.mark.parametrize("stream", ["0", "1", "2", "3"])
 @pytest.mark.parametrize("wide", ["0", "1"])
-def test_emulated_edge_cases(emu, monkeypatch, wide):
+def test_emulated_edge_cases(emu, monkeypatch, wide, stream):
+    """stream=1: events through abea_load_kernel (which also range-checks them: read 0 has an event that must send it
+    to the exact instantiation), pair lists written to the caller's buffer by the traceback; stream=0: staged copies."""
     monkeypatch.setenv("ABEA_WIDE", wide)
+    monkeypatch.setenv("ABEA_STREAM", stream)
     b = edge_batch()
     got = check(emu, b, "r9", "edge")
+    assert (got.timing["streamed"] & 2) == (int(stream) & 2)
+    if b.events.ctypes.data % 16 == 0:
+        assert (got.timing["streamed"] & 1) == (int(stream) & 1)
     assert got.n_pairs[1] == 0 and got.n_pairs[3] == 0 and got.n_pairs[4] == 0
     assert got.n_pairs[0] > 0 and got.n_pairs[2] > 0
 

@@ -43,6 +43,18 @@ def run_and_check(ctx, batch, model_name, what):
     assert np.array_equal(st["sum_emission"][sched], want.stats["sum_emission"][sched])
     assert np.array_equal(st["end_event"][sched], want.stats["end_event"][sched])
     assert got.timing["kernel_launches"] >= 2
+    assert got.timing["streamed"] == 0            # pageable numpy buffers: staged through the copy engine
+    # the same batch from pinned buffers: events streamed in by abea_load_kernel, pair lists written by the traceback
+    # straight into the caller's pinned buffer
+    pb = ctx.pin_batch(batch)
+    out = ctx.alloc_output(batch, pinned=True)
+    out[0].view(np.uint8)[...] = 0xA5
+    gs = ctx.align_batch(pb, out)
+    if batch.n_reads > 0 and int(batch.pair_capacity().sum()) > 0:
+        assert gs.timing["streamed"] == 3
+    ol.assert_same_alignment(gs, want, what + " (streamed)")
+    st2 = ctx.read_stats(batch.n_reads)
+    assert np.array_equal(st2["sum_emission"][sched], want.stats["sum_emission"][sched])
     return got, want
 
 
