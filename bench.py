@@ -8,8 +8,10 @@
 A "step" is one pass of the hot path over one synthetic batch (BASELINE.json configs[1], "cfg2": R9.4.1, 4096 reads
 per GPU, mean 4k events/read; other configs via --config). `value` is device-timed (CUDA events inside the library,
 on the stream the kernels are launched on) with the batch already resident in HBM; `e2e` is the same metric through
-the C-ABI call with HOST (pinned) buffers in and out — H2D, kernels, D2H and unpack inside the timed region — plus,
-for N > 1, the NCCL gather of all ranks' results to rank 0. Reads are partitioned read-wise across ranks (weak
+the C-ABI call with HOST (pinned) buffers in and out — everything inside the timed region: the events are pulled over
+PCIe by abea_load_kernel while the fill runs and the pair lists are written straight into the caller's pinned buffer
+by the traceback (timing["streamed"] == 3; ABEA_STREAM=0 stages through the copy engine instead) — plus, for N > 1,
+the NCCL gather of all ranks' device-resident results to rank 0. Reads are partitioned read-wise across ranks (weak
 scaling: 4096 reads per GPU); there is no collective on the data path, only the final result gather.
 """
 from __future__ import annotations
@@ -204,7 +206,8 @@ def main():
         e2e_launches += r.timing["kernel_launches"]
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
-    e2e_parts = {kk: r.timing[kk] for kk in ("pack_ms", "h2d_ms", "kernel_ms", "d2h_ms", "unpack_ms")}
+    e2e_parts = {kk: r.timing[kk] for kk in ("pack_ms", "h2d_ms", "load_ms", "kernel_ms", "d2h_ms", "unpack_ms")}
+    e2e_parts["streamed"] = r.timing["streamed"]
 
     # ---- reduce over ranks: MAX of times, SUM of units -------------------------------------------------------------
     def reduce(x, op):

@@ -72,7 +72,9 @@ struct abea_ctx {
     /* resident batch */
     DevBuf d_seq, d_events, d_reads, d_kparams, d_trace, d_pairs, d_results, d_queue, d_flags, d_npairs;
     std::vector<int64_t> cap_ptr;     /* canonical pair_ptr of the caller's batch: prefix sum of E+L over ALL reads */
-    HostBuf h_results, h_pairs;
+    HostBuf h_results, h_pairs, h_reads, h_items; /* pinned staging */
+    bool prepared = false;            /* abea_prepare_kernel of the resident batch was already launched by the upload */
+    int prep_launches = 0;
     std::vector<abea_read_t> reads;   /* scheduled reads, longest first */
     int32_t n_batch_reads = 0;        /* reads in the caller's batch */
     int64_t total_kmers = 0, total_trace_words = 0, total_pair_cap = 0, total_bands = 0, total_events = 0;
@@ -100,7 +102,7 @@ struct abea_ctx {
     cudaStream_t load_stream = nullptr;
     cudaEvent_t ev_meta = nullptr, ev_loaded = nullptr, ev_load0 = nullptr;
     bool streaming = false;    /* the resident batch is being streamed in: its fill must wait on d_ready */
-    bool results_on_device = false; /* d_pairs / d_npairs hold the final lists (false after a streamed-out run) */
+    bool results_on_device = false; /* d_pairs / d_npairs hold the final lists of the last run */
     int64_t event_bytes = 0;   /* size of the batch's event array */
 };
 
@@ -134,6 +136,8 @@ int dev_reserve(abea_ctx* c, DevBuf& b, size_t bytes) {
     /* once per growth, not per batch: the traceback stages whole 32-band chunks of trace lines, so it copies (and
      * never looks at) the padding words of a line and the lines past a read's last band */
     CU(cudaMemsetAsync(b.p, 0, want, c->stream));
+    /* growth is rare; the buffer may next be written from another stream of the context (the loader's) */
+    CU(cudaStreamSynchronize(c->stream));
     b.cap = want;
     return 0;
 }
@@ -169,6 +173,90 @@ void* mapped_alias(const void* host) {
     if (at.type != cudaMemoryTypeHost) return nullptr;
     return at.devicePointer;
 #endif
+}
+
+
+/* abea_prepare_kernel over the scheduled reads; check_events = 0 when the loader validates the event means */
+void launch_prepare(abea_ctx* c, int64_t check_events) {
+    const int32_t n = (int32_t)c->reads.size();
+    const int threads = 256;
+    const int64_t work = std::max(c->total_kmers, check_events);
+    int blocks = (int)std::min<int64_t>((work + threads - 1) / threads, (int64_t)c->sm_count * 16);
+    if (blocks < 1) blocks = 1;
+    ABEA_LAUNCH(abea_prepare_kernel, blocks, threads, c->stream,
+        (const abea_read_t*)c->d_reads.p, n, (const uint8_t*)c->d_seq.p, (const abea_model_t*)c->d_model.p,
+        c->kmer_size, (const abea_event_t*)c->d_events.p, (float4*)c->d_kparams.p, (uint32_t*)c->d_flags.p,
+        c->total_kmers, check_events);
+}
+
+/* see upload_impl */
+void build_load_order(abea_ctx* c) {
+    const int64_t n = (int64_t)c->reads.size();
+    const int nw = c->n_wide;
+    const int wpc = c->fill_warps_per_cta;
+    const int wide_sms = nw > 0 ? std::min(c->sm_count, nw) : 0;
+    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((int64_t)(c->sm_count - wide_sms) * c->fill_ctas_per_sm,
+                                                                  (n - nw + wpc - 1) / wpc));
+    const int64_t n_pri = 4 * blocks, n_sec = (int64_t)(wpc - 4) * blocks;
+    /* cycles per band (wide CTA; narrow warp sharing its sub-partition; narrow warp alone on it = a "long" read) and
+     * per traceback step. The longest reads set the makespan, so their pieces are asked for early rather than late. */
+    const double CYC_WIDE = 450.0, CYC_NARROW = 1000.0, CYC_LONG = 600.0, CYC_TRACE = 350.0;
+    const double cyc_batch = (double)c->total_bands * 360.0 / ((double)c->sm_count * 4.0);
+    const double long_thr = std::max(1.0, c->long_alpha * cyc_batch / 780.0); /* as in run_impl */
+    auto rate = [&](int64_t r) {
+        if (r < nw) return CYC_WIDE;
+        const double nb = (double)c->reads[r].n_events + c->reads[r].n_kmers + 2;
+        return nb > long_thr ? CYC_LONG : CYC_NARROW;
+    };
+    std::vector<double> start((size_t)n, 0.0);
+    /* (time a warp becomes free, kind: 0 wide, 1 primary, 2 secondary); a min-heap */
+    typedef std::pair<double, int> slot_t;
+    std::vector<slot_t> heap;
+    /* at t = 0 the three kinds ask in this order of urgency; the tiny offsets only order the first requests: the
+     * reads that set the makespan first, and primary and secondary warps served alternately after that */
+    for (int i = 0; i < std::min<int64_t>(nw, c->sm_count); i++) heap.push_back(slot_t(0.0, 0));
+    for (int64_t i = 0; i < n_pri; i++) heap.push_back(slot_t(1e-3 * (double)i / (double)n_pri, 1));
+    for (int64_t i = 0; i < n_sec; i++) heap.push_back(slot_t(1.5e-3 * (double)i / (double)std::max<int64_t>(1, n_sec), 2));
+    auto later = [](const slot_t& x, const slot_t& y) { return x.first > y.first; };
+    std::make_heap(heap.begin(), heap.end(), later);
+    int64_t w = 0, h = nw, t = n - 1;
+    while ((w < nw || h <= t) && !heap.empty()) {
+        std::pop_heap(heap.begin(), heap.end(), later);
+        slot_t sl = heap.back();
+        heap.pop_back();
+        int64_t r;
+        if (sl.second == 0) {
+            if (w >= nw) continue;
+            r = w++;
+        } else {
+            if (h > t) continue;
+            r = (sl.second == 1) ? h++ : t--;
+        }
+        const abea_read_t& rd = c->reads[r];
+        const double nb = (double)rd.n_events + rd.n_kmers + 2;
+        start[r] = sl.first;
+        sl.first += nb * rate(r) + (double)rd.n_events * CYC_TRACE;
+        heap.push_back(sl);
+        std::push_heap(heap.begin(), heap.end(), later);
+    }
+    struct need_t { double t; int32_t read, piece; };
+    std::vector<need_t> need;
+    need.reserve((size_t)n + (size_t)(c->event_bytes / ABEA_LOAD_PIECE_BYTES) + 8);
+    for (int64_t r = 0; r < n; r++) {
+        const abea_read_t& rd = c->reads[r];
+        const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, c->event_bytes);
+        const double nb = (double)rd.n_events + rd.n_kmers + 2;
+        const double fill = nb * rate(r);
+        for (int32_t q = 0; q < g.n_pieces; q++) {
+            /* the fill touches event e when it is about e/E of the way through the read's bands */
+            const double frac = (double)abea_piece_first_event(g, q) / (double)rd.n_events;
+            need.push_back(need_t{start[r] + frac * fill, (int32_t)r, q});
+        }
+    }
+    std::stable_sort(need.begin(), need.end(), [](const need_t& x, const need_t& y) { return x.t < y.t; });
+    c->items.clear();
+    c->items.reserve(need.size());
+    for (const need_t& x : need) c->items.push_back(abea_load_item_t{x.read, x.piece});
 }
 
 } // namespace
@@ -254,10 +342,12 @@ int abea_create(abea_ctx_t** out, int device) {
         const int carve = 100; /* percent of the maximum: cudaSharedmemCarveoutMaxShared */
         if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_load_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_fill_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_fill_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_fill_wide_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_fill_wide_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        const void* fills[] = {(const void*)abea_fill_kernel<true, false>,      (const void*)abea_fill_kernel<false, false>,
+                               (const void*)abea_fill_kernel<true, true>,       (const void*)abea_fill_kernel<false, true>,
+                               (const void*)abea_fill_wide_kernel<true, false>, (const void*)abea_fill_wide_kernel<false, false>,
+                               (const void*)abea_fill_wide_kernel<true, true>,  (const void*)abea_fill_wide_kernel<false, true>};
+        for (const void* f : fills)
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) {
             delete c;
             return ABEA_ERR_CUDA;
@@ -279,6 +369,8 @@ void abea_destroy(abea_ctx_t* c) {
         if (b->p) cudaFree(b->p);
     if (c->h_results.p) cudaFreeHost(c->h_results.p);
     if (c->h_pairs.p) cudaFreeHost(c->h_pairs.p);
+    if (c->h_reads.p) cudaFreeHost(c->h_reads.p);
+    if (c->h_items.p) cudaFreeHost(c->h_items.p);
     for (int i = 0; i < EV_COUNT; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -422,41 +514,40 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
     c->streaming = false;
     c->results_on_device = false;
     double t2 = t1;
+    c->prepared = false;
     CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
-    if (n_sched)
-        CU(cudaMemcpyAsync(c->d_reads.p, c->reads.data(), n_sched * sizeof(abea_read_t), cudaMemcpyHostToDevice,
-                           c->stream));
+    if (n_sched) { /* descriptors through pinned staging: a pageable source would make the copy synchronous */
+        if (host_reserve(c, c->h_reads, n_sched * sizeof(abea_read_t))) return ABEA_ERR_CUDA;
+        memcpy(c->h_reads.p, c->reads.data(), n_sched * sizeof(abea_read_t));
+        CU(cudaMemcpyAsync(c->d_reads.p, c->h_reads.p, n_sched * sizeof(abea_read_t), cudaMemcpyHostToDevice, c->stream));
+    }
     if (ev_alias && n_sched) {
-        /* Work list of the loader, in the order the fill is going to ask: the longest reads (they set the makespan:
-         * wide CTAs and the first pulls of the primary warps), then the two ends of the schedule interleaved —
-         * primary warps walk it from the head, the (twice as many) secondary warps from the tail. */
-        c->items.clear();
-        int64_t h = 0, t = (int64_t)n_sched - 1, ev_head = 0, ev_tail = 0;
-        const int64_t first = std::min<int64_t>((int64_t)n_sched, c->sm_count);
-        auto push = [&](int64_t r) {
-            const uint32_t np = abea_load_pieces(c->reads[r].ev_off, c->reads[r].n_events, c->event_bytes);
-            for (uint32_t q = 0; q < np; q++) c->items.push_back(abea_load_item_t{(int32_t)r, (int32_t)q});
-        };
-        for (; h < first; h++) push(h);
-        while (h <= t) {
-            if (ev_tail < 2 * ev_head) {
-                ev_tail += c->reads[t].n_events;
-                push(t--);
-            } else {
-                ev_head += c->reads[h].n_events;
-                push(h++);
-            }
-        }
-        if (dev_reserve(c, c->d_items, c->items.size() * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
-        if (dev_reserve(c, c->d_ready, (n_sched + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
-        t2 = now_ms();
-        CU(cudaMemcpyAsync(c->d_items.p, c->items.data(), c->items.size() * sizeof(abea_load_item_t),
-                           cudaMemcpyHostToDevice, c->stream));
+        /* Everything the k-mer parameter kernel needs goes first, and the kernel with it: the host then works out
+         * the loader's order while the GPU is busy with that. */
+        if (dev_reserve(c, c->d_ready, ABEA_READY_WORDS * (n_sched + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
+        if (seq_bytes) CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
         CU(cudaMemsetAsync(c->d_flags.p, 0x01, n_sched * sizeof(uint32_t), c->stream));
-        CU(cudaMemsetAsync(c->d_ready.p, 0, n_sched * sizeof(uint32_t), c->stream));
+        CU(cudaMemsetAsync(c->d_ready.p, 0, ABEA_READY_WORDS * n_sched * sizeof(uint32_t), c->stream));
         CU(cudaEventRecord(c->ev_meta, c->stream));
+        CU(cudaEventRecord(c->ev[EV_K0], c->stream));
+        launch_prepare(c, 0);
+        CU(cudaEventRecord(c->ev[EV_K1], c->stream));
+        c->prepared = true;
+        /* Work list of the loader: every (read, piece) in the order the fill is expected to NEED it. The fill starts
+         * a read when its first piece has landed and then chases the loader piece by piece, so what matters is when
+         * each piece is first touched. That is predicted by replaying the schedule with nominal rates (cycles per
+         * band measured on B200, profiles/README.md): wide CTAs take reads [0, n_wide) in order, primary warps pull
+         * from the head of the longest-first order, secondary warps from the tail. */
+        build_load_order(c);
+        if (dev_reserve(c, c->d_items, c->items.size() * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
+        if (host_reserve(c, c->h_items, c->items.size() * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
+        memcpy(c->h_items.p, c->items.data(), c->items.size() * sizeof(abea_load_item_t));
+        t2 = now_ms();
+        /* the loader's stream waits for the descriptors and the cleared counters, not for the k-mer kernel */
         CU(cudaStreamWaitEvent(c->load_stream, c->ev_meta, 0));
+        CU(cudaMemcpyAsync(c->d_items.p, c->h_items.p, c->items.size() * sizeof(abea_load_item_t),
+                           cudaMemcpyHostToDevice, c->load_stream));
         CU(cudaEventRecord(c->ev_load0, c->load_stream));
         const int blocks = (int)std::min<size_t>(c->items.size(), (size_t)c->load_ctas);
         ABEA_LAUNCH(abea_load_kernel, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
@@ -469,7 +560,8 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         CU(cudaMemcpyAsync(c->d_events.p, b->events, (size_t)n_ev_total * sizeof(abea_event_t),
                            cudaMemcpyHostToDevice, c->stream));
     }
-    if (seq_bytes) CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (seq_bytes && !c->streaming)
+        CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
     if (!c->streaming) CU(cudaStreamSynchronize(c->stream));
     c->uploaded = true;
@@ -502,29 +594,23 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
     const bool streaming = c->streaming; /* set by upload_impl: queue, flags and ready counters are already armed */
     abea_stream_t io;
     io.ready = streaming ? (const uint32_t*)c->d_ready.p : nullptr;
-    io.pairs_final = fin_pairs ? fin_pairs : (abea_pair_t*)c->d_pairs.p;
-    io.n_pairs_final = fin_np ? fin_np : (int32_t*)c->d_npairs.p;
+    io.pairs_final = fin_pairs;
+    io.n_pairs_final = fin_np;
+    io.n_pairs_dev = (int32_t*)c->d_npairs.p;
+    io.stalled = (uint32_t*)c->d_queue.p + 15; /* zeroed with the queue */
     if (!streaming) CU(cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
-    if (!fin_np) CU(cudaMemsetAsync(c->d_npairs.p, 0, ((size_t)c->n_batch_reads + 1) * sizeof(int32_t), c->stream));
-    CU(cudaEventRecord(c->ev[EV_K0], c->stream));
+    CU(cudaMemsetAsync(c->d_npairs.p, 0, ((size_t)c->n_batch_reads + 1) * sizeof(int32_t), c->stream));
+    if (!c->prepared) CU(cudaEventRecord(c->ev[EV_K0], c->stream));
     if (n > 0) {
         int32_t* queue = (int32_t*)c->d_queue.p;
-        {
+        if (!c->prepared) {
             /* every read starts as "fast"; abea_prepare_kernel clears the flag of reads with out-of-range inputs
-             * (when streaming, the loader checks the event means as they pass through it) */
-            if (!streaming) CU(cudaMemsetAsync(c->d_flags.p, 0x01, (size_t)n * sizeof(uint32_t), c->stream));
-            int threads = 256;
-            const int64_t check_events = streaming ? 0 : c->total_events;
-            int64_t work = std::max(c->total_kmers, check_events);
-            int blocks = (int)std::min<int64_t>((work + threads - 1) / threads, (int64_t)c->sm_count * 16);
-            if (blocks < 1) blocks = 1;
-            ABEA_LAUNCH(abea_prepare_kernel, blocks, threads, c->stream,
-                (const abea_read_t*)c->d_reads.p, n, (const uint8_t*)c->d_seq.p, (const abea_model_t*)c->d_model.p,
-                c->kmer_size, (const abea_event_t*)c->d_events.p, (float4*)c->d_kparams.p, (uint32_t*)c->d_flags.p,
-                c->total_kmers, check_events);
-            launches++;
+             * (a streamed batch: launched by the upload; the loader checks the event means as they pass through it) */
+            CU(cudaMemsetAsync(c->d_flags.p, 0x01, (size_t)n * sizeof(uint32_t), c->stream));
+            launch_prepare(c, c->total_events);
+            CU(cudaEventRecord(c->ev[EV_K1], c->stream));
         }
-        CU(cudaEventRecord(c->ev[EV_K1], c->stream));
+        launches++;
         {
             /* The longest n_wide reads: one CTA of 4 warps each (wide kernel) on a second stream, beside the persistent
              * narrow warps (4 CTAs of 4 warps per SM, each warp pulls reads longest-first). The FAST instantiations
@@ -538,16 +624,19 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                  * cycles/band alone, 800 beside a narrow CTA). It therefore asks for so much dynamic shared memory
                  * that no narrow CTA fits on the same SM. Tiny batches (every read wide) do not need the exclusion. */
                 const size_t excl = (n > nw) ? (size_t)160 * 1024 : 0;
-                CU(cudaFuncSetAttribute(abea_fill_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)excl));
-                CU(cudaFuncSetAttribute(abea_fill_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)excl));
-                ABEA_LAUNCH_SMEM(abea_fill_wide_kernel<true>, wblocks, 128, excl, c->wide_stream,
+                /* the STREAM instantiations chase the loader (abea_wait_landed_events); the others assume a resident batch */
+                auto wide_fast = streaming ? abea_fill_wide_kernel<true, true> : abea_fill_wide_kernel<true, false>;
+                auto wide_exact = streaming ? abea_fill_wide_kernel<false, true> : abea_fill_wide_kernel<false, false>;
+                CU(cudaFuncSetAttribute((const void*)wide_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)excl));
+                CU(cudaFuncSetAttribute((const void*)wide_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)excl));
+                ABEA_LAUNCH_SMEM(wide_fast, wblocks, 128, excl, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, io, c->event_bytes, c->cst, queue + 6);
-                ABEA_LAUNCH_SMEM(abea_fill_wide_kernel<false>, wblocks, 128, excl, c->wide_stream,
+                    (abea_result_t*)c->d_results.p, io, c->cst, queue + 6);
+                ABEA_LAUNCH_SMEM(wide_exact, wblocks, 128, excl, c->wide_stream,
                     (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, io, c->event_bytes, c->cst, queue + 7);
+                    (abea_result_t*)c->d_results.p, io, c->cst, queue + 7);
                 CU(cudaEventRecord(c->ev_join, c->wide_stream));
                 launches += 2;
             }
@@ -560,27 +649,29 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                 if (blocks < 1) blocks = 1;
                 const size_t smem = (size_t)wpc * (sizeof(abea_fill_smem_t) +
                                                    sizeof(uint32_t) * ABEA_TB_RING_GROUPS * ABEA_TRACE_GROUP_WORDS);
-                CU(cudaFuncSetAttribute(abea_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                CU(cudaFuncSetAttribute(abea_fill_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                auto fill_fast = streaming ? abea_fill_kernel<true, true> : abea_fill_kernel<true, false>;
+                auto fill_exact = streaming ? abea_fill_kernel<false, true> : abea_fill_kernel<false, false>;
+                CU(cudaFuncSetAttribute((const void*)fill_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                CU(cudaFuncSetAttribute((const void*)fill_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 /* a narrow read is "long" when, sharing its sub-partition (~780 cycles/band), it would take more than
                  * long_alpha of the time the whole batch needs at full throughput */
                 const double cyc_batch = (double)c->total_bands * 360.0 / ((double)c->sm_count * 4.0);
                 const int32_t long_thr = (int32_t)std::min(2.0e9, std::max(1.0, c->long_alpha * cyc_batch / 780.0));
-                ABEA_LAUNCH_SMEM(abea_fill_kernel<true>, blocks, 32 * wpc, smem, c->stream,
+                ABEA_LAUNCH_SMEM(fill_fast, blocks, 32 * wpc, smem, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, io, c->event_bytes, c->cst, queue, nw, long_thr);
-                ABEA_LAUNCH_SMEM(abea_fill_kernel<false>, blocks, 32 * wpc, smem, c->stream,
+                    (abea_result_t*)c->d_results.p, io, c->cst, queue, nw, long_thr);
+                ABEA_LAUNCH_SMEM(fill_exact, blocks, 32 * wpc, smem, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, io, c->event_bytes, c->cst, queue + 8, nw, long_thr);
+                    (abea_result_t*)c->d_results.p, io, c->cst, queue + 8, nw, long_thr);
                 launches += 2;
             }
             if (nw > 0) CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         }
         CU(cudaEventRecord(c->ev[EV_K2], c->stream)); /* traceback + QC are fused into the fill kernels */
     } else {
-        CU(cudaEventRecord(c->ev[EV_K1], c->stream));
+        if (!c->prepared) CU(cudaEventRecord(c->ev[EV_K1], c->stream));
         CU(cudaEventRecord(c->ev[EV_K2], c->stream));
     }
     if (streaming) {
@@ -588,11 +679,21 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
         launches++;
     }
     CU(cudaEventRecord(c->ev[EV_K3], c->stream));
+    uint32_t stalled = 0;
+    if (streaming)
+        CU(cudaMemcpyAsync(&stalled, (uint32_t*)c->d_queue.p + 15, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
+    if (stalled) {
+        c->streaming = false;
+        c->prepared = false;
+        c->uploaded = false;
+        return fail(c, ABEA_ERR_CUDA, "streaming stalled: events did not arrive from the caller's pinned buffer");
+    }
     c->ran = true;
+    c->prepared = false;
     c->streaming = false; /* everything has landed: a further abea_run works on the resident copy */
-    c->results_on_device = (fin_pairs == nullptr && fin_np == nullptr);
+    c->results_on_device = true; /* a streamed-out run keeps the device copy too */
     if (streaming) {
         c->last.h2d_ms = ev_ms(c, EV_H2D0, EV_H2D1);
         float ms = 0.f;
@@ -614,7 +715,7 @@ int abea_download(abea_ctx_t* c, abea_pair_t* pairs, const int64_t* pair_ptr, in
                   abea_timing_t* timing) {
     if (!c || !n_pairs || (!pairs && c->total_pair_cap > 0) || !pair_ptr) return fail(c, ABEA_ERR_ARG, "bad output");
     if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_download before abea_run");
-    if (!c->results_on_device) return fail(c, ABEA_ERR_STATE, "the last run wrote its results to the caller's buffers");
+    if (!c->results_on_device) return fail(c, ABEA_ERR_STATE, "no results on the device yet");
     CU(cudaSetDevice(c->device));
     const int32_t nb = c->n_batch_reads;
     /* The device holds the pairs in the canonical capacity layout (read i at prefix-sum(E+L)); when the caller's
@@ -720,7 +821,7 @@ int abea_device_results(abea_ctx_t* c, const abea_pair_t** d_pairs, const int32_
                         int64_t* total_pairs_capacity, int32_t* n_reads) {
     if (!c) return ABEA_ERR_ARG;
     if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_device_results before abea_run");
-    if (!c->results_on_device) return fail(c, ABEA_ERR_STATE, "the last run wrote its results to the caller's buffers");
+    if (!c->results_on_device) return fail(c, ABEA_ERR_STATE, "no results on the device yet");
     if (d_pairs) *d_pairs = (const abea_pair_t*)c->d_pairs.p;
     if (d_n_pairs) *d_n_pairs = (const int32_t*)c->d_npairs.p;
     if (total_pairs_capacity) *total_pairs_capacity = c->total_pair_cap;

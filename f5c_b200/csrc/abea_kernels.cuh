@@ -196,11 +196,14 @@ __global__ void abea_prepare_kernel(const abea_read_t* __restrict__ reads, int32
  * pairs the kernels run on data that is already resident (abea_upload_batch / abea_run / abea_download). */
 struct abea_stream_t {
     const uint32_t* ready;      /* [scheduled read] pieces of its events landed so far; NULL: everything is resident */
-    abea_pair_t* pairs_final;   /* where the finished lists go: d_pairs, or the caller's mapped host buffer */
-    int32_t* n_pairs_final;     /* [batch read] pair counts: device, or the caller's mapped host buffer */
+    abea_pair_t* pairs_final;   /* the caller's mapped host buffer (canonical layout), or NULL: the lists stay in d_pairs only */
+    int32_t* n_pairs_final;     /* [batch read] pair counts in the caller's mapped host buffer, or NULL */
+    int32_t* n_pairs_dev;       /* [batch read] pair counts on the device (always written) */
+    uint32_t* stalled;          /* set to 1 if a wait for streamed events gave up (the host reports an error) */
 };
 
-#define ABEA_LOAD_PIECE_BYTES (96 * 1024) /* one work item of the loader: 768 lines of 128 B = 4096 events */
+#define ABEA_LOAD_PIECE_BYTES (96 * 1024) /* smallest work item of the loader: 768 lines of 128 B = 4096 events */
+#define ABEA_LOAD_MAX_PIECES 64           /* per read: its landed pieces are a 64-bit mask (two words of d_ready) */
 #define ABEA_LOAD_THREADS 128
 #define ABEA_LOAD_UNROLL 8                /* 16-B loads in flight per thread */
 
@@ -210,18 +213,30 @@ struct abea_load_item_t {
 };
 
 /* The byte range of a read's events, widened to whole 128-B lines (clamped to the buffer): a line shared by two reads
- * is copied for both, so whichever is published first the line is complete — no SM can cache half a line. */
-__device__ __host__ __forceinline__ void abea_load_range(int64_t ev_off, int32_t n_events, int64_t total_bytes,
-                                                         int64_t* lo, int64_t* hi) {
-    const int64_t a = ev_off * (int64_t)sizeof(abea_event_t), b = a + (int64_t)n_events * (int64_t)sizeof(abea_event_t);
-    int64_t h = (b + 127) & ~(int64_t)127;
-    *lo = a & ~(int64_t)127;
-    *hi = h < total_bytes ? h : total_bytes;
+ * is copied for both, so whichever is published first the line is complete — no SM can cache half a line. The range
+ * is cut into at most 64 pieces of at least 96 KB (whole lines). */
+struct abea_load_geom_t {
+    int64_t a, b;   /* the read's own bytes [a, b) */
+    int64_t lo, hi; /* widened to lines */
+    int64_t piece;  /* bytes per piece */
+    int32_t n_pieces;
+};
+__device__ __host__ __forceinline__ abea_load_geom_t abea_load_geom(int64_t ev_off, int32_t n_events, int64_t total_bytes) {
+    abea_load_geom_t g;
+    g.a = ev_off * (int64_t)sizeof(abea_event_t);
+    g.b = g.a + (int64_t)n_events * (int64_t)sizeof(abea_event_t);
+    const int64_t h = (g.b + 127) & ~(int64_t)127;
+    g.lo = g.a & ~(int64_t)127;
+    g.hi = h < total_bytes ? h : total_bytes;
+    int64_t per = (((g.hi - g.lo) + ABEA_LOAD_MAX_PIECES - 1) / ABEA_LOAD_MAX_PIECES + 127) & ~(int64_t)127;
+    g.piece = per > ABEA_LOAD_PIECE_BYTES ? per : ABEA_LOAD_PIECE_BYTES;
+    g.n_pieces = (int32_t)((g.hi - g.lo + g.piece - 1) / g.piece);
+    return g;
 }
-__device__ __host__ __forceinline__ uint32_t abea_load_pieces(int64_t ev_off, int32_t n_events, int64_t total_bytes) {
-    int64_t lo, hi;
-    abea_load_range(ev_off, n_events, total_bytes, &lo, &hi);
-    return (uint32_t)((hi - lo + ABEA_LOAD_PIECE_BYTES - 1) / ABEA_LOAD_PIECE_BYTES);
+/* first event of the read that lies (at least partly) in piece p */
+__device__ __host__ __forceinline__ int64_t abea_piece_first_event(const abea_load_geom_t& g, int32_t p) {
+    const int64_t off = g.lo + (int64_t)p * g.piece - g.a;
+    return off <= 0 ? 0 : off / (int64_t)sizeof(abea_event_t);
 }
 
 __device__ __forceinline__ uint32_t abea_ld_acquire_u32(const uint32_t* p) {
@@ -244,26 +259,38 @@ __device__ __forceinline__ uint32_t abea_ld_relaxed_u32(const uint32_t* p) {
 #endif
 }
 
-/* Called by ALL lanes of a warp (all threads of a wide CTA), warp-uniformly: every lane polls the same word (one
+/* Streaming: per scheduled read, d_ready holds four words: [0] how many leading events of the read have landed in
+ * d_events (0x7fffffff once all have), [2..3] the 64-bit mask of landed pieces it is derived from (loader only).
+ * abea_wait_landed_events blocks until event `last` (and every event before it) has landed and returns the count it
+ * saw, so that the caller asks again only when it runs past that: a fill warp starts a read as soon as its first
+ * piece is in and chases the loader from there.
+ * Called by ALL lanes of a warp (all threads of a wide CTA), warp-uniformly: every lane polls the same word (one
  * broadcast transaction). A single spinning lane would leave the warp split after the loop — the convergence barrier
  * around a NANOSLEEP loop is not a reconverging one — and a split warp executes the whole read at a quarter of the
- * speed (measured: every read that had waited here ran at 4000 instead of 1000 cycles per band). */
-__device__ __forceinline__ void abea_wait_landed(const uint32_t* ready, int32_t ridx, const abea_read_t& rd,
-                                                 int64_t total_event_bytes) {
-    if (ready == nullptr) return;
-    const uint32_t need = abea_load_pieces(rd.ev_off, rd.n_events, total_event_bytes);
-    /* Poll with RELAXED loads and acquire once at the end: an acquire load at gpu scope is LDG.STRONG + CCTL.IVALL
-     * (the whole SM's L1 is invalidated), and a warp doing that every few hundred nanoseconds slowed every warp
-     * sharing its SM four-fold (measured: 1000 -> 4000 cycles per band while the loader ran). */
-    /* the vote makes the exit warp-uniform by construction */
-    while (__any_sync(ABEA_FULL, abea_ld_relaxed_u32(ready + ridx) < need)) {
+ * speed (measured: every read that had waited ran at 4000 instead of 1000 cycles per band). The polling loads are
+ * RELAXED, with one acquire at the end: an acquire load at gpu scope is LDG.STRONG + CCTL.IVALL (the SM's whole L1). */
+#define ABEA_READY_WORDS 4
+#define ABEA_WAIT_SPINS_MAX (1 << 22) /* x >= 1 us: a loader that has not delivered in seconds never will */
+__device__ __forceinline__ int32_t abea_wait_landed_events(const uint32_t* w, int32_t last, uint32_t* stalled) {
+    uint32_t v;
+    for (int spins = 0;; spins++) {
+        v = abea_ld_relaxed_u32(w);
+        /* the vote makes the exit warp-uniform by construction */
+        if (!__any_sync(ABEA_FULL, v <= (uint32_t)last)) break;
+        /* never hang the GPU: flag the batch as failed and carry on (at once if another warp already gave up) */
+        if (spins >= ABEA_WAIT_SPINS_MAX || ((spins & 255) == 255 && *(volatile uint32_t*)stalled != 0u)) {
+            *stalled = 1u;
+            v = 0x7fffffffu;
+            break;
+        }
 #ifndef ABEA_SIMT_EMU
         __nanosleep(1000);
 #else
         break; /* the emulator runs kernels one after the other: the loader has finished */
 #endif
     }
-    (void)abea_ld_acquire_u32(ready + ridx);
+    (void)abea_ld_acquire_u32(w);
+    return (int32_t)v;
 }
 
 /* src: the caller's events (pinned host memory, mapped); dst: d_events; both 16-B aligned, same layout. The event
@@ -284,12 +311,10 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
         if (it >= n_items) break;
         const abea_load_item_t item = items[it];
         const abea_read_t rd = reads[item.read];
-        const int64_t a = rd.ev_off * (int64_t)sizeof(abea_event_t);
-        const int64_t b = a + (int64_t)rd.n_events * (int64_t)sizeof(abea_event_t);
-        int64_t lo, hi;
-        abea_load_range(rd.ev_off, rd.n_events, total_bytes, &lo, &hi);
-        const int64_t p0 = lo + (int64_t)item.piece * ABEA_LOAD_PIECE_BYTES;
-        const int64_t p1 = (p0 + ABEA_LOAD_PIECE_BYTES < hi) ? p0 + ABEA_LOAD_PIECE_BYTES : hi;
+        const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, total_bytes);
+        const int64_t a = g.a, b = g.b;
+        const int64_t p0 = g.lo + (int64_t)item.piece * g.piece;
+        const int64_t p1 = (p0 + g.piece < g.hi) ? p0 + g.piece : g.hi;
         const int64_t u1 = p1 >> 4;
         bool bad = false;
         for (int64_t u = (p0 >> 4) + tid; u < u1; u += ABEA_LOAD_THREADS * ABEA_LOAD_UNROLL) {
@@ -318,7 +343,19 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
         if (bad) atomicAnd(&read_flags[item.read], ~ABEA_READ_FAST);
         __threadfence();
         __syncthreads();
-        if (tid == 0) atomicAdd(&ready[item.read], 1u);
+        if (tid == 0) { /* mark the piece, then publish the read's landed prefix (in events) */
+            uint32_t* w = ready + (int64_t)ABEA_READY_WORDS * item.read;
+            const int wi = item.piece >> 5;
+            const uint32_t mine = atomicOr(&w[2 + wi], 1u << (item.piece & 31)) | (1u << (item.piece & 31));
+            const uint32_t other = atomicOr(&w[2 + (wi ^ 1)], 0u);
+            const uint32_t m0 = wi == 0 ? mine : other, m1 = wi == 0 ? other : mine;
+            const int32_t np = (m0 != 0xffffffffu) ? (__ffs((int)~m0) - 1) : ((m1 != 0xffffffffu) ? 32 + (__ffs((int)~m1) - 1) : 64);
+            const int64_t end = g.lo + (int64_t)np * g.piece;
+            uint32_t nev = 0x7fffffffu;
+            if (end < g.b && np < g.n_pieces) nev = end <= g.a ? 0u : (uint32_t)((end - g.a) / (int64_t)sizeof(abea_event_t));
+            __threadfence(); /* pieces whose bits were observed above are ordered before the count */
+            atomicMax(&w[0], nev);
+        }
     }
 }
 
@@ -571,15 +608,17 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
         results[ridx].n_aligned = n;
         results[ridx].n_pairs = fail ? 0 : n;
         results[ridx].max_gap = max_gap;
-        io.n_pairs_final[rd.orig_index] = fail ? 0 : n; /* db->n_event_align_pairs[i] */
+        io.n_pairs_dev[rd.orig_index] = fail ? 0 : n; /* db->n_event_align_pairs[i] */
+        if (io.n_pairs_final) io.n_pairs_final[rd.orig_index] = fail ? 0 : n;
     }
-    /* move the list to the front of the read's capacity region of the destination (the layout the caller's buffer
-     * has). The destination is d_pairs itself (in place: destination index t <= source index cap-n+t, batches of 32
-     * are loaded before they are stored) or the caller's mapped host buffer (posted writes over PCIe). */
+    /* move the list to the front of the read's capacity region (the layout the caller's buffer has): in place in
+     * d_pairs (destination index t <= source index cap-n+t, batches of 32 are loaded before they are stored), and,
+     * when the caller's buffer is mapped, also straight into it (posted writes over PCIe) — the device copy stays
+     * for consumers on the GPU (abea_device_results, the NCCL gather of a multi-GPU driver). */
     __syncwarp();
     const int32_t src0 = rd.pair_cap - n;
-    abea_pair_t* __restrict__ fin = io.pairs_final + rd.pair_off;
-    if (!fail && (src0 > 0 || fin != out)) {
+    abea_pair_t* fin = io.pairs_final ? io.pairs_final + rd.pair_off : nullptr;
+    if (!fail && (src0 > 0 || fin != nullptr)) {
         for (int32_t t0 = 0; t0 < n; t0 += 32) {
             const int32_t t = t0 + lane;
             abea_pair_t p;
@@ -587,7 +626,10 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
             p.read_pos = 0;
             if (t < n) p = out[src0 + t];
             __syncwarp();
-            if (t < n) fin[t] = p;
+            if (t < n) {
+                if (src0 > 0) out[t] = p;
+                if (fin) fin[t] = p;
+            }
             __syncwarp();
         }
     }
@@ -605,6 +647,10 @@ struct abea_band_t {
 struct abea_fill_smem_t {
     float ev[ABEA_RING];   /* event means, slot = event index & 63 */
     float4 kp[ABEA_RING];  /* k-mer parameters, slot = k-mer index & 63 */
+    /* streaming: looked at once per 32 events, so they live here and not in registers of the band loop */
+    const uint32_t* ready_w; /* the read's words of d_ready */
+    int32_t ev_landed;       /* leading events of the read known to be in d_events */
+    int32_t pad;
 };
 
 /* asynchronously stage chunk `chunk` (indices 32*chunk .. +31, clamped into the read) of the event means / k-mer
@@ -670,9 +716,10 @@ struct abea_fill_ctx_t {
 /* One band: A holds band b-1, B holds band b-2 and receives band b. `right` is this band's move; returns the next
  * band's move (Suzuki's rule, reference src/align.c:304-322), decided as soon as this band's scores exist so that its
  * shuffle/vote latency overlaps the trace bookkeeping. */
-template <bool FAST>
+template <bool FAST, bool STREAM>
 __device__ __forceinline__ bool abea_fill_step(abea_fill_ctx_t& cx, float* x, float4* kp, const abea_band_t& A,
-                                               abea_band_t& B, abea_fill_smem_t* sm, bool right, int lane) {
+                                               abea_band_t& B, abea_fill_smem_t* sm, bool right, int lane,
+                                               uint32_t* io_stalled) {
     const double NEG = abea_neg_inf_d();
     double Rn[ABEA_CPL];
     uint32_t fr[ABEA_CPL];
@@ -707,6 +754,16 @@ __device__ __forceinline__ bool abea_fill_step(abea_fill_ctx_t& cx, float* x, fl
         if ((en & 31) == 0) {
             abea_cp_async_wait_all();
             __syncwarp();
+            /* streaming: the chunk about to be staged (events en+32 .. en+63) may not have crossed PCIe yet */
+            if (STREAM) {
+                const int32_t last = (en + 63 < cx.E) ? en + 63 : cx.E - 1;
+                if (last >= sm->ev_landed) {
+                    const int32_t got = abea_wait_landed_events(sm->ready_w, last, io_stalled);
+                    __syncwarp();
+                    if (lane == 0) sm->ev_landed = got;
+                    __syncwarp();
+                }
+            }
             abea_stage_events(sm, cx.ev, (en >> 5) + 1, cx.E, lane);
         }
         cx.x_next = sm->ev[en & (ABEA_RING - 1)];
@@ -802,12 +859,12 @@ __device__ __forceinline__ void abea_backoff() {
 #endif
 }
 
-template <bool FAST>
+template <bool FAST, bool STREAM>
 __global__ void __launch_bounds__(32 * ABEA_NARROW_WARPS_MAX)
 abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const abea_event_t* __restrict__ events,
                  const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                  uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
-                 abea_stream_t io, int64_t total_event_bytes, abea_consts_t cst, int32_t* __restrict__ queue,
+                 abea_stream_t io, abea_consts_t cst, int32_t* __restrict__ queue,
                  int32_t first, int32_t long_thr) {
     /* dynamic shared memory: per warp one abea_fill_smem_t and one 4-KB traceback ring */
 #ifdef ABEA_SIMT_EMU
@@ -846,9 +903,22 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
         ridx = __shfl_sync(ABEA_FULL, ridx, 0);
         if (ridx >= n_reads) break;
         const abea_read_t rd = reads[ridx];
-        abea_wait_landed(io.ready, ridx, rd, total_event_bytes); /* streaming: the read's events */
+        /* streaming: the read starts as soon as its first events (0..95: the first window and two chunks of the
+         * ring) have landed, and from there chases the loader piece by piece (abea_fill_step) */
+        if (STREAM) {
+            const uint32_t* w = io.ready + (int64_t)ABEA_READY_WORDS * ridx;
+            const int32_t got = abea_wait_landed_events(w, rd.n_events > 96 ? 95 : rd.n_events - 1, io.stalled);
+            __syncwarp();
+            if (lane == 0) {
+                sm->ready_w = w;
+                sm->ev_landed = got;
+            }
+        }
         __syncwarp();
-        /* each instantiation takes only the reads validated for its arithmetic */
+        /* each instantiation takes only the reads validated for its arithmetic. Streaming: the loader clears the FAST
+         * bit of a read when an out-of-range event mean passes through it, always BEFORE it publishes that piece; a
+         * read whose bit is cleared after this test is filled here in vain and again, last, by the EXACT instantiation
+         * (which runs after this kernel and overwrites every result of the read). */
         if (((abea_ld_acquire_u32(read_flags + ridx) & ABEA_READ_FAST) != 0u) != FAST) continue;
 
         if (primary && lane == 0) atomicExch(&long_flag[slot], (rd.n_events + rd.n_kmers + 2 > long_thr) ? 1 : 0);
@@ -906,9 +976,9 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
         /* move of band 2: both extreme cells of band 1 are -inf, so it alternates: band 2 is even -> down */
         bool right = false;
         while (cx.b < cx.NB) {
-            right = abea_fill_step<FAST>(cx, x, kp, P, Q, sm, right, lane); /* Q <- band b */
+            right = abea_fill_step<FAST, STREAM>(cx, x, kp, P, Q, sm, right, lane, io.stalled); /* Q <- band b */
             if (cx.b >= cx.NB) break;
-            right = abea_fill_step<FAST>(cx, x, kp, Q, P, sm, right, lane); /* P <- band b */
+            right = abea_fill_step<FAST, STREAM>(cx, x, kp, Q, P, sm, right, lane, io.stalled); /* P <- band b */
         }
         abea_cp_async_wait_all(); /* nothing may still be landing in the ring when the next read reuses it */
 
@@ -984,12 +1054,12 @@ __device__ __forceinline__ void abea_wide_stage(abea_wide_smem_t* sm, const abea
     }
 }
 
-template <bool FAST>
+template <bool FAST, bool STREAM>
 __global__ void __launch_bounds__(32 * ABEA_WIDE_WARPS)
 abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, const abea_event_t* __restrict__ events,
                       const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                       uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
-                      abea_stream_t io, int64_t total_event_bytes, abea_consts_t cst, int32_t* __restrict__ queue) {
+                      abea_stream_t io, abea_consts_t cst, int32_t* __restrict__ queue) {
     __shared__ __align__(16) abea_wide_smem_t sm;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -1006,7 +1076,11 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
         const int32_t ridx = sm.ridx;
         if (ridx >= n_wide) break;
         const abea_read_t rd = reads[ridx];
-        abea_wait_landed(io.ready, ridx, rd, total_event_bytes); /* streaming: the read's events */
+        /* streaming: start when the first three chunks of the ring (events 0..191) have landed, then chase the loader */
+        int32_t ev_landed = 0x7fffffff;
+        if (STREAM)
+            ev_landed = abea_wait_landed_events(io.ready + (int64_t)ABEA_READY_WORDS * ridx,
+                                                rd.n_events > 3 * ABEA_WCHUNK ? 3 * ABEA_WCHUNK - 1 : rd.n_events - 1, io.stalled);
         __syncthreads();
         if (((abea_ld_acquire_u32(read_flags + ridx) & ABEA_READ_FAST) != 0u) != FAST) continue;
 
@@ -1079,7 +1153,13 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                 if (need_e || need_k) {
                     abea_cp_async_wait_all();
                     __syncthreads();
-                    if (need_e) { echunk_hi += 1; abea_wide_stage(&sm, ev, kpr, echunk_hi, -1, E, K, tid); }
+                    if (need_e) {
+                        echunk_hi += 1;
+                        const int32_t last = (echunk_hi * ABEA_WCHUNK + ABEA_WCHUNK - 1 < E) ? echunk_hi * ABEA_WCHUNK + ABEA_WCHUNK - 1 : E - 1;
+                        if (STREAM && last >= ev_landed) /* not every warp need take this path (each polls for itself) */
+                            ev_landed = abea_wait_landed_events(io.ready + (int64_t)ABEA_READY_WORDS * ridx, last, io.stalled);
+                        abea_wide_stage(&sm, ev, kpr, echunk_hi, -1, E, K, tid);
+                    }
                     if (need_k) { kchunk_hi += 1; abea_wide_stage(&sm, ev, kpr, -1, kchunk_hi, E, K, tid); }
                 }
             }

@@ -29,6 +29,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ static
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
@@ -142,6 +143,8 @@ static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline unsigned atomicAnd(unsigned* p, unsigned v) { unsigned o = *p; *p = o & v; return o; }
 static inline int atomicOr(int* p, int v) { int o = *p; *p = o | v; return o; }
+static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p = o | v; return o; }
 static inline int atomicExch(int* p, int v) { int o = *p; *p = v; return o; }
 
 /* ---- the slice of the CUDA runtime the host code uses ------------------------------------------------------- */
