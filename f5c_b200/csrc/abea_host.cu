@@ -85,13 +85,14 @@ struct abea_ctx {
     cudaStream_t wide_stream = nullptr; /* the wide fill runs beside the narrow one */
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int wide_mode = 1;                /* ABEA_WIDE=0 disables the wide kernel */
-    double wide_alpha = 1.0;          /* ABEA_WIDE_ALPHA scales the wide/narrow threshold */
+    double wide_alpha = 0.8;          /* ABEA_WIDE_ALPHA scales the wide/narrow threshold (sweeps in profiles/) */
     int wide_cap = 0;                 /* ABEA_WIDE_CAP: most reads (= SMs) given to the wide kernel; default sm_count/4 */
     double wide_min_bands = 1024.0;   /* ABEA_WIDE_MIN_BANDS: reads shorter than this are never wide */
     int fill_ctas_per_sm = 1;  /* persistent narrow grid = sm_count * this (ABEA_FILL_CTAS_PER_SM) */
     int fill_warps_per_cta = 12; /* 4 primary + 8 secondary warps (ABEA_FILL_WARPS_PER_CTA, multiple of 4, <= 16; 12 measured best) */
     double long_alpha = 0.8;   /* ABEA_LONG_ALPHA: a read is "long" (runs alone on its sub-partition) above this share of the batch time */
     int trace_ctas_per_sm = 4; /* ABEA_TRACE_CTAS_PER_SM */
+    int sched_policy = 1;      /* ABEA_SCHED: 0 two-ended queue (secondary warps shortest-first), 1 longest-first for every warp */
 
     /* streaming (abea_align_batch with pinned host buffers): events pulled over PCIe by abea_load_kernel in the order
      * the fill asks for them, pair lists written to the caller's mapped buffer by the traceback */
@@ -230,7 +231,7 @@ void build_load_order(abea_ctx* c) {
             r = w++;
         } else {
             if (h > t) continue;
-            r = (sl.second == 1) ? h++ : t--;
+            r = (sl.second == 1 || c->sched_policy == 1) ? h++ : t--;
         }
         const abea_read_t& rd = c->reads[r];
         const double nb = (double)rd.n_events + rd.n_kmers + 2;
@@ -325,6 +326,7 @@ int abea_create(abea_ctx_t** out, int device) {
     if (const char* e = getenv("ABEA_FILL_WARPS_PER_CTA")) c->fill_warps_per_cta = std::min(16, std::max(4, atoi(e) / 4 * 4));
     if (const char* e = getenv("ABEA_LONG_ALPHA")) c->long_alpha = atof(e);
     if (const char* e = getenv("ABEA_TRACE_CTAS_PER_SM")) c->trace_ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("ABEA_SCHED")) c->sched_policy = atoi(e) ? 1 : 0;
     if (const char* e = getenv("ABEA_STREAM")) c->stream_mode = atoi(e);
     if (const char* e = getenv("ABEA_LOAD_CTAS")) c->load_ctas = std::max(1, atoi(e));
     if (cudaStreamCreateWithFlags(&c->load_stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -660,11 +662,11 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                 ABEA_LAUNCH_SMEM(fill_fast, blocks, 32 * wpc, smem, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, io, c->cst, queue, nw, long_thr);
+                    (abea_result_t*)c->d_results.p, io, c->cst, queue, nw, long_thr, c->sched_policy);
                 ABEA_LAUNCH_SMEM(fill_exact, blocks, 32 * wpc, smem, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
-                    (abea_result_t*)c->d_results.p, io, c->cst, queue + 8, nw, long_thr);
+                    (abea_result_t*)c->d_results.p, io, c->cst, queue + 8, nw, long_thr, c->sched_policy);
                 launches += 2;
             }
             if (nw > 0) CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));

@@ -131,12 +131,14 @@ __device__ __forceinline__ void abea_cell(float lp, float up, float left, float 
  * -0.918938f - level_log_stdv, RN(1/level_stdv)} for k-mer i of each read (the reference builds this cache with ONE
  * thread per read, src/align.cu:203-209); (2) range validation of every value the fast arithmetic of the fill
  * kernel touches — a read keeps ABEA_READ_FAST in read_flags only if all of its event means and scaled level means
- * are 0 or within [2^-6, 2^16] in magnitude and all stdv are within [2^-6, 2^12] with a mantissa that is not all
+ * are 0 or within [2^-60, 2^16] in magnitude (so that x - mean is 0 or at least 2^-83: every intermediate of the
+ * quotient correction stays exactly representable; tools/validate_fast_arith.c checks the whole admitted range against
+ * the plain IEEE expressions) and all stdv are within [2^-6, 2^12] with a mantissa that is not all
  * ones (the one case Markstein's quotient correction excludes). read_flags must be pre-set to ABEA_READ_FAST.     */
 
 __device__ __forceinline__ bool abea_sane_level(float v) {
     float a = fabsf(v);
-    return (a == 0.0f) || (a >= 0.015625f && a <= 65536.0f); /* NaN fails both */
+    return (a == 0.0f) || (a >= 8.6736174e-19f /* 2^-60 */ && a <= 65536.0f); /* NaN fails both */
 }
 __device__ __forceinline__ bool abea_sane_stdv(float v) {
     return (v >= 0.015625f) && (v <= 4096.0f) && ((__float_as_uint(v) & 0x007fffffu) != 0x007fffffu);
@@ -865,7 +867,7 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
                  const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                  uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
                  abea_stream_t io, abea_consts_t cst, int32_t* __restrict__ queue,
-                 int32_t first, int32_t long_thr) {
+                 int32_t first, int32_t long_thr, int32_t policy) {
     /* dynamic shared memory: per warp one abea_fill_smem_t and one 4-KB traceback ring */
 #ifdef ABEA_SIMT_EMU
     unsigned char* dyn = (unsigned char*)simt::g_dynsmem;
@@ -882,7 +884,19 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
                         (size_t)wid * (ABEA_TB_RING_GROUPS * ABEA_TRACE_GROUP_WORDS);
     const bool primary = wid < 4;
     const int slot = wid & 3;
-    if (threadIdx.x < 4) long_flag[threadIdx.x] = 0;
+    /* policy 1 (longest-first for every warp): the first reads of the primary warps are assigned statically — the
+     * longest reads, spread over the SMs — and every sub-partition knows from the start whether its primary has a long
+     * one, so that no secondary warp starts beside a long read before its primary has had the time to say so */
+    const int32_t n_pri = 4 * (int32_t)gridDim.x;
+    bool first_pull = (policy == 1) && primary;
+    if (threadIdx.x < 4) {
+        int flag = 0;
+        if (policy == 1) {
+            const int32_t r = first + (int32_t)threadIdx.x * (int32_t)gridDim.x + (int32_t)blockIdx.x;
+            if (r < n_reads) flag = (reads[r].n_events + reads[r].n_kmers + 2 > long_thr) ? 1 : 0;
+        }
+        long_flag[threadIdx.x] = flag;
+    }
     __syncthreads();
     const double NEG = abea_neg_inf_d();
 
@@ -896,12 +910,20 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
             }
         }
         int32_t ridx = n_reads;
-        if (lane == 0) { /* reads [0, first) are filled by the wide kernel */
-            if (first + atomicAdd(queue, 1) < n_reads)
-                ridx = primary ? first + atomicAdd(queue + 1, 1) : n_reads - 1 - atomicAdd(queue + 2, 1);
+        if (first_pull) {
+            first_pull = false;
+            ridx = first + slot * (int32_t)gridDim.x + (int32_t)blockIdx.x;
+        } else {
+            if (lane == 0) { /* reads [0, first) are filled by the wide kernel */
+                if (policy == 1) {
+                    ridx = first + n_pri + atomicAdd(queue + 1, 1);
+                } else if (first + atomicAdd(queue, 1) < n_reads) {
+                    ridx = primary ? first + atomicAdd(queue + 1, 1) : n_reads - 1 - atomicAdd(queue + 2, 1);
+                }
+            }
+            ridx = __shfl_sync(ABEA_FULL, ridx, 0);
         }
-        ridx = __shfl_sync(ABEA_FULL, ridx, 0);
-        if (ridx >= n_reads) break;
+        if (ridx >= n_reads || ridx < 0) break;
         const abea_read_t rd = reads[ridx];
         /* streaming: the read starts as soon as its first events (0..95: the first window and two chunks of the
          * ring) have landed, and from there chases the loader piece by piece (abea_fill_step) */
@@ -919,7 +941,10 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
          * bit of a read when an out-of-range event mean passes through it, always BEFORE it publishes that piece; a
          * read whose bit is cleared after this test is filled here in vain and again, last, by the EXACT instantiation
          * (which runs after this kernel and overwrites every result of the read). */
-        if (((abea_ld_acquire_u32(read_flags + ridx) & ABEA_READ_FAST) != 0u) != FAST) continue;
+        if (((abea_ld_acquire_u32(read_flags + ridx) & ABEA_READ_FAST) != 0u) != FAST) {
+            if (primary && lane == 0) atomicExch(&long_flag[slot], 0);
+            continue;
+        }
 
         if (primary && lane == 0) atomicExch(&long_flag[slot], (rd.n_events + rd.n_kmers + 2 > long_thr) ? 1 : 0);
         const long long t_start = abea_clock();

@@ -19,7 +19,8 @@ def edge_batch(model="r9", seed=9):
     seqs[5] = seqs[5][:30]; evs[5] = evs[5][:40]                  # tiny
     seqs[6] = seqs[6][: k + 1]; evs[6] = evs[6][:5]               # two k-mers
     evs[7] = evs[7][: len(evs[7]) // 3]                           # truncated events -> cannot span / odd band path
-    evs[0]["mean"][7] = 1e-4                                      # outside the fast-arithmetic range -> EXACT kernel
+    evs[0]["mean"][7] = 1e-30                                     # outside the fast-arithmetic range -> EXACT kernel
+    evs[7]["mean"][3] = 1e-4                                      # tiny but inside it (>= 2^-60): stays FAST
     evs[2]["mean"][11] = 3e7                                      # ditto (absurd outlier event)
     good = np.ones(b.n_reads, dtype=np.uint8)
     good[4] = 0                                                   # bad read

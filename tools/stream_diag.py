@@ -49,4 +49,8 @@ for mode in modes:
             print("  ranks %4d-%4d: start ms min/med/max %6.2f %6.2f %6.2f | end max %6.2f | cyc/band med %5.0f | trace cyc/step med %4.0f" %
                   (lo, hi, rel[seg].min(), np.median(rel[seg]), rel[seg].max(), (rel[seg] + dur[seg]).max(),
                    np.median(fpb[seg]), np.median(cyc["trace_cycles"][seg] / np.maximum(1, r.n_pairs[seg]))), flush=True)
+    late = [i for i in range(min(200, len(el))) if rel[el[i]] > 1.0]
+    if late:
+        print("  late starters among the 200 longest (rank, bands, start ms, dur ms, cyc/band, wide):",
+              [(i, int(b.n_bands[el[i]]), round(float(rel[el[i]]), 2), round(float(dur[el[i]]), 2), int(fpb[el[i]]), int(cyc["wide"][el[i]])) for i in late][:12])
     ctx.close()
