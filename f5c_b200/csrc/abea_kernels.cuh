@@ -1048,6 +1048,42 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
  * Warps exchange their two boundary cells and the two cells of Suzuki's rule through shared memory, one
  * __syncthreads per band, double-buffered by band parity. Arithmetic is the same templates as the narrow kernel.   */
 
+/* Split-phase CTA barrier (mbarrier in shared memory): a warp ARRIVES as soon as its boundary cells of the band are
+ * published and WAITS only when it needs the other warps' cells at the top of the next band; everything in between
+ * (next band's speculative emissions, shuffles, trace bookkeeping) overlaps the other warps' arrival. One arrival per
+ * warp. The CPU emulator, which runs the warps of a block in lock-step, turns the wait into a plain block barrier. */
+__device__ __forceinline__ void abea_mbar_init(uint64_t* bar, unsigned count) {
+#ifndef ABEA_SIMT_EMU
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+#else
+    (void)bar; (void)count;
+#endif
+}
+__device__ __forceinline__ void abea_mbar_arrive(uint64_t* bar) {
+#ifndef ABEA_SIMT_EMU
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(a) : "memory");
+#else
+    (void)bar;
+#endif
+}
+__device__ __forceinline__ void abea_mbar_wait(uint64_t* bar, unsigned parity) {
+#ifndef ABEA_SIMT_EMU
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "ABEA_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra ABEA_MBAR_DONE;\n\t"
+        "bra ABEA_MBAR_WAIT;\n"
+        "ABEA_MBAR_DONE:\n\t}" ::"r"(a), "r"(parity) : "memory");
+#else
+    (void)bar; (void)parity;
+    __syncthreads();
+#endif
+}
+
 #define ABEA_WIDE_WARPS 4
 #define ABEA_WIDE_SPAN 28   /* offsets per warp */
 #define ABEA_WRING 256      /* ring entries (window of 100 + chunks in flight) */
@@ -1060,6 +1096,7 @@ struct abea_wide_smem_t {
     double red_s[ABEA_WIDE_WARPS];
     int32_t red_e[ABEA_WIDE_WARPS];
     int32_t ridx;
+    uint64_t bar; /* the per-band split-phase barrier */
 };
 
 __device__ __forceinline__ void abea_wide_stage(abea_wide_smem_t* sm, const abea_event_t* __restrict__ ev,
@@ -1093,6 +1130,8 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
     const bool active = (lane < ABEA_WIDE_SPAN) && (o < ABEA_W);
     const int last_lane = (w == ABEA_WIDE_WARPS - 1) ? (ABEA_W - 1 - ABEA_WIDE_SPAN * (ABEA_WIDE_WARPS - 1)) : (ABEA_WIDE_SPAN - 1);
     const double NEG = abea_neg_inf_d();
+    if (tid == 0) abea_mbar_init(&sm.bar, ABEA_WIDE_WARPS);
+    unsigned bar_parity = 0; /* parity of the barrier phase the next wait is for */
 
     for (;;) {
         __syncthreads();
@@ -1126,6 +1165,7 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
         if (tid < 2 * ABEA_WIDE_WARPS) sm.edge[1][tid >> 1][tid & 1] = NEG; /* band 1's boundary cells are all -inf */
         abea_cp_async_wait_all();
         __syncthreads();
+        if (lane == 0) abea_mbar_arrive(&sm.bar); /* "band 1 is published": the loop's first wait falls through */
         abea_wide_stage(&sm, ev, kpr, 2, 2, E, K, tid); /* in flight while chunks 0 and 1 are consumed */
         int32_t echunk_hi = 2, kchunk_hi = 2;           /* highest chunk staged; it may still be in flight */
 
@@ -1159,7 +1199,9 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
         double lpd_dn = (double)abea_emission_t<FAST>(x_dn, kp_cur);
 
         for (int32_t b = 2; b < NB; b++) {
-            /* ---- band b-1 is complete and published: halos across warp boundaries and this band's move ---- */
+            /* ---- wait until every warp has published band b-1, then: halos across warp boundaries, this band's move ---- */
+            abea_mbar_wait(&sm.bar, bar_parity);
+            bar_parity ^= 1u;
             const int pp = (b - 1) & 1;
             if (lane == 0) lo1 = (w > 0) ? sm.edge[pp][w - 1][1] : NEG;
             if (lane >= last_lane) hi1 = (w < ABEA_WIDE_WARPS - 1 && lane == last_lane) ? sm.edge[pp][w + 1][0] : NEG;
@@ -1249,6 +1291,8 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
             const int par = b & 1;
             if (lane == 0) sm.edge[par][w][0] = Rn;
             if (lane == last_lane) sm.edge[par][w][1] = Rn;
+            __syncwarp(); /* orders the other lane's store before lane 0's arrival */
+            if (lane == 0) abea_mbar_arrive(&sm.bar);
             lo2 = lo1; hi2 = hi1;
             lo1 = __shfl_up_sync(ABEA_FULL, Rn, 1);
             hi1 = __shfl_down_sync(ABEA_FULL, Rn, 1);
@@ -1273,9 +1317,11 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                 if (w == 3 && lane >= 28) line[ABEA_LANES + (lane - 28)] = (uint32_t)eb_keep;
                 acc = 0u;
             }
-            __syncthreads();
         }
+        abea_mbar_wait(&sm.bar, bar_parity); /* the last band's arrivals: every arrival is matched by a wait */
+        bar_parity ^= 1u;
         abea_cp_async_wait_all();
+        __syncthreads(); /* the trace lines of the whole read are written before warp 0 walks them */
 
         /* best end cell over the CTA: max score, ties to the smaller event */
 #pragma unroll
