@@ -428,9 +428,8 @@ __device__ __forceinline__ float abea_emission_t(float x, const float4& kp) {
 /* One DP cell on float-valued doubles (reference src/align.c:378-392): the three sums are formed in double,
  * each rounded once to float precision, then compared with ties L > U > D. */
 template <bool FAST>
-__device__ __forceinline__ void abea_cell_d(float lp, double up, double left, double diag, double lp_step,
-                                            double lp_stay, double lp_skip, double& score, uint32_t& from) {
-    double lpd = (double)lp;
+__device__ __forceinline__ void abea_cell_dd(double lpd, double up, double left, double diag, double lp_step,
+                                             double lp_stay, double lp_skip, double& score, uint32_t& from) {
     double rd = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(diag, lp_step), lpd), diag);
     double ru = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(up, lp_stay), lpd), up);
     double rl = abea_round_f32<FAST>(__dadd_rn(left, lp_skip), left);
@@ -439,6 +438,11 @@ __device__ __forceinline__ void abea_cell_d(float lp, double up, double left, do
     bool isL = rl >= m;
     score = isL ? rl : m;
     from = isL ? ABEA_FROM_L : (isU ? ABEA_FROM_U : ABEA_FROM_D);
+}
+template <bool FAST>
+__device__ __forceinline__ void abea_cell_d(float lp, double up, double left, double diag, double lp_step,
+                                            double lp_stay, double lp_skip, double& score, uint32_t& from) {
+    abea_cell_dd<FAST>((double)lp, up, left, diag, lp_step, lp_stay, lp_skip, score, from);
 }
 
 /* cp.async helpers (LDGSTS on sm_100a); the CPU emulator copies synchronously */
@@ -1060,6 +1064,14 @@ __device__ __forceinline__ void abea_mbar_init(uint64_t* bar, unsigned count) {
     (void)bar; (void)count;
 #endif
 }
+__device__ __forceinline__ void abea_mbar_inval(uint64_t* bar) {
+#ifndef ABEA_SIMT_EMU
+    unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+#else
+    (void)bar;
+#endif
+}
 __device__ __forceinline__ void abea_mbar_arrive(uint64_t* bar) {
 #ifndef ABEA_SIMT_EMU
     unsigned a = (unsigned)__cvta_generic_to_shared(bar);
@@ -1088,11 +1100,13 @@ __device__ __forceinline__ void abea_mbar_wait(uint64_t* bar, unsigned parity) {
 #define ABEA_WIDE_SPAN 28   /* offsets per warp */
 #define ABEA_WRING 256      /* ring entries (window of 100 + chunks in flight) */
 #define ABEA_WCHUNK 64
+#define ABEA_WBAND 120      /* entries of a published band: [0] = offset -1 (-inf), [1..100] = the cells, [101] = offset 100 (-inf),
+                             * the rest is only ever read by lanes that own no cell */
 
 struct abea_wide_smem_t {
     float ev[ABEA_WRING];
     float4 kp[ABEA_WRING];
-    double edge[2][ABEA_WIDE_WARPS][2]; /* [band parity][warp][0 = first cell, 1 = last cell] */
+    double band[2][ABEA_WBAND]; /* [band parity][1 + offset]: the scores of bands b-1 and b, read by every lane's neighbours */
     double red_s[ABEA_WIDE_WARPS];
     int32_t red_e[ABEA_WIDE_WARPS];
     int32_t ridx;
@@ -1116,6 +1130,162 @@ __device__ __forceinline__ void abea_wide_stage(abea_wide_smem_t* sm, const abea
     }
 }
 
+/* A lane's view of one band: its own cell and the cells at offset-1 / offset+1 (read from the published band). */
+struct abea_wband_t {
+    double R, lo, hi;
+};
+
+/* Per-read state of a wide lane. Everything but the scores, the window values and the trace bits is CTA-uniform. */
+struct abea_wide_ctx_t {
+    const abea_event_t* ev;
+    const float4* kpr;
+    uint32_t* tr;
+    const uint32_t* ready_w; /* streaming: the read's words of d_ready */
+    uint32_t* stalled;
+    double lp_stay, lp_step, lp_skip, lp_trim;
+    int32_t E, K, NB;
+    int32_t eb, kb;          /* lower-left of the current band */
+    int32_t b;               /* band being filled */
+    int32_t safe;            /* further bands guaranteed to be interior */
+    int32_t e_cnt, k_cnt;    /* down / right moves until the chunk in flight is entered (land it, stage the next) */
+    int32_t echunk_hi, kchunk_hi; /* highest chunk staged; it may still be in flight */
+    int32_t ev_landed;       /* streaming: leading events of the read known to be in d_events */
+    uint32_t acc;            /* this lane's trace bits of the current 4-band group */
+    int32_t eb_keep;         /* warp 3, lanes 28..31: event index of the group's bands */
+    double best_s;           /* best end cell seen by this lane */
+    int32_t best_e;
+    /* the lane's event / k-mer of band b-1 and, speculatively, what it would hold after either move: a right move keeps
+     * the event and takes k-mer kb+1+o, a down move keeps the k-mer and takes event eb+1-o */
+    float x_cur, x_dn;
+    float4 kp_cur, kp_rt;
+    double lpd_rt, lpd_dn;   /* emission of the lane's cell of the next band after a right / down move */
+    bool prev_right;
+};
+
+/* One band of the wide fill for band index b with b % 4 == Q. A holds band b-1 (its R in a register since the last
+ * step, its neighbours read here from the published copy), B holds band b-2 and receives band b. */
+template <bool FAST, bool STREAM, int Q>
+__device__ __forceinline__ void abea_wide_step(abea_wide_ctx_t& cx, abea_wide_smem_t& sm, abea_wband_t& A, abea_wband_t& B,
+                                               const int tid, const int o, const int oa, const bool active,
+                                               const uint32_t sh0) {
+    const double NEG = abea_neg_inf_d();
+    constexpr int PAR = Q & 1;      /* parity of band b: where it is published, and the phase parity of "b-1 is published" */
+    constexpr int PP = PAR ^ 1;     /* parity of band b-1 */
+    /* ---- wait until every warp has published band b-1, then: neighbours, the two corner cells, this band's move ---- */
+    abea_mbar_wait(&sm.bar, PAR);
+    const double* bp = sm.band[PP];
+    A.lo = bp[o];
+    A.hi = bp[o + 2];
+    const double ll = bp[1], ur = bp[ABEA_W];
+    /* src/align.c:304-314: both corners -inf -> right iff b is odd, else right iff ll < ur. With both at -inf the
+     * comparison is false, so for an even band it alone decides; for an odd one the two -inf tests are integer compares of
+     * the high words (a band score is never NaN), off the FP64 pipe and in parallel with the comparison */
+    bool right = ll < ur;
+    if (PAR == 1) right = right || ((__double2hiint(ll) == (int)0xfff00000) && (__double2hiint(ur) == (int)0xfff00000));
+
+    /* ---- the cell (same arithmetic templates as the narrow kernel), specialised by (this move, previous move) ---- */
+    double Rn;
+    uint32_t fr;
+    if (right) {
+        cx.kb += 1;
+        cx.kp_cur = cx.kp_rt;
+        /* keep the rings ahead of what the next band may touch (event eb+1, k-mer kb+100): when that index is the first
+         * of the chunk in flight, land it and start the next one. Chunk c+1 reuses the ring slots of chunk c-3, which
+         * left the 100-wide window long before. */
+        if (--cx.k_cnt == 0) {
+            cx.k_cnt = ABEA_WCHUNK;
+            abea_cp_async_wait_all();
+            __syncthreads();
+            cx.kchunk_hi += 1;
+            abea_wide_stage(&sm, cx.ev, cx.kpr, -1, cx.kchunk_hi, cx.E, cx.K, tid);
+        }
+        if (cx.prev_right) abea_cell_dd<FAST>(cx.lpd_rt, A.hi, A.R, B.hi, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+        else abea_cell_dd<FAST>(cx.lpd_rt, A.hi, A.R, B.R, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+    } else {
+        cx.eb += 1;
+        cx.x_cur = cx.x_dn;
+        if (--cx.e_cnt == 0) {
+            cx.e_cnt = ABEA_WCHUNK;
+            abea_cp_async_wait_all();
+            __syncthreads();
+            cx.echunk_hi += 1;
+            if (STREAM) { /* the chunk about to be staged may not have crossed PCIe yet */
+                const int32_t last = (cx.echunk_hi * ABEA_WCHUNK + ABEA_WCHUNK - 1 < cx.E) ? cx.echunk_hi * ABEA_WCHUNK + ABEA_WCHUNK - 1 : cx.E - 1;
+                if (last >= cx.ev_landed) cx.ev_landed = abea_wait_landed_events(cx.ready_w, last, cx.stalled);
+            }
+            abea_wide_stage(&sm, cx.ev, cx.kpr, cx.echunk_hi, -1, cx.E, cx.K, tid);
+        }
+        if (cx.prev_right) abea_cell_dd<FAST>(cx.lpd_dn, A.R, A.lo, B.R, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+        else abea_cell_dd<FAST>(cx.lpd_dn, A.R, A.lo, B.lo, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+    }
+    cx.prev_right = right;
+
+    /* ---- band edges (validity window, trim column, end column); interior bands skip this ---- */
+    if (cx.safe > 0) {
+        cx.safe -= 1;
+    } else {
+        const int32_t kb = cx.kb, eb = cx.eb, E = cx.E, K = cx.K;
+        const bool interior = (kb >= 0) && (kb + ABEA_W < K) && (eb >= ABEA_W - 1) && (eb <= E - 1);
+        if (interior) {
+            int32_t s1 = K - ABEA_W - 1 - kb, s2 = E - 1 - eb;
+            cx.safe = s1 < s2 ? s1 : s2;
+        } else {
+            int32_t lo = -kb;
+            if (eb - (E - 1) > lo) lo = eb - (E - 1);
+            if (lo < 0) lo = 0;
+            int32_t hi = K - kb;
+            if (eb + 1 < hi) hi = eb + 1;
+            if (hi > ABEA_W) hi = ABEA_W;
+            const int32_t to = -1 - kb;
+            const int32_t te = eb - to;
+            const bool trim_in = (to >= 0) && (to < ABEA_W) && (te >= 0) && (te < E);
+            const double trim_s = (double)__double2float_rn(__dmul_rn(cx.lp_trim, (double)(te + 1)));
+            const int32_t oe = (K - 1) - kb;
+            const bool valid = active && (o >= lo) && (o < hi);
+            Rn = valid ? Rn : NEG;
+            fr = valid ? fr : 0u;
+            if (active && o == to && trim_in) {
+                Rn = trim_s;
+                fr = ABEA_FROM_U;
+            }
+            if (o == oe && valid) {
+                const int32_t e = eb - o;
+                double s = (double)__double2float_rn(__dadd_rn(Rn, __dmul_rn((double)(E - e), cx.lp_trim)));
+                if (s > cx.best_s) {
+                    cx.best_s = s;
+                    cx.best_e = e;
+                }
+            }
+        }
+    }
+
+    /* ---- publish the band; everything below is independent of the other warps and overlaps their arrival ---- */
+    if (active) sm.band[PAR][o + 1] = Rn;
+    __syncwarp(); /* orders the other lanes' stores before lane 0's arrival */
+    if ((tid & 31) == 0) abea_mbar_arrive(&sm.bar);
+    B.R = Rn;
+
+    /* speculative emissions of band b+1 for both moves (lanes past offset 99 read the ring at offset 99 so that they
+     * never touch a chunk that is still in flight) */
+    cx.x_dn = sm.ev[(cx.eb + 1 - oa) & (ABEA_WRING - 1)];
+    cx.kp_rt = sm.kp[(cx.kb + 1 + oa) & (ABEA_WRING - 1)];
+    cx.lpd_rt = (double)abea_emission_t<FAST>(cx.x_cur, cx.kp_rt);
+    cx.lpd_dn = (double)abea_emission_t<FAST>(cx.x_dn, cx.kp_cur);
+
+    /* trace: this lane's 2 bits go to bit 8q + 2(o&3) of word o>>2 of the 128-B line of the 4-band group */
+    cx.acc += (fr << sh0) << (8 * Q);
+    if (tid == 32 * 3 + 28 + Q) cx.eb_keep = cx.eb;
+    if (Q == 3 || cx.b == cx.NB - 1) {
+        uint32_t word = cx.acc | __shfl_xor_sync(ABEA_FULL, cx.acc, 1);
+        word |= __shfl_xor_sync(ABEA_FULL, word, 2);
+        uint32_t* line = cx.tr + (int64_t)(cx.b >> 2) * ABEA_TRACE_GROUP_WORDS;
+        if (active && (tid & 3) == 0) line[o >> 2] = word;
+        if (tid >= 32 * 3 + 28) line[ABEA_LANES + (tid - (32 * 3 + 28))] = (uint32_t)cx.eb_keep;
+        cx.acc = 0u;
+    }
+    cx.b += 1;
+}
+
 template <bool FAST, bool STREAM>
 __global__ void __launch_bounds__(32 * ABEA_WIDE_WARPS)
 abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, const abea_event_t* __restrict__ events,
@@ -1128,202 +1298,109 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
     const int w = tid >> 5;
     const int o = ABEA_WIDE_SPAN * w + lane;                       /* this lane's band offset */
     const bool active = (lane < ABEA_WIDE_SPAN) && (o < ABEA_W);
-    const int last_lane = (w == ABEA_WIDE_WARPS - 1) ? (ABEA_W - 1 - ABEA_WIDE_SPAN * (ABEA_WIDE_WARPS - 1)) : (ABEA_WIDE_SPAN - 1);
+    const int oa = o < ABEA_W ? o : ABEA_W - 1;
+    const uint32_t sh0 = 2u * (uint32_t)(o & 3);
     const double NEG = abea_neg_inf_d();
-    if (tid == 0) abea_mbar_init(&sm.bar, ABEA_WIDE_WARPS);
-    unsigned bar_parity = 0; /* parity of the barrier phase the next wait is for */
+    for (int i = tid; i < 2 * ABEA_WBAND; i += 32 * ABEA_WIDE_WARPS) (&sm.band[0][0])[i] = NEG; /* incl. the -inf sentinels */
+    bool bar_live = false;
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) sm.ridx = atomicAdd(queue, 1);
+        __syncthreads(); /* nobody is still waiting on, or arriving at, the previous read's barrier */
+        if (tid == 0) {
+            sm.ridx = atomicAdd(queue, 1);
+            /* a fresh barrier per read: its phase parity then follows the band index (band b waits for parity b & 1) */
+            if (bar_live) abea_mbar_inval(&sm.bar);
+            abea_mbar_init(&sm.bar, ABEA_WIDE_WARPS);
+            bar_live = true;
+        }
         __syncthreads();
         const int32_t ridx = sm.ridx;
         if (ridx >= n_wide) break;
         const abea_read_t rd = reads[ridx];
+        abea_wide_ctx_t cx;
         /* streaming: start when the first three chunks of the ring (events 0..191) have landed, then chase the loader */
-        int32_t ev_landed = 0x7fffffff;
-        if (STREAM)
-            ev_landed = abea_wait_landed_events(io.ready + (int64_t)ABEA_READY_WORDS * ridx,
-                                                rd.n_events > 3 * ABEA_WCHUNK ? 3 * ABEA_WCHUNK - 1 : rd.n_events - 1, io.stalled);
+        cx.ev_landed = 0x7fffffff;
+        cx.ready_w = nullptr;
+        cx.stalled = io.stalled;
+        if (STREAM) {
+            cx.ready_w = io.ready + (int64_t)ABEA_READY_WORDS * ridx;
+            cx.ev_landed = abea_wait_landed_events(cx.ready_w, rd.n_events > 3 * ABEA_WCHUNK ? 3 * ABEA_WCHUNK - 1 : rd.n_events - 1,
+                                                   io.stalled);
+        }
         __syncthreads();
         if (((abea_ld_acquire_u32(read_flags + ridx) & ABEA_READ_FAST) != 0u) != FAST) continue;
 
         const long long t_start = abea_clock();
         if (tid == 0) results[ridx].start_us = abea_now_us();
-        const int32_t E = rd.n_events, K = rd.n_kmers;
-        const int32_t NB = E + K + 2;
-        const abea_event_t* __restrict__ ev = events + rd.ev_off;
-        const float4* __restrict__ kpr = kparams + rd.kp_off;
-        uint32_t* __restrict__ tr = trace + rd.trace_off;
-        const double lp_stay = rd.lp_stay, lp_step = rd.lp_step, lp_skip = cst.lp_skip, lp_trim = cst.lp_trim;
-
-        int32_t eb = ABEA_W / 2, kb = -1 - ABEA_W / 2; /* band 1 (reference src/align.c:277-279) */
+        cx.E = rd.n_events;
+        cx.K = rd.n_kmers;
+        cx.NB = cx.E + cx.K + 2;
+        cx.ev = events + rd.ev_off;
+        cx.kpr = kparams + rd.kp_off;
+        cx.tr = trace + rd.trace_off;
+        cx.lp_stay = rd.lp_stay;
+        cx.lp_step = rd.lp_step;
+        cx.lp_skip = cst.lp_skip;
+        cx.lp_trim = cst.lp_trim;
+        cx.eb = ABEA_W / 2;          /* band 1 (reference src/align.c:277-279) */
+        cx.kb = -1 - ABEA_W / 2;
+        cx.b = 2;
+        cx.safe = 0;
+        cx.prev_right = false;       /* band 1 was a down move */
+        cx.best_s = NEG;
+        cx.best_e = 0x7fffffff;
         /* stage the chunks covering events [0, eb+64) and k-mers [0, kb+99+64): chunk 0 and 1 of each (indices < 0 are
          * never valid cells; the ring slots they alias hold clamped garbage that the validity mask discards) */
-        abea_wide_stage(&sm, ev, kpr, 0, 0, E, K, tid);
-        abea_wide_stage(&sm, ev, kpr, 1, 1, E, K, tid);
-        if (tid < 2 * ABEA_WIDE_WARPS) sm.edge[1][tid >> 1][tid & 1] = NEG; /* band 1's boundary cells are all -inf */
+        abea_wide_stage(&sm, cx.ev, cx.kpr, 0, 0, cx.E, cx.K, tid);
+        abea_wide_stage(&sm, cx.ev, cx.kpr, 1, 1, cx.E, cx.K, tid);
+        /* band 1 as published: -inf but for the trim cell at offset 50 (src/align.c:290) */
+        const double R1 = (o == ABEA_W / 2) ? (double)__double2float_rn(cx.lp_trim) : NEG;
+        if (active) sm.band[1][o + 1] = R1;
         abea_cp_async_wait_all();
         __syncthreads();
-        if (lane == 0) abea_mbar_arrive(&sm.bar); /* "band 1 is published": the loop's first wait falls through */
-        abea_wide_stage(&sm, ev, kpr, 2, 2, E, K, tid); /* in flight while chunks 0 and 1 are consumed */
-        int32_t echunk_hi = 2, kchunk_hi = 2;           /* highest chunk staged; it may still be in flight */
+        if (lane == 0) abea_mbar_arrive(&sm.bar); /* "band 1 is published": the first wait (band 2, parity 0) falls through */
+        abea_wide_stage(&sm, cx.ev, cx.kpr, 2, 2, cx.E, cx.K, tid); /* in flight while chunks 0 and 1 are consumed */
+        cx.echunk_hi = 2;
+        cx.kchunk_hi = 2;
+        /* event eb+1 / k-mer kb+100 first enter the chunk in flight (chunk 2) at index 128 */
+        cx.e_cnt = 2 * ABEA_WCHUNK - (cx.eb + 1);
+        cx.k_cnt = 2 * ABEA_WCHUNK - (cx.kb + ABEA_W);
 
-        double R1 = (o == ABEA_W / 2) ? (double)__double2float_rn(lp_trim) : NEG; /* band 1, src/align.c:290 */
-        double R2 = (o == ABEA_W / 2) ? 0.0 : NEG;                                 /* band 0, src/align.c:284 */
-        if (!active) { R1 = NEG; R2 = NEG; }
-        /* neighbour cells inside the warp; the two warp-boundary lanes are patched from shared memory each band.
-         * The only finite cells of bands 0 and 1 sit at offset 50 = warp 1 lane 22: no warp boundary is involved. */
-        double lo1 = __shfl_up_sync(ABEA_FULL, R1, 1), hi1 = __shfl_down_sync(ABEA_FULL, R1, 1);
-        double lo2 = __shfl_up_sync(ABEA_FULL, R2, 1), hi2 = __shfl_down_sync(ABEA_FULL, R2, 1);
-        if (lane == 0) lo2 = NEG;
-        if (lane >= last_lane) hi2 = NEG;
+        abea_wband_t P, Qb; /* P = band 1, Qb = band 0 (0 at offset 50, src/align.c:284); P's neighbours are read in step 2 */
+        P.R = active ? R1 : NEG;
+        P.lo = P.hi = NEG;
+        Qb.R = (o == ABEA_W / 2) ? 0.0 : NEG;
+        Qb.lo = (o - 1 == ABEA_W / 2) ? 0.0 : NEG;
+        Qb.hi = (o + 1 == ABEA_W / 2) ? 0.0 : NEG;
 
-        uint32_t acc = (o == ABEA_W / 2) ? (ABEA_FROM_U << (8 + 2 * (o & 3))) : 0u; /* band 1's trim cell */
-        int32_t eb_keep = (w == 3 && lane == 28) ? (ABEA_W / 2 - 1) : ((w == 3 && lane == 29) ? ABEA_W / 2 : 0);
-        double best_s = NEG;
-        int32_t best_e = 0x7fffffff;
-        bool prev_right = false; /* band 1 was a down move */
-        int32_t safe = 0;
+        cx.acc = (o == ABEA_W / 2) ? (ABEA_FROM_U << (8 + 2 * (o & 3))) : 0u; /* band 1's trim cell */
+        cx.eb_keep = (tid == 32 * 3 + 28) ? (ABEA_W / 2 - 1) : ((tid == 32 * 3 + 29) ? ABEA_W / 2 : 0);
 
-        /* the lane's event / k-mer of band b-1 and, speculatively, what it would hold after either move:
-         * a right move keeps the event and takes k-mer kb+1+o, a down move keeps the k-mer and takes event eb+1-o */
-        /* lanes past offset 99 hold no cell: they read the ring at offset 99 so that they never touch a chunk that is
-         * still in flight */
-        const int oa = o < ABEA_W ? o : ABEA_W - 1;
-        float x_cur = sm.ev[(eb - oa) & (ABEA_WRING - 1)];
-        float4 kp_cur = sm.kp[(kb + oa) & (ABEA_WRING - 1)];
-        float x_dn = sm.ev[(eb + 1 - oa) & (ABEA_WRING - 1)];
-        float4 kp_rt = sm.kp[(kb + 1 + oa) & (ABEA_WRING - 1)];
-        double lpd_rt = (double)abea_emission_t<FAST>(x_cur, kp_rt);
-        double lpd_dn = (double)abea_emission_t<FAST>(x_dn, kp_cur);
+        cx.x_cur = sm.ev[(cx.eb - oa) & (ABEA_WRING - 1)];
+        cx.kp_cur = sm.kp[(cx.kb + oa) & (ABEA_WRING - 1)];
+        cx.x_dn = sm.ev[(cx.eb + 1 - oa) & (ABEA_WRING - 1)];
+        cx.kp_rt = sm.kp[(cx.kb + 1 + oa) & (ABEA_WRING - 1)];
+        cx.lpd_rt = (double)abea_emission_t<FAST>(cx.x_cur, cx.kp_rt);
+        cx.lpd_dn = (double)abea_emission_t<FAST>(cx.x_dn, cx.kp_cur);
 
-        for (int32_t b = 2; b < NB; b++) {
-            /* ---- wait until every warp has published band b-1, then: halos across warp boundaries, this band's move ---- */
-            abea_mbar_wait(&sm.bar, bar_parity);
-            bar_parity ^= 1u;
-            const int pp = (b - 1) & 1;
-            if (lane == 0) lo1 = (w > 0) ? sm.edge[pp][w - 1][1] : NEG;
-            if (lane >= last_lane) hi1 = (w < ABEA_WIDE_WARPS - 1 && lane == last_lane) ? sm.edge[pp][w + 1][0] : NEG;
-            const double ll = sm.edge[pp][0][0], ur = sm.edge[pp][ABEA_WIDE_WARPS - 1][1];
-            const bool right = (ll == NEG && ur == NEG) ? ((b & 1) == 1) : (ll < ur); /* src/align.c:304-314 */
-            double lpd;
-            if (right) { kb += 1; kp_cur = kp_rt; lpd = lpd_rt; }
-            else { eb += 1; x_cur = x_dn; lpd = lpd_dn; }
-
-            /* keep the rings ahead of what the next band may touch (event eb+1, k-mer kb+100): when that index is the
-             * first of the chunk in flight, land it and start the next one. Chunk c+1 reuses the ring slots of chunk
-             * c-3, which left the 100-wide window long before. */
-            {
-                const bool need_e = (((eb + 1) & (ABEA_WCHUNK - 1)) == 0) && (((eb + 1) >> 6) == echunk_hi);
-                const bool need_k = (((kb + ABEA_W) & (ABEA_WCHUNK - 1)) == 0) && (((kb + ABEA_W) >> 6) == kchunk_hi);
-                if (need_e || need_k) {
-                    abea_cp_async_wait_all();
-                    __syncthreads();
-                    if (need_e) {
-                        echunk_hi += 1;
-                        const int32_t last = (echunk_hi * ABEA_WCHUNK + ABEA_WCHUNK - 1 < E) ? echunk_hi * ABEA_WCHUNK + ABEA_WCHUNK - 1 : E - 1;
-                        if (STREAM && last >= ev_landed) /* not every warp need take this path (each polls for itself) */
-                            ev_landed = abea_wait_landed_events(io.ready + (int64_t)ABEA_READY_WORDS * ridx, last, io.stalled);
-                        abea_wide_stage(&sm, ev, kpr, echunk_hi, -1, E, K, tid);
-                    }
-                    if (need_k) { kchunk_hi += 1; abea_wide_stage(&sm, ev, kpr, -1, kchunk_hi, E, K, tid); }
-                }
-            }
-
-            /* ---- the cell (same templates as the narrow kernel) ---- */
-            const double up = right ? hi1 : R1;
-            const double left = right ? R1 : lo1;
-            const double diag = (right == prev_right) ? (right ? hi2 : lo2) : R2;
-            double Rn;
-            uint32_t fr;
-            {
-                double rd = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(diag, lp_step), lpd), diag);
-                double ru = abea_round_f32<FAST>(__dadd_rn(__dadd_rn(up, lp_stay), lpd), up);
-                double rl = abea_round_f32<FAST>(__dadd_rn(left, lp_skip), left);
-                bool isU = ru >= rd;
-                double m = isU ? ru : rd;
-                bool isL = rl >= m;
-                Rn = isL ? rl : m;
-                fr = isL ? ABEA_FROM_L : (isU ? ABEA_FROM_U : ABEA_FROM_D);
-            }
-            if (!active) { Rn = NEG; fr = 0u; }
-
-            if (safe > 0) {
-                safe -= 1;
-            } else {
-                const bool interior = (kb >= 0) && (kb + ABEA_W < K) && (eb >= ABEA_W - 1) && (eb <= E - 1);
-                if (interior) {
-                    int32_t s1 = K - ABEA_W - 1 - kb, s2 = E - 1 - eb;
-                    safe = s1 < s2 ? s1 : s2;
-                } else {
-                    int32_t lo = -kb;
-                    if (eb - (E - 1) > lo) lo = eb - (E - 1);
-                    if (lo < 0) lo = 0;
-                    int32_t hi = K - kb;
-                    if (eb + 1 < hi) hi = eb + 1;
-                    if (hi > ABEA_W) hi = ABEA_W;
-                    const int32_t to = -1 - kb;
-                    const int32_t te = eb - to;
-                    const bool trim_in = (to >= 0) && (to < ABEA_W) && (te >= 0) && (te < E);
-                    const double trim_s = (double)__double2float_rn(__dmul_rn(lp_trim, (double)(te + 1)));
-                    const int32_t oe = (K - 1) - kb;
-                    const bool valid = active && (o >= lo) && (o < hi);
-                    Rn = valid ? Rn : NEG;
-                    fr = valid ? fr : 0u;
-                    if (active && o == to && trim_in) {
-                        Rn = trim_s;
-                        fr = ABEA_FROM_U;
-                    }
-                    if (o == oe && valid) {
-                        const int32_t e = eb - o;
-                        double s = (double)__double2float_rn(__dadd_rn(Rn, __dmul_rn((double)(E - e), lp_trim)));
-                        if (s > best_s) {
-                            best_s = s;
-                            best_e = e;
-                        }
-                    }
-                }
-            }
-
-            /* ---- publish this warp's boundary cells; everything below is independent of the other warps and
-             * overlaps their arrival at the barrier ---- */
-            const int par = b & 1;
-            if (lane == 0) sm.edge[par][w][0] = Rn;
-            if (lane == last_lane) sm.edge[par][w][1] = Rn;
-            __syncwarp(); /* orders the other lane's store before lane 0's arrival */
-            if (lane == 0) abea_mbar_arrive(&sm.bar);
-            lo2 = lo1; hi2 = hi1;
-            lo1 = __shfl_up_sync(ABEA_FULL, Rn, 1);
-            hi1 = __shfl_down_sync(ABEA_FULL, Rn, 1);
-            R2 = R1; R1 = Rn;
-            prev_right = right;
-
-            /* speculative emissions of band b+1 for both moves */
-            x_dn = sm.ev[(eb + 1 - oa) & (ABEA_WRING - 1)];
-            kp_rt = sm.kp[(kb + 1 + oa) & (ABEA_WRING - 1)];
-            lpd_rt = (double)abea_emission_t<FAST>(x_cur, kp_rt);
-            lpd_dn = (double)abea_emission_t<FAST>(x_dn, kp_cur);
-
-            /* trace: this lane's 2 bits go to bit 8q + 2(o&3) of word o>>2 of the 128-B line of the 4-band group */
-            const int q = b & 3;
-            acc |= fr << (8 * q + 2 * (o & 3));
-            if (w == 3 && lane == 28 + q) eb_keep = eb;
-            if (q == 3 || b == NB - 1) {
-                uint32_t word = acc | __shfl_xor_sync(ABEA_FULL, acc, 1);
-                word |= __shfl_xor_sync(ABEA_FULL, word, 2);
-                uint32_t* line = tr + (int64_t)(b >> 2) * ABEA_TRACE_GROUP_WORDS;
-                if (active && (lane & 3) == 0) line[o >> 2] = word;
-                if (w == 3 && lane >= 28) line[ABEA_LANES + (lane - 28)] = (uint32_t)eb_keep;
-                acc = 0u;
-            }
+        /* bands 2, 3, 4, 5, ...: four steps per trip so that the trace position and the barrier parity are static, and
+         * the two band registers swap roles instead of being copied */
+        for (;;) {
+            abea_wide_step<FAST, STREAM, 2>(cx, sm, P, Qb, tid, o, oa, active, sh0); /* Qb <- band b */
+            if (cx.b >= cx.NB) break;
+            abea_wide_step<FAST, STREAM, 3>(cx, sm, Qb, P, tid, o, oa, active, sh0); /* P <- band b */
+            if (cx.b >= cx.NB) break;
+            abea_wide_step<FAST, STREAM, 0>(cx, sm, P, Qb, tid, o, oa, active, sh0);
+            if (cx.b >= cx.NB) break;
+            abea_wide_step<FAST, STREAM, 1>(cx, sm, Qb, P, tid, o, oa, active, sh0);
+            if (cx.b >= cx.NB) break;
         }
-        abea_mbar_wait(&sm.bar, bar_parity); /* the last band's arrivals: every arrival is matched by a wait */
-        bar_parity ^= 1u;
         abea_cp_async_wait_all();
         __syncthreads(); /* the trace lines of the whole read are written before warp 0 walks them */
 
         /* best end cell over the CTA: max score, ties to the smaller event */
+        double best_s = cx.best_s;
+        int32_t best_e = cx.best_e;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             double os = __shfl_xor_sync(ABEA_FULL, best_s, d);
