@@ -15,7 +15,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .batch import MODEL_DTYPE, PAIR_DTYPE, CBatch, ReadBatch
+from .batch import (INDEX_PAIR_DTYPE, MIN_NUM_EVENTS_TO_RESCALE, MODEL_DTYPE, PAIR_DTYPE, SCALING_RESULT_DTYPE,
+                    SCALINGS_DTYPE, CBatch, ReadBatch)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libabea_b200.so")
@@ -32,7 +33,8 @@ class Timing(ctypes.Structure):
                 ("d2h_ms", ctypes.c_double), ("unpack_ms", ctypes.c_double), ("h2d_bytes", ctypes.c_int64),
                 ("d2h_bytes", ctypes.c_int64), ("kernel_launches", ctypes.c_int32),
                 ("n_scheduled", ctypes.c_int32), ("n_wide", ctypes.c_int32), ("streamed", ctypes.c_int32),
-                ("n_bands", ctypes.c_int64), ("n_events", ctypes.c_int64), ("load_ms", ctypes.c_double)]
+                ("n_bands", ctypes.c_int64), ("n_events", ctypes.c_int64), ("load_ms", ctypes.c_double),
+                ("mom_ms", ctypes.c_double), ("scaling_ms", ctypes.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -61,6 +63,10 @@ def _bind(path: str):
     lib.abea_read_cycles.argtypes = [vp, vp, vp, vp]
     lib.abea_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
                                         ctypes.POINTER(i32)]
+    lib.abea_estimate_scalings.argtypes = [vp, ctypes.c_int, vp, ctypes.POINTER(Timing)]
+    lib.abea_scaling_stage.argtypes = [vp, i32, ctypes.POINTER(Timing)]
+    lib.abea_scaling_download.argtypes = [vp, vp, vp, vp]
+    lib.abea_scaling_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64)]
     lib.abea_host_alloc.argtypes = [ctypes.c_size_t]
     lib.abea_host_alloc.restype = vp
     lib.abea_host_free.argtypes = [vp]
@@ -91,6 +97,19 @@ class Alignment:
     def read_pairs(self, i: int) -> np.ndarray:
         p = int(self.pair_ptr[i])
         return self.pairs[p:p + int(self.n_pairs[i])]
+
+
+@dataclass
+class Scaling:
+    """Output of scaling_db: per read what scaling_single (reference src/f5c.c:736-807) leaves in db_t —
+    scalings[i] (recalibrated), events_per_base[i], read_stat_flag bits, n_event_alignment, base_to_event_map[i]."""
+    results: np.ndarray    # SCALING_RESULT_DTYPE [n]
+    maps: np.ndarray       # INDEX_PAIR_DTYPE, read i at map_ptr[i] .. map_ptr[i+1]
+    map_ptr: np.ndarray    # int64 [n+1]
+    timing: dict
+
+    def read_map(self, i: int) -> np.ndarray:
+        return self.maps[int(self.map_ptr[i]):int(self.map_ptr[i + 1])]
 
 
 class AbeaContext:
@@ -190,10 +209,13 @@ class AbeaContext:
                                               n_pairs.ctypes.data, ctypes.byref(t)), "abea_align_batch")
         return Alignment(pairs, pair_ptr, n_pairs, t.as_dict())
 
-    def upload(self, batch: ReadBatch) -> dict:
+    def upload(self, batch: ReadBatch, with_scalings: bool = True) -> dict:
+        """abea_upload_batch. with_scalings=False leaves abea_batch_t.scalings NULL: estimate_scalings() must follow."""
         assert batch.kmer_size == self.kmer_size
         t = Timing()
         cb = batch.as_c()
+        if not with_scalings:
+            cb.scalings = None
         self._check(self.lib.abea_upload_batch(self._h, ctypes.byref(cb), ctypes.byref(t)), "abea_upload_batch")
         return t.as_dict()
 
@@ -208,6 +230,30 @@ class AbeaContext:
         self._check(self.lib.abea_download(self._h, pairs.ctypes.data, pair_ptr.ctypes.data, n_pairs.ctypes.data,
                                            ctypes.byref(t)), "abea_download")
         return Alignment(pairs, pair_ptr, n_pairs, t.as_dict())
+
+    # -- the stages either side of the alignment ----------------------------------------------------------
+    def estimate_scalings(self, n_reads: int, reverse_events: bool = False):
+        """abea_estimate_scalings on the resident batch: (SCALINGS_DTYPE [n], timing). Reference
+        estimate_scalings_using_mom (src/align.c:58-106) + the RNA event reversal (src/f5c.c:713-721)."""
+        out = np.zeros(n_reads, dtype=SCALINGS_DTYPE)
+        t = Timing()
+        self._check(self.lib.abea_estimate_scalings(self._h, int(bool(reverse_events)), out.ctypes.data,
+                                                    ctypes.byref(t)), "abea_estimate_scalings")
+        return out, t.as_dict()
+
+    def scaling_stage(self, min_num_events_to_rescale: int = MIN_NUM_EVENTS_TO_RESCALE) -> dict:
+        t = Timing()
+        self._check(self.lib.abea_scaling_stage(self._h, int(min_num_events_to_rescale), ctypes.byref(t)),
+                    "abea_scaling_stage")
+        return t.as_dict()
+
+    def scaling_download(self, batch: ReadBatch, timing: dict | None = None) -> Scaling:
+        mp = batch.map_ptr()
+        res = np.zeros(batch.n_reads, dtype=SCALING_RESULT_DTYPE)
+        maps = np.full(2 * int(mp[-1]), -1, dtype=np.int32).view(INDEX_PAIR_DTYPE)
+        self._check(self.lib.abea_scaling_download(self._h, res.ctypes.data, maps.ctypes.data, mp.ctypes.data),
+                    "abea_scaling_download")
+        return Scaling(res, maps, mp, timing or {})
 
     def read_cycles(self, n_reads: int) -> dict:
         fc = np.zeros(n_reads, dtype=np.int64)
@@ -242,3 +288,11 @@ class AbeaContext:
 def align_db(ctx: AbeaContext, batch: ReadBatch) -> Alignment:
     """The reference's align_db(core, db) for the GPU build (src/f5c.c:833-845): ABEA for a data batch."""
     return ctx.align_batch(batch)
+
+
+def scaling_db(ctx: AbeaContext, batch: ReadBatch,
+               min_num_events_to_rescale: int = MIN_NUM_EVENTS_TO_RESCALE) -> Scaling:
+    """The reference's scaling_db(core, db) (scaling_single per read, src/f5c.c:736-807) on the pair lists the last
+    align left on the device: postalign + recalibrate_model + the read flags."""
+    t = ctx.scaling_stage(min_num_events_to_rescale)
+    return ctx.scaling_download(batch, t)

@@ -23,6 +23,16 @@ PAIR_DTYPE = np.dtype([("ref_pos", "<i4"), ("read_pos", "<i4")])
 # reference: model_t with CACHED_LOG, src/f5c.h:147-155 (12 bytes)
 MODEL_DTYPE = np.dtype([("level_mean", "<f4"), ("level_stdv", "<f4"), ("level_log_stdv", "<f4")])
 
+# reference: index_pair_t, src/f5c.h:187-190 (8 bytes)
+INDEX_PAIR_DTYPE = np.dtype([("start", "<i4"), ("stop", "<i4")])
+# abea_scaling_result_t (include/abea_types.h): what scaling_single (src/f5c.c:736-807) leaves behind per read
+SCALING_RESULT_DTYPE = np.dtype([("scalings", SCALINGS_DTYPE), ("var_d", "<f8"), ("events_per_base", "<f8"),
+                                 ("n_event_alignment", "<i4"), ("num_m_state", "<i4"), ("flags", "<u4"),
+                                 ("calibrated", "<i4")])
+assert SCALING_RESULT_DTYPE.itemsize == 48
+FAILED_CALIBRATION, FAILED_ALIGNMENT, FAILED_QUALITY_CHK = 0x1, 0x2, 0x4   # src/f5c.h:66-68
+MIN_NUM_EVENTS_TO_RESCALE = 200    # src/f5c.c:1185
+
 ALN_BANDWIDTH = 100                # src/f5c.h:34
 AVG_EVENTS_PER_KMER_MAX = 15.0     # src/f5cmisc.h:18
 
@@ -87,6 +97,13 @@ class ReadBatch:
         out = np.zeros(self.n_reads, dtype=np.int64)
         if self.n_reads > 1:
             np.cumsum(cap[:-1], out=out[1:])
+        return out
+
+    def map_ptr(self) -> np.ndarray:
+        """Flat layout of the per-read base_to_event_map (reference src/f5c.c:746): read i owns max(K_i, 0) entries."""
+        nk = np.maximum(self.n_kmers, 0)
+        out = np.zeros(self.n_reads + 1, dtype=np.int64)
+        np.cumsum(nk, out=out[1:])
         return out
 
     def eligible(self) -> np.ndarray:

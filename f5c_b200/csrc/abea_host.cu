@@ -30,6 +30,7 @@
 
 #include "../../include/abea_b200.h"
 #include "abea_kernels.cuh"
+#include "scaling_kernels.cuh"
 
 #define ABEA_VERSION_STR "abea-b200 0.1 (sm_100a)"
 
@@ -41,7 +42,7 @@ double now_ms() {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-enum { EV_H2D0, EV_H2D1, EV_K0, EV_K1, EV_K2, EV_K3, EV_D2H0, EV_D2H1, EV_COUNT };
+enum { EV_H2D0, EV_H2D1, EV_K0, EV_K1, EV_K2, EV_K3, EV_D2H0, EV_D2H1, EV_S0, EV_S1, EV_COUNT };
 
 } // namespace
 
@@ -105,6 +106,16 @@ struct abea_ctx {
     bool streaming = false;    /* the resident batch is being streamed in: its fill must wait on d_ready */
     bool results_on_device = false; /* d_pairs / d_npairs hold the final lists of the last run */
     int64_t event_bytes = 0;   /* size of the batch's event array */
+
+    /* the stages either side of ABEA (scaling_kernels.cuh): descriptors of ALL reads in the caller's order */
+    std::vector<abea_sread_t> sreads;
+    std::vector<abea_scalings_t> in_scalings; /* the caller's scalings (empty: to be estimated on the device) */
+    DevBuf d_sreads, d_scalings, d_maps, d_sres;
+    int64_t total_map = 0;           /* entries of d_maps: sum of max(K, 0) over the batch */
+    bool sreads_on_device = false;   /* d_sreads holds the resident batch's descriptors */
+    bool scalings_on_device = false; /* d_scalings holds the batch's scalings (uploaded or estimated) */
+    bool need_scalings = false;      /* the batch came without scalings: abea_estimate_scalings must run before abea_run */
+    bool scaled = false;             /* abea_scaling_stage has run on the last abea_run's results */
 };
 
 namespace {
@@ -366,7 +377,7 @@ void abea_destroy(abea_ctx_t* c) {
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_reads, &c->d_kparams,
                       &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags, &c->d_npairs,
-                      &c->d_ready, &c->d_items};
+                      &c->d_ready, &c->d_items, &c->d_sreads, &c->d_scalings, &c->d_maps, &c->d_sres};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_results.p) cudaFreeHost(c->h_results.p);
@@ -449,8 +460,8 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         r.n_kmers = L - k + 1;
         r.pair_cap = E + L;
         r.orig_index = i;
-        r.scale = b->scalings[i].scale;
-        r.shift = b->scalings[i].shift;
+        r.scale = b->scalings ? b->scalings[i].scale : 0.f;
+        r.shift = b->scalings ? b->scalings[i].shift : 0.f;
         /* per-read transition penalties in host double (reference src/align.c:207-215) */
         double events_per_kmer = (double)(size_t)E / (size_t)r.n_kmers;
         double p_stay = 1 - (1 / (events_per_kmer + 1));
@@ -498,6 +509,29 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
     c->total_bands = nb;
     c->total_events = ne;
     const size_t n_sched = c->reads.size();
+    /* descriptors for the stages either side of the alignment: every read, caller's order */
+    c->sreads.assign((size_t)b->n_reads, abea_sread_t());
+    c->total_map = 0;
+    for (int32_t i = 0; i < b->n_reads; i++) {
+        abea_sread_t& sr = c->sreads[i];
+        const int32_t E = b->n_events[i], L = b->read_len[i];
+        sr.seq_off = b->seq_ptr[i];
+        sr.ev_off = b->event_ptr[i];
+        sr.map_off = c->total_map;
+        sr.pair_off = c->cap_ptr[i];
+        sr.n_events = E;
+        sr.read_len = L;
+        sr.sched = -1;
+        sr.usable = ((b->good ? b->good[i] != 0 : true) && E >= 1 && L >= k) ? 1 : 0;
+        c->total_map += std::max(L - k + 1, 0);
+    }
+    for (size_t j = 0; j < n_sched; j++) c->sreads[c->reads[j].orig_index].sched = (int32_t)j;
+    if (b->scalings) c->in_scalings.assign(b->scalings, b->scalings + b->n_reads);
+    else c->in_scalings.clear();
+    c->need_scalings = (b->scalings == nullptr);
+    c->sreads_on_device = false;
+    c->scalings_on_device = false;
+    c->scaled = false;
     double t1 = now_ms();
 
     if (dev_reserve(c, c->d_seq, (size_t)seq_bytes + 16)) return ABEA_ERR_CUDA;
@@ -523,6 +557,7 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         memcpy(c->h_reads.p, c->reads.data(), n_sched * sizeof(abea_read_t));
         CU(cudaMemcpyAsync(c->d_reads.p, c->h_reads.p, n_sched * sizeof(abea_read_t), cudaMemcpyHostToDevice, c->stream));
     }
+    if (ev_alias && c->need_scalings) ev_alias = nullptr; /* the estimate needs a read's events before its fill */
     if (ev_alias && n_sched) {
         /* Everything the k-mer parameter kernel needs goes first, and the kernel with it: the host then works out
          * the loader's order while the GPU is busy with that. */
@@ -590,7 +625,10 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
 static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea_timing_t* timing) {
     if (!c) return ABEA_ERR_ARG;
     if (!c->uploaded) return fail(c, ABEA_ERR_STATE, "abea_run before abea_upload_batch");
+    if (c->need_scalings)
+        return fail(c, ABEA_ERR_STATE, "the batch has no scalings: call abea_estimate_scalings before abea_run");
     CU(cudaSetDevice(c->device));
+    c->scaled = false;
     const int32_t n = (int32_t)c->reads.size();
     int launches = 0;
     const bool streaming = c->streaming; /* set by upload_impl: queue, flags and ready counters are already armed */
@@ -831,6 +869,115 @@ int abea_device_results(abea_ctx_t* c, const abea_pair_t** d_pairs, const int32_
     return ABEA_OK;
 }
 
+/* ---- the stages either side of ABEA ------------------------------------------------------------------------- */
+
+static int scaling_descriptors(abea_ctx_t* c) {
+    const size_t nb = (size_t)c->n_batch_reads;
+    if (!c->sreads_on_device) {
+        if (dev_reserve(c, c->d_sreads, (nb + 1) * sizeof(abea_sread_t))) return ABEA_ERR_CUDA;
+        if (dev_reserve(c, c->d_scalings, (nb + 1) * sizeof(abea_scalings_t))) return ABEA_ERR_CUDA;
+        if (nb) CU(cudaMemcpyAsync(c->d_sreads.p, c->sreads.data(), nb * sizeof(abea_sread_t), cudaMemcpyHostToDevice, c->stream));
+        c->sreads_on_device = true;
+    }
+    if (!c->scalings_on_device && !c->in_scalings.empty()) {
+        CU(cudaMemcpyAsync(c->d_scalings.p, c->in_scalings.data(), nb * sizeof(abea_scalings_t), cudaMemcpyHostToDevice, c->stream));
+        c->scalings_on_device = true;
+    }
+    return ABEA_OK;
+}
+
+int abea_estimate_scalings(abea_ctx_t* c, int reverse_events, abea_scalings_t* scalings_out, abea_timing_t* timing) {
+    if (!c) return ABEA_ERR_ARG;
+    if (!c->uploaded) return fail(c, ABEA_ERR_STATE, "abea_estimate_scalings before abea_upload_batch");
+    if (c->streaming) return fail(c, ABEA_ERR_STATE, "abea_estimate_scalings needs a resident batch (abea_upload_batch)");
+    CU(cudaSetDevice(c->device));
+    const int32_t nb = c->n_batch_reads;
+    int rc = scaling_descriptors(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev[EV_S0], c->stream));
+    if (nb > 0) {
+        if (!c->scalings_on_device) CU(cudaMemsetAsync(c->d_scalings.p, 0, (size_t)nb * sizeof(abea_scalings_t), c->stream));
+        ABEA_LAUNCH(abea_mom_kernel, (nb + SCL_WARPS - 1) / SCL_WARPS, 32 * SCL_WARPS, c->stream,
+                    (const abea_sread_t*)c->d_sreads.p, nb, (const uint8_t*)c->d_seq.p, (abea_event_t*)c->d_events.p,
+                    (const abea_model_t*)c->d_model.p, c->kmer_size, (abea_scalings_t*)c->d_scalings.p,
+                    (abea_read_t*)c->d_reads.p, (int32_t)(reverse_events ? 1 : 0));
+    }
+    CU(cudaEventRecord(c->ev[EV_S1], c->stream));
+    if (scalings_out && nb > 0)
+        CU(cudaMemcpyAsync(scalings_out, c->d_scalings.p, (size_t)nb * sizeof(abea_scalings_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->scalings_on_device = true;
+    c->need_scalings = false;
+    c->prepared = false; /* the k-mer parameter cache depends on scale / shift */
+    c->last.mom_ms = ev_ms(c, EV_S0, EV_S1);
+    if (timing) *timing = c->last;
+    return ABEA_OK;
+}
+
+int abea_scaling_stage(abea_ctx_t* c, int32_t min_num_events_to_rescale, abea_timing_t* timing) {
+    if (!c) return ABEA_ERR_ARG;
+    if (!c->ran || !c->results_on_device) return fail(c, ABEA_ERR_STATE, "abea_scaling_stage before abea_run");
+    CU(cudaSetDevice(c->device));
+    const int32_t nb = c->n_batch_reads;
+    int rc = scaling_descriptors(c);
+    if (rc) return rc;
+    if (!c->scalings_on_device) return fail(c, ABEA_ERR_STATE, "no scalings on the device");
+    if (dev_reserve(c, c->d_maps, (size_t)(c->total_map + 1) * sizeof(abea_index_pair_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_sres, ((size_t)nb + 1) * sizeof(abea_scaling_result_t))) return ABEA_ERR_CUDA;
+    CU(cudaEventRecord(c->ev[EV_S0], c->stream));
+    if (nb > 0)
+        ABEA_LAUNCH(abea_scaling_kernel, (nb + SCL_WARPS - 1) / SCL_WARPS, 32 * SCL_WARPS, c->stream,
+                    (const abea_sread_t*)c->d_sreads.p, nb, (const uint8_t*)c->d_seq.p,
+                    (const abea_event_t*)c->d_events.p, (const abea_model_t*)c->d_model.p, c->kmer_size,
+                    (const abea_pair_t*)c->d_pairs.p, (const int32_t*)c->d_npairs.p,
+                    (const abea_scalings_t*)c->d_scalings.p, (abea_index_pair_t*)c->d_maps.p,
+                    (abea_scaling_result_t*)c->d_sres.p, min_num_events_to_rescale);
+    CU(cudaEventRecord(c->ev[EV_S1], c->stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    c->scaled = true;
+    c->last.scaling_ms = ev_ms(c, EV_S0, EV_S1);
+    if (timing) *timing = c->last;
+    return ABEA_OK;
+}
+
+int abea_scaling_download(abea_ctx_t* c, abea_scaling_result_t* results, abea_index_pair_t* maps, const int64_t* map_ptr) {
+    if (!c || !results) return fail(c, ABEA_ERR_ARG, "bad output");
+    if (!c->scaled) return fail(c, ABEA_ERR_STATE, "abea_scaling_download before abea_scaling_stage");
+    if (maps && !map_ptr) return fail(c, ABEA_ERR_ARG, "maps without map_ptr");
+    CU(cudaSetDevice(c->device));
+    const int32_t nb = c->n_batch_reads;
+    if (nb > 0) CU(cudaMemcpy(results, c->d_sres.p, (size_t)nb * sizeof(abea_scaling_result_t), cudaMemcpyDeviceToHost));
+    for (int32_t i = 0; i < nb; i++) /* CACHED_LOG: scallings->log_var = log(var), glibc double log (src/align.c:757) */
+        if (results[i].calibrated) results[i].scalings.log_var = (float)log(results[i].var_d);
+    if (maps && c->total_map > 0) {
+        bool canonical = true;
+        for (int32_t i = 0; i < nb && canonical; i++) canonical = (map_ptr[i] == c->sreads[i].map_off);
+        if (canonical) {
+            CU(cudaMemcpy(maps, c->d_maps.p, (size_t)c->total_map * sizeof(abea_index_pair_t), cudaMemcpyDeviceToHost));
+        } else {
+            for (int32_t i = 0; i < nb; i++) {
+                const int64_t K = (int64_t)c->sreads[i].read_len - (int64_t)c->kmer_size + 1;
+                if (K > 0 && results[i].n_event_alignment > 0)
+                    CU(cudaMemcpy(maps + map_ptr[i], (const abea_index_pair_t*)c->d_maps.p + c->sreads[i].map_off,
+                                  (size_t)K * sizeof(abea_index_pair_t), cudaMemcpyDeviceToHost));
+            }
+        }
+    }
+    return ABEA_OK;
+}
+
+int abea_scaling_device_results(abea_ctx_t* c, const abea_scaling_result_t** d_results, const abea_index_pair_t** d_maps,
+                                int64_t* total_map_entries) {
+    if (!c) return ABEA_ERR_ARG;
+    if (!c->scaled) return fail(c, ABEA_ERR_STATE, "abea_scaling_device_results before abea_scaling_stage");
+    if (d_results) *d_results = (const abea_scaling_result_t*)c->d_sres.p;
+    if (d_maps) *d_maps = (const abea_index_pair_t*)c->d_maps.p;
+    if (total_map_entries) *total_map_entries = c->total_map;
+    return ABEA_OK;
+}
+
 int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pairs, const int64_t* pair_ptr,
                      int32_t* n_pairs, abea_timing_t* timing) {
     if (!c || !batch) return fail(c, ABEA_ERR_ARG, "bad batch");
@@ -853,6 +1000,10 @@ int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pair
         }
     }
     if (fin_np) memset(n_pairs, 0, (size_t)batch->n_reads * sizeof(int32_t)); /* reads that are not scheduled */
+    if (c->need_scalings) { /* batch->scalings == NULL: method-of-moments estimate on the device first */
+        rc = abea_estimate_scalings(c, 0, nullptr, nullptr);
+        if (rc) return rc;
+    }
     rc = run_impl(c, fin_pairs, fin_np, nullptr);
     if (rc) return rc;
     if (!fin_np) {

@@ -5,6 +5,13 @@
  *     void free_cuda(core_t* core);              reference src/f5c.cu:204-234
  *     void align_cuda(core_t* core, db_t* db);   reference src/f5cmisc.h:122-125, src/f5c.cu:647-1061
  *
+ * plus two entry points the reference has no GPU counterpart for (it runs these stages per read on CPU threads):
+ *
+ *     void scaling_cuda(core_t* core, db_t* db);   replaces pthread_db(core, db, scaling_single) in process_db,
+ *                                                  src/f5c.c:932 (scaling_single: src/f5c.c:736-807)
+ *     void estimate_scalings_cuda(core_t*, db_t*); the estimate_scalings_using_mom call of event_single for a whole
+ *                                                  batch, src/f5c.c:709-711 (src/align.c:58-106)
+ *
  * with the reference's own C++ linkage, structs (core_t/db_t from the reference's f5c.h, -DHAVE_CUDA=1) and error
  * convention (message on stderr + exit, src/f5cmisc.cuh:54-118). It is a thin packer over the C ABI in
  * include/abea_b200.h: ragged db_t -> flat pinned staging -> abea_align_batch -> db->event_align_pairs[i] /
@@ -29,6 +36,9 @@ static_assert(sizeof(abea_model_t) == sizeof(model_t), "model_t layout differs (
 static_assert(sizeof(abea_scalings_t) == sizeof(scalings_t), "scalings_t layout differs");
 static_assert(sizeof(abea_pair_t) == sizeof(AlignedPair), "AlignedPair layout differs");
 static_assert(ABEA_BANDWIDTH == ALN_BANDWIDTH, "band width differs");
+static_assert(sizeof(abea_index_pair_t) == sizeof(index_pair_t), "index_pair_t layout differs");
+static_assert(ABEA_FAILED_CALIBRATION == FAILED_CALIBRATION && ABEA_FAILED_ALIGNMENT == FAILED_ALIGNMENT &&
+              ABEA_FAILED_QUALITY_CHK == FAILED_QUALITY_CHK, "read_stat_flag bits differ");
 
 namespace {
 
@@ -44,6 +54,11 @@ struct dropin_data {
     int32_t* read_len; int32_t* n_events; int32_t* n_pairs;
     abea_scalings_t* scalings; uint8_t* good;
     size_t read_cap;
+    /* scaling_cuda staging */
+    abea_scaling_result_t* sres; size_t sres_cap;
+    abea_index_pair_t* maps; size_t map_cap;
+    int64_t* map_ptr; size_t map_ptr_cap;
+    const db_t* aligned_db; /* the batch whose pair lists are resident on the device */
 };
 
 void die(const char* func, const char* what, abea_ctx_t* ctx) {
@@ -85,18 +100,15 @@ void free_cuda(core_t* core) {
     if (!d) return;
     abea_destroy(d->ctx);
     void* bufs[] = {d->seq, d->events, d->pairs, d->seq_ptr, d->event_ptr, d->pair_ptr, d->read_len, d->n_events,
-                    d->n_pairs, d->scalings, d->good};
+                    d->n_pairs, d->scalings, d->good, d->sres, d->maps, d->map_ptr};
     for (void* b : bufs) abea_host_free(b);
     free(d);
     core->cuda = NULL;
 }
 
-void align_cuda(core_t* core, db_t* db) {
-    dropin_data* d = (dropin_data*)core->cuda;
+/* flatten the ragged batch (what the reference does at src/f5c.cu:744-800) into pinned staging */
+static void pack_db(dropin_data* d, const db_t* db, abea_batch_t& b, bool with_scalings) {
     const int32_t n = db->n_bam_rec;
-    double t0 = realtime();
-
-    /* flatten the ragged batch (what the reference does at src/f5c.cu:744-800) into pinned staging */
     if ((size_t)n > d->read_cap) {
         size_t c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;
         grow(d->seq_ptr, c1, (size_t)n); grow(d->event_ptr, c2, (size_t)n); grow(d->pair_ptr, c3, (size_t)n);
@@ -122,13 +134,22 @@ void align_cuda(core_t* core, db_t* db) {
         d->seq[d->seq_ptr[i] + db->read_len[i]] = 0;
         if (db->et[i].n) memcpy(d->events + d->event_ptr[i], db->et[i].event, db->et[i].n * sizeof(event_t));
     }
-    abea_batch_t b;
     b.n_reads = n; b.seq = d->seq; b.seq_ptr = d->seq_ptr; b.read_len = d->read_len; b.events = d->events;
-    b.event_ptr = d->event_ptr; b.n_events = d->n_events; b.scalings = d->scalings; b.good = d->good;
+    b.event_ptr = d->event_ptr; b.n_events = d->n_events; b.scalings = with_scalings ? d->scalings : NULL;
+    b.good = d->good;
+}
+
+void align_cuda(core_t* core, db_t* db) {
+    dropin_data* d = (dropin_data*)core->cuda;
+    const int32_t n = db->n_bam_rec;
+    double t0 = realtime();
+    abea_batch_t b;
+    pack_db(d, db, b, true);
     double t1 = realtime();
 
     abea_timing_t tm;
     if (abea_align_batch(d->ctx, &b, d->pairs, d->pair_ptr, d->n_pairs, &tm)) die("align_cuda", "Cuda error", d->ctx);
+    d->aligned_db = db;
     double t2 = realtime();
 
     /* un-flatten (src/f5c.cu:1005-1030): pairs already ascending, no host-side reversal */
@@ -150,6 +171,64 @@ void align_cuda(core_t* core, db_t* db) {
     if (core->opt.verbosity > 1)
         fprintf(stderr, "[align_cuda] Load : GPU %d entries (%.1fM events), CPU 0 entries; kernels %.3f ms\n",
                 tm.n_scheduled, tm.n_events / 1e6, tm.kernel_ms);
+}
+
+/* The estimate_scalings_using_mom call of event_single (src/f5c.c:709-711) for the whole batch: db->scalings[i].shift
+ * and .scale of every read with events. RNA batches must call it BEFORE event_single's reversal (src/f5c.c:713-721);
+ * the reversal itself stays where it is. */
+void estimate_scalings_cuda(core_t* core, db_t* db) {
+    dropin_data* d = (dropin_data*)core->cuda;
+    abea_batch_t b;
+    pack_db(d, db, b, false);
+    if (abea_upload_batch(d->ctx, &b, NULL)) die("estimate_scalings_cuda", "Cuda error", d->ctx);
+    if (abea_estimate_scalings(d->ctx, 0, d->scalings, NULL)) die("estimate_scalings_cuda", "Cuda error", d->ctx);
+    d->aligned_db = NULL;
+    for (int32_t i = 0; i < db->n_bam_rec; i++)
+        if (d->good[i] && db->et[i].n >= 1 && db->read_len[i] >= (int32_t)core->kmer_size) {
+            db->scalings[i].shift = d->scalings[i].shift;
+            db->scalings[i].scale = d->scalings[i].scale;
+        }
+}
+
+/* scaling_single (src/f5c.c:736-807) for every read of the batch align_cuda has just aligned: fills
+ * db->base_to_event_map[i] (malloc'd here like the reference does, freed by free_db_tmp), db->events_per_base[i],
+ * db->scalings[i], db->n_event_alignment[i] and ORs the FAILED_* bits into db->read_stat_flag[i].
+ * db->event_alignment[i] is left NULL: the reference frees it before scaling_single returns. */
+void scaling_cuda(core_t* core, db_t* db) {
+    dropin_data* d = (dropin_data*)core->cuda;
+    const int32_t n = db->n_bam_rec;
+    if (d->aligned_db != db) { fprintf(stderr, "[scaling_cuda::ERROR] align_cuda has not been called on this batch\n"); exit(EXIT_FAILURE); }
+    double t0 = realtime();
+    if (abea_scaling_stage(d->ctx, core->opt.min_num_events_to_rescale, NULL)) die("scaling_cuda", "Cuda error", d->ctx);
+    grow(d->sres, d->sres_cap, (size_t)n + 1);
+    grow(d->map_ptr, d->map_ptr_cap, (size_t)n + 1);
+    int64_t mp = 0;
+    for (int32_t i = 0; i < n; i++) {
+        d->map_ptr[i] = mp;
+        const int32_t K = db->read_len[i] - (int32_t)core->kmer_size + 1;
+        mp += K > 0 ? K : 0;
+    }
+    grow(d->maps, d->map_cap, (size_t)mp + 1);
+    if (abea_scaling_download(d->ctx, d->sres, d->maps, d->map_ptr)) die("scaling_cuda", "Cuda error", d->ctx);
+    for (int32_t i = 0; i < n; i++) {
+        const abea_scaling_result_t& r = d->sres[i];
+        db->event_alignment[i] = NULL;
+        db->n_event_alignment[i] = 0;
+        db->events_per_base[i] = 0;
+        if (db->n_event_align_pairs[i] > 0) {
+            const int32_t K = db->read_len[i] - (int32_t)core->kmer_size + 1;
+            db->base_to_event_map[i] = (index_pair_t*)malloc(sizeof(index_pair_t) * (size_t)K);
+            MALLOC_CHK(db->base_to_event_map[i]);
+            memcpy(db->base_to_event_map[i], d->maps + d->map_ptr[i], sizeof(index_pair_t) * (size_t)K);
+            db->n_event_alignment[i] = r.n_event_alignment;
+            db->events_per_base[i] = r.events_per_base;
+            if (r.calibrated) memcpy(&db->scalings[i], &r.scalings, sizeof(scalings_t));
+        } else {
+            db->base_to_event_map[i] = NULL;
+        }
+        db->read_stat_flag[i] |= (int32_t)r.flags;
+    }
+    core->est_scale_time += realtime() - t0;
 }
 
 /* ---- self-test door (used by tests/test_dropin.py): builds core_t/db_t from a flat batch, calls the three entry
@@ -197,6 +276,67 @@ extern "C" int f5c_dropin_selftest(const abea_batch_t* b, const abea_model_t* mo
     free_cuda(core);
     free(db->read); free(db->read_len); free(db->et); free(db->scalings); free(db->sig);
     free(db->event_align_pairs); free(db->n_event_align_pairs);
+    free(db); free(core);
+    return 0;
+}
+
+/* Second door: event_single's estimate -> align_db -> scaling_db through the drop-in, on real core_t / db_t. */
+extern "C" int f5c_dropin_selftest_scaling(const abea_batch_t* b, const abea_model_t* model, uint32_t kmer_size, int device,
+                                           int32_t min_num_events_to_rescale, int32_t* n_pairs,
+                                           abea_scaling_result_t* results, abea_index_pair_t* maps, const int64_t* map_ptr) {
+    core_t* core = (core_t*)calloc(1, sizeof(core_t));
+    db_t* db = (db_t*)calloc(1, sizeof(db_t));
+    core->model = (model_t*)model;
+    core->kmer_size = kmer_size;
+    core->opt.cuda_dev_id = device;
+    core->opt.min_num_events_to_rescale = min_num_events_to_rescale;
+    const int32_t n = b->n_reads;
+    db->n_bam_rec = n;
+    db->capacity_bam_rec = n;
+    db->read = (char**)calloc(n, sizeof(char*));
+    db->read_len = (int32_t*)calloc(n, sizeof(int32_t));
+    db->et = (event_table*)calloc(n, sizeof(event_table));
+    db->scalings = (scalings_t*)calloc(n, sizeof(scalings_t));
+    db->sig = (signal_t**)calloc(n, sizeof(signal_t*));
+    db->event_align_pairs = (AlignedPair**)calloc(n, sizeof(AlignedPair*));
+    db->n_event_align_pairs = (int32_t*)calloc(n, sizeof(int32_t));
+    db->event_alignment = (event_alignment_t**)calloc(n, sizeof(event_alignment_t*));
+    db->n_event_alignment = (int32_t*)calloc(n, sizeof(int32_t));
+    db->events_per_base = (double*)calloc(n, sizeof(double));
+    db->base_to_event_map = (index_pair_t**)calloc(n, sizeof(index_pair_t*));
+    db->read_stat_flag = (int32_t*)calloc(n, sizeof(int32_t));
+    for (int32_t i = 0; i < n; i++) {
+        db->read[i] = (char*)(b->seq + b->seq_ptr[i]);
+        db->read_len[i] = b->read_len[i];
+        db->et[i].n = (size_t)b->n_events[i];
+        db->et[i].end = (size_t)b->n_events[i];
+        db->et[i].event = (event_t*)(b->events + b->event_ptr[i]);
+        db->sig[i] = (signal_t*)calloc(1, sizeof(signal_t));
+        db->sig[i]->nsample = (b->good && !b->good[i]) ? 0 : 1;
+        db->event_align_pairs[i] = db->sig[i]->nsample ? (AlignedPair*)malloc(sizeof(AlignedPair) * ((size_t)b->n_events[i] + b->read_len[i])) : NULL;
+    }
+    init_cuda(core);
+    estimate_scalings_cuda(core, db);
+    align_cuda(core, db);
+    scaling_cuda(core, db);
+    for (int32_t i = 0; i < n; i++) {
+        n_pairs[i] = db->n_event_align_pairs[i];
+        memset(&results[i], 0, sizeof(results[i]));
+        memcpy(&results[i].scalings, &db->scalings[i], sizeof(scalings_t));
+        results[i].events_per_base = db->events_per_base[i];
+        results[i].n_event_alignment = db->n_event_alignment[i];
+        results[i].flags = (uint32_t)db->read_stat_flag[i];
+        if (db->base_to_event_map[i]) {
+            memcpy(maps + map_ptr[i], db->base_to_event_map[i], sizeof(index_pair_t) * (size_t)(b->read_len[i] - (int32_t)kmer_size + 1));
+            free(db->base_to_event_map[i]);
+        }
+        free(db->event_align_pairs[i]);
+        free(db->sig[i]);
+    }
+    free_cuda(core);
+    free(db->read); free(db->read_len); free(db->et); free(db->scalings); free(db->sig);
+    free(db->event_align_pairs); free(db->n_event_align_pairs); free(db->event_alignment); free(db->n_event_alignment);
+    free(db->events_per_base); free(db->base_to_event_map); free(db->read_stat_flag);
     free(db); free(core);
     return 0;
 }

@@ -10,6 +10,10 @@
  *   abea_upload_batch / abea_run /  the three phases of align_cuda   src/f5c.cu:744-899 (pack + H2D),
  *   abea_download                   kept separable for measurement   :910-960 (kernels), :979-1030 (D2H + unpack)
  *   abea_model_fill_log_stdv        set_model's CACHED_LOG fill      src/model.c:179
+ *   abea_estimate_scalings          estimate_scalings_using_mom      src/align.c:58-106, called per read by event_single
+ *                                   (+ the RNA event reversal)       src/f5c.c:709-721
+ *   abea_scaling_stage /            scaling_db = scaling_single per  src/f5c.c:736-807: postalign src/align.c:561-660,
+ *   abea_scaling_download           read                             recalibrate_model src/align.c:665-773, read flags
  *
  * The drop-in with the reference's own C++-linkage symbols (align_cuda/init_cuda/free_cuda over core_t/db_t) is
  * f5c_b200/csrc/f5c_dropin.cu, a thin packer over this ABI that is compiled inside the f5c tree.
@@ -65,6 +69,8 @@ typedef struct {
     int64_t n_bands;         /* sum of NB over scheduled reads */
     int64_t n_events;        /* sum of E over scheduled reads (the metric's numerator) */
     double load_ms;          /* device: abea_load_kernel, first CTA start to last piece landed (streaming only) */
+    double mom_ms;           /* device: abea_mom_kernel (abea_estimate_scalings) */
+    double scaling_ms;       /* device: abea_scaling_kernel (abea_scaling_stage) */
 } abea_timing_t;
 
 /* Create a context on CUDA device `device` (cudaSetDevice is applied on every call). */
@@ -87,6 +93,35 @@ int abea_upload_batch(abea_ctx_t* ctx, const abea_batch_t* batch, abea_timing_t*
 int abea_run(abea_ctx_t* ctx, abea_timing_t* timing);
 int abea_download(abea_ctx_t* ctx, abea_pair_t* pairs, const int64_t* pair_ptr, int32_t* n_pairs,
                   abea_timing_t* timing);
+
+/* ---- the stages either side of the alignment; bit-identical to the reference's CPU code ----
+ *
+ * abea_estimate_scalings: estimate_scalings_using_mom (src/align.c:58-106) for every read of the RESIDENT batch
+ * (abea_upload_batch; batch->scalings may then be NULL) that the reference would have run event_single on (good,
+ * at least one event, at least k bases). The estimates replace the batch's scalings on the device — the next
+ * abea_run aligns with them — and are copied to scalings_out (caller's order, var = log_var = 0) when it is not
+ * NULL. reverse_events != 0 reverses every read's event array in place afterwards, as event_single does for RNA
+ * (src/f5c.c:713-721): upload RNA events in signal order and let this call turn them 3'->5'.
+ * abea_align_batch on a batch without scalings runs this stage itself (copy-engine path, no streaming). */
+int abea_estimate_scalings(abea_ctx_t* ctx, int reverse_events, abea_scalings_t* scalings_out, abea_timing_t* timing);
+
+/* abea_scaling_stage: scaling_single (src/f5c.c:736-807) for every read, on the pair lists the last abea_run left
+ * on the device: the k-mer -> event-range map and events_per_base of postalign, the recalibrated shift / scale / var
+ * of recalibrate_model (when at least min_num_events_to_rescale 'M' rows exist; the reference default is
+ * ABEA_MIN_NUM_EVENTS_TO_RESCALE), and the ABEA_FAILED_* flags. Results stay on the device. */
+int abea_scaling_stage(abea_ctx_t* ctx, int32_t min_num_events_to_rescale, abea_timing_t* timing);
+
+/* Copy the stage's results to the host: results[n_reads] in the caller's order (log_var filled here with the host's
+ * log(), as the reference does), and — when maps is not NULL — read i's base_to_event_map (K_i = read_len-k+1
+ * entries) at maps[map_ptr[i]]. Only reads with n_event_alignment > 0 have a map (the reference allocates none for
+ * the others, src/f5c.c:787). */
+int abea_scaling_download(abea_ctx_t* ctx, abea_scaling_result_t* results, abea_index_pair_t* maps,
+                          const int64_t* map_ptr);
+
+/* Device-resident results of the stage for consumers that stay on the GPU: results in the caller's order, maps in
+ * the canonical layout (read i at the prefix sum of max(K, 0)). Valid until the next upload / destroy. */
+int abea_scaling_device_results(abea_ctx_t* ctx, const abea_scaling_result_t** d_results,
+                                const abea_index_pair_t** d_maps, int64_t* total_map_entries);
 
 /* Per-read diagnostics of the last run, indexed like the batch (any pointer may be NULL):
  * sum of emissions along the traceback (the quantity in the reference's adaptive.exp debug dumps), pairs before

@@ -45,6 +45,44 @@ typedef struct {
     int32_t read_pos;
 } abea_pair_t;
 
+/* reference: index_pair_t, src/f5c.h:187-190 — events [start, stop] (inclusive) mapped to one k-mer, -1/-1 = none */
+typedef struct {
+    int32_t start;
+    int32_t stop;
+} abea_index_pair_t;
+
+/* reference read_stat_flag bits, src/f5c.h:66-68 */
+#define ABEA_FAILED_CALIBRATION 0x001u
+#define ABEA_FAILED_ALIGNMENT 0x002u
+#define ABEA_FAILED_QUALITY_CHK 0x004u
+/* reference: MIN_CALIBRATION_VAR src/f5cmisc.h:16; opt.min_num_events_to_rescale default src/f5c.c (200); the
+ * events-per-base ceiling of scaling_single src/f5c.c:798 */
+#define ABEA_MIN_CALIBRATION_VAR 2.5
+#define ABEA_MIN_NUM_EVENTS_TO_RESCALE 200
+#define ABEA_MAX_EVENTS_PER_BASE 5.0
+
+/* What scaling_single (src/f5c.c:736-807) leaves behind for one read: the outputs of postalign
+ * (src/align.c:561-660) and recalibrate_model (src/align.c:665-773) and the read_stat_flag bits it sets.
+ *   scalings          db->scalings[i] after the call: recalibrated {shift, scale, var, log_var} when num_m_state >=
+ *                     min_num_events_to_rescale, otherwise the input (method-of-moments) values unchanged
+ *   var_d             recalibrate_model's `var` before it is narrowed to float (log_var = (float)log(var_d))
+ *   events_per_base   postalign: (max_event - min_event) / n_kmers, 0 when the read has no pairs
+ *   n_event_alignment entries postalign writes to its event_alignment_t list (every event of every k-mer's range)
+ *   num_m_state       of those, entries with hmm_state 'M' (first event of a k-mer whose rank differs from the
+ *                     previous k-mer that has events) — the rows of recalibrate_model's least-squares system
+ *   flags             ABEA_FAILED_* bits OR-ed into read_stat_flag
+ *   calibrated        recalibrate_model's return value
+ */
+typedef struct {
+    abea_scalings_t scalings;
+    double var_d;
+    double events_per_base;
+    int32_t n_event_alignment;
+    int32_t num_m_state;
+    uint32_t flags;
+    int32_t calibrated;
+} abea_scaling_result_t;
+
 /* reference constants: src/f5c.h:30-34, src/f5cmisc.h:18 */
 #define ABEA_BANDWIDTH 100
 #define ABEA_MAX_KMER_SIZE 9

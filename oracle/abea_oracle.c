@@ -268,6 +268,119 @@ void abea_oracle_estimate_scalings(const char* seq, int32_t seq_len, const abea_
     out->log_var = 0;
 }
 
+/* ---- the stage after ABEA: scaling_single = postalign + recalibrate_model + read flags ------------- */
+
+/* postalign (src/align.c:561-660). Walk the pair list once: a pair whose event differs from the previous pair's
+ * opens / extends the event range of its k-mer (:585-598). Then every k-mer with a range contributes its events
+ * start..stop to the alignment list (:611-655); an entry is 'M' when its k-mer rank differs from the rank of the
+ * entry before it, so only the first event of a k-mer can be 'M' (:640). recalibrate_model reads nothing but the
+ * 'M' entries (their k-mer rank and event index), so the list is returned as two int arrays of those.
+ * m_kmer / m_event need room for n_kmers entries (may be NULL). Returns the length of the full list. */
+static int32_t oracle_postalign(abea_index_pair_t* map, double* events_per_base, const char* seq, int32_t n_kmers,
+                                const abea_pair_t* pairs, int32_t n_pairs, uint32_t k, int32_t* m_rank,
+                                int32_t* m_event, int32_t* n_m) {
+    for (int32_t i = 0; i < n_kmers; i++) map[i].start = map[i].stop = -1;
+    int32_t max_event = 0, min_event = INT32_MAX, prev_event = -1;
+    for (int32_t i = 0; i < n_pairs; i++) {
+        int32_t ki = pairs[i].ref_pos, e = pairs[i].read_pos;
+        if (e != prev_event) {
+            if (map[ki].start == -1) map[ki].start = e;
+            map[ki].stop = e;
+        }
+        if (e > max_event) max_event = e;
+        if (e < min_event) min_event = e;
+        prev_event = e;
+    }
+    *events_per_base = (double)(max_event - min_event) / n_kmers;
+    int32_t n = 0, nm = 0, prev_rank = -1;
+    for (int32_t ki = 0; ki < n_kmers; ki++) {
+        if (map[ki].start == -1) continue;
+        int32_t rank = (int32_t)kmer_rank(seq + ki, k);
+        for (int32_t e = map[ki].start; e <= map[ki].stop; e++) {
+            if (prev_rank != rank) {
+                if (m_rank) m_rank[nm] = rank;
+                if (m_event) m_event[nm] = e;
+                nm++;
+            }
+            n++;
+            prev_rank = rank;
+        }
+    }
+    *n_m = nm;
+    return n;
+}
+
+/* recalibrate_model (src/align.c:665-773) over the 'M' entries: weighted least squares for (shift, scale) from
+ * the 2x2 normal equations accumulated in list order in double (:703-724), closed-form solve (:729-731), then
+ * var = sqrt(mean of squared residuals / stdv^2) (:738-751). Narrowing to float happens when the results are
+ * stored in scalings_t (:753-758). Returns 1 if recalibrated. */
+static int oracle_recalibrate(const abea_model_t* model, const abea_event_t* ev, const int32_t* m_rank,
+                              const int32_t* m_event, int32_t n_m, int32_t min_events, abea_scalings_t* sc,
+                              double* var_d) {
+    *var_d = 0;
+    if (n_m < min_events) return 0;
+    double A00 = 0, A01 = 0, A11 = 0, b0 = 0, b1 = 0;
+    for (int32_t j = 0; j < n_m; j++) {
+        double e = ev[m_event[j]].mean;
+        double mu = model[m_rank[j]].level_mean;
+        double sd = model[m_rank[j]].level_stdv;
+        double inv_var = 1. / (sd * sd);
+        A00 += inv_var;
+        A01 += mu * inv_var;
+        A11 += mu * mu * inv_var;
+        b0 += e * inv_var;
+        b1 += mu * e * inv_var;
+    }
+    double A10 = A01;
+    double div = A00 * A11 - A01 * A10;
+    double shift = -(A01 * b1 - A11 * b0) / div;
+    double scale = (A00 * b1 - A10 * b0) / div;
+    double var = 0.;
+    for (int32_t j = 0; j < n_m; j++) {
+        double e = ev[m_event[j]].mean;
+        double mu = model[m_rank[j]].level_mean;
+        double sd = model[m_rank[j]].level_stdv;
+        double yi = (e - shift - scale * mu);
+        var += yi * yi / (sd * sd);
+    }
+    var /= n_m;
+    var = sqrt(var);
+    sc->shift = (float)shift;
+    sc->scale = (float)scale;
+    sc->var = (float)var;
+    sc->log_var = (float)log(var);
+    *var_d = var;
+    return 1;
+}
+
+/* scaling_single (src/f5c.c:736-807): sc is db->scalings[i], in = method-of-moments, out = as the reference
+ * leaves it; map needs n_kmers entries when n_pairs > 0. */
+void abea_oracle_scaling_single(const abea_pair_t* pairs, int32_t n_pairs, const char* seq, int32_t seq_len,
+                                const abea_event_t* ev, int64_t n_events, const abea_model_t* model, uint32_t k,
+                                int32_t min_num_events_to_rescale, abea_scalings_t* sc, abea_index_pair_t* map,
+                                abea_scaling_result_t* out) {
+    (void)n_events;
+    memset(out, 0, sizeof(*out));
+    int32_t n_kmers = seq_len - (int32_t)k + 1;
+    if (n_pairs > 0) {
+        int32_t* m_rank = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_kmers > 0 ? n_kmers : 1));
+        int32_t* m_event = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_kmers > 0 ? n_kmers : 1));
+        int32_t n_m = 0;
+        out->n_event_alignment = oracle_postalign(map, &out->events_per_base, seq, n_kmers, pairs, n_pairs, k,
+                                                  m_rank, m_event, &n_m);
+        out->num_m_state = n_m;
+        out->calibrated = oracle_recalibrate(model, ev, m_rank, m_event, n_m, min_num_events_to_rescale, sc,
+                                             &out->var_d);
+        free(m_rank);
+        free(m_event);
+        if (!out->calibrated || sc->var > ABEA_MIN_CALIBRATION_VAR) out->flags |= ABEA_FAILED_CALIBRATION; /* :776-781 */
+        else if (out->events_per_base > ABEA_MAX_EVENTS_PER_BASE) out->flags |= ABEA_FAILED_QUALITY_CHK;   /* :798-803 */
+    } else {
+        out->flags |= ABEA_FAILED_ALIGNMENT; /* :787-793 */
+    }
+    out->scalings = *sc;
+}
+
 /* ---- batch driver: CPU branch of align_db (src/f5c.c:811-845) over a flat batch ------------------- */
 
 typedef struct {

@@ -88,6 +88,45 @@ int64_t f5cref_getevents(int64_t nsample, float* raw_pa, int8_t rna, abea_event_
     return n;
 }
 
+/* scaling_single (src/f5c.c:736-807) for one read: the reference's own postalign (src/align.c:561) and
+ * recalibrate_model (src/align.c:665) called in the order and with the flag logic of scaling_single, which lives
+ * in f5c.c and cannot link here. sc is db->scalings[i] (in: method-of-moments values; out: as the reference leaves
+ * it). map must hold n_kmers entries when n_pairs > 0 (the reference mallocs it there, src/f5c.c:746). */
+void f5cref_scaling_single(const abea_pair_t* pairs, int32_t n_pairs, const char* seq, int32_t seq_len,
+                           const abea_event_t* ev, int64_t n_events, const abea_model_t* model, uint32_t kmer_size,
+                           int32_t min_num_events_to_rescale, abea_scalings_t* sc, abea_index_pair_t* map,
+                           abea_scaling_result_t* out) {
+    static_assert(sizeof(abea_index_pair_t) == sizeof(index_pair_t), "index_pair_t layout");
+    memset(out, 0, sizeof(*out));
+    int32_t n_kmers = seq_len - (int32_t)kmer_size + 1;
+    scalings_t s;
+    memcpy(&s, sc, sizeof(s));
+    if (n_pairs > 0) {
+        event_alignment_t* ea = (event_alignment_t*)malloc(sizeof(event_alignment_t) * (size_t)(n_pairs + 1));
+        double epb = 0;
+        int32_t n_ea = postalign(ea, (index_pair_t*)map, &epb, (char*)seq, n_kmers, (AlignedPair*)pairs, n_pairs,
+                                 kmer_size);
+        out->events_per_base = epb;
+        out->n_event_alignment = n_ea;
+        for (int32_t j = 0; j < n_ea; j++) out->num_m_state += (ea[j].hmm_state == 'M');
+        event_table et;
+        et.n = (size_t)n_events;
+        et.start = 0;
+        et.end = (size_t)n_events;
+        et.event = (event_t*)ev;
+        bool calibrated = recalibrate_model((model_t*)model, kmer_size, et, &s, ea, n_ea, 1, min_num_events_to_rescale);
+        free(ea);
+        out->calibrated = calibrated ? 1 : 0;
+        if (!calibrated || s.var > MIN_CALIBRATION_VAR) out->flags |= FAILED_CALIBRATION;
+        else if (epb > 5.0) out->flags |= FAILED_QUALITY_CHK;
+    } else {
+        out->flags |= FAILED_ALIGNMENT;
+    }
+    memcpy(sc, &s, sizeof(s));
+    memcpy(&out->scalings, &s, sizeof(s));
+    out->var_d = 0; /* internal to recalibrate_model; only the restatement and the CUDA path report it */
+}
+
 typedef struct {
     const abea_batch_t* b;
     const abea_model_t* model;

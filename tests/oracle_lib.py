@@ -12,7 +12,8 @@ import subprocess
 
 import numpy as np
 
-from f5c_b200.batch import MODEL_DTYPE, PAIR_DTYPE, ReadBatch, CBatch
+from f5c_b200.batch import (MODEL_DTYPE, PAIR_DTYPE, SCALINGS_DTYPE, INDEX_PAIR_DTYPE, SCALING_RESULT_DTYPE,
+                             MIN_NUM_EVENTS_TO_RESCALE, ReadBatch, CBatch)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
@@ -33,6 +34,9 @@ assert STATS_DTYPE.itemsize == ctypes.sizeof(OracleStats)
 
 _port = None
 _ref = None
+# (pairs, n_pairs, seq, seq_len, events, n_events, model, k, min_num_events_to_rescale, scalings io, map, result)
+_SCALING_ARGS = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64,
+                 ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
 
 
 def build_port():
@@ -53,6 +57,7 @@ def port():
         lib.abea_oracle_estimate_scalings.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_void_p,
                                                       ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64,
                                                       ctypes.c_void_p]
+        lib.abea_oracle_scaling_single.argtypes = _SCALING_ARGS
         lib.abea_oracle_transitions.argtypes = [ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 4
         _port = lib
     return _port
@@ -74,6 +79,7 @@ def ref():
         lib.f5cref_estimate_scalings.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_void_p,
                                                  ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64,
                                                  ctypes.c_void_p]
+        lib.f5cref_scaling_single.argtypes = _SCALING_ARGS
         lib.f5cref_getevents.restype = ctypes.c_int64
         lib.f5cref_getevents.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int8, ctypes.c_void_p,
                                          ctypes.c_int64]
@@ -145,3 +151,76 @@ def assert_same_alignment(a: AlignResult, b: AlignResult, what: str = ""):
         if not np.array_equal(pa, pb):
             d = np.nonzero((pa["ref_pos"] != pb["ref_pos"]) | (pa["read_pos"] != pb["read_pos"]))[0]
             raise AssertionError(f"{what}: read {i} pairs differ first at {d[:5]}: {pa[d[:3]]} vs {pb[d[:3]]}")
+
+
+class ScalingResult:
+    """Per-read outputs of the stage after ABEA (scaling_single, reference src/f5c.c:736-807)."""
+
+    def __init__(self, batch: ReadBatch, res, maps):
+        self.map_ptr = batch.map_ptr()
+        self.res = res      # SCALING_RESULT_DTYPE [n]
+        self.maps = maps    # INDEX_PAIR_DTYPE [sum K]; meaningful only for reads with pairs
+
+    def read_map(self, i: int) -> np.ndarray:
+        return self.maps[int(self.map_ptr[i]):int(self.map_ptr[i + 1])]
+
+
+def _estimate(fn, batch: ReadBatch, model: np.ndarray) -> np.ndarray:
+    out = np.zeros(batch.n_reads, dtype=SCALINGS_DTYPE)
+    for i in range(batch.n_reads):
+        ev = np.ascontiguousarray(batch.read_events(i))
+        seq = batch.read_seq(i)
+        fn(seq, len(seq), model.ctypes.data, batch.kmer_size, ev.ctypes.data, len(ev), out[i:i + 1].ctypes.data)
+    return out
+
+
+def port_estimate_scalings(batch, model):
+    """estimate_scalings_using_mom per read through the restatement."""
+    return _estimate(port().abea_oracle_estimate_scalings, batch, model)
+
+
+def ref_estimate_scalings(batch, model):
+    """... and through the reference's own object code."""
+    return _estimate(ref().f5cref_estimate_scalings, batch, model)
+
+
+def _scaling(fn, batch: ReadBatch, model: np.ndarray, aln: AlignResult, scalings=None,
+             min_events: int = MIN_NUM_EVENTS_TO_RESCALE) -> ScalingResult:
+    res = np.zeros(batch.n_reads, dtype=SCALING_RESULT_DTYPE)
+    mp = batch.map_ptr()
+    maps = np.full(int(mp[-1]), -1, dtype=np.int32).repeat(2).view(INDEX_PAIR_DTYPE).copy()
+    sc = np.ascontiguousarray((batch.scalings if scalings is None else scalings).copy())
+    for i in range(batch.n_reads):
+        ev = np.ascontiguousarray(batch.read_events(i))
+        seq = batch.read_seq(i)
+        pairs = np.ascontiguousarray(aln.read_pairs(i))
+        m = maps[int(mp[i]):int(mp[i + 1])]
+        fn(pairs.ctypes.data if len(pairs) else None, int(aln.n_pairs[i]), seq, len(seq), ev.ctypes.data, len(ev),
+           model.ctypes.data, batch.kmer_size, min_events, sc[i:i + 1].ctypes.data,
+           m.ctypes.data if len(m) else None, res[i:i + 1].ctypes.data)
+    return ScalingResult(batch, res, maps)
+
+
+def port_scaling(batch, model, aln, scalings=None, min_events=MIN_NUM_EVENTS_TO_RESCALE):
+    return _scaling(port().abea_oracle_scaling_single, batch, model, aln, scalings, min_events)
+
+
+def ref_scaling(batch, model, aln, scalings=None, min_events=MIN_NUM_EVENTS_TO_RESCALE):
+    return _scaling(ref().f5cref_scaling_single, batch, model, aln, scalings, min_events)
+
+
+def assert_same_scaling(a: ScalingResult, b: ScalingResult, what: str = "", check_var_d: bool = True):
+    """Bit-exact parity of the scaling stage: the stored floats, the flags, the counts and the k-mer -> event map."""
+    for f in ("n_event_alignment", "num_m_state", "flags", "calibrated", "events_per_base"):
+        np.testing.assert_array_equal(a.res[f], b.res[f], err_msg=f"{what}: {f}")
+    if check_var_d:
+        np.testing.assert_array_equal(a.res["var_d"], b.res["var_d"], err_msg=f"{what}: var_d")
+    for f in ("shift", "scale", "var", "log_var"):
+        cal = a.res["calibrated"] != 0   # var / log_var are undefined (never written) for reads that were not recalibrated
+        x, y = a.res["scalings"][f], b.res["scalings"][f]
+        if f in ("var", "log_var"):
+            x, y = x[cal], y[cal]
+        np.testing.assert_array_equal(x.view(np.uint32), y.view(np.uint32), err_msg=f"{what}: scalings.{f}")
+    for i in range(a.res.shape[0]):
+        if a.res["n_event_alignment"][i] > 0:
+            assert np.array_equal(a.read_map(i), b.read_map(i)), f"{what}: base_to_event_map of read {i}"

@@ -138,6 +138,7 @@ static inline int __double2hiint(double d) { return (int)(simt::pack(d) >> 32); 
 static inline int __double2loint(double d) { return (int)(simt::pack(d) & 0xffffffffu); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }

@@ -44,3 +44,53 @@ def test_dropin_align_cuda_matches_oracle(built, which):
                                    n_pairs.ctypes.data) == 0
     got = ol.AlignResult(b, pairs, n_pairs)
     ol.assert_same_alignment(got, ol.port_align(b, m), "drop-in " + which)
+
+
+@needs_so
+def test_dropin_exports_scaling_entry_points():
+    out = subprocess.check_output(["nm", "-D", "--defined-only", SO]).decode()
+    for sym in ("_Z12scaling_cudaP6core_tP4db_t", "_Z22estimate_scalings_cudaP6core_tP4db_t"):
+        assert sym in out, sym
+
+
+@needs_so
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["synthetic", "edge"])
+def test_dropin_estimate_align_scaling_matches_oracle(built, which):
+    """estimate_scalings_cuda -> align_cuda -> scaling_cuda on real core_t / db_t against the oracle's
+    estimate_scalings_using_mom -> align -> scaling_single."""
+    from f5c_b200.batch import INDEX_PAIR_DTYPE, SCALING_RESULT_DTYPE, ReadBatch
+    lib = ctypes.CDLL(SO)
+    vp = ctypes.c_void_p
+    lib.f5c_dropin_selftest_scaling.argtypes = [ctypes.POINTER(CBatch), vp, ctypes.c_uint32, ctypes.c_int,
+                                                ctypes.c_int32, vp, vp, vp, vp]
+    b = synth.make_config("cfg2", seed=62, n_reads=64) if which == "synthetic" else edge_batch()
+    min_events = 200 if which == "synthetic" else 50
+    k, m = models.load_model("r9")
+    m = ol.full_model(m)
+    mp = b.map_ptr()
+    n_pairs = np.full(b.n_reads, -1, dtype=np.int32)
+    res = np.zeros(b.n_reads, dtype=SCALING_RESULT_DTYPE)
+    maps = np.full(2 * int(mp[-1]), -1, dtype=np.int32).view(INDEX_PAIR_DTYPE)
+    cb = b.as_c()
+    assert lib.f5c_dropin_selftest_scaling(ctypes.byref(cb), m.ctypes.data, k, 0, min_events, n_pairs.ctypes.data,
+                                           res.ctypes.data, maps.ctypes.data, mp.ctypes.data) == 0
+    usable = (b.good != 0) & (b.n_events >= 1) & (b.read_len >= k)
+    est = np.zeros(b.n_reads, dtype=b.scalings.dtype)
+    idx = np.flatnonzero(usable)
+    est[idx] = ol.port_estimate_scalings(b.subset(idx), m)
+    wb = ReadBatch(b.seq, b.seq_ptr, b.read_len, b.events, b.event_ptr, b.n_events, est, b.good, k)
+    want_aln = ol.port_align(wb, m)
+    want = ol.port_scaling(wb, m, want_aln, min_events=min_events)
+    assert np.array_equal(n_pairs, want_aln.n_pairs)
+    for f in ("flags", "n_event_alignment", "events_per_base"):
+        assert np.array_equal(res[f], want.res[f]), f
+    cal = want.res["calibrated"] != 0
+    for f in ("shift", "scale"):
+        assert np.array_equal(res["scalings"][f].view(np.uint32), want.res["scalings"][f].view(np.uint32)), f
+    for f in ("var", "log_var"):
+        assert np.array_equal(res["scalings"][f][cal].view(np.uint32), want.res["scalings"][f][cal].view(np.uint32)), f
+    got = ol.ScalingResult(b, res, maps)
+    for i in range(b.n_reads):
+        if want.res["n_event_alignment"][i] > 0:
+            assert np.array_equal(got.read_map(i), want.read_map(i)), i
