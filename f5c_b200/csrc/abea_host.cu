@@ -99,6 +99,8 @@ struct abea_ctx {
      * the fill asks for them, pair lists written to the caller's mapped buffer by the traceback */
     int stream_mode = 3;       /* ABEA_STREAM: bit 0 events in, bit 1 pair lists out; 0: always stage through the copy engine */
     int load_ctas = 64;        /* ABEA_LOAD_CTAS */
+    int64_t load_piece = ABEA_LOAD_PIECE_BYTES; /* ABEA_LOAD_PIECE_KB: smallest piece of a read the loader delivers */
+    double load_crit = 1.0;    /* ABEA_LOAD_CRIT: need times of the makespan-setting reads (wide, long) are scaled by this */
     DevBuf d_ready, d_items;
     std::vector<abea_load_item_t> items;
     cudaStream_t load_stream = nullptr;
@@ -212,7 +214,7 @@ void build_load_order(abea_ctx* c) {
     const int64_t n_pri = 4 * blocks, n_sec = (int64_t)(wpc - 4) * blocks;
     /* cycles per band (wide CTA; narrow warp sharing its sub-partition; narrow warp alone on it = a "long" read) and
      * per traceback step. The longest reads set the makespan, so their pieces are asked for early rather than late. */
-    const double CYC_WIDE = 450.0, CYC_NARROW = 1000.0, CYC_LONG = 600.0, CYC_TRACE = 350.0;
+    const double CYC_WIDE = 400.0, CYC_NARROW = 1000.0, CYC_LONG = 650.0, CYC_TRACE = 350.0;
     const double cyc_batch = (double)c->total_bands * 360.0 / ((double)c->sm_count * 4.0);
     const double long_thr = std::max(1.0, c->long_alpha * cyc_batch / 780.0); /* as in run_impl */
     auto rate = [&](int64_t r) {
@@ -253,12 +255,13 @@ void build_load_order(abea_ctx* c) {
     }
     struct need_t { double t; int32_t read, piece; };
     std::vector<need_t> need;
-    need.reserve((size_t)n + (size_t)(c->event_bytes / ABEA_LOAD_PIECE_BYTES) + 8);
+    need.reserve((size_t)n + (size_t)(c->event_bytes / c->load_piece) + 8);
     for (int64_t r = 0; r < n; r++) {
         const abea_read_t& rd = c->reads[r];
-        const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, c->event_bytes);
+        const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, c->event_bytes, c->load_piece);
         const double nb = (double)rd.n_events + rd.n_kmers + 2;
-        const double fill = nb * rate(r);
+        const double rt = rate(r);
+        const double fill = nb * rt * (rt < CYC_NARROW ? c->load_crit : 1.0);
         for (int32_t q = 0; q < g.n_pieces; q++) {
             /* the fill touches event e when it is about e/E of the way through the read's bands */
             const double frac = (double)abea_piece_first_event(g, q) / (double)rd.n_events;
@@ -340,6 +343,8 @@ int abea_create(abea_ctx_t** out, int device) {
     if (const char* e = getenv("ABEA_SCHED")) c->sched_policy = atoi(e) ? 1 : 0;
     if (const char* e = getenv("ABEA_STREAM")) c->stream_mode = atoi(e);
     if (const char* e = getenv("ABEA_LOAD_CTAS")) c->load_ctas = std::max(1, atoi(e));
+    if (const char* e = getenv("ABEA_LOAD_PIECE_KB")) c->load_piece = (int64_t)std::max(1, atoi(e)) * 1024;
+    if (const char* e = getenv("ABEA_LOAD_CRIT")) c->load_crit = atof(e);
     if (cudaStreamCreateWithFlags(&c->load_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_meta) != cudaSuccess || cudaEventCreate(&c->ev_loaded) != cudaSuccess ||
         cudaEventCreate(&c->ev_load0) != cudaSuccess) {
@@ -590,7 +595,7 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         ABEA_LAUNCH(abea_load_kernel, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
                     (const abea_load_item_t*)c->d_items.p, (int32_t)c->items.size(), (const uint4*)ev_alias,
                     (uint4*)c->d_events.p, c->event_bytes, (uint32_t*)c->d_flags.p, (uint32_t*)c->d_ready.p,
-                    (int32_t*)c->d_queue.p + 12);
+                    (int32_t*)c->d_queue.p + 12, c->load_piece);
         CU(cudaEventRecord(c->ev_loaded, c->load_stream));
         c->streaming = true;
     } else if (n_ev_total) {

@@ -204,7 +204,8 @@ struct abea_stream_t {
     uint32_t* stalled;          /* set to 1 if a wait for streamed events gave up (the host reports an error) */
 };
 
-#define ABEA_LOAD_PIECE_BYTES (96 * 1024) /* smallest work item of the loader: 768 lines of 128 B = 4096 events */
+#define ABEA_LOAD_PIECE_BYTES (48 * 1024) /* default smallest work item of the loader (384 lines of 128 B = 2048 events);
+                                           * the host passes the value in use (ABEA_LOAD_PIECE_KB) to both sides */
 #define ABEA_LOAD_MAX_PIECES 64           /* per read: its landed pieces are a 64-bit mask (two words of d_ready) */
 #define ABEA_LOAD_THREADS 128
 #define ABEA_LOAD_UNROLL 8                /* 16-B loads in flight per thread */
@@ -216,14 +217,15 @@ struct abea_load_item_t {
 
 /* The byte range of a read's events, widened to whole 128-B lines (clamped to the buffer): a line shared by two reads
  * is copied for both, so whichever is published first the line is complete — no SM can cache half a line. The range
- * is cut into at most 64 pieces of at least 96 KB (whole lines). */
+ * is cut into at most 64 pieces of at least piece_min bytes (whole lines). */
 struct abea_load_geom_t {
     int64_t a, b;   /* the read's own bytes [a, b) */
     int64_t lo, hi; /* widened to lines */
     int64_t piece;  /* bytes per piece */
     int32_t n_pieces;
 };
-__device__ __host__ __forceinline__ abea_load_geom_t abea_load_geom(int64_t ev_off, int32_t n_events, int64_t total_bytes) {
+__device__ __host__ __forceinline__ abea_load_geom_t abea_load_geom(int64_t ev_off, int32_t n_events, int64_t total_bytes,
+                                                                     int64_t piece_min) {
     abea_load_geom_t g;
     g.a = ev_off * (int64_t)sizeof(abea_event_t);
     g.b = g.a + (int64_t)n_events * (int64_t)sizeof(abea_event_t);
@@ -231,7 +233,7 @@ __device__ __host__ __forceinline__ abea_load_geom_t abea_load_geom(int64_t ev_o
     g.lo = g.a & ~(int64_t)127;
     g.hi = h < total_bytes ? h : total_bytes;
     int64_t per = (((g.hi - g.lo) + ABEA_LOAD_MAX_PIECES - 1) / ABEA_LOAD_MAX_PIECES + 127) & ~(int64_t)127;
-    g.piece = per > ABEA_LOAD_PIECE_BYTES ? per : ABEA_LOAD_PIECE_BYTES;
+    g.piece = per > piece_min ? per : piece_min;
     g.n_pieces = (int32_t)((g.hi - g.lo + g.piece - 1) / g.piece);
     return g;
 }
@@ -302,7 +304,8 @@ __device__ __forceinline__ int32_t abea_wait_landed_events(const uint32_t* w, in
 __global__ void __launch_bounds__(ABEA_LOAD_THREADS)
 abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* __restrict__ items, int32_t n_items,
                  const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t total_bytes,
-                 uint32_t* __restrict__ read_flags, uint32_t* __restrict__ ready, int32_t* __restrict__ counter) {
+                 uint32_t* __restrict__ read_flags, uint32_t* __restrict__ ready, int32_t* __restrict__ counter,
+                 int64_t piece_min) {
     __shared__ int s_item;
     const int tid = threadIdx.x;
     for (;;) {
@@ -313,7 +316,7 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
         if (it >= n_items) break;
         const abea_load_item_t item = items[it];
         const abea_read_t rd = reads[item.read];
-        const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, total_bytes);
+        const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, total_bytes, piece_min);
         const int64_t a = g.a, b = g.b;
         const int64_t p0 = g.lo + (int64_t)item.piece * g.piece;
         const int64_t p1 = (p0 + g.piece < g.hi) ? p0 + g.piece : g.hi;
