@@ -26,6 +26,13 @@ class AbeaError(RuntimeError):
     pass
 
 
+class CSignals(ctypes.Structure):
+    """ctypes image of abea_signals_t."""
+    _fields_ = [("n_reads", ctypes.c_int32), ("raw", ctypes.c_void_p), ("raw_ptr", ctypes.c_void_p),
+                ("n_samples", ctypes.c_void_p), ("offset", ctypes.c_void_p), ("range", ctypes.c_void_p),
+                ("digitisation", ctypes.c_void_p)]
+
+
 class Timing(ctypes.Structure):
     """abea_timing_t"""
     _fields_ = [("pack_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("kmer_ms", ctypes.c_double),
@@ -34,7 +41,8 @@ class Timing(ctypes.Structure):
                 ("d2h_bytes", ctypes.c_int64), ("kernel_launches", ctypes.c_int32),
                 ("n_scheduled", ctypes.c_int32), ("n_wide", ctypes.c_int32), ("streamed", ctypes.c_int32),
                 ("n_bands", ctypes.c_int64), ("n_events", ctypes.c_int64), ("load_ms", ctypes.c_double),
-                ("mom_ms", ctypes.c_double), ("scaling_ms", ctypes.c_double)]
+                ("mom_ms", ctypes.c_double), ("scaling_ms", ctypes.c_double), ("events_ms", ctypes.c_double),
+                ("n_samples", ctypes.c_int64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -63,6 +71,8 @@ def _bind(path: str):
     lib.abea_read_cycles.argtypes = [vp, vp, vp, vp]
     lib.abea_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
                                         ctypes.POINTER(i32)]
+    lib.abea_getevents.argtypes = [vp, ctypes.POINTER(CSignals), ctypes.c_int, vp, ctypes.POINTER(Timing)]
+    lib.abea_getevents_download.argtypes = [vp, vp, vp]
     lib.abea_estimate_scalings.argtypes = [vp, ctypes.c_int, vp, ctypes.POINTER(Timing)]
     lib.abea_scaling_stage.argtypes = [vp, i32, ctypes.POINTER(Timing)]
     lib.abea_scaling_download.argtypes = [vp, vp, vp, vp]
@@ -230,6 +240,35 @@ class AbeaContext:
         self._check(self.lib.abea_download(self._h, pairs.ctypes.data, pair_ptr.ctypes.data, n_pairs.ctypes.data,
                                            ctypes.byref(t)), "abea_download")
         return Alignment(pairs, pair_ptr, n_pairs, t.as_dict())
+
+    # -- event detection ---------------------------------------------------------------------------------
+    def getevents(self, raw, raw_ptr, n_samples, calibration=None, rna: bool = False):
+        """abea_getevents + abea_getevents_download: the reference's getevents (src/events.c:562-582) per read.
+
+        raw: float32 samples (ADC counts, or pA when calibration is None); calibration: (offset, range, digitisation)
+        float32 arrays per read. Returns (events EVENT_DTYPE, event_ptr int64 [n], n_events int32 [n], timing)."""
+        from .batch import EVENT_DTYPE
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        raw_ptr = np.ascontiguousarray(raw_ptr, dtype=np.int64)
+        n_samples = np.ascontiguousarray(n_samples, dtype=np.int32)
+        n = int(n_samples.shape[0])
+        cs = CSignals(n, raw.ctypes.data, raw_ptr.ctypes.data, n_samples.ctypes.data, None, None, None)
+        keep = None
+        if calibration is not None:
+            keep = [np.ascontiguousarray(a, dtype=np.float32) for a in calibration]
+            cs.offset, cs.range, cs.digitisation = (a.ctypes.data for a in keep)
+        n_events = np.zeros(n, dtype=np.int32)
+        t = Timing()
+        self._check(self.lib.abea_getevents(self._h, ctypes.byref(cs), int(bool(rna)), n_events.ctypes.data,
+                                            ctypes.byref(t)), "abea_getevents")
+        cnt = np.maximum(n_events, 0).astype(np.int64)
+        event_ptr = np.zeros(n, dtype=np.int64)
+        if n > 1:
+            np.cumsum(cnt[:-1], out=event_ptr[1:])
+        events = np.zeros(int(cnt.sum()), dtype=EVENT_DTYPE)
+        self._check(self.lib.abea_getevents_download(self._h, events.ctypes.data if len(events) else None,
+                                                     event_ptr.ctypes.data), "abea_getevents_download")
+        return events, event_ptr, n_events, t.as_dict()
 
     # -- the stages either side of the alignment ----------------------------------------------------------
     def estimate_scalings(self, n_reads: int, reverse_events: bool = False):

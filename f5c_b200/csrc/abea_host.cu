@@ -31,6 +31,7 @@
 #include "../../include/abea_b200.h"
 #include "abea_kernels.cuh"
 #include "scaling_kernels.cuh"
+#include "events_kernels.cuh"
 
 #define ABEA_VERSION_STR "abea-b200 0.1 (sm_100a)"
 
@@ -118,6 +119,12 @@ struct abea_ctx {
     bool scalings_on_device = false; /* d_scalings holds the batch's scalings (uploaded or estimated) */
     bool need_scalings = false;      /* the batch came without scalings: abea_estimate_scalings must run before abea_run */
     bool scaled = false;             /* abea_scaling_stage has run on the last abea_run's results */
+
+    /* event detection (events_kernels.cuh) */
+    std::vector<abea_sig_t> sigs;
+    DevBuf d_raw, d_sum, d_sumsq, d_peaks, d_evcap, d_sigs, d_nev, d_evptr, d_evout;
+    std::vector<int32_t> nev;        /* event counts of the last abea_getevents */
+    bool events_ready = false;
 };
 
 namespace {
@@ -382,7 +389,8 @@ void abea_destroy(abea_ctx_t* c) {
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_reads, &c->d_kparams,
                       &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags, &c->d_npairs,
-                      &c->d_ready, &c->d_items, &c->d_sreads, &c->d_scalings, &c->d_maps, &c->d_sres};
+                      &c->d_ready, &c->d_items, &c->d_sreads, &c->d_scalings, &c->d_maps, &c->d_sres,
+                      &c->d_raw, &c->d_sum, &c->d_sumsq, &c->d_peaks, &c->d_evcap, &c->d_sigs, &c->d_nev, &c->d_evptr, &c->d_evout};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_results.p) cudaFreeHost(c->h_results.p);
@@ -871,6 +879,89 @@ int abea_device_results(abea_ctx_t* c, const abea_pair_t** d_pairs, const int32_
     if (d_n_pairs) *d_n_pairs = (const int32_t*)c->d_npairs.p;
     if (total_pairs_capacity) *total_pairs_capacity = c->total_pair_cap;
     if (n_reads) *n_reads = c->n_batch_reads;
+    return ABEA_OK;
+}
+
+/* ---- event detection ----------------------------------------------------------------------------------------- */
+
+int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_events_out, abea_timing_t* timing) {
+    if (!c || !s || s->n_reads < 0 || !n_events_out) return fail(c, ABEA_ERR_ARG, "bad signals");
+    if (s->n_reads > 0 && (!s->raw || !s->raw_ptr || !s->n_samples)) return fail(c, ABEA_ERR_ARG, "bad signals");
+    if (s->offset && (!s->range || !s->digitisation)) return fail(c, ABEA_ERR_ARG, "offset without range / digitisation");
+    CU(cudaSetDevice(c->device));
+    c->events_ready = false;
+    const int32_t n = s->n_reads;
+    c->sigs.assign((size_t)n, abea_sig_t());
+    int64_t raw_total = 0, sum_total = 0, cap_total = 0;
+    for (int32_t i = 0; i < n; i++) {
+        abea_sig_t& g = c->sigs[i];
+        const int32_t ns = s->n_samples[i] > 0 ? s->n_samples[i] : 0;
+        g.raw_off = s->raw_ptr[i];
+        g.sum_off = sum_total;
+        g.cap_off = cap_total;
+        g.n_samples = ns;
+        g.cap = ns / 2 + 2;
+        g.offset = s->offset ? s->offset[i] : 0.f;
+        g.raw_unit = s->offset ? s->range[i] / s->digitisation[i] : 0.f; /* float division, src/f5c.c:693 */
+        raw_total = std::max(raw_total, g.raw_off + ns);
+        sum_total += (int64_t)ns + 1;
+        cap_total += g.cap;
+    }
+    if (dev_reserve(c, c->d_raw, (size_t)(raw_total + 1) * sizeof(float))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_sum, (size_t)(sum_total + 1) * sizeof(double))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_sumsq, (size_t)(sum_total + 1) * sizeof(double))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_peaks, (size_t)(cap_total + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_evcap, (size_t)(cap_total + 1) * sizeof(abea_event_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_sigs, ((size_t)n + 1) * sizeof(abea_sig_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_nev, ((size_t)n + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
+    CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
+    if (n > 0) {
+        CU(cudaMemcpyAsync(c->d_sigs.p, c->sigs.data(), (size_t)n * sizeof(abea_sig_t), cudaMemcpyHostToDevice, c->stream));
+        if (raw_total > 0) CU(cudaMemcpyAsync(c->d_raw.p, s->raw, (size_t)raw_total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
+    abea_det_param_t P;
+    if (rna) { P.w1 = 7; P.w2 = 14; P.thr1 = 2.5f; P.thr2 = 9.0f; P.peak_height = 1.0f; }  /* src/events.c:59-63 */
+    else     { P.w1 = 3; P.w2 = 6;  P.thr1 = 1.4f; P.thr2 = 9.0f; P.peak_height = 0.2f; }  /* src/events.c:52-56 */
+    CU(cudaEventRecord(c->ev[EV_S0], c->stream));
+    if (n > 0)
+        ABEA_LAUNCH(abea_events_kernel, (n + EVT_WARPS - 1) / EVT_WARPS, 32 * EVT_WARPS, c->stream,
+                    (const abea_sig_t*)c->d_sigs.p, n, (const float*)c->d_raw.p, (double*)c->d_sum.p, (double*)c->d_sumsq.p,
+                    (int32_t*)c->d_peaks.p, (abea_event_t*)c->d_evcap.p, (int32_t*)c->d_nev.p, P);
+    CU(cudaEventRecord(c->ev[EV_S1], c->stream));
+    c->nev.assign((size_t)n, 0);
+    if (n > 0) CU(cudaMemcpyAsync(c->nev.data(), c->d_nev.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    for (int32_t i = 0; i < n; i++) n_events_out[i] = c->nev[i];
+    c->events_ready = true;
+    c->last.events_ms = ev_ms(c, EV_S0, EV_S1);
+    c->last.h2d_ms = ev_ms(c, EV_H2D0, EV_H2D1);
+    c->last.n_samples = raw_total;
+    if (timing) *timing = c->last;
+    return ABEA_OK;
+}
+
+int abea_getevents_download(abea_ctx_t* c, abea_event_t* events, const int64_t* event_ptr) {
+    if (!c || !event_ptr) return fail(c, ABEA_ERR_ARG, "bad output");
+    if (!c->events_ready) return fail(c, ABEA_ERR_STATE, "abea_getevents_download before abea_getevents");
+    CU(cudaSetDevice(c->device));
+    const int32_t n = (int32_t)c->sigs.size();
+    int64_t total = 0;
+    for (int32_t i = 0; i < n; i++)
+        if (c->nev[i] > 0) total = std::max(total, event_ptr[i] + (int64_t)c->nev[i]);
+    if (total == 0) return ABEA_OK;
+    if (!events) return fail(c, ABEA_ERR_ARG, "bad output");
+    if (dev_reserve(c, c->d_evptr, ((size_t)n + 1) * sizeof(int64_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_evout, (size_t)(total + 1) * sizeof(abea_event_t))) return ABEA_ERR_CUDA;
+    CU(cudaMemcpyAsync(c->d_evptr.p, event_ptr, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_evout.p, 0, (size_t)total * sizeof(abea_event_t), c->stream));
+    ABEA_LAUNCH(abea_events_compact_kernel, (n + 3) / 4, 128, c->stream, (const abea_sig_t*)c->d_sigs.p, n,
+                (const abea_event_t*)c->d_evcap.p, (const int32_t*)c->d_nev.p, (const int64_t*)c->d_evptr.p,
+                (abea_event_t*)c->d_evout.p);
+    CU(cudaMemcpyAsync(events, c->d_evout.p, (size_t)total * sizeof(abea_event_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
     return ABEA_OK;
 }
 

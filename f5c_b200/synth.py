@@ -160,3 +160,33 @@ def make_config_shard(name: str, rank: int, world: int, seed: int = 42, reads_pe
     b = make_batch(seed=seed * 1000003 + rank + 1, e_star=e_star[shards[rank]], **p)
     b.meta.update(config=name, rank=rank, world=world, global_reads=per * world)
     return b
+
+
+def make_signals(n_reads: int, mean_events: float, sigma: float, seed: int, samples_per_event: float = 5.0,
+                 noise: float = 1.6, min_events: int = 40):
+    """Seeded synthetic raw signals for event detection (reference getevents, src/events.c): per read a piecewise
+    constant current (levels ~ N(90, 13) pA, dwell 1 + Geometric samples with the given mean) plus Gaussian noise,
+    quantised to int16 ADC counts with a MinION-like calibration. Returns a dict with
+    raw (float32 ADC counts, flat), raw_ptr, n_samples, offset, range, digitisation, and pa (the same samples in pA,
+    converted exactly as event_single does, src/f5c.c:692-696)."""
+    rng = np.random.default_rng(seed)
+    e_star = np.maximum(draw_lengths(n_reads, mean_events, sigma, rng), min_events).astype(np.int64)
+    total_e = int(e_star.sum())
+    dwell = rng.geometric(min(1.0, 1.0 / max(1.0, samples_per_event - 1.0)), total_e).astype(np.int64) + 1
+    level = rng.normal(90.0, 13.0, total_e)
+    read_of_event = np.repeat(np.arange(n_reads, dtype=np.int64), e_star)
+    n_samples = np.bincount(read_of_event, weights=dwell, minlength=n_reads).astype(np.int64)
+    pa_true = np.repeat(level, dwell) + noise * rng.standard_normal(int(dwell.sum()))
+    digitisation = np.full(n_reads, 8192.0, dtype=np.float32)
+    rng_pa = rng.uniform(1380.0, 1480.0, n_reads).astype(np.float32)
+    offset = np.round(rng.uniform(2.0, 20.0, n_reads)).astype(np.float32)
+    read_of_sample = np.repeat(np.arange(n_reads, dtype=np.int64), n_samples)
+    adc = np.round(pa_true * (digitisation[read_of_sample] / rng_pa[read_of_sample]) - offset[read_of_sample])
+    raw = np.clip(adc, -32768, 32767).astype(np.int16).astype(np.float32)
+    raw_ptr = np.zeros(n_reads, dtype=np.int64)
+    if n_reads > 1:
+        np.cumsum(n_samples[:-1], out=raw_ptr[1:])
+    raw_unit = (rng_pa / digitisation).astype(np.float32)
+    pa = ((raw + offset[read_of_sample]).astype(np.float32) * raw_unit[read_of_sample]).astype(np.float32)
+    return dict(raw=raw, raw_ptr=raw_ptr, n_samples=n_samples.astype(np.int32), offset=offset, range=rng_pa,
+                digitisation=digitisation, pa=pa)

@@ -10,6 +10,8 @@
  *   abea_upload_batch / abea_run /  the three phases of align_cuda   src/f5c.cu:744-899 (pack + H2D),
  *   abea_download                   kept separable for measurement   :910-960 (kernels), :979-1030 (D2H + unpack)
  *   abea_model_fill_log_stdv        set_model's CACHED_LOG fill      src/model.c:179
+ *   abea_getevents /                getevents (event detection) per  src/events.c:562-582, called by event_single
+ *   abea_getevents_download         read + the pA conversion         src/f5c.c:692-703
  *   abea_estimate_scalings          estimate_scalings_using_mom      src/align.c:58-106, called per read by event_single
  *                                   (+ the RNA event reversal)       src/f5c.c:709-721
  *   abea_scaling_stage /            scaling_db = scaling_single per  src/f5c.c:736-807: postalign src/align.c:561-660,
@@ -71,6 +73,8 @@ typedef struct {
     double load_ms;          /* device: abea_load_kernel, first CTA start to last piece landed (streaming only) */
     double mom_ms;           /* device: abea_mom_kernel (abea_estimate_scalings) */
     double scaling_ms;       /* device: abea_scaling_kernel (abea_scaling_stage) */
+    double events_ms;        /* device: abea_events_kernel (abea_getevents) */
+    int64_t n_samples;       /* raw samples of the last abea_getevents */
 } abea_timing_t;
 
 /* Create a context on CUDA device `device` (cudaSetDevice is applied on every call). */
@@ -93,6 +97,18 @@ int abea_upload_batch(abea_ctx_t* ctx, const abea_batch_t* batch, abea_timing_t*
 int abea_run(abea_ctx_t* ctx, abea_timing_t* timing);
 int abea_download(abea_ctx_t* ctx, abea_pair_t* pairs, const int64_t* pair_ptr, int32_t* n_pairs,
                   abea_timing_t* timing);
+
+/* ---- event detection; bit-identical to the reference's CPU code ----
+ *
+ * abea_getevents: getevents(nsample, rawptr, rna) (src/events.c:562-582) for every read of a batch of raw signals,
+ * including event_single's conversion to picoamperes when the calibration arrays are given. n_events_out[i]
+ * receives the number of events of read i (0 for signals shorter than 100 samples, which the reference asserts
+ * on; -1 if a signal produced more than n_samples/2 + 1 boundaries, which no real signal does). The event tables stay
+ * on the device until abea_getevents_download copies them to events[event_ptr[i] ..] — the caller sizes and lays
+ * out that array from the counts (e.g. a prefix sum), which is the abea_batch_t.events / event_ptr of the alignment.
+ * rna != 0 selects the RNA detector parameters (src/events.c:59-63). */
+int abea_getevents(abea_ctx_t* ctx, const abea_signals_t* signals, int rna, int32_t* n_events_out, abea_timing_t* timing);
+int abea_getevents_download(abea_ctx_t* ctx, abea_event_t* events, const int64_t* event_ptr);
 
 /* ---- the stages either side of the alignment; bit-identical to the reference's CPU code ----
  *

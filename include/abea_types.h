@@ -95,6 +95,23 @@ typedef struct {
 #define ABEA_MODEL_ID_DNA_R10 4
 #define ABEA_MODEL_ID_RNA_RNA004 6
 
+/* A batch of raw nanopore signals in flat form, the input of event detection (reference: signal_t / db->sig[i],
+ * src/f5c.h:262-287, as event_single reads it, src/f5c.c:684-696).
+ *   raw          : concatenated samples as float — the ADC counts the reader hands over (slow5/fast5 int16 widened
+ *                  to float), or picoamperes when offset == NULL
+ *   raw_ptr      : first sample of read i; n_samples: its length
+ *   offset, range, digitisation : per read; pA = (raw + offset) * (range / digitisation), all in float
+ */
+typedef struct {
+    int32_t n_reads;
+    const float* raw;
+    const int64_t* raw_ptr;
+    const int32_t* n_samples;
+    const float* offset;
+    const float* range;
+    const float* digitisation;
+} abea_signals_t;
+
 /* A ragged batch of reads in flat (CSR-style) form: what the reference's align_cuda packs db_t into
  * (src/f5c.cu:744-800) and what every implementation in this repo (CUDA path, oracle, _ref shim)
  * consumes. All pointers are host pointers unless a function says otherwise.

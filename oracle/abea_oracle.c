@@ -16,6 +16,7 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this library. The product path (f5c_b200/) never does.
  */
+#include <float.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdint.h>
@@ -379,6 +380,119 @@ void abea_oracle_scaling_single(const abea_pair_t* pairs, int32_t n_pairs, const
         out->flags |= ABEA_FAILED_ALIGNMENT; /* :787-793 */
     }
     out->scalings = *sc;
+}
+
+/* ---- the stage before everything: getevents (src/events.c:562-582) ----------------------------------------- */
+
+/* getevents ignores what trim_and_segment_raw returns (src/events.c:572), so event detection runs over the whole
+ * signal: cumulative sums in double (:297-307; the square is a FLOAT product), two windowed t-statistics
+ * (:320-372), the short/long peak detector (:379-448), and one event per gap between peaks (:463-515).
+ * Mixed float/double expressions are restated with the C++ promotion rules the reference is compiled under
+ * (fabs / sqrt on float arguments are the float overloads). Cases the reference leaves undefined — fewer than 100
+ * samples (an assert in trim_raw_by_mad), no peak at all (create_events reads peaks[-1]) — yield 0 events / one
+ * event over the whole signal here. */
+typedef struct {
+    int32_t w1, w2;
+    float thr1, thr2, peak_height;
+} det_param_t;
+static const det_param_t DET_DNA = {3, 6, 1.4f, 9.0f, 0.2f};   /* src/events.c:52-56 */
+static const det_param_t DET_RNA = {7, 14, 2.5f, 9.0f, 1.0f};  /* src/events.c:59-63 */
+
+static float tstat_at(const double* sum, const double* sumsq, int64_t n, int64_t i, int32_t w) {
+    if (n < 2 * (int64_t)w || w < 2) return 0.f;
+    if (i < w || i > n - w) return 0.f;
+    const float wf = (float)w;
+    double sum1 = sum[i], sumsq1 = sumsq[i];
+    if (i > w) {
+        sum1 -= sum[i - w];
+        sumsq1 -= sumsq[i - w];
+    }
+    float sum2 = (float)(sum[i + w] - sum[i]);
+    float sumsq2 = (float)(sumsq[i + w] - sumsq[i]);
+    float mean1 = (float)(sum1 / wf);
+    float mean2 = sum2 / wf;
+    float combined_var = (float)(sumsq1 / wf - (double)(mean1 * mean1) + (double)(sumsq2 / wf) - (double)(mean2 * mean2));
+    combined_var = fmaxf(combined_var, FLT_MIN);
+    const float delta_mean = mean2 - mean1;
+    return fabsf(delta_mean) / sqrtf(combined_var / wf);
+}
+
+typedef struct {
+    int64_t masked_to;
+    int64_t peak_pos; /* -1 = none */
+    float peak_value, threshold;
+    int32_t window;
+    int valid;
+} det_t;
+
+/* events must have room for n_samples / 2 + 2 entries. Returns the number of events. */
+int64_t abea_oracle_getevents(int64_t n_samples, const float* raw, int8_t rna, abea_event_t* events) {
+    const det_param_t P = rna ? DET_RNA : DET_DNA;
+    const int64_t n = n_samples;
+    if (n < 100) return 0;
+    double* sum = (double*)malloc(sizeof(double) * (size_t)(n + 1));
+    double* sumsq = (double*)malloc(sizeof(double) * (size_t)(n + 1));
+    int64_t* peaks = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n + 1));
+    sum[0] = 0.0;
+    sumsq[0] = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        sum[i + 1] = sum[i] + raw[i];
+        sumsq[i + 1] = sumsq[i] + raw[i] * raw[i];
+    }
+    det_t d[2] = {{0, -1, FLT_MAX, P.thr1, P.w1, 0}, {0, -1, FLT_MAX, P.thr2, P.w2, 0}};
+    int64_t n_peaks = 0;
+    for (int64_t i = 0; i < n; i++) {
+        for (int k = 0; k < 2; k++) {
+            det_t* t = &d[k];
+            if (t->masked_to >= i) continue;
+            const float v = tstat_at(sum, sumsq, n, i, t->window);
+            if (t->peak_pos == -1) {
+                if (v < t->peak_value) {
+                    t->peak_value = v;
+                } else if (v - t->peak_value > P.peak_height) {
+                    t->peak_value = v;
+                    t->peak_pos = i;
+                }
+            } else {
+                if (v > t->peak_value) {
+                    t->peak_value = v;
+                    t->peak_pos = i;
+                }
+                if (k == 0 && t->peak_value > t->threshold) { /* the short detector silences the long one */
+                    d[1].masked_to = t->peak_pos + t->window;
+                    d[1].peak_pos = -1;
+                    d[1].peak_value = FLT_MAX;
+                    d[1].valid = 0;
+                }
+                if (t->peak_value - v > P.peak_height && t->peak_value > t->threshold) t->valid = 1;
+                if (t->valid && (i - t->peak_pos) > t->window / 2) {
+                    peaks[n_peaks++] = t->peak_pos;
+                    t->peak_pos = -1;
+                    t->peak_value = v;
+                    t->valid = 0;
+                }
+            }
+        }
+    }
+    /* create_events counts the entries of the zero-padded peak list that are > 0 and < nsample (:485-489) */
+    int64_t n_ev = 1;
+    for (int64_t j = 0; j < n_peaks; j++) n_ev += (peaks[j] > 0 && peaks[j] < n);
+    for (int64_t e = 0; e < n_ev; e++) {
+        const int64_t start = e == 0 ? 0 : peaks[e - 1];
+        const int64_t end = (e == n_ev - 1) ? n : peaks[e];
+        abea_event_t ev;
+        ev.start = (uint64_t)start;
+        ev.length = (float)(end - start);
+        ev.mean = (float)(sum[end] - sum[start]) / ev.length;
+        const float deltasqr = (float)(sumsq[end] - sumsq[start]);
+        const float var = deltasqr / ev.length - ev.mean * ev.mean;
+        ev.stdv = sqrtf(fmaxf(var, 0.0f));
+        events[e] = ev;
+    }
+    free(sum);
+    free(sumsq);
+    free(peaks);
+    return n_ev;
 }
 
 /* ---- batch driver: CPU branch of align_db (src/f5c.c:811-845) over a flat batch ------------------- */

@@ -85,7 +85,8 @@ def single_read(model, k):
     return name, seq, ev, sc, gold
 
 
-def ecoli_reads(model, k):
+def ecoli_raw():
+    """{read_id: (digitisation, offset, range, sample_rate, int16 signal)} of test/ecoli_2kb_region/reads.blow5."""
     tmp = tempfile.mkdtemp(prefix="slow5build")
     src = os.path.join(tmp, "slow5lib")
     shutil.copytree(os.path.join(REF, "slow5lib"), src)
@@ -107,16 +108,24 @@ def ecoli_reads(model, k):
             sig = np.frombuffer(f.read(2 * n), dtype=np.int16)
             raw[rid] = (dig, off, rng, sr, sig)
     shutil.rmtree(tmp)
+    return raw
+
+
+def to_pa(sig, dig, off, rng):
+    """event_single, src/f5c.c:692-696: all float"""
+    rawf = sig.astype(np.float32)
+    raw_unit = np.float32(np.float32(rng) / np.float32(dig))
+    return np.ascontiguousarray(((rawf + np.float32(off)) * raw_unit).astype(np.float32))
+
+
+def ecoli_reads(model, k):
+    raw = ecoli_raw()
     reads = []
     for name, seq in read_fasta(os.path.join(ECOLI, "reads.fasta")):
         if name not in raw:
             continue
         dig, off, rng, sr, sig = raw[name]
-        # event_single, src/f5c.c:692-696: all float
-        rawf = sig.astype(np.float32)
-        raw_unit = np.float32(np.float32(rng) / np.float32(dig))
-        pa = ((rawf + np.float32(off)) * raw_unit).astype(np.float32)
-        pa = np.ascontiguousarray(pa)
+        pa = to_pa(sig, dig, off, rng)
         ev = np.zeros(len(pa), dtype=EVENT_DTYPE)
         n = ol.ref().f5cref_getevents(len(pa), pa.ctypes.data, 0, ev.ctypes.data, len(ev))
         ev = ev[:n].copy()

@@ -58,6 +58,8 @@ def port():
                                                       ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64,
                                                       ctypes.c_void_p]
         lib.abea_oracle_scaling_single.argtypes = _SCALING_ARGS
+        lib.abea_oracle_getevents.restype = ctypes.c_int64
+        lib.abea_oracle_getevents.argtypes = [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int8, ctypes.c_void_p]
         lib.abea_oracle_transitions.argtypes = [ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 4
         _port = lib
     return _port
@@ -224,3 +226,25 @@ def assert_same_scaling(a: ScalingResult, b: ScalingResult, what: str = "", chec
     for i in range(a.res.shape[0]):
         if a.res["n_event_alignment"][i] > 0:
             assert np.array_equal(a.read_map(i), b.read_map(i)), f"{what}: base_to_event_map of read {i}"
+
+
+def _events_equal(a, b):
+    return len(a) == len(b) and all(np.array_equal(a[f], b[f]) for f in ("start", "length", "mean", "stdv"))
+
+
+def port_getevents(pa: np.ndarray, rna: bool = False) -> np.ndarray:
+    """getevents (reference src/events.c:562-582) through the restatement; pa = float32 samples in pA."""
+    from f5c_b200.batch import EVENT_DTYPE
+    pa = np.ascontiguousarray(pa, dtype=np.float32)
+    ev = np.zeros(len(pa) // 2 + 2, dtype=EVENT_DTYPE)
+    n = port().abea_oracle_getevents(len(pa), pa.ctypes.data, int(rna), ev.ctypes.data)
+    return ev[:n].copy()
+
+
+def ref_getevents(pa: np.ndarray, rna: bool = False) -> np.ndarray:
+    from f5c_b200.batch import EVENT_DTYPE
+    pa = np.ascontiguousarray(pa.copy(), dtype=np.float32)
+    ev = np.zeros(len(pa) // 2 + 2, dtype=EVENT_DTYPE)
+    n = ref().f5cref_getevents(len(pa), pa.ctypes.data, int(rna), ev.ctypes.data, len(ev))
+    assert n <= len(ev)
+    return ev[:n].copy()

@@ -1,0 +1,172 @@
+"""Event detection: the reference's getevents (src/events.c:562-582) + event_single's pA
+conversion (src/f5c.c:692-696).
+
+CPU tests pin the oracle restatement (oracle/abea_oracle.c abea_oracle_getevents) to the reference's golden event
+table test/ecoli_2kb_region/single_read/read1.events.exp and to committed real signals whose event tables reproduce
+adaptive.exp (tests/golden/make_events_golden.py), compare it with the reference object code where that is built,
+and run the CUDA kernel's control flow on the SIMT emulator. GPU tests are the parity tests proper, through the C
+ABI. Bar: bit-exact event tables (start, length, mean, stdv)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from f5c_b200 import synth
+from f5c_b200.abea import AbeaContext
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SIG = np.load(os.path.join(HERE, "golden", "events_golden.npz"))
+NPZ = np.load(os.path.join(HERE, "golden", "abea_golden.npz"))
+EMU = os.path.join(HERE, "simt", "libabea_emu.so")
+
+
+def to_pa(sig, cal):
+    """event_single, reference src/f5c.c:692-696 (all float)."""
+    off, rng, dig = (np.float32(x) for x in cal)
+    return ((sig.astype(np.float32) + off) * np.float32(rng / dig)).astype(np.float32)
+
+
+def fixture_reads():
+    """(int16 signal, (offset, range, digitisation), expected events) of the committed ecoli reads."""
+    out = []
+    for j in range(3):
+        i = int(SIG[f"idx{j}"][0])
+        p, n = int(NPZ["ecoli_event_ptr"][i]), int(NPZ["ecoli_n_events"][i])
+        out.append((SIG[f"sig{j}"], SIG[f"cal{j}"], NPZ["ecoli_events"][p:p + n]))
+    return out
+
+
+def check_single_read(ev):
+    """test/ecoli_2kb_region/single_read/read1.events.exp: 7165 events printed with %f."""
+    g = NPZ["single_events"]
+    assert len(ev) == len(g) == 7165
+    assert np.array_equal(ev["start"], g["start"]) and np.array_equal(ev["length"], g["length"])
+    assert np.abs(ev["mean"].astype(np.float64) - g["mean"]).max() < 1e-6
+    assert np.abs(ev["stdv"].astype(np.float64) - g["stdv"]).max() < 1e-6
+
+
+# ---- the oracle is pinned (CPU) ---------------------------------------------------------------------------------
+
+def test_port_reproduces_reference_golden_event_table():
+    check_single_read(ol.port_getevents(to_pa(SIG["single_sig"], SIG["single_cal"])))
+
+
+def test_port_reproduces_committed_event_tables():
+    for sig, cal, want in fixture_reads():
+        assert ol._events_equal(ol.port_getevents(to_pa(sig, cal)), want)
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("rna", [False, True])
+def test_port_equals_reference_object_code(rna):
+    sg = synth.make_signals(24, 1500, 0.7, seed=7 + rna, samples_per_event=12.0 if rna else 5.0)
+    for i in range(24):
+        pa = sg["pa"][sg["raw_ptr"][i]:sg["raw_ptr"][i] + sg["n_samples"][i]]
+        assert ol._events_equal(ol.port_getevents(pa, rna), ol.ref_getevents(pa, rna)), i
+    flat = np.full(500, 80.0, dtype=np.float32)          # a signal without a single boundary: one event here,
+    assert len(ol.port_getevents(flat)) == 1              # undefined in the reference (it reads peaks[-1])
+    assert len(ol.port_getevents(flat[:50])) == 0         # < 100 samples: the reference asserts
+
+
+# ---- the CUDA path --------------------------------------------------------------------------------------------------
+
+def check_device(ctx, sg, rna=False, calibrated=True):
+    if calibrated:
+        ev, ptr, nev, t = ctx.getevents(sg["raw"], sg["raw_ptr"], sg["n_samples"],
+                                        (sg["offset"], sg["range"], sg["digitisation"]), rna=rna)
+    else:
+        ev, ptr, nev, t = ctx.getevents(sg["pa"], sg["raw_ptr"], sg["n_samples"], None, rna=rna)
+    for i in range(len(nev)):
+        pa = sg["pa"][sg["raw_ptr"][i]:sg["raw_ptr"][i] + sg["n_samples"][i]]
+        want = ol.port_getevents(pa, rna)
+        assert ol._events_equal(ev[ptr[i]:ptr[i] + nev[i]], want), (i, int(nev[i]), len(want))
+    return ev, ptr, nev, t
+
+
+def fixture_signals():
+    reads = fixture_reads()
+    sigs = [r[0] for r in reads] + [SIG["single_sig"]]
+    cals = [r[1] for r in reads] + [SIG["single_cal"]]
+    n = np.array([len(s) for s in sigs], dtype=np.int32)
+    ptr = np.zeros(len(sigs), dtype=np.int64)
+    np.cumsum(n[:-1], out=ptr[1:])
+    raw = np.concatenate(sigs).astype(np.float32)
+    off, rng, dig = (np.array([c[k] for c in cals], dtype=np.float32) for k in range(3))
+    return raw, ptr, n, (off, rng, dig), [r[2] for r in reads]
+
+
+def check_fixture_on(ctx):
+    raw, ptr, n, cal, want = fixture_signals()
+    ev, eptr, nev, t = ctx.getevents(raw, ptr, n, cal)
+    for i, w in enumerate(want):
+        assert ol._events_equal(ev[eptr[i]:eptr[i] + nev[i]], w), i
+    check_single_read(ev[eptr[3]:eptr[3] + nev[3]])
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import subprocess
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "simt")])
+    return EMU
+
+
+@pytest.mark.parametrize("rna", [False, True])
+def test_emulated_kernel_matches_oracle(emu, rna):
+    sg = synth.make_signals(9, 400, 0.6, seed=11 + rna, samples_per_event=12.0 if rna else 5.0)
+    sg["n_samples"][3] = 60                                  # shorter than 100 samples: no events
+    with AbeaContext(0, lib_path=emu) as ctx:
+        ev, ptr, nev, t = check_device(ctx, sg, rna, calibrated=True)
+        assert nev[3] == 0 and (np.delete(nev, 3) > 20).all()
+        check_device(ctx, sg, rna, calibrated=False)
+
+
+def test_emulated_kernel_on_real_signals(emu):
+    with AbeaContext(0, lib_path=emu) as ctx:
+        check_fixture_on(ctx)
+
+
+@pytest.fixture(scope="module")
+def gctx(built):
+    c = AbeaContext(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rna,n,mean", [(False, 256, 4000), (True, 64, 6000), (False, 512, 150)])
+def test_gpu_getevents_synthetic(gctx, rna, n, mean):
+    sg = synth.make_signals(n, mean, 0.6, seed=21 + rna, samples_per_event=12.0 if rna else 5.0)
+    check_device(gctx, sg, rna, calibrated=True)
+    check_device(gctx, sg, rna, calibrated=False)
+
+
+@pytest.mark.gpu
+def test_gpu_getevents_golden_signals(gctx):
+    check_fixture_on(gctx)
+
+
+@pytest.mark.gpu
+def test_gpu_getevents_full_size_properties(gctx):
+    """4096 signals of cfg2's event counts (~81 M samples): size-independent properties on every read, oracle parity
+    on a sample, and the events feed the alignment."""
+    sg = synth.make_signals(4096, 4000, 0.5, seed=42)
+    ev, ptr, nev, t = gctx.getevents(sg["raw"], sg["raw_ptr"], sg["n_samples"],
+                                     (sg["offset"], sg["range"], sg["digitisation"]))
+    assert (nev > 0).all()
+    end = ev["start"].astype(np.int64) + ev["length"].astype(np.int64)
+    first = ptr
+    last = ptr + nev - 1
+    assert (ev["start"][first] == 0).all() and np.array_equal(end[last], sg["n_samples"].astype(np.int64))
+    inner = np.ones(len(ev), dtype=bool)
+    inner[last] = False
+    assert np.array_equal(end[inner], ev["start"][1:][inner[:-1]].astype(np.int64))   # events tile the signal
+    assert (ev["length"] >= 1).all() and (ev["stdv"] >= 0).all()
+    # sum over events of mean * length == sum of samples (within float accumulation of the check itself)
+    i = int(np.argmax(nev))
+    pa = sg["pa"][sg["raw_ptr"][i]:sg["raw_ptr"][i] + sg["n_samples"][i]]
+    e = ev[ptr[i]:ptr[i] + nev[i]]
+    assert abs(float((e["mean"].astype(np.float64) * e["length"]).sum()) - float(pa.astype(np.float64).sum())) < 1e-2 * len(e)
+    for i in list(np.random.default_rng(3).choice(4096, 24, replace=False)) + [int(np.argmax(nev))]:
+        pa = sg["pa"][sg["raw_ptr"][i]:sg["raw_ptr"][i] + sg["n_samples"][i]]
+        assert ol._events_equal(ev[ptr[i]:ptr[i] + nev[i]], ol.port_getevents(pa)), i
