@@ -122,7 +122,7 @@ struct abea_ctx {
 
     /* event detection (events_kernels.cuh) */
     std::vector<abea_sig_t> sigs;
-    DevBuf d_raw, d_sum, d_sumsq, d_peaks, d_evcap, d_sigs, d_nev, d_evptr, d_evout;
+    DevBuf d_raw, d_sum, d_sumsq, d_ts1, d_ts2, d_peaks, d_evcap, d_sigs, d_sigorder, d_nev, d_evptr, d_evout;
     std::vector<int32_t> nev;        /* event counts of the last abea_getevents */
     bool events_ready = false;
 };
@@ -390,7 +390,8 @@ void abea_destroy(abea_ctx_t* c) {
     DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_reads, &c->d_kparams,
                       &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags, &c->d_npairs,
                       &c->d_ready, &c->d_items, &c->d_sreads, &c->d_scalings, &c->d_maps, &c->d_sres,
-                      &c->d_raw, &c->d_sum, &c->d_sumsq, &c->d_peaks, &c->d_evcap, &c->d_sigs, &c->d_nev, &c->d_evptr, &c->d_evout};
+                      &c->d_raw, &c->d_sum, &c->d_sumsq, &c->d_ts1, &c->d_ts2, &c->d_peaks, &c->d_evcap, &c->d_sigs, &c->d_sigorder,
+                      &c->d_nev, &c->d_evptr, &c->d_evout};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_results.p) cudaFreeHost(c->h_results.p);
@@ -892,12 +893,13 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     c->events_ready = false;
     const int32_t n = s->n_reads;
     c->sigs.assign((size_t)n, abea_sig_t());
-    int64_t raw_total = 0, sum_total = 0, cap_total = 0;
+    int64_t raw_total = 0, sum_total = 0, cap_total = 0, ts_total = 0;
     for (int32_t i = 0; i < n; i++) {
         abea_sig_t& g = c->sigs[i];
         const int32_t ns = s->n_samples[i] > 0 ? s->n_samples[i] : 0;
         g.raw_off = s->raw_ptr[i];
         g.sum_off = sum_total;
+        g.ts_off = ts_total;
         g.cap_off = cap_total;
         g.n_samples = ns;
         g.cap = ns / 2 + 2;
@@ -905,11 +907,19 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
         g.raw_unit = s->offset ? s->range[i] / s->digitisation[i] : 0.f; /* float division, src/f5c.c:693 */
         raw_total = std::max(raw_total, g.raw_off + ns);
         sum_total += (int64_t)ns + 1;
+        ts_total += ((int64_t)ns + 3) & ~(int64_t)3;
         cap_total += g.cap;
     }
+    /* the detector runs one thread per read: longest first, so that the 32 reads of a warp end together */
+    std::vector<int32_t> order((size_t)n);
+    for (int32_t i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return c->sigs[x].n_samples > c->sigs[y].n_samples; });
     if (dev_reserve(c, c->d_raw, (size_t)(raw_total + 1) * sizeof(float))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_sum, (size_t)(sum_total + 1) * sizeof(double))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_sumsq, (size_t)(sum_total + 1) * sizeof(double))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_ts1, (size_t)(ts_total + 4) * sizeof(float))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_ts2, (size_t)(ts_total + 4) * sizeof(float))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_sigorder, ((size_t)n + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_peaks, (size_t)(cap_total + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_evcap, (size_t)(cap_total + 1) * sizeof(abea_event_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_sigs, ((size_t)n + 1) * sizeof(abea_sig_t))) return ABEA_ERR_CUDA;
@@ -917,6 +927,7 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
     if (n > 0) {
         CU(cudaMemcpyAsync(c->d_sigs.p, c->sigs.data(), (size_t)n * sizeof(abea_sig_t), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_sigorder.p, order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         if (raw_total > 0) CU(cudaMemcpyAsync(c->d_raw.p, s->raw, (size_t)raw_total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
     CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
@@ -924,10 +935,17 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     if (rna) { P.w1 = 7; P.w2 = 14; P.thr1 = 2.5f; P.thr2 = 9.0f; P.peak_height = 1.0f; }  /* src/events.c:59-63 */
     else     { P.w1 = 3; P.w2 = 6;  P.thr1 = 1.4f; P.thr2 = 9.0f; P.peak_height = 0.2f; }  /* src/events.c:52-56 */
     CU(cudaEventRecord(c->ev[EV_S0], c->stream));
-    if (n > 0)
-        ABEA_LAUNCH(abea_events_kernel, (n + EVT_WARPS - 1) / EVT_WARPS, 32 * EVT_WARPS, c->stream,
+    if (n > 0) {
+        ABEA_LAUNCH(abea_events_sums_kernel, (n + EVT_WARPS - 1) / EVT_WARPS, 32 * EVT_WARPS, c->stream,
                     (const abea_sig_t*)c->d_sigs.p, n, (const float*)c->d_raw.p, (double*)c->d_sum.p, (double*)c->d_sumsq.p,
-                    (int32_t*)c->d_peaks.p, (abea_event_t*)c->d_evcap.p, (int32_t*)c->d_nev.p, P);
+                    (float*)c->d_ts1.p, (float*)c->d_ts2.p, P);
+        ABEA_LAUNCH(abea_events_detect_kernel, (n + 31) / 32, 32, c->stream, (const abea_sig_t*)c->d_sigs.p,
+                    (const int32_t*)c->d_sigorder.p, n, (const float*)c->d_ts1.p, (const float*)c->d_ts2.p,
+                    (int32_t*)c->d_peaks.p, (int32_t*)c->d_nev.p, P);
+        ABEA_LAUNCH(abea_events_create_kernel, (n + EVT_WARPS - 1) / EVT_WARPS, 32 * EVT_WARPS, c->stream,
+                    (const abea_sig_t*)c->d_sigs.p, n, (const double*)c->d_sum.p, (const double*)c->d_sumsq.p,
+                    (const int32_t*)c->d_peaks.p, (abea_event_t*)c->d_evcap.p, (const int32_t*)c->d_nev.p);
+    }
     CU(cudaEventRecord(c->ev[EV_S1], c->stream));
     c->nev.assign((size_t)n, 0);
     if (n > 0) CU(cudaMemcpyAsync(c->nev.data(), c->d_nev.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

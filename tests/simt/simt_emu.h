@@ -126,6 +126,7 @@ static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c); }
 static inline float __double2float_rn(double a) { return (float)a; }
 static inline float __int_as_float(int i) { return simt::unpack<float>((uint64_t)(uint32_t)i); }
 static inline int __float_as_int(float f) { return (int)(uint32_t)simt::pack(f); }
