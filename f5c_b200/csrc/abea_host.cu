@@ -123,6 +123,8 @@ struct abea_ctx {
     /* event detection (events_kernels.cuh) */
     std::vector<abea_sig_t> sigs;
     DevBuf d_raw, d_sum, d_sumsq, d_ts1, d_ts2, d_peaks, d_evcap, d_sigs, d_sigorder, d_nev, d_evptr, d_evout;
+    DevBuf d_chunks, d_spec, d_fix, d_spec_cnt, d_fix_cnt, d_sync, d_spec_end;
+    int evt_chunk = 1024;            /* ABEA_EVT_CHUNK: samples per chunk of the speculative peak detector (multiple of 4) */
     std::vector<int32_t> nev;        /* event counts of the last abea_getevents */
     bool events_ready = false;
 };
@@ -352,6 +354,7 @@ int abea_create(abea_ctx_t** out, int device) {
     if (const char* e = getenv("ABEA_LOAD_CTAS")) c->load_ctas = std::max(1, atoi(e));
     if (const char* e = getenv("ABEA_LOAD_PIECE_KB")) c->load_piece = (int64_t)std::max(1, atoi(e)) * 1024;
     if (const char* e = getenv("ABEA_LOAD_CRIT")) c->load_crit = atof(e);
+    if (const char* e = getenv("ABEA_EVT_CHUNK")) c->evt_chunk = std::max(8, atoi(e) / 4 * 4);
     if (cudaStreamCreateWithFlags(&c->load_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&c->ev_meta) != cudaSuccess || cudaEventCreate(&c->ev_loaded) != cudaSuccess ||
         cudaEventCreate(&c->ev_load0) != cudaSuccess) {
@@ -391,7 +394,8 @@ void abea_destroy(abea_ctx_t* c) {
                       &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags, &c->d_npairs,
                       &c->d_ready, &c->d_items, &c->d_sreads, &c->d_scalings, &c->d_maps, &c->d_sres,
                       &c->d_raw, &c->d_sum, &c->d_sumsq, &c->d_ts1, &c->d_ts2, &c->d_peaks, &c->d_evcap, &c->d_sigs, &c->d_sigorder,
-                      &c->d_nev, &c->d_evptr, &c->d_evout};
+                      &c->d_nev, &c->d_evptr, &c->d_evout, &c->d_chunks, &c->d_spec, &c->d_fix, &c->d_spec_cnt, &c->d_fix_cnt,
+                      &c->d_sync, &c->d_spec_end};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_results.p) cudaFreeHost(c->h_results.p);
@@ -894,6 +898,8 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     const int32_t n = s->n_reads;
     c->sigs.assign((size_t)n, abea_sig_t());
     int64_t raw_total = 0, sum_total = 0, cap_total = 0, ts_total = 0;
+    const int32_t cl = c->evt_chunk, capc = cl / 2 + 8;
+    std::vector<abea_chunk_t> chunks;
     for (int32_t i = 0; i < n; i++) {
         abea_sig_t& g = c->sigs[i];
         const int32_t ns = s->n_samples[i] > 0 ? s->n_samples[i] : 0;
@@ -901,6 +907,9 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
         g.sum_off = sum_total;
         g.ts_off = ts_total;
         g.cap_off = cap_total;
+        g.chunk_off = (int64_t)chunks.size();
+        if (ns >= 100)
+            for (int32_t q = 0; q < (ns + cl - 1) / cl; q++) chunks.push_back(abea_chunk_t{i, q});
         g.n_samples = ns;
         g.cap = ns / 2 + 2;
         g.offset = s->offset ? s->offset[i] : 0.f;
@@ -920,6 +929,14 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     if (dev_reserve(c, c->d_ts1, (size_t)(ts_total + 4) * sizeof(float))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_ts2, (size_t)(ts_total + 4) * sizeof(float))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_sigorder, ((size_t)n + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
+    const size_t nck = chunks.size();
+    if (dev_reserve(c, c->d_chunks, (nck + 1) * sizeof(abea_chunk_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_spec, (nck + 1) * (size_t)capc * sizeof(int2))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_fix, (nck + 1) * (size_t)capc * sizeof(int2))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_spec_cnt, (nck + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_fix_cnt, (nck + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_sync, (nck + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_spec_end, (nck + 1) * sizeof(evt_state_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_peaks, (size_t)(cap_total + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_evcap, (size_t)(cap_total + 1) * sizeof(abea_event_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_sigs, ((size_t)n + 1) * sizeof(abea_sig_t))) return ABEA_ERR_CUDA;
@@ -928,6 +945,7 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     if (n > 0) {
         CU(cudaMemcpyAsync(c->d_sigs.p, c->sigs.data(), (size_t)n * sizeof(abea_sig_t), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->d_sigorder.p, order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        if (nck) CU(cudaMemcpyAsync(c->d_chunks.p, chunks.data(), nck * sizeof(abea_chunk_t), cudaMemcpyHostToDevice, c->stream));
         if (raw_total > 0) CU(cudaMemcpyAsync(c->d_raw.p, s->raw, (size_t)raw_total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     }
     CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
@@ -937,14 +955,25 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     CU(cudaEventRecord(c->ev[EV_S0], c->stream));
     if (n > 0) {
         ABEA_LAUNCH(abea_events_sums_kernel, (n + EVT_WARPS - 1) / EVT_WARPS, 32 * EVT_WARPS, c->stream,
-                    (const abea_sig_t*)c->d_sigs.p, n, (const float*)c->d_raw.p, (double*)c->d_sum.p, (double*)c->d_sumsq.p,
-                    (float*)c->d_ts1.p, (float*)c->d_ts2.p, P);
-        ABEA_LAUNCH(abea_events_detect_kernel, (n + 31) / 32, 32, c->stream, (const abea_sig_t*)c->d_sigs.p,
-                    (const int32_t*)c->d_sigorder.p, n, (const float*)c->d_ts1.p, (const float*)c->d_ts2.p,
-                    (int32_t*)c->d_peaks.p, (int32_t*)c->d_nev.p, P);
+                    (const abea_sig_t*)c->d_sigs.p, n, (const float*)c->d_raw.p, (double*)c->d_sum.p, (double*)c->d_sumsq.p);
+        if (nck) {
+            ABEA_LAUNCH(abea_events_tstat_kernel, (int)nck, 128, c->stream, (const abea_sig_t*)c->d_sigs.p,
+                        (const abea_chunk_t*)c->d_chunks.p, cl, (const double*)c->d_sum.p, (const double*)c->d_sumsq.p,
+                        (float*)c->d_ts1.p, (float*)c->d_ts2.p, P);
+            ABEA_LAUNCH(abea_events_spec_kernel, (int)((nck + 63) / 64), 64, c->stream, (const abea_sig_t*)c->d_sigs.p,
+                        (const abea_chunk_t*)c->d_chunks.p, (int32_t)nck, cl, capc, (const float*)c->d_ts1.p,
+                        (const float*)c->d_ts2.p, (int2*)c->d_spec.p, (int32_t*)c->d_spec_cnt.p,
+                        (evt_state_t*)c->d_spec_end.p, P);
+        }
+        ABEA_LAUNCH(abea_events_stitch_kernel, (n + 31) / 32, 32, c->stream, (const abea_sig_t*)c->d_sigs.p,
+                    (const int32_t*)c->d_sigorder.p, n, cl, capc, (const float*)c->d_ts1.p, (const float*)c->d_ts2.p,
+                    (const int2*)c->d_spec.p, (const int32_t*)c->d_spec_cnt.p, (const evt_state_t*)c->d_spec_end.p,
+                    (int2*)c->d_fix.p, (int32_t*)c->d_fix_cnt.p, (int32_t*)c->d_sync.p, (int32_t*)c->d_nev.p, P);
         ABEA_LAUNCH(abea_events_create_kernel, (n + EVT_WARPS - 1) / EVT_WARPS, 32 * EVT_WARPS, c->stream,
-                    (const abea_sig_t*)c->d_sigs.p, n, (const double*)c->d_sum.p, (const double*)c->d_sumsq.p,
-                    (const int32_t*)c->d_peaks.p, (abea_event_t*)c->d_evcap.p, (const int32_t*)c->d_nev.p);
+                    (const abea_sig_t*)c->d_sigs.p, n, cl, capc, (const double*)c->d_sum.p, (const double*)c->d_sumsq.p,
+                    (const int2*)c->d_spec.p, (const int32_t*)c->d_spec_cnt.p, (const int2*)c->d_fix.p,
+                    (const int32_t*)c->d_fix_cnt.p, (const int32_t*)c->d_sync.p, (int32_t*)c->d_peaks.p,
+                    (abea_event_t*)c->d_evcap.p, (const int32_t*)c->d_nev.p);
     }
     CU(cudaEventRecord(c->ev[EV_S1], c->stream));
     c->nev.assign((size_t)n, 0);

@@ -111,8 +111,12 @@ def emu():
     return EMU
 
 
-@pytest.mark.parametrize("rna", [False, True])
-def test_emulated_kernel_matches_oracle(emu, rna):
+@pytest.mark.parametrize("rna,chunk", [(False, None), (True, None), (False, "8"), (False, "64"), (True, "32")])
+def test_emulated_kernel_matches_oracle(emu, monkeypatch, rna, chunk):
+    """chunk: ABEA_EVT_CHUNK — tiny chunks make every read a long chain of speculative chunks, most of which never
+    synchronise with the true walk (8 samples rarely contain a boundary), so both stitch paths are exercised."""
+    if chunk:
+        monkeypatch.setenv("ABEA_EVT_CHUNK", chunk)
     sg = synth.make_signals(9, 400, 0.6, seed=11 + rna, samples_per_event=12.0 if rna else 5.0)
     sg["n_samples"][3] = 60                                  # shorter than 100 samples: no events
     with AbeaContext(0, lib_path=emu) as ctx:
@@ -121,7 +125,10 @@ def test_emulated_kernel_matches_oracle(emu, rna):
         check_device(ctx, sg, rna, calibrated=False)
 
 
-def test_emulated_kernel_on_real_signals(emu):
+@pytest.mark.parametrize("chunk", [None, "48"])
+def test_emulated_kernel_on_real_signals(emu, monkeypatch, chunk):
+    if chunk:
+        monkeypatch.setenv("ABEA_EVT_CHUNK", chunk)
     with AbeaContext(0, lib_path=emu) as ctx:
         check_fixture_on(ctx)
 
@@ -144,6 +151,15 @@ def test_gpu_getevents_synthetic(gctx, rna, n, mean):
 @pytest.mark.gpu
 def test_gpu_getevents_golden_signals(gctx):
     check_fixture_on(gctx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", ["16", "200"])
+def test_gpu_getevents_small_chunks(built, monkeypatch, chunk):
+    monkeypatch.setenv("ABEA_EVT_CHUNK", chunk)
+    with AbeaContext(0) as ctx:
+        check_device(ctx, synth.make_signals(128, 2000, 0.6, seed=29), False, calibrated=True)
+        check_fixture_on(ctx)
 
 
 @pytest.mark.gpu
