@@ -210,6 +210,20 @@ def main():
                                      "achieved_gbs": b_n1 / (scl_ms / reps * 1e-3) / 1e9},
                   "note": "abea_mom_kernel / abea_scaling_kernel on rank 0's batch, CUDA events, 3 runs after 1 warm-up; "
                           "latency-bound by the ordered double sums of the longest read, not by HBM"}
+        # N3: event detection on synthetic raw signals with the same event counts (there are no raw signals behind
+        # the synthetic event tables, so this stage runs on its own input: ~5 samples per event)
+        sg = synth.make_signals(batch.n_reads, batch.meta["mean_events"], batch.meta["sigma"], seed=a.seed)
+        cal = (sg["offset"], sg["range"], sg["digitisation"])
+        ev_ms = 0.0
+        for i in range(reps + 1):
+            _ev, _ptr, nev, t5 = ctx.getevents(sg["raw"], sg["raw_ptr"], sg["n_samples"], cal)
+            if i > 0:
+                ev_ms += t5["events_ms"]
+        ns = int(sg["n_samples"].astype(np.int64).sum())
+        stages["getevents"] = {"ms": ev_ms / reps, "samples": ns, "events_detected": int(nev.sum()),
+                               "samples_per_s": ns / (ev_ms / reps * 1e-3), "algorithmic_bytes": 57 * ns,
+                               "achieved_gbs": 57 * ns / (ev_ms / reps * 1e-3) / 1e9}
+        del sg, _ev
         ctx.upload(pinned)
 
     # ---- end to end through the C ABI with host buffers (+ NCCL result gather for N > 1) --------------------------
