@@ -94,6 +94,7 @@ struct abea_ctx {
     int fill_warps_per_cta = 12; /* 4 primary + 8 secondary warps (ABEA_FILL_WARPS_PER_CTA, multiple of 4, <= 16; 12 measured best) */
     double long_alpha = 0.8;   /* ABEA_LONG_ALPHA: a read is "long" (runs alone on its sub-partition) above this share of the batch time */
     int trace_ctas_per_sm = 4; /* ABEA_TRACE_CTAS_PER_SM */
+    int sm_reserve = 0;        /* ABEA_SM_RESERVE: SMs left out of the narrow grid in addition to the wide CTAs' (when there are wide CTAs) */
     int sched_policy = 1;      /* ABEA_SCHED: 0 two-ended queue (secondary warps shortest-first), 1 longest-first for every warp */
 
     /* streaming (abea_align_batch with pinned host buffers): events pulled over PCIe by abea_load_kernel in the order
@@ -217,9 +218,10 @@ void build_load_order(abea_ctx* c) {
     const int64_t n = (int64_t)c->reads.size();
     const int nw = c->n_wide;
     const int wpc = c->fill_warps_per_cta;
-    const int wide_sms = nw > 0 ? std::min(c->sm_count, nw) : 0;
-    const int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((int64_t)(c->sm_count - wide_sms) * c->fill_ctas_per_sm,
-                                                                  (n - nw + wpc - 1) / wpc));
+    const int wide_sms = nw > 0 ? std::min(c->sm_count, nw + c->sm_reserve) : 0;
+    int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((int64_t)(c->sm_count - wide_sms) * c->fill_ctas_per_sm,
+                                                            (n - nw + wpc - 1) / wpc));
+    if (nw > 0 && blocks > 1) blocks &= ~(int64_t)1; /* as in run_impl */
     const int64_t n_pri = 4 * blocks, n_sec = (int64_t)(wpc - 4) * blocks;
     /* cycles per band (wide CTA; narrow warp sharing its sub-partition; narrow warp alone on it = a "long" read) and
      * per traceback step. The longest reads set the makespan, so their pieces are asked for early rather than late. */
@@ -350,6 +352,7 @@ int abea_create(abea_ctx_t** out, int device) {
     if (const char* e = getenv("ABEA_LONG_ALPHA")) c->long_alpha = atof(e);
     if (const char* e = getenv("ABEA_TRACE_CTAS_PER_SM")) c->trace_ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("ABEA_SCHED")) c->sched_policy = atoi(e) ? 1 : 0;
+    if (const char* e = getenv("ABEA_SM_RESERVE")) c->sm_reserve = std::max(0, atoi(e));
     if (const char* e = getenv("ABEA_STREAM")) c->stream_mode = atoi(e);
     if (const char* e = getenv("ABEA_LOAD_CTAS")) c->load_ctas = std::max(1, atoi(e));
     if (const char* e = getenv("ABEA_LOAD_PIECE_KB")) c->load_piece = (int64_t)std::max(1, atoi(e)) * 1024;
@@ -519,6 +522,11 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         while (c->n_wide < (int32_t)c->reads.size() && c->n_wide < cap &&
                (double)c->reads[c->n_wide].n_events + c->reads[c->n_wide].n_kmers + 2 > thr)
             c->n_wide++;
+        /* The two SMs of a TPC are not independent: a wide CTA whose partner SM runs a narrow CTA needs 550-620 cycles
+         * per band instead of 396 (measured, profiles/sweep_tpc_pairing_r01.txt; a wide or an idle partner costs
+         * nothing). The hardware fills TPCs pairwise, so an EVEN number of wide CTAs beside an even narrow grid keeps
+         * every wide CTA next to another wide CTA: an odd count takes the next-longest read along. */
+        if ((c->n_wide & 1) && c->n_wide < (int32_t)c->reads.size() && (int32_t)c->reads.size() > c->sm_count) c->n_wide++;
     }
     c->total_kmers = kp;
     c->total_trace_words = tw;
@@ -702,8 +710,9 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                 const int wpc = c->fill_warps_per_cta;
                 /* SMs taken by SM-exclusive wide CTAs are left out of the persistent narrow grid, so that both kernels
                  * are resident from the start whatever order the hardware dispatches them in */
-                const int wide_sms = (nw > 0) ? std::min(c->sm_count, (int)nw) : 0;
+                const int wide_sms = (nw > 0) ? std::min(c->sm_count, (int)nw + c->sm_reserve) : 0;
                 int blocks = std::min((c->sm_count - wide_sms) * c->fill_ctas_per_sm, (n - nw + wpc - 1) / wpc);
+                if (nw > 0 && blocks > 1) blocks &= ~1; /* whole TPCs (see upload_impl) */
                 if (blocks < 1) blocks = 1;
                 const size_t smem = (size_t)wpc * (sizeof(abea_fill_smem_t) +
                                                    sizeof(uint32_t) * ABEA_TB_RING_GROUPS * ABEA_TRACE_GROUP_WORDS);
