@@ -219,13 +219,17 @@ class AbeaContext:
                                               n_pairs.ctypes.data, ctypes.byref(t)), "abea_align_batch")
         return Alignment(pairs, pair_ptr, n_pairs, t.as_dict())
 
-    def upload(self, batch: ReadBatch, with_scalings: bool = True) -> dict:
-        """abea_upload_batch. with_scalings=False leaves abea_batch_t.scalings NULL: estimate_scalings() must follow."""
+    def upload(self, batch: ReadBatch, with_scalings: bool = True, device_events: bool = False) -> dict:
+        """abea_upload_batch. with_scalings=False leaves abea_batch_t.scalings NULL: estimate_scalings() must follow.
+        device_events=True leaves abea_batch_t.events NULL: the event tables of the last getevents() are aligned where
+        they lie on the device (batch.n_events must repeat its counts)."""
         assert batch.kmer_size == self.kmer_size
         t = Timing()
         cb = batch.as_c()
         if not with_scalings:
             cb.scalings = None
+        if device_events:
+            cb.events = None
         self._check(self.lib.abea_upload_batch(self._h, ctypes.byref(cb), ctypes.byref(t)), "abea_upload_batch")
         return t.as_dict()
 
@@ -242,7 +246,7 @@ class AbeaContext:
         return Alignment(pairs, pair_ptr, n_pairs, t.as_dict())
 
     # -- event detection ---------------------------------------------------------------------------------
-    def getevents(self, raw, raw_ptr, n_samples, calibration=None, rna: bool = False):
+    def getevents(self, raw, raw_ptr, n_samples, calibration=None, rna: bool = False, download: bool = True):
         """abea_getevents + abea_getevents_download: the reference's getevents (src/events.c:562-582) per read.
 
         raw: float32 samples (ADC counts, or pA when calibration is None); calibration: (offset, range, digitisation)
@@ -261,6 +265,8 @@ class AbeaContext:
         t = Timing()
         self._check(self.lib.abea_getevents(self._h, ctypes.byref(cs), int(bool(rna)), n_events.ctypes.data,
                                             ctypes.byref(t)), "abea_getevents")
+        if not download:   # the tables stay on the device for upload(..., device_events=True)
+            return None, None, n_events, t.as_dict()
         cnt = np.maximum(n_events, 0).astype(np.int64)
         event_ptr = np.zeros(n, dtype=np.int64)
         if n > 1:

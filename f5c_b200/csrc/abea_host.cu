@@ -110,6 +110,7 @@ struct abea_ctx {
     bool streaming = false;    /* the resident batch is being streamed in: its fill must wait on d_ready */
     bool results_on_device = false; /* d_pairs / d_npairs hold the final lists of the last run */
     int64_t event_bytes = 0;   /* size of the batch's event array */
+    void* ev_dev = nullptr;    /* the resident batch's events: d_events, or d_evcap when they came from abea_getevents */
 
     /* the stages either side of ABEA (scaling_kernels.cuh): descriptors of ALL reads in the caller's order */
     std::vector<abea_sread_t> sreads;
@@ -209,7 +210,7 @@ void launch_prepare(abea_ctx* c, int64_t check_events) {
     if (blocks < 1) blocks = 1;
     ABEA_LAUNCH(abea_prepare_kernel, blocks, threads, c->stream,
         (const abea_read_t*)c->d_reads.p, n, (const uint8_t*)c->d_seq.p, (const abea_model_t*)c->d_model.p,
-        c->kmer_size, (const abea_event_t*)c->d_events.p, (float4*)c->d_kparams.p, (uint32_t*)c->d_flags.p,
+        c->kmer_size, (const abea_event_t*)c->ev_dev, (float4*)c->d_kparams.p, (uint32_t*)c->d_flags.p,
         c->total_kmers, check_events);
 }
 
@@ -450,12 +451,23 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
     c->reads.clear();
     c->reads.reserve(b->n_reads);
 
+    /* batch->events == NULL: the event tables are the ones the last abea_getevents left on the device (same reads,
+     * same order); they are used where they lie (capacity layout), nothing is copied */
+    const bool dev_events = (b->events == nullptr) && b->n_reads > 0;
+    if (dev_events) {
+        if (!c->events_ready || (int32_t)c->nev.size() != b->n_reads)
+            return fail(c, ABEA_ERR_STATE, "batch without events, but no matching abea_getevents result on the device");
+        for (int32_t i = 0; i < b->n_reads; i++)
+            if (b->n_events[i] != std::max(c->nev[i], 0))
+                return fail(c, ABEA_ERR_ARG, "n_events[%d] = %d does not match abea_getevents (%d)", i, b->n_events[i], c->nev[i]);
+        ev_alias = nullptr;
+    }
     /* total sizes of the caller's flat arrays */
     int64_t seq_bytes = 0, n_ev_total = 0;
     for (int32_t i = 0; i < b->n_reads; i++) {
         int64_t se = b->seq_ptr[i] + b->read_len[i] + 1;
         if (se > seq_bytes) seq_bytes = se;
-        int64_t ee = b->event_ptr[i] + b->n_events[i];
+        int64_t ee = dev_events ? 0 : b->event_ptr[i] + b->n_events[i];
         if (ee > n_ev_total) n_ev_total = ee;
     }
 
@@ -476,7 +488,7 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         abea_read_t r;
         memset(&r, 0, sizeof(r));
         r.seq_off = b->seq_ptr[i];
-        r.ev_off = b->event_ptr[i];
+        r.ev_off = dev_events ? c->sigs[i].cap_off : b->event_ptr[i];
         r.n_events = E;
         r.n_kmers = L - k + 1;
         r.pair_cap = E + L;
@@ -542,7 +554,7 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         abea_sread_t& sr = c->sreads[i];
         const int32_t E = b->n_events[i], L = b->read_len[i];
         sr.seq_off = b->seq_ptr[i];
-        sr.ev_off = b->event_ptr[i];
+        sr.ev_off = dev_events ? c->sigs[i].cap_off : b->event_ptr[i];
         sr.map_off = c->total_map;
         sr.pair_off = c->cap_ptr[i];
         sr.n_events = E;
@@ -573,6 +585,7 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
     if (dev_reserve(c, c->d_flags, (n_sched + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
 
     c->event_bytes = n_ev_total * (int64_t)sizeof(abea_event_t);
+    c->ev_dev = dev_events ? c->d_evcap.p : c->d_events.p;
     c->streaming = false;
     c->results_on_device = false;
     double t2 = t1;
@@ -696,11 +709,11 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                 CU(cudaFuncSetAttribute((const void*)wide_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)excl));
                 CU(cudaFuncSetAttribute((const void*)wide_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)excl));
                 ABEA_LAUNCH_SMEM(wide_fast, wblocks, 128, excl, c->wide_stream,
-                    (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                    (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->ev_dev, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
                     (abea_result_t*)c->d_results.p, io, c->cst, queue + 6);
                 ABEA_LAUNCH_SMEM(wide_exact, wblocks, 128, excl, c->wide_stream,
-                    (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                    (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->ev_dev, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
                     (abea_result_t*)c->d_results.p, io, c->cst, queue + 7);
                 CU(cudaEventRecord(c->ev_join, c->wide_stream));
@@ -725,11 +738,11 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                 const double cyc_batch = (double)c->total_bands * 360.0 / ((double)c->sm_count * 4.0);
                 const int32_t long_thr = (int32_t)std::min(2.0e9, std::max(1.0, c->long_alpha * cyc_batch / 780.0));
                 ABEA_LAUNCH_SMEM(fill_fast, blocks, 32 * wpc, smem, c->stream,
-                    (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                    (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->ev_dev, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
                     (abea_result_t*)c->d_results.p, io, c->cst, queue, nw, long_thr, c->sched_policy);
                 ABEA_LAUNCH_SMEM(fill_exact, blocks, 32 * wpc, smem, c->stream,
-                    (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->d_events.p, (const float4*)c->d_kparams.p,
+                    (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->ev_dev, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
                     (abea_result_t*)c->d_results.p, io, c->cst, queue + 8, nw, long_thr, c->sched_policy);
                 launches += 2;
@@ -904,6 +917,11 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     if (s->offset && (!s->range || !s->digitisation)) return fail(c, ABEA_ERR_ARG, "offset without range / digitisation");
     CU(cudaSetDevice(c->device));
     c->events_ready = false;
+    if (c->ev_dev && c->ev_dev == c->d_evcap.p) { /* a resident batch that borrowed the previous event tables dies with them */
+        c->uploaded = false;
+        c->ran = false;
+        c->ev_dev = nullptr;
+    }
     const int32_t n = s->n_reads;
     c->sigs.assign((size_t)n, abea_sig_t());
     int64_t raw_total = 0, sum_total = 0, cap_total = 0, ts_total = 0;
@@ -1050,7 +1068,7 @@ int abea_estimate_scalings(abea_ctx_t* c, int reverse_events, abea_scalings_t* s
     if (nb > 0) {
         if (!c->scalings_on_device) CU(cudaMemsetAsync(c->d_scalings.p, 0, (size_t)nb * sizeof(abea_scalings_t), c->stream));
         ABEA_LAUNCH(abea_mom_kernel, (nb + SCL_WARPS - 1) / SCL_WARPS, 32 * SCL_WARPS, c->stream,
-                    (const abea_sread_t*)c->d_sreads.p, nb, (const uint8_t*)c->d_seq.p, (abea_event_t*)c->d_events.p,
+                    (const abea_sread_t*)c->d_sreads.p, nb, (const uint8_t*)c->d_seq.p, (abea_event_t*)c->ev_dev,
                     (const abea_model_t*)c->d_model.p, c->kmer_size, (abea_scalings_t*)c->d_scalings.p,
                     (abea_read_t*)c->d_reads.p, (int32_t)(reverse_events ? 1 : 0));
     }
@@ -1081,7 +1099,7 @@ int abea_scaling_stage(abea_ctx_t* c, int32_t min_num_events_to_rescale, abea_ti
     if (nb > 0)
         ABEA_LAUNCH(abea_scaling_kernel, (nb + SCL_WARPS - 1) / SCL_WARPS, 32 * SCL_WARPS, c->stream,
                     (const abea_sread_t*)c->d_sreads.p, nb, (const uint8_t*)c->d_seq.p,
-                    (const abea_event_t*)c->d_events.p, (const abea_model_t*)c->d_model.p, c->kmer_size,
+                    (const abea_event_t*)c->ev_dev, (const abea_model_t*)c->d_model.p, c->kmer_size,
                     (const abea_pair_t*)c->d_pairs.p, (const int32_t*)c->d_npairs.p,
                     (const abea_scalings_t*)c->d_scalings.p, (abea_index_pair_t*)c->d_maps.p,
                     (abea_scaling_result_t*)c->d_sres.p, min_num_events_to_rescale);
@@ -1137,7 +1155,7 @@ int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pair
     /* Pinned (mapped) caller buffers are streamed: events in over PCIe while the fill runs, pair lists out as each
      * read finishes. Anything else is staged through the copy engine (abea_upload_batch / abea_download). */
     const void* ev_alias = nullptr;
-    if ((c->stream_mode & 1) && batch->n_reads > 0 && ((uintptr_t)batch->events & 15) == 0) ev_alias = mapped_alias(batch->events);
+    if ((c->stream_mode & 1) && batch->n_reads > 0 && batch->events && ((uintptr_t)batch->events & 15) == 0) ev_alias = mapped_alias(batch->events);
     int rc = upload_impl(c, batch, ev_alias, nullptr);
     if (rc) return rc;
     abea_pair_t* fin_pairs = nullptr;

@@ -190,3 +190,52 @@ def make_signals(n_reads: int, mean_events: float, sigma: float, seed: int, samp
     pa = ((raw + offset[read_of_sample]).astype(np.float32) * raw_unit[read_of_sample]).astype(np.float32)
     return dict(raw=raw, raw_ptr=raw_ptr, n_samples=n_samples.astype(np.int32), offset=offset, range=rng_pa,
                 digitisation=digitisation, pa=pa)
+
+
+def make_signal_batch(model: str, n_reads: int, mean_kmers: float, sigma: float, seed: int, dwell_mean: float = 9.0,
+                      noise: float = 1.5):
+    """Seeded raw signals WITH the sequences they come from, for the device-resident chain raw signal -> events ->
+    scalings -> alignment -> recalibration: per read a random ACGT sequence; every k-mer holds the current at its
+    model level (scaled / shifted per read) for 2 + Geometric samples, plus Gaussian sample noise; quantised to int16
+    ADC counts like make_signals. Returns (signals dict as make_signals, seq uint8 flat NUL-separated, seq_ptr,
+    read_len, kmer_size)."""
+    k, mt = load_model(model)
+    rng = np.random.default_rng(seed)
+    K = np.maximum(draw_lengths(n_reads, mean_kmers, sigma, rng).astype(np.int64), 40)
+    L = K + k - 1
+    seq_ptr = np.zeros(n_reads, dtype=np.int64)
+    if n_reads > 1:
+        np.cumsum(L[:-1] + 1, out=seq_ptr[1:])
+    seq = np.zeros(int(L.sum()) + n_reads, dtype=np.uint8)
+    bases = rng.integers(0, 4, int(L.sum()))
+    read_of_base = np.repeat(np.arange(n_reads, dtype=np.int64), L)
+    pos = np.arange(int(L.sum()), dtype=np.int64) - np.repeat(np.cumsum(L) - L, L)
+    seq[seq_ptr[read_of_base] + pos] = np.frombuffer(b"ACGT", dtype=np.uint8)[bases]
+    kptr = np.zeros(n_reads + 1, dtype=np.int64)
+    np.cumsum(K, out=kptr[1:])
+    read_of_kmer = np.repeat(np.arange(n_reads, dtype=np.int64), K)
+    kpos = np.arange(int(K.sum()), dtype=np.int64) - kptr[read_of_kmer]
+    bstart = (np.cumsum(L) - L)[read_of_kmer] + kpos
+    rank = np.zeros(int(K.sum()), dtype=np.int64)
+    for j in range(k):
+        rank = rank * 4 + bases[bstart + j]
+    shift_r = rng.normal(0.0, 8.0, n_reads)
+    scale_r = rng.normal(1.0, 0.04, n_reads)
+    level = scale_r[read_of_kmer] * mt["level_mean"].astype(np.float64)[rank] + shift_r[read_of_kmer]
+    dwell = rng.geometric(min(1.0, 1.0 / max(1.0, dwell_mean - 2.0)), int(K.sum())).astype(np.int64) + 2
+    n_samples = np.bincount(read_of_kmer, weights=dwell, minlength=n_reads).astype(np.int64)
+    pa_true = np.repeat(level, dwell) + noise * rng.standard_normal(int(dwell.sum()))
+    digitisation = np.full(n_reads, 8192.0, dtype=np.float32)
+    rng_pa = rng.uniform(1380.0, 1480.0, n_reads).astype(np.float32)
+    offset = np.round(rng.uniform(2.0, 20.0, n_reads)).astype(np.float32)
+    read_of_sample = np.repeat(np.arange(n_reads, dtype=np.int64), n_samples)
+    adc = np.round(pa_true * (digitisation[read_of_sample] / rng_pa[read_of_sample]) - offset[read_of_sample])
+    raw = np.clip(adc, -32768, 32767).astype(np.int16).astype(np.float32)
+    raw_ptr = np.zeros(n_reads, dtype=np.int64)
+    if n_reads > 1:
+        np.cumsum(n_samples[:-1], out=raw_ptr[1:])
+    raw_unit = (rng_pa / digitisation).astype(np.float32)
+    pa = ((raw + offset[read_of_sample]).astype(np.float32) * raw_unit[read_of_sample]).astype(np.float32)
+    sig = dict(raw=raw, raw_ptr=raw_ptr, n_samples=n_samples.astype(np.int32), offset=offset, range=rng_pa,
+               digitisation=digitisation, pa=pa)
+    return sig, seq, seq_ptr, L.astype(np.int32), k

@@ -106,7 +106,9 @@ int abea_download(abea_ctx_t* ctx, abea_pair_t* pairs, const int64_t* pair_ptr, 
  * on; -1 if a signal produced more than n_samples/2 + 1 boundaries, which no real signal does). The event tables stay
  * on the device until abea_getevents_download copies them to events[event_ptr[i] ..] — the caller sizes and lays
  * out that array from the counts (e.g. a prefix sum), which is the abea_batch_t.events / event_ptr of the alignment.
- * rna != 0 selects the RNA detector parameters (src/events.c:59-63). */
+ * rna != 0 selects the RNA detector parameters (src/events.c:59-63).
+ * A following abea_upload_batch whose batch->events is NULL aligns those device-resident tables directly (they stay
+ * valid until the next abea_getevents). */
 int abea_getevents(abea_ctx_t* ctx, const abea_signals_t* signals, int rna, int32_t* n_events_out, abea_timing_t* timing);
 int abea_getevents_download(abea_ctx_t* ctx, abea_event_t* events, const int64_t* event_ptr);
 

@@ -118,8 +118,10 @@ typedef struct {
  *
  *   seq      : concatenated read sequences, read i at seq[seq_ptr[i] .. seq_ptr[i]+read_len[i]) followed
  *              by one NUL (so seq_ptr advances by read_len+1, like the reference's read_ptr)
- *   events   : concatenated event tables, read i at events[event_ptr[i] .. +n_events[i])
- *   scalings : per read (from estimate_scalings_using_mom)
+ *   events   : concatenated event tables, read i at events[event_ptr[i] .. +n_events[i]); NULL = the event tables the
+ *              last abea_getevents left on the device (same reads, same order; n_events must repeat its counts,
+ *              event_ptr is ignored) — raw signal in, alignment out, no event table crosses PCIe
+ *   scalings : per read (from estimate_scalings_using_mom); NULL = estimate them on the device (abea_estimate_scalings)
  *   good     : per read, non-zero iff db->sig[i]->nsample > 0 (src/f5c.c:811); NULL = all good
  */
 typedef struct {

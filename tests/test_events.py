@@ -186,3 +186,51 @@ def test_gpu_getevents_full_size_properties(gctx):
     for i in list(np.random.default_rng(3).choice(4096, 24, replace=False)) + [int(np.argmax(nev))]:
         pa = sg["pa"][sg["raw_ptr"][i]:sg["raw_ptr"][i] + sg["n_samples"][i]]
         assert ol._events_equal(ev[ptr[i]:ptr[i] + nev[i]], ol.port_getevents(pa)), i
+
+
+# ---- raw signal in, alignment and recalibration out, everything resident on the device ---------------------------
+
+def check_resident_chain(ctx, model_name, n_reads, mean_kmers, seed, min_events=50):
+    """abea_getevents -> abea_upload_batch(events = NULL, scalings = NULL) -> abea_estimate_scalings -> abea_run ->
+    abea_scaling_stage against the oracle's getevents -> estimate_scalings_using_mom -> align -> scaling_single."""
+    from f5c_b200 import models
+    from f5c_b200.abea import scaling_db
+    from f5c_b200.batch import EVENT_DTYPE, SCALINGS_DTYPE, ReadBatch
+    sg, seq, seq_ptr, read_len, k = synth.make_signal_batch(model_name, n_reads, mean_kmers, 0.5, seed)
+    kk, m = models.load_model(model_name)
+    m = ctx.set_model(m, kk)
+    cal = (sg["offset"], sg["range"], sg["digitisation"])
+    _, _, nev, t = ctx.getevents(sg["raw"], sg["raw_ptr"], sg["n_samples"], cal, download=False)
+    assert (nev > 0).all()
+    shell = ReadBatch(seq, seq_ptr, read_len, np.zeros(0, dtype=EVENT_DTYPE), np.zeros(n_reads, dtype=np.int64),
+                      nev.astype(np.int32), np.zeros(n_reads, dtype=SCALINGS_DTYPE), np.ones(n_reads, dtype=np.uint8), k)
+    ctx.upload(shell, with_scalings=False, device_events=True)
+    est, _ = ctx.estimate_scalings(n_reads)
+    ctx.run()
+    aln = ctx.download(shell)
+    sc = scaling_db(ctx, shell, min_events)
+    # the oracle's chain on the host
+    evs = [ol.port_getevents(sg["pa"][sg["raw_ptr"][i]:sg["raw_ptr"][i] + sg["n_samples"][i]]) for i in range(n_reads)]
+    assert [len(e) for e in evs] == [int(x) for x in nev]
+    seqs = [seq[seq_ptr[i]:seq_ptr[i] + read_len[i]].tobytes() for i in range(n_reads)]
+    hb = ReadBatch.from_reads(seqs, evs, np.zeros(n_reads, dtype=SCALINGS_DTYPE), k)
+    hb.scalings[:] = ol.port_estimate_scalings(hb, m)
+    assert est.tobytes() == hb.scalings.tobytes()
+    want = ol.port_align(hb, m)
+    ol.assert_same_alignment(aln, want, "resident chain")
+    ol.assert_same_scaling(ol.ScalingResult(hb, sc.results, sc.maps), ol.port_scaling(hb, m, want, min_events=min_events),
+                           "resident chain")
+    return aln, sc
+
+
+def test_emulated_resident_chain(emu):
+    with AbeaContext(0, lib_path=emu) as ctx:
+        aln, sc = check_resident_chain(ctx, "r9", 6, 250, seed=5)
+        assert (aln.n_pairs > 0).sum() >= 4      # signals generated from the sequences do align
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,n,mean", [("r9", 192, 2500), ("r10", 64, 3000)])
+def test_gpu_resident_chain(gctx, model, n, mean):
+    aln, sc = check_resident_chain(gctx, model, n, mean, seed=17, min_events=200)
+    assert (aln.n_pairs > 0).mean() > 0.8 and (sc.results["flags"] == 0).mean() > 0.6
