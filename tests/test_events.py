@@ -234,3 +234,42 @@ def test_emulated_resident_chain(emu):
 def test_gpu_resident_chain(gctx, model, n, mean):
     aln, sc = check_resident_chain(gctx, model, n, mean, seed=17, min_events=200)
     assert (aln.n_pairs > 0).mean() > 0.8 and (sc.results["flags"] == 0).mean() > 0.6
+
+
+def adversarial_signals():
+    """Signals that stress the speculative detector's stitching: long flat stretches (chunks with no boundary at all,
+    so the re-walk never meets the speculative walk), boundaries every two samples, repeated identical values, a
+    staircase, heavy noise, and a jump exactly at a chunk edge."""
+    rng = np.random.default_rng(99)
+    sigs = []
+    sigs.append(np.concatenate([np.full(900, 80.0), 80 + 0.01 * rng.standard_normal(700), np.full(50, 120.0), np.full(1200, 95.0)]))
+    sigs.append(np.repeat(rng.normal(90, 15, 600), 2) + 0.3 * rng.standard_normal(1200))
+    sigs.append(np.tile(np.array([70.0, 70.0, 70.0, 110.0, 110.0, 110.0]), 300))
+    sigs.append(np.repeat(np.arange(60, 140, 0.5), 9).astype(np.float64))
+    sigs.append(90 + 25 * rng.standard_normal(3000))
+    s = np.full(2048, 85.0) + 0.5 * rng.standard_normal(2048)
+    s[1024:] += 30.0
+    sigs.append(s)
+    sigs.append(np.full(1500, 77.25))
+    n = np.array([len(x) for x in sigs], dtype=np.int32)
+    ptr = np.zeros(len(sigs), dtype=np.int64)
+    np.cumsum(n[:-1], out=ptr[1:])
+    pa = np.concatenate(sigs).astype(np.float32)
+    return dict(pa=pa, raw=pa, raw_ptr=ptr, n_samples=n)
+
+
+@pytest.mark.parametrize("chunk", ["8", "64", "1024"])
+def test_emulated_kernel_adversarial_signals(emu, monkeypatch, chunk):
+    monkeypatch.setenv("ABEA_EVT_CHUNK", chunk)
+    sg = adversarial_signals()
+    with AbeaContext(0, lib_path=emu) as ctx:
+        for rna in (False, True):
+            ev, ptr, nev, t = check_device(ctx, sg, rna, calibrated=False)
+        assert nev[-1] == 1                      # a constant signal: one event (undefined in the reference)
+
+
+@pytest.mark.gpu
+def test_gpu_getevents_adversarial_signals(gctx):
+    sg = adversarial_signals()
+    for rna in (False, True):
+        check_device(gctx, sg, rna, calibrated=False)
