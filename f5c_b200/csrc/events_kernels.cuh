@@ -11,8 +11,13 @@
  * The event table feeds the alignment, which is bit-exact integer work, so every float the reference stores is
  * reproduced exactly. A signal is cut into CHUNKS of `cl` samples (1024 by default); five kernels:
  *  1 abea_events_sums_kernel (one warp per read): the cumulative sums are ordered double additions (the square is
- *    a FLOAT product, as in the reference): the lanes stage the terms, lane 0 (sum) and lane 1 (sum of squares) run
- *    the two 8-cycle DADD chains and overwrite the terms with the running sums, which all lanes store coalesced.
+ *    a FLOAT product, as in the reference). When every partial sum is exactly representable — all terms are
+ *    multiples of one power of two q and n * max|term| < q * 2^53, which the kernel checks per read from the
+ *    exponents of its samples and which holds for any realistic signal (picoamperes in [16, 256): 47 of 53 bits for
+ *    a million samples) — no addition ever rounds, so the order of the additions cannot matter and the sums are
+ *    formed by a warp scan. Otherwise (e.g. samples of 1e-6 next to samples of 200) the lanes stage the terms, lane
+ *    0 (sum) and lane 1 (sum of squares) run the two 8-cycle DADD chains in the reference's order and overwrite the
+ *    terms with the running sums. Either way all lanes store the running sums coalesced.
  *  2 abea_events_tstat_kernel (one thread per sample): the two windowed t-statistics, with the reference's mix of
  *    float and double operations spelled out with _rn intrinsics.
  *  3 abea_events_spec_kernel (one thread per chunk): the short/long peak detector is a sequential state machine
@@ -146,6 +151,84 @@ abea_events_sums_kernel(const abea_sig_t* __restrict__ sigs, int32_t n_reads, co
         sum[0] = 0.0;
         sumsq[0] = 0.0;
     }
+    /* ---- optimistic pass: warp scan, valid iff no addition can round (checked from the samples' exponents, which
+     * are collected on the way); each lane owns 4 consecutive samples of a 128-sample round ---- */
+    {
+        int32_t e_min = 1000, e_max = -1000;
+        double c0 = 0.0, c1 = 0.0; /* carries */
+        float nx[EVT_CHUNK / 32];
+#pragma unroll
+        for (int u = 0; u < EVT_CHUNK / 32; u++) {
+            const int32_t i = lane * (EVT_CHUNK / 32) + u;
+            nx[u] = (i < n) ? x[i] : 0.f;
+        }
+        for (int32_t base = 0; base < n; base += EVT_CHUNK) {
+            const int32_t i0 = base + lane * (EVT_CHUNK / 32);
+            float cur[EVT_CHUNK / 32];
+#pragma unroll
+            for (int u = 0; u < EVT_CHUNK / 32; u++) cur[u] = nx[u];
+#pragma unroll
+            for (int u = 0; u < EVT_CHUNK / 32; u++) { /* next round in flight during the scan */
+                const int32_t i = i0 + EVT_CHUNK + u;
+                nx[u] = (i < n) ? x[i] : 0.f;
+            }
+            double a[EVT_CHUNK / 32], q[EVT_CHUNK / 32];
+            double l0 = 0.0, l1 = 0.0;
+#pragma unroll
+            for (int u = 0; u < EVT_CHUNK / 32; u++) {
+                float sv = cur[u];
+                if (i0 + u < n) {
+                    if (convert) sv = __fmul_rn(__fadd_rn(sv, sg.offset), sg.raw_unit);
+                    const uint32_t bits = __float_as_uint(sv);
+                    const int32_t be = (int32_t)((bits >> 23) & 0xffu);
+                    if ((bits & 0x7fffffffu) != 0u) {                  /* not +-0 */
+                        const int32_t e = (be == 0) ? -149 : be - 127;  /* denormals: as fine as floats get */
+                        e_min = e < e_min ? e : e_min;
+                        e_max = e > e_max ? e : e_max;
+                    }
+                } else {
+                    sv = 0.f;
+                }
+                l0 = __dadd_rn(l0, (double)sv);
+                l1 = __dadd_rn(l1, (double)__fmul_rn(sv, sv));
+                a[u] = l0;
+                q[u] = l1;
+            }
+            double s0 = l0, s1 = l1; /* inclusive scan of the lane totals */
+            for (int d = 1; d < 32; d <<= 1) {
+                const double u0 = __shfl_up_sync(ABEA_FULL, s0, d), u1 = __shfl_up_sync(ABEA_FULL, s1, d);
+                if (lane >= d) {
+                    s0 = __dadd_rn(s0, u0);
+                    s1 = __dadd_rn(s1, u1);
+                }
+            }
+            const double p0 = __dadd_rn(c0, __dadd_rn(s0, -l0)), p1 = __dadd_rn(c1, __dadd_rn(s1, -l1)); /* exclusive */
+#pragma unroll
+            for (int u = 0; u < EVT_CHUNK / 32; u++) {
+                if (i0 + u < n) {
+                    sum[i0 + u + 1] = __dadd_rn(p0, a[u]);
+                    sumsq[i0 + u + 1] = __dadd_rn(p1, q[u]);
+                }
+            }
+            c0 = __dadd_rn(c0, __shfl_sync(ABEA_FULL, s0, 31));
+            c1 = __dadd_rn(c1, __shfl_sync(ABEA_FULL, s1, 31));
+        }
+        for (int d = 16; d >= 1; d >>= 1) {
+            const int32_t a2 = __shfl_xor_sync(ABEA_FULL, e_min, d), b2 = __shfl_xor_sync(ABEA_FULL, e_max, d);
+            e_min = a2 < e_min ? a2 : e_min;
+            e_max = b2 > e_max ? b2 : e_max;
+        }
+        int32_t lg = 0;
+        while (((int64_t)1 << lg) < (int64_t)n) lg++;
+        /* terms of the sum: multiples of 2^(e_min-23), below 2^(e_max+1); of the sum of squares (float products):
+         * multiples of 2^(2 e_min - 23), below 2^(2 e_max + 2); both well inside the double range. Inf / NaN
+         * (exponent 128) never pass. If every partial sum is exact, the scan's association gave the reference's values. */
+        const bool exact = (e_max < 128) && (e_max >= e_min) && ((e_max + 1 + lg) - (e_min - 23) <= 53) &&
+                           ((2 * e_max + 2 + lg) - (2 * e_min - 23) <= 53);
+        if (exact || e_max < e_min) return; /* (all samples zero: every sum is 0) */
+        __syncwarp();
+    }
+    /* ---- some addition may round: redo the sums in the reference's order ---- */
     double acc = 0.0; /* lane 0: sum, lane 1: sum of squares */
     float v[EVT_CHUNK / 32];
     for (int u = 0; u < EVT_CHUNK / 32; u++) {

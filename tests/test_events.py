@@ -239,7 +239,8 @@ def test_gpu_resident_chain(gctx, model, n, mean):
 def adversarial_signals():
     """Signals that stress the speculative detector's stitching: long flat stretches (chunks with no boundary at all,
     so the re-walk never meets the speculative walk), boundaries every two samples, repeated identical values, a
-    staircase, heavy noise, and a jump exactly at a chunk edge."""
+    staircase, heavy noise, a jump exactly at a chunk edge, magnitudes 1e-6 and 150 mixed (inexact cumulative sums),
+    zeros and negative values."""
     rng = np.random.default_rng(99)
     sigs = []
     sigs.append(np.concatenate([np.full(900, 80.0), 80 + 0.01 * rng.standard_normal(700), np.full(50, 120.0), np.full(1200, 95.0)]))
@@ -250,6 +251,10 @@ def adversarial_signals():
     s = np.full(2048, 85.0) + 0.5 * rng.standard_normal(2048)
     s[1024:] += 30.0
     sigs.append(s)
+    # cumulative sums whose additions DO round (1e-6 next to 150: 62 bits needed) -> the ordered-chain path of the
+    # sums kernel; the signals before this one all take its exact warp-scan path
+    sigs.append(np.where(rng.random(1800) < 0.3, 1e-6 * (1 + rng.random(1800)), 150 + 12 * rng.standard_normal(1800)))
+    sigs.append(np.concatenate([np.zeros(300), -40 + 5 * rng.standard_normal(900), np.zeros(200), 60 + 3 * rng.standard_normal(700)]))
     sigs.append(np.full(1500, 77.25))
     n = np.array([len(x) for x in sigs], dtype=np.int32)
     ptr = np.zeros(len(sigs), dtype=np.int64)
