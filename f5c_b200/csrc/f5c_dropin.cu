@@ -11,6 +11,8 @@
  *                                                  src/f5c.c:932 (scaling_single: src/f5c.c:736-807)
  *     void estimate_scalings_cuda(core_t*, db_t*); the estimate_scalings_using_mom call of event_single for a whole
  *                                                  batch, src/f5c.c:709-711 (src/align.c:58-106)
+ *     void getevents_cuda(core_t*, db_t*);         the pA conversion + getevents() call of event_single for a whole
+ *                                                  batch, src/f5c.c:692-703 (src/events.c:562-582)
  *
  * with the reference's own C++ linkage, structs (core_t/db_t from the reference's f5c.h, -DHAVE_CUDA=1) and error
  * convention (message on stderr + exit, src/f5cmisc.cuh:54-118). It is a thin packer over the C ABI in
@@ -59,6 +61,10 @@ struct dropin_data {
     abea_index_pair_t* maps; size_t map_cap;
     int64_t* map_ptr; size_t map_ptr_cap;
     const db_t* aligned_db; /* the batch whose pair lists are resident on the device */
+    /* getevents_cuda staging */
+    float* raw; size_t raw_cap;
+    int64_t* raw_ptr; int32_t* n_samples; float* cal_off; float* cal_range; float* cal_dig; size_t sig_cap;
+    abea_event_t* ev_out; size_t ev_out_cap;
 };
 
 void die(const char* func, const char* what, abea_ctx_t* ctx) {
@@ -100,7 +106,8 @@ void free_cuda(core_t* core) {
     if (!d) return;
     abea_destroy(d->ctx);
     void* bufs[] = {d->seq, d->events, d->pairs, d->seq_ptr, d->event_ptr, d->pair_ptr, d->read_len, d->n_events,
-                    d->n_pairs, d->scalings, d->good, d->sres, d->maps, d->map_ptr};
+                    d->n_pairs, d->scalings, d->good, d->sres, d->maps, d->map_ptr, d->raw, d->raw_ptr, d->n_samples,
+                    d->cal_off, d->cal_range, d->cal_dig, d->ev_out};
     for (void* b : bufs) abea_host_free(b);
     free(d);
     core->cuda = NULL;
@@ -188,6 +195,71 @@ void estimate_scalings_cuda(core_t* core, db_t* db) {
             db->scalings[i].shift = d->scalings[i].shift;
             db->scalings[i].scale = d->scalings[i].scale;
         }
+}
+
+/* The first half of event_single (src/f5c.c:684-703) for the whole batch: db->sig[i]->rawptr is converted to pA in
+ * place exactly as the reference does (consumers downstream read it), and db->et[i] receives the event table of
+ * getevents(nsample, rawptr, rna) — allocated here with the reference's allocator so that free_db_tmp releases it.
+ * event_single then only has to do what follows (scalings, RNA reversal, the pair buffer). */
+void getevents_cuda(core_t* core, db_t* db) {
+    dropin_data* d = (dropin_data*)core->cuda;
+    const int32_t n = db->n_bam_rec;
+    if ((size_t)n > d->sig_cap) {
+        size_t c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+        grow(d->raw_ptr, c1, (size_t)n); grow(d->n_samples, c2, (size_t)n); grow(d->cal_off, c3, (size_t)n);
+        grow(d->cal_range, c4, (size_t)n); grow(d->cal_dig, c5, (size_t)n);
+        d->sig_cap = c1;
+    }
+    int64_t total = 0;
+    for (int32_t i = 0; i < n; i++) {
+        const int32_t ns = (db->sig[i] && db->sig[i]->nsample > 0) ? (int32_t)db->sig[i]->nsample : 0;
+        d->raw_ptr[i] = total;
+        d->n_samples[i] = ns;
+        d->cal_off[i] = ns ? db->sig[i]->offset : 0.f;
+        d->cal_range[i] = ns ? db->sig[i]->range : 1.f;
+        d->cal_dig[i] = ns ? db->sig[i]->digitisation : 1.f;
+        total += ns;
+    }
+    grow(d->raw, d->raw_cap, (size_t)total + 1);
+    for (int32_t i = 0; i < n; i++)
+        if (d->n_samples[i]) memcpy(d->raw + d->raw_ptr[i], db->sig[i]->rawptr, (size_t)d->n_samples[i] * sizeof(float));
+    abea_signals_t sg;
+    sg.n_reads = n; sg.raw = d->raw; sg.raw_ptr = d->raw_ptr; sg.n_samples = d->n_samples;
+    sg.offset = d->cal_off; sg.range = d->cal_range; sg.digitisation = d->cal_dig;
+    if ((size_t)n > d->read_cap) { /* n_events / event_ptr staging is shared with align_cuda */
+        size_t c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;
+        grow(d->seq_ptr, c1, (size_t)n); grow(d->event_ptr, c2, (size_t)n); grow(d->pair_ptr, c3, (size_t)n);
+        grow(d->read_len, c4, (size_t)n); grow(d->n_events, c5, (size_t)n); grow(d->n_pairs, c6, (size_t)n);
+        grow(d->scalings, c7, (size_t)n); grow(d->good, c8, (size_t)n);
+        d->read_cap = c1;
+    }
+    if (abea_getevents(d->ctx, &sg, (core->opt.flag & F5C_RNA) ? 1 : 0, d->n_events, NULL)) die("getevents_cuda", "Cuda error", d->ctx);
+    d->aligned_db = NULL;
+    int64_t ne = 0;
+    for (int32_t i = 0; i < n; i++) {
+        if (d->n_events[i] < 0) { fprintf(stderr, "[getevents_cuda::ERROR] read %d: event table overflow\n", i); exit(EXIT_FAILURE); }
+        d->event_ptr[i] = ne;
+        ne += d->n_events[i];
+    }
+    grow(d->ev_out, d->ev_out_cap, (size_t)ne + 1);
+    if (abea_getevents_download(d->ctx, d->ev_out, d->event_ptr)) die("getevents_cuda", "Cuda error", d->ctx);
+    for (int32_t i = 0; i < n; i++) {
+        if (d->n_samples[i]) { /* convert to pA in place, src/f5c.c:692-696 */
+            float* rawptr = db->sig[i]->rawptr;
+            const float raw_unit = db->sig[i]->range / db->sig[i]->digitisation, offset = db->sig[i]->offset;
+            for (int32_t j = 0; j < d->n_samples[i]; j++) rawptr[j] = (rawptr[j] + offset) * raw_unit;
+        }
+        const size_t m = (size_t)d->n_events[i];
+        db->et[i].n = m;
+        db->et[i].start = 0;
+        db->et[i].end = m;
+        db->et[i].event = NULL;
+        if (m) {
+            db->et[i].event = (event_t*)calloc(m, sizeof(event_t)); /* as create_events does, src/events.c:492 */
+            MALLOC_CHK(db->et[i].event);
+            memcpy(db->et[i].event, d->ev_out + d->event_ptr[i], m * sizeof(event_t));
+        }
+    }
 }
 
 /* scaling_single (src/f5c.c:736-807) for every read of the batch align_cuda has just aligned: fills
@@ -338,5 +410,45 @@ extern "C" int f5c_dropin_selftest_scaling(const abea_batch_t* b, const abea_mod
     free(db->event_align_pairs); free(db->n_event_align_pairs); free(db->event_alignment); free(db->n_event_alignment);
     free(db->events_per_base); free(db->base_to_event_map); free(db->read_stat_flag);
     free(db); free(core);
+    return 0;
+}
+
+/* Third door: getevents_cuda on real core_t / db_t; hands the event tables back flat. */
+extern "C" int f5c_dropin_selftest_events(const abea_signals_t* sg, int device, int rna, int32_t* n_events,
+                                          abea_event_t* events, const int64_t* event_cap_ptr, float* pa_out) {
+    core_t* core = (core_t*)calloc(1, sizeof(core_t));
+    db_t* db = (db_t*)calloc(1, sizeof(db_t));
+    abea_model_t* model = (abea_model_t*)calloc(4096, sizeof(abea_model_t)); /* any 6-mer table: not used here */
+    for (int i = 0; i < 4096; i++) { model[i].level_mean = 90.f; model[i].level_stdv = 2.f; }
+    core->model = (model_t*)model;
+    core->kmer_size = 6;
+    core->opt.cuda_dev_id = device;
+    if (rna) core->opt.flag |= F5C_RNA;
+    const int32_t n = sg->n_reads;
+    db->n_bam_rec = n;
+    db->capacity_bam_rec = n;
+    db->sig = (signal_t**)calloc(n, sizeof(signal_t*));
+    db->et = (event_table*)calloc(n, sizeof(event_table));
+    for (int32_t i = 0; i < n; i++) {
+        db->sig[i] = (signal_t*)calloc(1, sizeof(signal_t));
+        db->sig[i]->nsample = (uint64_t)sg->n_samples[i];
+        db->sig[i]->rawptr = (float*)malloc(sizeof(float) * (size_t)(sg->n_samples[i] + 1));
+        memcpy(db->sig[i]->rawptr, sg->raw + sg->raw_ptr[i], sizeof(float) * (size_t)sg->n_samples[i]);
+        db->sig[i]->offset = sg->offset[i];
+        db->sig[i]->range = sg->range[i];
+        db->sig[i]->digitisation = sg->digitisation[i];
+    }
+    init_cuda(core);
+    getevents_cuda(core, db);
+    for (int32_t i = 0; i < n; i++) {
+        n_events[i] = (int32_t)db->et[i].n;
+        if (db->et[i].n) memcpy(events + event_cap_ptr[i], db->et[i].event, db->et[i].n * sizeof(event_t));
+        memcpy(pa_out + sg->raw_ptr[i], db->sig[i]->rawptr, sizeof(float) * (size_t)sg->n_samples[i]);
+        free(db->et[i].event);
+        free(db->sig[i]->rawptr);
+        free(db->sig[i]);
+    }
+    free_cuda(core);
+    free(db->sig); free(db->et); free(db); free(model); free(core);
     return 0;
 }

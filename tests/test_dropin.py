@@ -94,3 +94,36 @@ def test_dropin_estimate_align_scaling_matches_oracle(built, which):
     for i in range(b.n_reads):
         if want.res["n_event_alignment"][i] > 0:
             assert np.array_equal(got.read_map(i), want.read_map(i)), i
+
+
+@needs_so
+def test_dropin_exports_getevents_entry_point():
+    out = subprocess.check_output(["nm", "-D", "--defined-only", SO]).decode()
+    assert "_Z14getevents_cudaP6core_tP4db_t" in out
+
+
+@needs_so
+@pytest.mark.gpu
+def test_dropin_getevents_matches_oracle(built):
+    """getevents_cuda on real core_t / db_t: event tables and the in-place pA conversion against the oracle."""
+    from f5c_b200.abea import CSignals
+    from f5c_b200.batch import EVENT_DTYPE
+    lib = ctypes.CDLL(SO)
+    vp = ctypes.c_void_p
+    lib.f5c_dropin_selftest_events.argtypes = [ctypes.POINTER(CSignals), ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    sg = synth.make_signals(48, 1500, 0.6, seed=33)
+    n = len(sg["n_samples"])
+    cs = CSignals(n, sg["raw"].ctypes.data, sg["raw_ptr"].ctypes.data, sg["n_samples"].ctypes.data,
+                  sg["offset"].ctypes.data, sg["range"].ctypes.data, sg["digitisation"].ctypes.data)
+    cap = sg["n_samples"].astype(np.int64) // 2 + 2
+    cap_ptr = np.zeros(n, dtype=np.int64)
+    np.cumsum(cap[:-1], out=cap_ptr[1:])
+    events = np.zeros(int(cap.sum()), dtype=EVENT_DTYPE)
+    nev = np.zeros(n, dtype=np.int32)
+    pa = np.zeros_like(sg["raw"])
+    assert lib.f5c_dropin_selftest_events(ctypes.byref(cs), 0, 0, nev.ctypes.data, events.ctypes.data,
+                                          cap_ptr.ctypes.data, pa.ctypes.data) == 0
+    assert np.array_equal(pa, sg["pa"])
+    for i in range(n):
+        want = ol.port_getevents(sg["pa"][sg["raw_ptr"][i]:sg["raw_ptr"][i] + sg["n_samples"][i]])
+        assert ol._events_equal(events[cap_ptr[i]:cap_ptr[i] + nev[i]], want), i
