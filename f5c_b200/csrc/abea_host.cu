@@ -349,7 +349,7 @@ int abea_create(abea_ctx_t** out, int device) {
         return ABEA_ERR_CUDA;
     }
     if (const char* e = getenv("ABEA_FILL_CTAS_PER_SM")) c->fill_ctas_per_sm = std::max(1, atoi(e));
-    if (const char* e = getenv("ABEA_FILL_WARPS_PER_CTA")) c->fill_warps_per_cta = std::min(16, std::max(4, atoi(e) / 4 * 4));
+    if (const char* e = getenv("ABEA_FILL_WARPS_PER_CTA")) c->fill_warps_per_cta = std::min(ABEA_NARROW_WARPS_MAX, std::max(4, atoi(e) / 4 * 4));
     if (const char* e = getenv("ABEA_LONG_ALPHA")) c->long_alpha = atof(e);
     if (const char* e = getenv("ABEA_TRACE_CTAS_PER_SM")) c->trace_ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("ABEA_SCHED")) c->sched_policy = atoi(e) ? 1 : 0;

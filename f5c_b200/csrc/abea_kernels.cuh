@@ -860,7 +860,7 @@ __device__ __forceinline__ bool abea_fill_step(abea_fill_ctx_t& cx, float* x, fl
  * read longer than long_thr bands, they wait between reads — so the reads that set the makespan run alone on their
  * sub-partition (~655 instead of ~780 cycles per band, profiles/README.md) at the cost of idling a few of the 592
  * sub-partitions' second slots. queue[0] counts pulls, queue[1] the head, queue[2] the tail. */
-#define ABEA_NARROW_WARPS_MAX 16
+#define ABEA_NARROW_WARPS_MAX 12
 
 __device__ __forceinline__ void abea_backoff() {
 #ifndef ABEA_SIMT_EMU
