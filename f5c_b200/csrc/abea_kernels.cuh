@@ -861,6 +861,12 @@ __device__ __forceinline__ bool abea_fill_step(abea_fill_ctx_t& cx, float* x, fl
  * sub-partition (~655 instead of ~780 cycles per band, profiles/README.md) at the cost of idling a few of the 592
  * sub-partitions' second slots. queue[0] counts pulls, queue[1] the head, queue[2] the tail. */
 #define ABEA_NARROW_WARPS_MAX 12
+/* Register budget. A resident batch: the CTA's 12 warps may use the whole register file (launch bound 384 threads ->
+ * 162 registers, 8 % fewer instructions than at 124: cfg2 11.08 -> 10.81 ms). A streamed batch: the CTAs of
+ * abea_load_kernel must fit on the same SMs BESIDE the persistent narrow CTAs (with 162 x 384 registers taken they do
+ * not, the narrow grid then waits for the loader to finish and the end-to-end time goes from 13.5 to 20.7 ms — measured),
+ * so the STREAM instantiations keep the bound of 512 threads (124 registers). */
+#define ABEA_NARROW_BOUND(STREAM) ((STREAM) ? 32 * 16 : 32 * ABEA_NARROW_WARPS_MAX)
 
 __device__ __forceinline__ void abea_backoff() {
 #ifndef ABEA_SIMT_EMU
@@ -869,7 +875,7 @@ __device__ __forceinline__ void abea_backoff() {
 }
 
 template <bool FAST, bool STREAM>
-__global__ void __launch_bounds__(32 * ABEA_NARROW_WARPS_MAX)
+__global__ void __launch_bounds__(ABEA_NARROW_BOUND(STREAM))
 abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const abea_event_t* __restrict__ events,
                  const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                  uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
