@@ -278,3 +278,46 @@ def test_gpu_getevents_adversarial_signals(gctx):
     sg = adversarial_signals()
     for rna in (False, True):
         check_device(gctx, sg, rna, calibrated=False)
+
+
+def test_exact_sum_condition_is_what_makes_the_scan_legal():
+    """The sums kernel replaces the reference's ordered additions by a warp scan when
+    (e_max + 1 + ceil(log2 n)) - (e_min - 23) <= 53 (and the analogous bound for the float squares). Under that
+    condition every partial sum is exactly representable, so ANY association gives the sequential result; outside it
+    the association matters (which is why the kernel then keeps the reference's order)."""
+    rng = np.random.default_rng(8)
+    x = rng.uniform(16.0, 256.0, 200000).astype(np.float32)             # e_min = 4, e_max = 7, n < 2^18: 49 bits
+    assert (7 + 1 + 18) - (4 - 23) <= 53
+    seq = np.cumsum(x.astype(np.float64))                                 # sequential, as compute_sum_sumsq
+    blocks = x.astype(np.float64).reshape(-1, 100).sum(axis=1)            # a different association
+    assert np.array_equal(np.cumsum(blocks), seq[99::100])
+    assert float(np.sum(x.astype(np.float64)[::-1])) == float(seq[-1])    # reversed order
+    sq = (x * x).astype(np.float64)                                       # float product, promoted afterwards
+    assert (2 * 7 + 2 + 18) - (2 * 4 - 23) <= 53
+    assert float(np.sum(sq[::-1])) == float(np.cumsum(sq)[-1])
+    y = np.where(rng.random(200000) < 0.3, 1e-6, 150.0).astype(np.float32) * rng.uniform(1, 2, 200000).astype(np.float32)
+    assert (8 + 1 + 18) - (-20 - 23) > 53                                 # 1e-6 next to 150: additions round
+    assert float(np.sum(y.astype(np.float64)[::-1])) != float(np.cumsum(y.astype(np.float64))[-1])
+
+
+def test_getevents_argument_errors(emu):
+    from f5c_b200.abea import AbeaError
+    with AbeaContext(0, lib_path=emu) as ctx:
+        sg = synth.make_signals(2, 200, 0.3, seed=1)
+        with pytest.raises(AbeaError):       # offset without range / digitisation
+            import ctypes
+            from f5c_b200.abea import CSignals, Timing
+            cs = CSignals(2, sg["raw"].ctypes.data, sg["raw_ptr"].ctypes.data, sg["n_samples"].ctypes.data,
+                          sg["offset"].ctypes.data, None, None)
+            nev = np.zeros(2, dtype=np.int32)
+            ctx._check(ctx.lib.abea_getevents(ctx._h, ctypes.byref(cs), 0, nev.ctypes.data, None), "abea_getevents")
+        ev, ptr, nev, t = ctx.getevents(np.zeros(0, dtype=np.float32), np.zeros(0, dtype=np.int64),
+                                        np.zeros(0, dtype=np.int32))          # an empty batch is fine
+        assert len(ev) == 0 and len(nev) == 0
+        from f5c_b200 import models
+        from f5c_b200.batch import EVENT_DTYPE, SCALINGS_DTYPE, ReadBatch
+        k, m = models.load_model("r9")
+        ctx.set_model(m, k)
+        b = synth.make_batch("r9", n_reads=2, mean_events=100, sigma=0.2, epk=1.8, seed=3)
+        with pytest.raises(AbeaError):       # events == NULL, but the device holds no tables for these reads
+            ctx.upload(b, device_events=True)
