@@ -57,6 +57,19 @@ def measured_traffic():
     return None
 
 
+def measured_issue():
+    """What actually bounds the dominant kernel, from the same committed capture: issue slots, not HBM."""
+    p = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "issue_active_per_cycle_active" in d:
+            return {"issue_slots_used_while_active": d["issue_active_per_cycle_active"],
+                    "sub_partitions_active_fraction": d["smsp_cycles_active_avg"] / d["sm_cycles_elapsed_max"],
+                    "pipes_pct_of_peak_active": d.get("pipes_pct_of_peak_active"),
+                    "source": "profiles/fill_narrow_final_r01.txt (ncu --set full of the same kernel and workload)"}
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -302,7 +315,8 @@ def main():
                          "kernel": "abea_fill_kernel<true> = band fill + fused traceback (dominant; bytes and time cover the whole step incl. abea_prepare_kernel)",
                          "kernel_share": fill_ms / dev_ms if dev_ms else None,
                          "algorithmic_bytes_per_step_rank0": int(alg_bytes),
-                         "bytes_per_event": alg_bytes / max(1.0, float(my_events))},
+                         "bytes_per_event": alg_bytes / max(1.0, float(my_events)),
+                         "binding_resource": (measured_issue() if a.config == "cfg2" and a.reads_per_gpu is None else None)},
             "clocks": clocks,
             "stages": stages,
         }
