@@ -125,3 +125,10 @@ def test_emulated_degenerate_batches(emu):
         b.good[:] = 1            # the same context keeps working afterwards
         got = ctx.align_batch(b)
         assert (got.n_pairs > 0).all()
+
+
+def test_smoke_entry_point_on_the_emulator(emu):
+    """__graft_entry__.smoke() — the driver's GPU smoke test — with the emulator build in place of the CUDA library:
+    both of its legs (alignment; raw signal -> events -> scalings -> alignment -> recalibration) stay runnable."""
+    import __graft_entry__ as g
+    g.smoke(lib_path=emu)
