@@ -280,6 +280,7 @@ void build_load_order(abea_ctx* c) {
             need.push_back(need_t{start[r] + frac * fill, (int32_t)r, q});
         }
     }
+    /* nearly sorted already (reads in schedule order, pieces ascending): a merge sort is the fast one here */
     std::stable_sort(need.begin(), need.end(), [](const need_t& x, const need_t& y) { return x.t < y.t; });
     c->items.clear();
     c->items.reserve(need.size());
@@ -479,6 +480,7 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
     /* eligibility: align_single's filter (reference src/f5c.c:811-830). Reads with no events or fewer bases than
      * k are undefined in the reference; they get 0 pairs here. */
     const int32_t k = (int32_t)c->kmer_size;
+    const double exp_lp_skip = exp(c->cst.lp_skip); /* the same double for every read (src/align.c:215) */
     for (int32_t i = 0; i < b->n_reads; i++) {
         const int32_t E = b->n_events[i], L = b->read_len[i];
         const bool good = b->good ? (b->good[i] != 0) : true;
@@ -499,13 +501,21 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         double events_per_kmer = (double)(size_t)E / (size_t)r.n_kmers;
         double p_stay = 1 - (1 / (events_per_kmer + 1));
         r.lp_stay = log(p_stay);
-        r.lp_step = log(1.0 - exp(c->cst.lp_skip) - exp(r.lp_stay));
+        r.lp_step = log(1.0 - exp_lp_skip - exp(r.lp_stay));
         c->reads.push_back(r);
     }
-    /* longest-first schedule: a read is a serial chain of NB = E+K+2 bands */
-    std::stable_sort(c->reads.begin(), c->reads.end(), [](const abea_read_t& x, const abea_read_t& y) {
-        return (int64_t)x.n_events + x.n_kmers > (int64_t)y.n_events + y.n_kmers;
-    });
+    /* longest-first schedule: a read is a serial chain of NB = E+K+2 bands. Sorted through 12-byte keys, not by
+     * moving the 96-byte descriptors around (this is on the critical path of abea_align_batch) */
+    {
+        struct key_t { int64_t nb; int32_t idx; };
+        std::vector<key_t> keys(c->reads.size());
+        for (size_t j = 0; j < keys.size(); j++)
+            keys[j] = key_t{(int64_t)c->reads[j].n_events + c->reads[j].n_kmers, (int32_t)j};
+        std::stable_sort(keys.begin(), keys.end(), [](const key_t& x, const key_t& y) { return x.nb > y.nb; });
+        std::vector<abea_read_t> sorted(c->reads.size());
+        for (size_t j = 0; j < keys.size(); j++) sorted[j] = c->reads[(size_t)keys[j].idx];
+        c->reads.swap(sorted);
+    }
     int64_t kp = 0, tw = 0, pc = 0, nb = 0, ne = 0;
     for (abea_read_t& r : c->reads) {
         const int64_t NB = (int64_t)r.n_events + r.n_kmers + 2;
