@@ -28,6 +28,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
 #include "f5c.h"
 #include "f5cmisc.h"
 
@@ -72,6 +77,48 @@ void die(const char* func, const char* what, abea_ctx_t* ctx) {
     exit(-1);
 }
 
+/* The per-read copies between db_t's ragged arrays and the flat staging buffers are the bulk of the host time of a
+ * batch (cfg2: 389 MB of events in, 130 MB of pairs out), so they run on core->opt.num_thread threads — the threads
+ * the reference uses for pthread_db (src/f5c.c:590-676) — pulling blocks of reads from a shared counter. */
+template <typename F> void parallel_reads(int32_t n, int threads, F f) {
+    if (threads <= 1 || n < 64) {
+        for (int32_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<int32_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int32_t i0 = next.fetch_add(16);
+            if (i0 >= n) break;
+            const int32_t i1 = std::min(n, i0 + 16);
+            for (int32_t i = i0; i < i1; i++) f(i);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (std::thread& t : pool) t.join();
+}
+
+/* db->read[i] / db->et[i].event -> flat seq / events at the given offsets */
+void copy_in(const db_t* db, const int64_t* seq_ptr, const int64_t* event_ptr, char* seq, abea_event_t* events, int threads) {
+    parallel_reads(db->n_bam_rec, threads, [&](int32_t i) {
+        memcpy(seq + seq_ptr[i], db->read[i], (size_t)db->read_len[i]);
+        seq[seq_ptr[i] + db->read_len[i]] = 0;
+        if (db->et[i].n) memcpy(events + event_ptr[i], db->et[i].event, db->et[i].n * sizeof(event_t));
+    });
+}
+
+/* flat pairs -> db->event_align_pairs[i] (src/f5c.cu:1005-1030): already ascending, no host-side reversal */
+void copy_out(db_t* db, const int32_t* n_pairs, const int64_t* pair_ptr, const abea_pair_t* pairs, int threads) {
+    parallel_reads(db->n_bam_rec, threads, [&](int32_t i) {
+        db->n_event_align_pairs[i] = n_pairs[i];
+        if (n_pairs[i] > 0) memcpy(db->event_align_pairs[i], pairs + pair_ptr[i], (size_t)n_pairs[i] * sizeof(AlignedPair));
+    });
+}
+
+int host_threads(const core_t* core) { return core->opt.num_thread > 0 ? core->opt.num_thread : 1; }
+
 template <typename T> void grow(T*& p, size_t& cap, size_t need) {
     if (need <= cap) return;
     if (p) abea_host_free(p);
@@ -114,7 +161,7 @@ void free_cuda(core_t* core) {
 }
 
 /* flatten the ragged batch (what the reference does at src/f5c.cu:744-800) into pinned staging */
-static void pack_db(dropin_data* d, const db_t* db, abea_batch_t& b, bool with_scalings) {
+static void pack_db(dropin_data* d, const db_t* db, abea_batch_t& b, bool with_scalings, int threads) {
     const int32_t n = db->n_bam_rec;
     if ((size_t)n > d->read_cap) {
         size_t c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, c6 = 0, c7 = 0, c8 = 0;
@@ -136,11 +183,7 @@ static void pack_db(dropin_data* d, const db_t* db, abea_batch_t& b, bool with_s
     grow(d->seq, d->seq_cap, (size_t)sp + 1);
     grow(d->events, d->ev_cap, (size_t)ep + 1);
     grow(d->pairs, d->pair_cap, (size_t)pp + 1);
-    for (int32_t i = 0; i < n; i++) {
-        memcpy(d->seq + d->seq_ptr[i], db->read[i], (size_t)db->read_len[i]);
-        d->seq[d->seq_ptr[i] + db->read_len[i]] = 0;
-        if (db->et[i].n) memcpy(d->events + d->event_ptr[i], db->et[i].event, db->et[i].n * sizeof(event_t));
-    }
+    copy_in(db, d->seq_ptr, d->event_ptr, d->seq, d->events, threads);
     b.n_reads = n; b.seq = d->seq; b.seq_ptr = d->seq_ptr; b.read_len = d->read_len; b.events = d->events;
     b.event_ptr = d->event_ptr; b.n_events = d->n_events; b.scalings = with_scalings ? d->scalings : NULL;
     b.good = d->good;
@@ -148,10 +191,9 @@ static void pack_db(dropin_data* d, const db_t* db, abea_batch_t& b, bool with_s
 
 void align_cuda(core_t* core, db_t* db) {
     dropin_data* d = (dropin_data*)core->cuda;
-    const int32_t n = db->n_bam_rec;
     double t0 = realtime();
     abea_batch_t b;
-    pack_db(d, db, b, true);
+    pack_db(d, db, b, true, host_threads(core));
     double t1 = realtime();
 
     abea_timing_t tm;
@@ -159,11 +201,7 @@ void align_cuda(core_t* core, db_t* db) {
     d->aligned_db = db;
     double t2 = realtime();
 
-    /* un-flatten (src/f5c.cu:1005-1030): pairs already ascending, no host-side reversal */
-    for (int32_t i = 0; i < n; i++) {
-        db->n_event_align_pairs[i] = d->n_pairs[i];
-        if (d->n_pairs[i] > 0) memcpy(db->event_align_pairs[i], d->pairs + d->pair_ptr[i], (size_t)d->n_pairs[i] * sizeof(AlignedPair));
-    }
+    copy_out(db, d->n_pairs, d->pair_ptr, d->pairs, host_threads(core));
     double t3 = realtime();
 
     /* the reference's timer split (src/f5c.h:457-466), printed by meth_main (src/meth_main.c:767-788) */
@@ -186,7 +224,7 @@ void align_cuda(core_t* core, db_t* db) {
 void estimate_scalings_cuda(core_t* core, db_t* db) {
     dropin_data* d = (dropin_data*)core->cuda;
     abea_batch_t b;
-    pack_db(d, db, b, false);
+    pack_db(d, db, b, false, host_threads(core));
     if (abea_upload_batch(d->ctx, &b, NULL)) die("estimate_scalings_cuda", "Cuda error", d->ctx);
     if (abea_estimate_scalings(d->ctx, 0, d->scalings, NULL)) die("estimate_scalings_cuda", "Cuda error", d->ctx);
     d->aligned_db = NULL;
@@ -221,8 +259,9 @@ void getevents_cuda(core_t* core, db_t* db) {
         total += ns;
     }
     grow(d->raw, d->raw_cap, (size_t)total + 1);
-    for (int32_t i = 0; i < n; i++)
+    parallel_reads(n, host_threads(core), [&](int32_t i) {
         if (d->n_samples[i]) memcpy(d->raw + d->raw_ptr[i], db->sig[i]->rawptr, (size_t)d->n_samples[i] * sizeof(float));
+    });
     abea_signals_t sg;
     sg.n_reads = n; sg.raw = d->raw; sg.raw_ptr = d->raw_ptr; sg.n_samples = d->n_samples;
     sg.offset = d->cal_off; sg.range = d->cal_range; sg.digitisation = d->cal_dig;
@@ -243,7 +282,7 @@ void getevents_cuda(core_t* core, db_t* db) {
     }
     grow(d->ev_out, d->ev_out_cap, (size_t)ne + 1);
     if (abea_getevents_download(d->ctx, d->ev_out, d->event_ptr)) die("getevents_cuda", "Cuda error", d->ctx);
-    for (int32_t i = 0; i < n; i++) {
+    parallel_reads(n, host_threads(core), [&](int32_t i) {
         if (d->n_samples[i]) { /* convert to pA in place, src/f5c.c:692-696 */
             float* rawptr = db->sig[i]->rawptr;
             const float raw_unit = db->sig[i]->range / db->sig[i]->digitisation, offset = db->sig[i]->offset;
@@ -259,7 +298,7 @@ void getevents_cuda(core_t* core, db_t* db) {
             MALLOC_CHK(db->et[i].event);
             memcpy(db->et[i].event, d->ev_out + d->event_ptr[i], m * sizeof(event_t));
         }
-    }
+    });
 }
 
 /* scaling_single (src/f5c.c:736-807) for every read of the batch align_cuda has just aligned: fills
@@ -451,4 +490,37 @@ extern "C" int f5c_dropin_selftest_events(const abea_signals_t* sg, int device, 
     free_cuda(core);
     free(db->sig); free(db->et); free(db); free(model); free(core);
     return 0;
+}
+
+/* Fourth door, runnable without a GPU: the threaded copies of the packer / unpacker on a db_t built over a flat
+ * batch. seq_out / events_out receive the flattened copy (same offsets as the batch), pairs_rt the pairs copied out
+ * of pairs_in into per-read buffers and back. Returns the milliseconds the two copies took. */
+extern "C" double f5c_dropin_selftest_pack(const abea_batch_t* b, int threads, char* seq_out, abea_event_t* events_out,
+                                           const abea_pair_t* pairs_in, const int64_t* pair_ptr, const int32_t* n_pairs,
+                                           abea_pair_t* pairs_rt) {
+    const int32_t n = b->n_reads;
+    db_t* db = (db_t*)calloc(1, sizeof(db_t));
+    db->n_bam_rec = n;
+    db->read = (char**)calloc(n, sizeof(char*));
+    db->read_len = (int32_t*)calloc(n, sizeof(int32_t));
+    db->et = (event_table*)calloc(n, sizeof(event_table));
+    db->event_align_pairs = (AlignedPair**)calloc(n, sizeof(AlignedPair*));
+    db->n_event_align_pairs = (int32_t*)calloc(n, sizeof(int32_t));
+    for (int32_t i = 0; i < n; i++) {
+        db->read[i] = (char*)(b->seq + b->seq_ptr[i]);
+        db->read_len[i] = b->read_len[i];
+        db->et[i].n = (size_t)b->n_events[i];
+        db->et[i].event = (event_t*)(b->events + b->event_ptr[i]);
+        db->event_align_pairs[i] = (AlignedPair*)malloc(sizeof(AlignedPair) * ((size_t)b->n_events[i] + b->read_len[i] + 1));
+    }
+    const double t0 = realtime();
+    copy_in(db, b->seq_ptr, b->event_ptr, seq_out, events_out, threads);
+    copy_out(db, n_pairs, pair_ptr, pairs_in, threads);
+    const double t1 = realtime();
+    for (int32_t i = 0; i < n; i++) {
+        if (n_pairs[i] > 0) memcpy(pairs_rt + pair_ptr[i], db->event_align_pairs[i], (size_t)n_pairs[i] * sizeof(AlignedPair));
+        free(db->event_align_pairs[i]);
+    }
+    free(db->read); free(db->read_len); free(db->et); free(db->event_align_pairs); free(db->n_event_align_pairs); free(db);
+    return (t1 - t0) * 1e3;
 }

@@ -127,3 +127,30 @@ def test_dropin_getevents_matches_oracle(built):
     for i in range(n):
         want = ol.port_getevents(sg["pa"][sg["raw_ptr"][i]:sg["raw_ptr"][i] + sg["n_samples"][i]])
         assert ol._events_equal(events[cap_ptr[i]:cap_ptr[i] + nev[i]], want), i
+
+
+@needs_so
+@pytest.mark.parametrize("threads", [1, 4])
+def test_dropin_threaded_copies_roundtrip(threads):
+    """The packer / unpacker copies of the drop-in (db_t's ragged arrays <-> flat staging) on N host threads; runs
+    without a GPU (no CUDA call behind this door)."""
+    lib = ctypes.CDLL(SO)
+    vp = ctypes.c_void_p
+    lib.f5c_dropin_selftest_pack.restype = ctypes.c_double
+    lib.f5c_dropin_selftest_pack.argtypes = [ctypes.POINTER(CBatch), ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    b = synth.make_config("cfg2", seed=63, n_reads=300)
+    k, m = models.load_model("r9")
+    want = ol.port_align(b, ol.full_model(m))
+    seq_out = np.full_like(b.seq, 0xEE)
+    ev_out = np.zeros_like(b.events)
+    pairs_rt = np.zeros_like(want.pairs)
+    pp = b.pair_ptr()
+    cb = b.as_c()
+    ms = lib.f5c_dropin_selftest_pack(ctypes.byref(cb), threads, seq_out.ctypes.data, ev_out.ctypes.data,
+                                      want.pairs.ctypes.data, pp.ctypes.data, want.n_pairs.ctypes.data,
+                                      pairs_rt.ctypes.data)
+    assert ms >= 0
+    assert np.array_equal(seq_out, b.seq) and ev_out.tobytes() == b.events.tobytes()
+    for i in range(b.n_reads):
+        p, n = int(pp[i]), int(want.n_pairs[i])
+        assert np.array_equal(pairs_rt[p:p + n], want.pairs[p:p + n])
