@@ -63,9 +63,10 @@ def lpt_shards(weights: np.ndarray, n_shards: int):
 
 def make_batch(model: str = "r9", n_reads: int = 64, mean_events: float = 4000.0, sigma: float = 0.5,
                epk: float = 1.8, seed: int = 42, model_table=None, min_len: int = 200,
-               e_star: np.ndarray | None = None) -> ReadBatch:
+               e_star: np.ndarray | None = None, p_skip: float = 0.03) -> ReadBatch:
     """Generate a ragged batch. model_table=(k, MODEL_DTYPE array) overrides the named built-in table;
-    e_star (target event counts per read) overrides the log-normal draw (used for read-wise sharding)."""
+    e_star (target event counts per read) overrides the log-normal draw (used for read-wise sharding); p_skip is the
+    share of k-mers without any event (0.03 in the validated recipe; tests raise it to stress skip runs)."""
     k, mt = model_table if model_table is not None else load_model(model)
     rng = np.random.default_rng(seed)
     if e_star is None:
@@ -95,7 +96,7 @@ def make_batch(model: str = "r9", n_reads: int = 64, mean_events: float = 4000.0
 
     # events per k-mer: 3% skips, otherwise Geometric (>=1) with overall mean epk
     cnt = rng.geometric(min(1.0, 0.97 / epk), total_k).astype(np.int64)
-    cnt[rng.random(total_k) < 0.03] = 0
+    cnt[rng.random(total_k) < p_skip] = 0
     # every read needs at least one event on its first and last k-mer so it can span
     cnt[kptr[:-1]] = np.maximum(cnt[kptr[:-1]], 1)
     cnt[kptr[1:] - 1] = np.maximum(cnt[kptr[1:] - 1], 1)

@@ -289,3 +289,23 @@ def test_gpu_stages_full_size_cfg2(gctx):
         if want.res["n_event_alignment"][j] > 0:
             assert np.array_equal(sc.read_map(i), want.read_map(j))
     assert (r["flags"] & FAILED_CALIBRATION).mean() < 0.05
+
+
+def test_emulated_stages_with_many_skips(emu):
+    """15 % of the k-mers without any event: hundreds of skip steps (pairs that repeat the previous event), runs of
+    them, and k-mers whose only pair was reached by a skip — the cases postalign's map logic has to get right."""
+    b = synth.make_batch("r9", n_reads=8, mean_events=500, sigma=0.4, epk=1.8, seed=5, p_skip=0.15)
+    with AbeaContext(0, lib_path=emu) as ctx:
+        est, aln, sc = check_device_stages(ctx, b, "r9", "skips", min_events=100)
+    skips = empty = 0
+    for i in range(b.n_reads):
+        p = aln.read_pairs(i)
+        skips += int(((np.diff(p["read_pos"]) == 0) & (np.diff(p["ref_pos"]) == 1)).sum())
+        empty += int((sc.read_map(i)["start"] == -1).sum()) if aln.n_pairs[i] > 0 else 0
+    assert skips > 100 and empty > 50
+
+
+@pytest.mark.gpu
+def test_gpu_stages_with_many_skips(gctx):
+    b = synth.make_batch("r9", n_reads=128, mean_events=2000, sigma=0.5, epk=1.8, seed=6, p_skip=0.15)
+    check_device_stages(gctx, b, "r9", "skips")
