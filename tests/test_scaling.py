@@ -304,8 +304,3 @@ def test_emulated_stages_with_many_skips(emu):
         empty += int((sc.read_map(i)["start"] == -1).sum()) if aln.n_pairs[i] > 0 else 0
     assert skips > 50 and empty > 20
 
-
-@pytest.mark.gpu
-def test_gpu_stages_with_many_skips(gctx):
-    b = synth.make_batch("r9", n_reads=128, mean_events=2000, sigma=0.5, epk=1.8, seed=6, p_skip=0.15)
-    check_device_stages(gctx, b, "r9", "skips")
