@@ -304,3 +304,37 @@ def test_emulated_stages_with_many_skips(emu):
         empty += int((sc.read_map(i)["start"] == -1).sum()) if aln.n_pairs[i] > 0 else 0
     assert skips > 50 and empty > 20
 
+
+
+def test_emulated_scaling_download_layouts_and_device_results(emu):
+    """abea_scaling_download with a caller layout that is not the canonical prefix sum (per-read copies), and
+    abea_scaling_device_results (on the emulator the 'device' pointers are host pointers and can be read back)."""
+    import ctypes
+    from f5c_b200.batch import INDEX_PAIR_DTYPE, SCALING_RESULT_DTYPE
+    b = synth.make_batch("r9", n_reads=5, mean_events=300, sigma=0.3, epk=1.8, seed=8)
+    k, m = models.load_model("r9")
+    with AbeaContext(0, lib_path=emu) as ctx:
+        ctx.set_model(m, k)
+        ctx.upload(b)
+        ctx.run()
+        ctx.scaling_stage(100)
+        canon = ctx.scaling_download(b)
+        mp = b.map_ptr()
+        gap = 7                                              # every read's map 7 entries further apart
+        mp2 = mp[:-1] + gap * np.arange(b.n_reads, dtype=np.int64)
+        res = np.zeros(b.n_reads, dtype=SCALING_RESULT_DTYPE)
+        maps = np.full(2 * (int(mp[-1]) + gap * b.n_reads), -7, dtype=np.int32).view(INDEX_PAIR_DTYPE)
+        ctx._check(ctx.lib.abea_scaling_download(ctx._h, res.ctypes.data, maps.ctypes.data, mp2.ctypes.data), "download")
+        assert res.tobytes() == canon.results.tobytes()
+        K = b.n_kmers
+        for i in range(b.n_reads):
+            if canon.results["n_event_alignment"][i] > 0:
+                assert np.array_equal(maps[int(mp2[i]):int(mp2[i]) + int(K[i])], canon.read_map(i))
+        dres, dmaps, total = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+        ctx._check(ctx.lib.abea_scaling_device_results(ctx._h, ctypes.byref(dres), ctypes.byref(dmaps), ctypes.byref(total)),
+                   "device results")
+        assert total.value == int(mp[-1])
+        raw = (ctypes.c_char * (SCALING_RESULT_DTYPE.itemsize * b.n_reads)).from_address(dres.value)
+        on_dev = np.frombuffer(raw, dtype=SCALING_RESULT_DTYPE)
+        for f in ("flags", "n_event_alignment", "num_m_state", "events_per_base", "var_d"):
+            assert np.array_equal(on_dev[f], canon.results[f]), f       # (log_var is filled by the download, on the host)
