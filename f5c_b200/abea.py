@@ -209,27 +209,35 @@ class AbeaContext:
             n_pairs = np.empty(batch.n_reads, dtype=np.int32)
         return pairs, batch.pair_ptr(), n_pairs
 
-    def align_batch(self, batch: ReadBatch, out=None) -> Alignment:
-        """abea_align_batch: host buffers in, host buffers out (the e2e path)."""
+    def align_batch(self, batch: ReadBatch, out=None, means: np.ndarray | None = None) -> Alignment:
+        """abea_align_batch: host buffers in, host buffers out (the e2e path). means: flat float32 event means handed
+        over instead of the event table (abea_batch_t.event_means): 4 bytes per event cross PCIe instead of 24."""
         assert batch.kmer_size == self.kmer_size, "batch k-mer size does not match the uploaded model"
         pairs, pair_ptr, n_pairs = out if out is not None else self.alloc_output(batch)
         t = Timing()
-        cb = batch.as_c()
+        cb = batch.as_c(means)
         self._check(self.lib.abea_align_batch(self._h, ctypes.byref(cb), pairs.ctypes.data, pair_ptr.ctypes.data,
                                               n_pairs.ctypes.data, ctypes.byref(t)), "abea_align_batch")
         return Alignment(pairs, pair_ptr, n_pairs, t.as_dict())
 
-    def upload(self, batch: ReadBatch, with_scalings: bool = True, device_events: bool = False) -> dict:
+    def pin_array(self, a: np.ndarray) -> np.ndarray:
+        out = self.pinned_empty(a.shape, a.dtype)
+        out[...] = a
+        return out
+
+    def upload(self, batch: ReadBatch, with_scalings: bool = True, device_events: bool = False,
+               means: np.ndarray | None = None) -> dict:
         """abea_upload_batch. with_scalings=False leaves abea_batch_t.scalings NULL: estimate_scalings() must follow.
         device_events=True leaves abea_batch_t.events NULL: the event tables of the last getevents() are aligned where
         they lie on the device (batch.n_events must repeat its counts)."""
         assert batch.kmer_size == self.kmer_size
         t = Timing()
-        cb = batch.as_c()
+        cb = batch.as_c(means)
         if not with_scalings:
             cb.scalings = None
         if device_events:
             cb.events = None
+            cb.event_means = None
         self._check(self.lib.abea_upload_batch(self._h, ctypes.byref(cb), ctypes.byref(t)), "abea_upload_batch")
         return t.as_dict()
 

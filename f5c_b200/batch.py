@@ -47,7 +47,8 @@ class CBatch(ctypes.Structure):
                 ("event_ptr", ctypes.c_void_p),
                 ("n_events", ctypes.c_void_p),
                 ("scalings", ctypes.c_void_p),
-                ("good", ctypes.c_void_p)]
+                ("good", ctypes.c_void_p),
+                ("event_means", ctypes.c_void_p)]
 
 
 @dataclass
@@ -128,13 +129,22 @@ class ReadBatch:
         per_read = 24 * E + (L + 1) + 100 * NB + 40 * P + 36
         return int(per_read.sum()) + 12 * (4 ** self.kmer_size)
 
-    def as_c(self) -> CBatch:
+    def event_means(self) -> np.ndarray:
+        """The events' means alone as a flat float32 array (abea_batch_t.event_means): all ABEA reads of an event."""
+        return np.ascontiguousarray(self.events["mean"], dtype=np.float32)
+
+    def as_c(self, means: np.ndarray | None = None) -> CBatch:
+        """ctypes image of the batch. means: a flat float32 array of event means (same indexing as `events`) to hand
+        over instead of the 24-byte event table (abea_batch_t.event_means; `events` is then NULL)."""
         for name in ("seq", "seq_ptr", "read_len", "events", "event_ptr", "n_events", "scalings", "good"):
             a = getattr(self, name)
             assert a.flags["C_CONTIGUOUS"], name
+        if means is not None:
+            assert means.dtype == np.float32 and means.flags["C_CONTIGUOUS"] and means.shape[0] == self.events.shape[0]
         return CBatch(self.n_reads, self.seq.ctypes.data, self.seq_ptr.ctypes.data, self.read_len.ctypes.data,
-                      self.events.ctypes.data, self.event_ptr.ctypes.data, self.n_events.ctypes.data,
-                      self.scalings.ctypes.data, self.good.ctypes.data)
+                      None if means is not None else self.events.ctypes.data, self.event_ptr.ctypes.data,
+                      self.n_events.ctypes.data, self.scalings.ctypes.data, self.good.ctypes.data,
+                      means.ctypes.data if means is not None else None)
 
     def read_seq(self, i: int) -> bytes:
         p = int(self.seq_ptr[i])

@@ -72,7 +72,7 @@ struct abea_ctx {
     bool have_model = false;
 
     /* resident batch */
-    DevBuf d_seq, d_events, d_reads, d_kparams, d_trace, d_pairs, d_results, d_queue, d_flags, d_npairs;
+    DevBuf d_seq, d_events, d_means, d_reads, d_kparams, d_trace, d_pairs, d_results, d_queue, d_flags, d_npairs;
     std::vector<int64_t> cap_ptr;     /* canonical pair_ptr of the caller's batch: prefix sum of E+L over ALL reads */
     HostBuf h_results, h_pairs, h_reads, h_items; /* pinned staging */
     bool prepared = false;            /* abea_prepare_kernel of the resident batch was already launched by the upload */
@@ -101,7 +101,8 @@ struct abea_ctx {
      * the fill asks for them, pair lists written to the caller's mapped buffer by the traceback */
     int stream_mode = 3;       /* ABEA_STREAM: bit 0 events in, bit 1 pair lists out; 0: always stage through the copy engine */
     int load_ctas = 64;        /* ABEA_LOAD_CTAS */
-    int64_t load_piece = ABEA_LOAD_PIECE_BYTES; /* ABEA_LOAD_PIECE_KB: smallest piece of a read the loader delivers */
+    int64_t load_piece = 0;    /* ABEA_LOAD_PIECE_KB: smallest piece of a read the loader delivers (0: 2048 events) */
+    int64_t load_piece_cur = ABEA_LOAD_PIECE_BYTES; /* the value in use for the batch being streamed */
     double load_crit = 1.0;    /* ABEA_LOAD_CRIT: need times of the makespan-setting reads (wide, long) are scaled by this */
     DevBuf d_ready, d_items;
     std::vector<abea_load_item_t> items;
@@ -109,8 +110,11 @@ struct abea_ctx {
     cudaEvent_t ev_meta = nullptr, ev_loaded = nullptr, ev_load0 = nullptr;
     bool streaming = false;    /* the resident batch is being streamed in: its fill must wait on d_ready */
     bool results_on_device = false; /* d_pairs / d_npairs hold the final lists of the last run */
-    int64_t event_bytes = 0;   /* size of the batch's event array */
-    void* ev_dev = nullptr;    /* the resident batch's events: d_events, or d_evcap when they came from abea_getevents */
+    int64_t event_bytes = 0;   /* size in bytes of the batch's event array as the caller holds it (means: 4 B, AoS: 24 B per event) */
+    bool load_aos = false;     /* the streamed source is the reference's AoS event table (else a flat array of means) */
+    bool means_from_evcap = false; /* d_means was extracted from the tables abea_getevents left on the device */
+    bool means_reversed = false;   /* abea_estimate_scalings(reverse_events) has turned the resident means 3'->5' */
+    int64_t evcap_total = 0;   /* entries of d_evcap (capacity layout of the last abea_getevents) */
 
     /* the stages either side of ABEA (scaling_kernels.cuh): descriptors of ALL reads in the caller's order */
     std::vector<abea_sread_t> sreads;
@@ -210,7 +214,7 @@ void launch_prepare(abea_ctx* c, int64_t check_events) {
     if (blocks < 1) blocks = 1;
     ABEA_LAUNCH(abea_prepare_kernel, blocks, threads, c->stream,
         (const abea_read_t*)c->d_reads.p, n, (const uint8_t*)c->d_seq.p, (const abea_model_t*)c->d_model.p,
-        c->kmer_size, (const abea_event_t*)c->ev_dev, (float4*)c->d_kparams.p, (uint32_t*)c->d_flags.p,
+        c->kmer_size, (const float*)c->d_means.p, (float4*)c->d_kparams.p, (uint32_t*)c->d_flags.p,
         c->total_kmers, check_events);
 }
 
@@ -267,16 +271,17 @@ void build_load_order(abea_ctx* c) {
     }
     struct need_t { double t; int32_t read, piece; };
     std::vector<need_t> need;
-    need.reserve((size_t)n + (size_t)(c->event_bytes / c->load_piece) + 8);
+    const int64_t esz = c->load_aos ? (int64_t)sizeof(abea_event_t) : (int64_t)sizeof(float);
+    need.reserve((size_t)n + (size_t)(c->event_bytes / c->load_piece_cur) + 8);
     for (int64_t r = 0; r < n; r++) {
         const abea_read_t& rd = c->reads[r];
-        const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, c->event_bytes, c->load_piece);
+        const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, c->event_bytes, c->load_piece_cur, esz);
         const double nb = (double)rd.n_events + rd.n_kmers + 2;
         const double rt = rate(r);
         const double fill = nb * rt * (rt < CYC_NARROW ? c->load_crit : 1.0);
         for (int32_t q = 0; q < g.n_pieces; q++) {
             /* the fill touches event e when it is about e/E of the way through the read's bands */
-            const double frac = (double)abea_piece_first_event(g, q) / (double)rd.n_events;
+            const double frac = (double)abea_piece_first_event(g, q, esz) / (double)rd.n_events;
             need.push_back(need_t{start[r] + frac * fill, (int32_t)r, q});
         }
     }
@@ -373,7 +378,9 @@ int abea_create(abea_ctx_t** out, int device) {
     {
         cudaError_t e = cudaSuccess;
         const int carve = 100; /* percent of the maximum: cudaSharedmemCarveoutMaxShared */
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_load_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_load_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_load_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_extract_means_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_prepare_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         const void* fills[] = {(const void*)abea_fill_kernel<true, false>,      (const void*)abea_fill_kernel<false, false>,
                                (const void*)abea_fill_kernel<true, true>,       (const void*)abea_fill_kernel<false, true>,
@@ -395,7 +402,7 @@ int abea_create(abea_ctx_t** out, int device) {
 void abea_destroy(abea_ctx_t* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_reads, &c->d_kparams,
+    DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_means, &c->d_reads, &c->d_kparams,
                       &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags, &c->d_npairs,
                       &c->d_ready, &c->d_items, &c->d_sreads, &c->d_scalings, &c->d_maps, &c->d_sres,
                       &c->d_raw, &c->d_sum, &c->d_sumsq, &c->d_ts1, &c->d_ts2, &c->d_peaks, &c->d_evcap, &c->d_sigs, &c->d_sigorder,
@@ -439,9 +446,11 @@ int abea_set_model(abea_ctx_t* c, const abea_model_t* model, uint32_t kmer_size)
     return ABEA_OK;
 }
 
-/* ev_alias: device-side alias of the caller's pinned event array (the batch is streamed in by abea_load_kernel while
- * the fill runs), or NULL (the events go through the copy engine before anything starts). */
-static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alias, abea_timing_t* timing) {
+/* ev_alias: device-side alias of the caller's pinned event array — batch->event_means when it is given, else
+ * batch->events — (the batch is streamed in by abea_load_kernel while the fill runs), or NULL (the events go through
+ * the copy engine before anything starts). host_ready: see abea_load_kernel. */
+static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alias, abea_timing_t* timing,
+                       const uint32_t* host_ready = nullptr) {
     if (!c || !b || b->n_reads < 0) return fail(c, ABEA_ERR_ARG, "bad batch");
     if (!c->have_model) return fail(c, ABEA_ERR_NOMODEL, "abea_set_model has not been called");
     CU(cudaSetDevice(c->device));
@@ -454,7 +463,8 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
 
     /* batch->events == NULL: the event tables are the ones the last abea_getevents left on the device (same reads,
      * same order); they are used where they lie (capacity layout), nothing is copied */
-    const bool dev_events = (b->events == nullptr) && b->n_reads > 0;
+    const bool have_means = (b->event_means != nullptr);
+    const bool dev_events = (b->events == nullptr) && !have_means && b->n_reads > 0;
     if (dev_events) {
         if (!c->events_ready || (int32_t)c->nev.size() != b->n_reads)
             return fail(c, ABEA_ERR_STATE, "batch without events, but no matching abea_getevents result on the device");
@@ -583,7 +593,14 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
     double t1 = now_ms();
 
     if (dev_reserve(c, c->d_seq, (size_t)seq_bytes + 16)) return ABEA_ERR_CUDA;
-    if (dev_reserve(c, c->d_events, (size_t)n_ev_total * sizeof(abea_event_t) + 16)) return ABEA_ERR_CUDA;
+    /* the alignment reads event means only (reference src/align.cu:415): they live in d_means, indexed like the source
+     * (the caller's event_ptr space, or the capacity layout of abea_getevents). An AoS table that goes through the copy
+     * engine is staged in d_events and its means are extracted on the device. */
+    const int64_t n_means = dev_events ? c->evcap_total : n_ev_total;
+    if (c->need_scalings || n_sched == 0) ev_alias = nullptr; /* the estimate needs a read's events before its fill */
+    const bool stage_aos = !dev_events && !have_means && !ev_alias;
+    if (stage_aos && dev_reserve(c, c->d_events, (size_t)n_ev_total * sizeof(abea_event_t) + 16)) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_means, (size_t)n_means * sizeof(float) + 64)) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_reads, (n_sched + 1) * sizeof(abea_read_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_kparams, (size_t)(kp + 1) * sizeof(float4))) return ABEA_ERR_CUDA;
     /* + one traceback chunk of slack: the prefetcher copies whole 16-group chunks */
@@ -594,8 +611,11 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
     if (dev_reserve(c, c->d_queue, 64)) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_flags, (n_sched + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
 
-    c->event_bytes = n_ev_total * (int64_t)sizeof(abea_event_t);
-    c->ev_dev = dev_events ? c->d_evcap.p : c->d_events.p;
+    c->load_aos = !have_means;
+    c->event_bytes = n_ev_total * (int64_t)(have_means ? sizeof(float) : sizeof(abea_event_t));
+    c->load_piece_cur = c->load_piece > 0 ? c->load_piece : (have_means ? ABEA_LOAD_PIECE_BYTES_MEANS : ABEA_LOAD_PIECE_BYTES);
+    c->means_from_evcap = dev_events;
+    c->means_reversed = false;
     c->streaming = false;
     c->results_on_device = false;
     double t2 = t1;
@@ -606,7 +626,6 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         memcpy(c->h_reads.p, c->reads.data(), n_sched * sizeof(abea_read_t));
         CU(cudaMemcpyAsync(c->d_reads.p, c->h_reads.p, n_sched * sizeof(abea_read_t), cudaMemcpyHostToDevice, c->stream));
     }
-    if (ev_alias && c->need_scalings) ev_alias = nullptr; /* the estimate needs a read's events before its fill */
     if (ev_alias && n_sched) {
         /* Everything the k-mer parameter kernel needs goes first, and the kernel with it: the host then works out
          * the loader's order while the GPU is busy with that. */
@@ -636,15 +655,32 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
                            cudaMemcpyHostToDevice, c->load_stream));
         CU(cudaEventRecord(c->ev_load0, c->load_stream));
         const int blocks = (int)std::min<size_t>(c->items.size(), (size_t)c->load_ctas);
-        ABEA_LAUNCH(abea_load_kernel, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
-                    (const abea_load_item_t*)c->d_items.p, (int32_t)c->items.size(), (const uint4*)ev_alias,
-                    (uint4*)c->d_events.p, c->event_bytes, (uint32_t*)c->d_flags.p, (uint32_t*)c->d_ready.p,
-                    (int32_t*)c->d_queue.p + 12, c->load_piece);
+        if (c->load_aos)
+            ABEA_LAUNCH(abea_load_kernel<true>, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
+                        (const abea_load_item_t*)c->d_items.p, (int32_t)c->items.size(), (const uint4*)ev_alias,
+                        (float*)c->d_means.p, c->event_bytes, (uint32_t*)c->d_flags.p, (uint32_t*)c->d_ready.p,
+                        (int32_t*)c->d_queue.p + 12, c->load_piece_cur, (const volatile uint32_t*)host_ready,
+                        (uint32_t*)c->d_queue.p + 15);
+        else
+            ABEA_LAUNCH(abea_load_kernel<false>, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
+                        (const abea_load_item_t*)c->d_items.p, (int32_t)c->items.size(), (const uint4*)ev_alias,
+                        (float*)c->d_means.p, c->event_bytes, (uint32_t*)c->d_flags.p, (uint32_t*)c->d_ready.p,
+                        (int32_t*)c->d_queue.p + 12, c->load_piece_cur, (const volatile uint32_t*)host_ready,
+                        (uint32_t*)c->d_queue.p + 15);
         CU(cudaEventRecord(c->ev_loaded, c->load_stream));
         c->streaming = true;
-    } else if (n_ev_total) {
-        CU(cudaMemcpyAsync(c->d_events.p, b->events, (size_t)n_ev_total * sizeof(abea_event_t),
-                           cudaMemcpyHostToDevice, c->stream));
+    } else if (have_means) {
+        if (n_ev_total)
+            CU(cudaMemcpyAsync(c->d_means.p, b->event_means, (size_t)n_ev_total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    } else {
+        const abea_event_t* src_tab = dev_events ? (const abea_event_t*)c->d_evcap.p : (const abea_event_t*)c->d_events.p;
+        if (!dev_events && n_ev_total)
+            CU(cudaMemcpyAsync(c->d_events.p, b->events, (size_t)n_ev_total * sizeof(abea_event_t),
+                               cudaMemcpyHostToDevice, c->stream));
+        if (n_means > 0) {
+            const int blocks = (int)std::min<int64_t>((n_means + 255) / 256, (int64_t)c->sm_count * 16);
+            ABEA_LAUNCH(abea_extract_means_kernel, blocks, 256, c->stream, src_tab, (float*)c->d_means.p, n_means);
+        }
     }
     if (seq_bytes && !c->streaming)
         CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
@@ -655,7 +691,7 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
     c->last = abea_timing_t();
     c->last.pack_ms = (c->streaming ? t2 : t1) - t0;
     c->last.h2d_ms = c->streaming ? 0.f : ev_ms(c, EV_H2D0, EV_H2D1); /* streamed: filled in after the run */
-    c->last.h2d_bytes = seq_bytes + n_ev_total * (int64_t)sizeof(abea_event_t) + (int64_t)(n_sched * sizeof(abea_read_t));
+    c->last.h2d_bytes = seq_bytes + (dev_events ? 0 : c->event_bytes) + (int64_t)(n_sched * sizeof(abea_read_t));
     c->last.n_scheduled = (int32_t)n_sched;
     c->last.n_wide = c->n_wide;
     c->last.streamed = c->streaming ? 1 : 0;
@@ -719,11 +755,11 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                 CU(cudaFuncSetAttribute((const void*)wide_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)excl));
                 CU(cudaFuncSetAttribute((const void*)wide_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)excl));
                 ABEA_LAUNCH_SMEM(wide_fast, wblocks, 128, excl, c->wide_stream,
-                    (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->ev_dev, (const float4*)c->d_kparams.p,
+                    (const abea_read_t*)c->d_reads.p, nw, (const float*)c->d_means.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
                     (abea_result_t*)c->d_results.p, io, c->cst, queue + 6);
                 ABEA_LAUNCH_SMEM(wide_exact, wblocks, 128, excl, c->wide_stream,
-                    (const abea_read_t*)c->d_reads.p, nw, (const abea_event_t*)c->ev_dev, (const float4*)c->d_kparams.p,
+                    (const abea_read_t*)c->d_reads.p, nw, (const float*)c->d_means.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
                     (abea_result_t*)c->d_results.p, io, c->cst, queue + 7);
                 CU(cudaEventRecord(c->ev_join, c->wide_stream));
@@ -748,11 +784,11 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                 const double cyc_batch = (double)c->total_bands * 360.0 / ((double)c->sm_count * 4.0);
                 const int32_t long_thr = (int32_t)std::min(2.0e9, std::max(1.0, c->long_alpha * cyc_batch / 780.0));
                 ABEA_LAUNCH_SMEM(fill_fast, blocks, 32 * wpc, smem, c->stream,
-                    (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->ev_dev, (const float4*)c->d_kparams.p,
+                    (const abea_read_t*)c->d_reads.p, n, (const float*)c->d_means.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
                     (abea_result_t*)c->d_results.p, io, c->cst, queue, nw, long_thr, c->sched_policy);
                 ABEA_LAUNCH_SMEM(fill_exact, blocks, 32 * wpc, smem, c->stream,
-                    (const abea_read_t*)c->d_reads.p, n, (const abea_event_t*)c->ev_dev, (const float4*)c->d_kparams.p,
+                    (const abea_read_t*)c->d_reads.p, n, (const float*)c->d_means.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
                     (abea_result_t*)c->d_results.p, io, c->cst, queue + 8, nw, long_thr, c->sched_policy);
                 launches += 2;
@@ -927,10 +963,10 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     if (s->offset && (!s->range || !s->digitisation)) return fail(c, ABEA_ERR_ARG, "offset without range / digitisation");
     CU(cudaSetDevice(c->device));
     c->events_ready = false;
-    if (c->ev_dev && c->ev_dev == c->d_evcap.p) { /* a resident batch that borrowed the previous event tables dies with them */
+    if (c->means_from_evcap) { /* a resident batch whose means came out of the previous event tables dies with them */
         c->uploaded = false;
         c->ran = false;
-        c->ev_dev = nullptr;
+        c->means_from_evcap = false;
     }
     const int32_t n = s->n_reads;
     c->sigs.assign((size_t)n, abea_sig_t());
@@ -976,6 +1012,7 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     if (dev_reserve(c, c->d_spec_end, (nck + 1) * sizeof(evt_state_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_peaks, (size_t)(cap_total + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_evcap, (size_t)(cap_total + 1) * sizeof(abea_event_t))) return ABEA_ERR_CUDA;
+    c->evcap_total = cap_total;
     if (dev_reserve(c, c->d_sigs, ((size_t)n + 1) * sizeof(abea_sig_t))) return ABEA_ERR_CUDA;
     if (dev_reserve(c, c->d_nev, ((size_t)n + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
     CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
@@ -1078,9 +1115,9 @@ int abea_estimate_scalings(abea_ctx_t* c, int reverse_events, abea_scalings_t* s
     if (nb > 0) {
         if (!c->scalings_on_device) CU(cudaMemsetAsync(c->d_scalings.p, 0, (size_t)nb * sizeof(abea_scalings_t), c->stream));
         ABEA_LAUNCH(abea_mom_kernel, (nb + SCL_WARPS - 1) / SCL_WARPS, 32 * SCL_WARPS, c->stream,
-                    (const abea_sread_t*)c->d_sreads.p, nb, (const uint8_t*)c->d_seq.p, (abea_event_t*)c->ev_dev,
+                    (const abea_sread_t*)c->d_sreads.p, nb, (const uint8_t*)c->d_seq.p, (float*)c->d_means.p,
                     (const abea_model_t*)c->d_model.p, c->kmer_size, (abea_scalings_t*)c->d_scalings.p,
-                    (abea_read_t*)c->d_reads.p, (int32_t)(reverse_events ? 1 : 0));
+                    (abea_read_t*)c->d_reads.p, (int32_t)((reverse_events && !c->means_reversed) ? 1 : 0));
     }
     CU(cudaEventRecord(c->ev[EV_S1], c->stream));
     if (scalings_out && nb > 0)
@@ -1089,6 +1126,7 @@ int abea_estimate_scalings(abea_ctx_t* c, int reverse_events, abea_scalings_t* s
     CU(cudaStreamSynchronize(c->stream));
     c->scalings_on_device = true;
     c->need_scalings = false;
+    if (reverse_events) c->means_reversed = true; /* a second request leaves the resident means 3'->5' as they are */
     c->prepared = false; /* the k-mer parameter cache depends on scale / shift */
     c->last.mom_ms = ev_ms(c, EV_S0, EV_S1);
     if (timing) *timing = c->last;
@@ -1109,7 +1147,7 @@ int abea_scaling_stage(abea_ctx_t* c, int32_t min_num_events_to_rescale, abea_ti
     if (nb > 0)
         ABEA_LAUNCH(abea_scaling_kernel, (nb + SCL_WARPS - 1) / SCL_WARPS, 32 * SCL_WARPS, c->stream,
                     (const abea_sread_t*)c->d_sreads.p, nb, (const uint8_t*)c->d_seq.p,
-                    (const abea_event_t*)c->ev_dev, (const abea_model_t*)c->d_model.p, c->kmer_size,
+                    (const float*)c->d_means.p, (const abea_model_t*)c->d_model.p, c->kmer_size,
                     (const abea_pair_t*)c->d_pairs.p, (const int32_t*)c->d_npairs.p,
                     (const abea_scalings_t*)c->d_scalings.p, (abea_index_pair_t*)c->d_maps.p,
                     (abea_scaling_result_t*)c->d_sres.p, min_num_events_to_rescale);
@@ -1165,7 +1203,8 @@ int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pair
     /* Pinned (mapped) caller buffers are streamed: events in over PCIe while the fill runs, pair lists out as each
      * read finishes. Anything else is staged through the copy engine (abea_upload_batch / abea_download). */
     const void* ev_alias = nullptr;
-    if ((c->stream_mode & 1) && batch->n_reads > 0 && batch->events && ((uintptr_t)batch->events & 15) == 0) ev_alias = mapped_alias(batch->events);
+    const void* ev_host = batch->event_means ? (const void*)batch->event_means : (const void*)batch->events;
+    if ((c->stream_mode & 1) && batch->n_reads > 0 && ev_host && ((uintptr_t)ev_host & 15) == 0) ev_alias = mapped_alias(ev_host);
     int rc = upload_impl(c, batch, ev_alias, nullptr);
     if (rc) return rc;
     abea_pair_t* fin_pairs = nullptr;

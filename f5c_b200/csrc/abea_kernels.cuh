@@ -43,7 +43,7 @@
 /* Per-read descriptor built by the host packer (abea_host.cu), in scheduling (longest-first) order. */
 struct abea_read_t {
     int64_t seq_off;    /* first base in d_seq */
-    int64_t ev_off;     /* first event in d_events (AoS abea_event_t) */
+    int64_t ev_off;     /* first event mean in d_means (flat float array: only .mean of event_t is ever read, reference src/align.cu:415) */
     int64_t evs_off;    /* running sum of n_events over the schedule (flat index space of abea_prepare_kernel) */
     int64_t kp_off;     /* first k-mer in d_kparams */
     int64_t trace_off;  /* first 32-bit word of this read's trace in d_trace */
@@ -157,7 +157,7 @@ __device__ __forceinline__ int32_t abea_find_read(const abea_read_t* __restrict_
 
 __global__ void abea_prepare_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads,
                                     const uint8_t* __restrict__ seq, const abea_model_t* __restrict__ model,
-                                    uint32_t kmer_size, const abea_event_t* __restrict__ events,
+                                    uint32_t kmer_size, const float* __restrict__ means,
                                     float4* __restrict__ kparams, uint32_t* __restrict__ read_flags,
                                     int64_t total_kmers, int64_t total_events) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -183,7 +183,7 @@ __global__ void abea_prepare_kernel(const abea_read_t* __restrict__ reads, int32
     for (int64_t idx = tid; idx < total_events; idx += stride) {
         int32_t r = abea_find_read(reads, n_reads, idx, true);
         const abea_read_t rd = reads[r];
-        float x = events[rd.ev_off + (idx - rd.evs_off)].mean;
+        float x = means[rd.ev_off + (idx - rd.evs_off)];
         if (!abea_sane_level(x)) atomicAnd(&read_flags[r], ~ABEA_READ_FAST);
     }
 }
@@ -204,8 +204,10 @@ struct abea_stream_t {
     uint32_t* stalled;          /* set to 1 if a wait for streamed events gave up (the host reports an error) */
 };
 
-#define ABEA_LOAD_PIECE_BYTES (48 * 1024) /* default smallest work item of the loader (384 lines of 128 B = 2048 events);
-                                           * the host passes the value in use (ABEA_LOAD_PIECE_KB) to both sides */
+/* default smallest work item of the loader: 2048 events, i.e. 48 KB of an AoS event table or 8 KB of a flat array of
+ * means; the host passes the value in use (ABEA_LOAD_PIECE_KB overrides it) to both sides */
+#define ABEA_LOAD_PIECE_BYTES (48 * 1024)
+#define ABEA_LOAD_PIECE_BYTES_MEANS (8 * 1024)
 #define ABEA_LOAD_MAX_PIECES 64           /* per read: its landed pieces are a 64-bit mask (two words of d_ready) */
 #define ABEA_LOAD_THREADS 128
 #define ABEA_LOAD_UNROLL 8                /* 16-B loads in flight per thread */
@@ -215,9 +217,10 @@ struct abea_load_item_t {
     int32_t piece; /* piece of that read's line-aligned byte range */
 };
 
-/* The byte range of a read's events, widened to whole 128-B lines (clamped to the buffer): a line shared by two reads
- * is copied for both, so whichever is published first the line is complete — no SM can cache half a line. The range
- * is cut into at most 64 pieces of at least piece_min bytes (whole lines). */
+/* The byte range of a read's events in the caller's pinned array (elements of esz bytes: 4 for a flat array of event
+ * means, sizeof(abea_event_t) for the reference's AoS table), widened to whole 128-B lines (clamped to the buffer): a line
+ * shared by two reads is copied for both, so whichever is published first the line is complete. The range is cut into
+ * at most 64 pieces of at least piece_min bytes (whole lines). */
 struct abea_load_geom_t {
     int64_t a, b;   /* the read's own bytes [a, b) */
     int64_t lo, hi; /* widened to lines */
@@ -225,10 +228,10 @@ struct abea_load_geom_t {
     int32_t n_pieces;
 };
 __device__ __host__ __forceinline__ abea_load_geom_t abea_load_geom(int64_t ev_off, int32_t n_events, int64_t total_bytes,
-                                                                     int64_t piece_min) {
+                                                                     int64_t piece_min, int64_t esz) {
     abea_load_geom_t g;
-    g.a = ev_off * (int64_t)sizeof(abea_event_t);
-    g.b = g.a + (int64_t)n_events * (int64_t)sizeof(abea_event_t);
+    g.a = ev_off * esz;
+    g.b = g.a + (int64_t)n_events * esz;
     const int64_t h = (g.b + 127) & ~(int64_t)127;
     g.lo = g.a & ~(int64_t)127;
     g.hi = h < total_bytes ? h : total_bytes;
@@ -238,9 +241,9 @@ __device__ __host__ __forceinline__ abea_load_geom_t abea_load_geom(int64_t ev_o
     return g;
 }
 /* first event of the read that lies (at least partly) in piece p */
-__device__ __host__ __forceinline__ int64_t abea_piece_first_event(const abea_load_geom_t& g, int32_t p) {
+__device__ __host__ __forceinline__ int64_t abea_piece_first_event(const abea_load_geom_t& g, int32_t p, int64_t esz) {
     const int64_t off = g.lo + (int64_t)p * g.piece - g.a;
-    return off <= 0 ? 0 : off / (int64_t)sizeof(abea_event_t);
+    return off <= 0 ? 0 : off / esz;
 }
 
 __device__ __forceinline__ uint32_t abea_ld_acquire_u32(const uint32_t* p) {
@@ -297,17 +300,23 @@ __device__ __forceinline__ int32_t abea_wait_landed_events(const uint32_t* w, in
     return (int32_t)v;
 }
 
-/* src: the caller's events (pinned host memory, mapped); dst: d_events; both 16-B aligned, same layout. The event
- * means pass through here, so this is also where they are range-checked for the fast arithmetic (the resident path
- * does that in abea_prepare_kernel). In a 16-B unit u of the AoS array the mean is .w when u % 3 == 0 and .y when
- * u % 3 == 2 (24-B events, mean at byte 12). */
+/* src: the caller's pinned (mapped) host array, 16-B aligned; dst: d_means, the flat array of event means the
+ * alignment kernels read (same event indexing as the source). AOS = false: the source is a flat array of event means
+ * (abea_batch_t.event_means) — 4 bytes per event cross PCIe; AOS = true: the source is the reference's event table
+ * (24-B event_t, reference src/f5c.h:129-136), of which only .mean is kept: in a 16-B unit u of the table the mean is
+ * .w when u % 3 == 0 (event 2(u/3)) and .y when u % 3 == 2 (event 2(u/3)+1). The means pass through here, so this is also
+ * where they are range-checked for the fast arithmetic (the resident path does that in abea_prepare_kernel).
+ * host_ready (or NULL): per scheduled read, a word in mapped host memory that the packer threads of abea_align_ragged
+ * set once the read's means are in the pinned array — a piece is copied only after its read has been packed. */
+template <bool AOS>
 __global__ void __launch_bounds__(ABEA_LOAD_THREADS)
 abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* __restrict__ items, int32_t n_items,
-                 const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t total_bytes,
+                 const uint4* __restrict__ src, float* __restrict__ dst, int64_t total_bytes,
                  uint32_t* __restrict__ read_flags, uint32_t* __restrict__ ready, int32_t* __restrict__ counter,
-                 int64_t piece_min) {
+                 int64_t piece_min, const volatile uint32_t* host_ready, uint32_t* stalled) {
     __shared__ int s_item;
     const int tid = threadIdx.x;
+    const int64_t esz = AOS ? (int64_t)sizeof(abea_event_t) : (int64_t)sizeof(float);
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = atomicAdd(counter, 1);
@@ -316,7 +325,24 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
         if (it >= n_items) break;
         const abea_load_item_t item = items[it];
         const abea_read_t rd = reads[item.read];
-        const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, total_bytes, piece_min);
+        if (host_ready) { /* the host packs reads in the order of this work list; normally it is far ahead */
+            if (tid == 0) {
+                int spins = 0;
+                while (host_ready[item.read] == 0u) {
+                    if (++spins > ABEA_WAIT_SPINS_MAX) {
+                        *stalled = 1u;
+                        break;
+                    }
+#ifndef ABEA_SIMT_EMU
+                    __nanosleep(500);
+#else
+                    break;
+#endif
+                }
+            }
+            __syncthreads();
+        }
+        const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, total_bytes, piece_min, esz);
         const int64_t a = g.a, b = g.b;
         const int64_t p0 = g.lo + (int64_t)item.piece * g.piece;
         const int64_t p1 = (p0 + g.piece < g.hi) ? p0 + g.piece : g.hi;
@@ -333,18 +359,33 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
             for (int j = 0; j < ABEA_LOAD_UNROLL; j++) {
                 const int64_t uj = u + (int64_t)j * ABEA_LOAD_THREADS;
                 if (uj < u1) {
-                    dst[uj] = v[j];
-                    const int m3 = (int)(uj % 3);
-                    if (m3 != 1) {
-                        const int64_t mb = (uj << 4) + (m3 == 0 ? 12 : 4);
-                        const float x = __uint_as_float(m3 == 0 ? v[j].w : v[j].y);
-                        if (mb >= a && mb < b && !abea_sane_level(x)) bad = true;
+                    if (AOS) {
+                        const int m3 = (int)(uj % 3);
+                        if (m3 != 1) {
+                            const int64_t mb = (uj << 4) + (m3 == 0 ? 12 : 4);
+                            const float x = __uint_as_float(m3 == 0 ? v[j].w : v[j].y);
+                            dst[2 * (uj / 3) + (m3 == 0 ? 0 : 1)] = x;
+                            if (mb >= a && mb < b && !abea_sane_level(x)) bad = true;
+                        }
+                    } else {
+                        ((uint4*)dst)[uj] = v[j];
+                        const int64_t mb = uj << 4;
+                        const uint32_t w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (mb + 4 * q >= a && mb + 4 * q < b && !abea_sane_level(__uint_as_float(w4[q]))) bad = true;
                     }
                 }
             }
         }
-        if (tid == 0 && (p1 & 8)) /* the buffer ends on half a unit: {pos, state} of the last event */
-            ((uint2*)dst)[p1 / 8 - 1] = ((const uint2*)src)[p1 / 8 - 1];
+        if (!AOS && tid < 3) { /* the array ends on part of a unit: its last one to three means */
+            const int64_t f = (u1 << 2) + tid;
+            if ((f << 2) < p1) {
+                const float x = ((const float*)src)[f];
+                dst[f] = x;
+                if ((f << 2) >= a && (f << 2) < b && !abea_sane_level(x)) bad = true;
+            }
+        }
         if (bad) atomicAnd(&read_flags[item.read], ~ABEA_READ_FAST);
         __threadfence();
         __syncthreads();
@@ -357,11 +398,18 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
             const int32_t np = (m0 != 0xffffffffu) ? (__ffs((int)~m0) - 1) : ((m1 != 0xffffffffu) ? 32 + (__ffs((int)~m1) - 1) : 64);
             const int64_t end = g.lo + (int64_t)np * g.piece;
             uint32_t nev = 0x7fffffffu;
-            if (end < g.b && np < g.n_pieces) nev = end <= g.a ? 0u : (uint32_t)((end - g.a) / (int64_t)sizeof(abea_event_t));
+            if (end < g.b && np < g.n_pieces) nev = end <= g.a ? 0u : (uint32_t)((end - g.a) / esz);
             __threadfence(); /* pieces whose bits were observed above are ordered before the count */
             atomicMax(&w[0], nev);
         }
     }
+}
+
+/* Event means out of a device-resident event table (the copy-engine upload of an AoS batch; the tables abea_getevents
+ * leaves on the device): means[i] = events[i].mean over the whole index space, one thread per event. */
+__global__ void abea_extract_means_kernel(const abea_event_t* __restrict__ events, float* __restrict__ means, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) means[i] = events[i].mean;
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */
@@ -382,9 +430,9 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
 
 __device__ __forceinline__ double abea_neg_inf_d() { return __hiloint2double((int)0xfff00000, 0); }
 
-__device__ __forceinline__ float abea_load_event_mean(const abea_event_t* __restrict__ ev, int32_t e, int32_t E) {
+__device__ __forceinline__ float abea_load_event_mean(const float* __restrict__ ev, int32_t e, int32_t E) {
     e = e < 0 ? 0 : (e >= E ? E - 1 : e);
-    return ev[e].mean;
+    return ev[e];
 }
 
 __device__ __forceinline__ float4 abea_load_kparam(const float4* __restrict__ kp, int32_t k, int32_t K) {
@@ -513,7 +561,7 @@ __device__ __forceinline__ void abea_tb_prefetch(uint32_t* ring, const uint32_t*
 
 /* emissions of the pairs parked in the lanes (first `cnt` lanes valid), added to `sum` in lane order */
 __device__ __forceinline__ double abea_tb_flush(double sum, int cnt, int lane, int32_t pk, int32_t pe, int32_t n_before,
-                                                const abea_event_t* __restrict__ ev, const float4* __restrict__ kpr,
+                                                const float* __restrict__ ev, const float4* __restrict__ kpr,
                                                 abea_pair_t* __restrict__ out, int32_t pair_cap) {
     double lpd = 0.0;
     if (lane < cnt) {
@@ -522,7 +570,7 @@ __device__ __forceinline__ double abea_tb_flush(double sum, int cnt, int lane, i
         p.read_pos = pe;
         out[pair_cap - 1 - (n_before + lane)] = p;
         float4 kp = kpr[pk];
-        lpd = (double)abea_emission(ev[pe].mean, kp.x, kp.y, kp.z);
+        lpd = (double)abea_emission(ev[pe], kp.x, kp.y, kp.z);
     }
     for (int j = 0; j < cnt; j++) sum = __dadd_rn(sum, __shfl_sync(ABEA_FULL, lpd, j));
     return sum;
@@ -531,12 +579,12 @@ __device__ __forceinline__ double abea_tb_flush(double sum, int cnt, int lane, i
 /* Traceback + QC of one read by one warp. `ring` is the warp's 4 KB shared-memory ring (32 trace lines). The trace
  * lines were written by lanes of this warp or CTA; the caller has synchronised (__syncwarp / __syncthreads). */
 __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32_t ridx, int32_t end_event, uint32_t* ring,
-                                                    int lane, const abea_event_t* __restrict__ events,
+                                                    int lane, const float* __restrict__ means,
                                                     const float4* __restrict__ kparams, const uint32_t* __restrict__ trace,
                                                     abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
                                                     const abea_stream_t& io) {
     const int32_t K = rd.n_kmers;
-    const abea_event_t* __restrict__ ev = events + rd.ev_off;
+    const float* __restrict__ ev = means + rd.ev_off;
     const float4* __restrict__ kpr = kparams + rd.kp_off;
     const uint32_t* __restrict__ tr = trace + rd.trace_off;
     abea_pair_t* out = pairs + rd.pair_off;
@@ -618,7 +666,6 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
         results[ridx].n_pairs = fail ? 0 : n;
         results[ridx].max_gap = max_gap;
         io.n_pairs_dev[rd.orig_index] = fail ? 0 : n; /* db->n_event_align_pairs[i] */
-        if (io.n_pairs_final) io.n_pairs_final[rd.orig_index] = fail ? 0 : n;
     }
     /* move the list to the front of the read's capacity region (the layout the caller's buffer has): in place in
      * d_pairs (destination index t <= source index cap-n+t, batches of 32 are loaded before they are stored), and,
@@ -642,6 +689,16 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
             __syncwarp();
         }
     }
+    /* the count in the caller's buffer doubles as the read's "done" flag: it is written after the list, behind a
+     * system-scope fence, so a host thread that sees a count >= 0 may copy the list out while other reads are still
+     * being aligned (abea_align_ragged) */
+    if (io.n_pairs_final) {
+#ifndef ABEA_SIMT_EMU
+        __threadfence_system();
+#endif
+        __syncwarp();
+        if (lane == 0) *(volatile int32_t*)(io.n_pairs_final + rd.orig_index) = fail ? 0 : n;
+    }
 }
 
 /* One band of scores as held by a lane, with the two neighbour-lane cells next to its four ("halos"). */
@@ -664,11 +721,11 @@ struct abea_fill_smem_t {
 
 /* asynchronously stage chunk `chunk` (indices 32*chunk .. +31, clamped into the read) of the event means / k-mer
  * parameters into the warp's ring: the "TMA/async-copy staging of the active band window" of the design */
-__device__ __forceinline__ void abea_stage_events(abea_fill_smem_t* sm, const abea_event_t* __restrict__ ev, int32_t chunk,
+__device__ __forceinline__ void abea_stage_events(abea_fill_smem_t* sm, const float* __restrict__ ev, int32_t chunk,
                                                   int32_t E, int lane) {
     int32_t e = chunk * 32 + lane;
     int32_t ec = e < 0 ? 0 : (e >= E ? E - 1 : e);
-    abea_cp_async4(&sm->ev[e & (ABEA_RING - 1)], &ev[ec].mean);
+    abea_cp_async4(&sm->ev[e & (ABEA_RING - 1)], &ev[ec]);
 }
 __device__ __forceinline__ void abea_stage_kparams(abea_fill_smem_t* sm, const float4* __restrict__ kpr, int32_t chunk,
                                                    int32_t K, int lane) {
@@ -704,7 +761,7 @@ __device__ __forceinline__ void abea_band_cells(const float* x, const float4* kp
 
 /* Per-read constants and cursors of the fill, warp-uniform. */
 struct abea_fill_ctx_t {
-    const abea_event_t* ev;
+    const float* ev;
     const float4* kpr;
     uint32_t* tr;
     double lp_stay, lp_step, lp_skip, lp_trim;
@@ -876,7 +933,7 @@ __device__ __forceinline__ void abea_backoff() {
 
 template <bool FAST, bool STREAM>
 __global__ void __launch_bounds__(ABEA_NARROW_BOUND(STREAM))
-abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const abea_event_t* __restrict__ events,
+abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const float* __restrict__ means,
                  const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                  uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
                  abea_stream_t io, abea_consts_t cst, int32_t* __restrict__ queue,
@@ -966,7 +1023,7 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
         cx.E = rd.n_events;
         cx.K = rd.n_kmers;
         cx.NB = cx.E + cx.K + 2; /* the host rejects reads with E + K + 2 >= 2^31 */
-        cx.ev = events + rd.ev_off;
+        cx.ev = means + rd.ev_off;
         cx.kpr = kparams + rd.kp_off;
         cx.tr = trace + rd.trace_off;
         cx.lp_stay = rd.lp_stay;
@@ -1041,7 +1098,7 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const a
          * is a serial chain too, and fusing it here takes it off the tail of the batch */
         __syncwarp();
         const long long t_fill = abea_clock();
-        abea_traceback_read(rd, ridx, end_event, tb_ring, lane, events, kparams, trace, pairs, results, io);
+        abea_traceback_read(rd, ridx, end_event, tb_ring, lane, means, kparams, trace, pairs, results, io);
         if (lane == 0) {
             results[ridx].wide = 0;
             results[ridx].fill_cycles = t_fill - t_start;
@@ -1122,14 +1179,14 @@ struct abea_wide_smem_t {
     uint64_t bar; /* the per-band split-phase barrier */
 };
 
-__device__ __forceinline__ void abea_wide_stage(abea_wide_smem_t* sm, const abea_event_t* __restrict__ ev,
+__device__ __forceinline__ void abea_wide_stage(abea_wide_smem_t* sm, const float* __restrict__ ev,
                                                 const float4* __restrict__ kpr, int32_t echunk, int32_t kchunk,
                                                 int32_t E, int32_t K, int tid) {
     if (tid < ABEA_WCHUNK) {
         if (echunk >= 0) {
             int32_t e = echunk * ABEA_WCHUNK + tid;
             int32_t ec = e >= E ? E - 1 : e;
-            abea_cp_async4(&sm->ev[e & (ABEA_WRING - 1)], &ev[ec].mean);
+            abea_cp_async4(&sm->ev[e & (ABEA_WRING - 1)], &ev[ec]);
         }
         if (kchunk >= 0) {
             int32_t k = kchunk * ABEA_WCHUNK + tid;
@@ -1146,7 +1203,7 @@ struct abea_wband_t {
 
 /* Per-read state of a wide lane. Everything but the scores, the window values and the trace bits is CTA-uniform. */
 struct abea_wide_ctx_t {
-    const abea_event_t* ev;
+    const float* ev;
     const float4* kpr;
     uint32_t* tr;
     const uint32_t* ready_w; /* streaming: the read's words of d_ready */
@@ -1297,7 +1354,7 @@ __device__ __forceinline__ void abea_wide_step(abea_wide_ctx_t& cx, abea_wide_sm
 
 template <bool FAST, bool STREAM>
 __global__ void __launch_bounds__(32 * ABEA_WIDE_WARPS)
-abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, const abea_event_t* __restrict__ events,
+abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, const float* __restrict__ means,
                       const float4* __restrict__ kparams, const uint32_t* __restrict__ read_flags,
                       uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs, abea_result_t* __restrict__ results,
                       abea_stream_t io, abea_consts_t cst, int32_t* __restrict__ queue) {
@@ -1344,7 +1401,7 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
         cx.E = rd.n_events;
         cx.K = rd.n_kmers;
         cx.NB = cx.E + cx.K + 2;
-        cx.ev = events + rd.ev_off;
+        cx.ev = means + rd.ev_off;
         cx.kpr = kparams + rd.kp_off;
         cx.tr = trace + rd.trace_off;
         cx.lp_stay = rd.lp_stay;
@@ -1430,7 +1487,7 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                 results[ridx].end_event = end_event;
             }
             const long long t_fill = abea_clock();
-            abea_traceback_read(rd, ridx, end_event, (uint32_t*)sm.kp, lane, events, kparams, trace, pairs, results, io);
+            abea_traceback_read(rd, ridx, end_event, (uint32_t*)sm.kp, lane, means, kparams, trace, pairs, results, io);
             if (lane == 0) {
                 results[ridx].wide = 1;
                 results[ridx].fill_cycles = t_fill - t_start;

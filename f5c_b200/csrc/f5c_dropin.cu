@@ -187,6 +187,7 @@ static void pack_db(dropin_data* d, const db_t* db, abea_batch_t& b, bool with_s
     b.n_reads = n; b.seq = d->seq; b.seq_ptr = d->seq_ptr; b.read_len = d->read_len; b.events = d->events;
     b.event_ptr = d->event_ptr; b.n_events = d->n_events; b.scalings = with_scalings ? d->scalings : NULL;
     b.good = d->good;
+    b.event_means = NULL;
 }
 
 void align_cuda(core_t* core, db_t* db) {

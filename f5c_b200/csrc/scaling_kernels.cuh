@@ -25,7 +25,7 @@
 /* Per-read descriptor of the scaling stages, in the CALLER's order (every read of the batch has one). */
 struct abea_sread_t {
     int64_t seq_off;   /* first base in d_seq */
-    int64_t ev_off;    /* first event in d_events */
+    int64_t ev_off;    /* first event mean in d_means */
     int64_t map_off;   /* first entry of the read's base_to_event_map in d_maps (prefix sum of max(K, 0)) */
     int64_t pair_off;  /* first pair slot in d_pairs (canonical capacity layout) */
     int32_t n_events;  /* E */
@@ -66,7 +66,7 @@ __device__ __forceinline__ double scl_chain_d(const double* t, int32_t cnt, doub
  * round's values are loaded into registers before the current round is summed, so the loads hide behind the chain. */
 __global__ void __launch_bounds__(32 * SCL_WARPS)
 abea_mom_kernel(const abea_sread_t* __restrict__ sreads, int32_t n_reads, const uint8_t* __restrict__ seq,
-                abea_event_t* __restrict__ events, const abea_model_t* __restrict__ model, uint32_t kmer_size,
+                float* __restrict__ means, const abea_model_t* __restrict__ model, uint32_t kmer_size,
                 abea_scalings_t* __restrict__ scalings, abea_read_t* __restrict__ reads, int32_t reverse_events) {
     __shared__ __align__(16) double stage[SCL_WARPS][2][SCL_CHUNK];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -77,7 +77,7 @@ abea_mom_kernel(const abea_sread_t* __restrict__ sreads, int32_t n_reads, const 
     double* t0 = stage[w][0];
     double* t1 = stage[w][1];
     const int32_t E = rd.n_events, K = rd.read_len - (int32_t)kmer_size + 1;
-    abea_event_t* ev = events + rd.ev_off;
+    float* ev = means + rd.ev_off;
     const uint8_t* s = seq + rd.seq_off;
 
     /* The lanes turn the loaded floats into finished double terms (conversion on the XU pipe, products on the FP64
@@ -90,7 +90,7 @@ abea_mom_kernel(const abea_sread_t* __restrict__ sreads, int32_t n_reads, const 
         for (int u = 0; u < SCL_CHUNK / 32; u++) {
             const int32_t i = lane + 32 * u;
             v[u] = 0.f;
-            if (i < n) v[u] = (pass == 1) ? model[scl_kmer_rank(s + i, kmer_size)].level_mean : ev[i].mean;
+            if (i < n) v[u] = (pass == 1) ? model[scl_kmer_rank(s + i, kmer_size)].level_mean : ev[i];
         }
         acc0 = 0.0;
         for (int32_t base = 0; base < n; base += SCL_CHUNK) {
@@ -108,7 +108,7 @@ abea_mom_kernel(const abea_sread_t* __restrict__ sreads, int32_t n_reads, const 
             }
             for (int u = 0; u < SCL_CHUNK / 32; u++) { /* next round, in flight while this one is summed */
                 const int32_t i = base + SCL_CHUNK + lane + 32 * u;
-                if (i < n) v[u] = (pass == 1) ? model[scl_kmer_rank(s + i, kmer_size)].level_mean : ev[i].mean;
+                if (i < n) v[u] = (pass == 1) ? model[scl_kmer_rank(s + i, kmer_size)].level_mean : ev[i];
             }
             __syncwarp();
             const int32_t cnt = (n - base < SCL_CHUNK) ? n - base : SCL_CHUNK;
@@ -138,15 +138,12 @@ abea_mom_kernel(const abea_sread_t* __restrict__ sreads, int32_t n_reads, const 
             reads[rd.sched].shift = out.shift;
         }
     }
-    if (reverse_events) { /* RNA: events become 3'->5' AFTER the estimate (src/f5c.c:713-721) */
+    if (reverse_events) { /* RNA: events become 3'->5' AFTER the estimate (src/f5c.c:713-721); only their means live here */
         __syncwarp();
-        unsigned long long* e64 = (unsigned long long*)ev; /* abea_event_t = three 8-byte words */
         for (int32_t i = lane; i < E / 2; i += 32) {
-            unsigned long long* a = e64 + 3 * (int64_t)i;
-            unsigned long long* b = e64 + 3 * (int64_t)(E - 1 - i);
-            const unsigned long long a0 = a[0], a1 = a[1], a2 = a[2], b0 = b[0], b1 = b[1], b2 = b[2];
-            a[0] = b0; a[1] = b1; a[2] = b2;
-            b[0] = a0; b[1] = a1; b[2] = a2;
+            const float a = ev[i], b = ev[E - 1 - i];
+            ev[i] = b;
+            ev[E - 1 - i] = a;
         }
     }
 }
@@ -226,7 +223,7 @@ __device__ __forceinline__ int scl_round_rows(const abea_index_pair_t* map, cons
 
 __global__ void __launch_bounds__(32 * SCL_WARPS)
 abea_scaling_kernel(const abea_sread_t* __restrict__ sreads, int32_t n_reads, const uint8_t* __restrict__ seq,
-                    const abea_event_t* __restrict__ events, const abea_model_t* __restrict__ model,
+                    const float* __restrict__ means, const abea_model_t* __restrict__ model,
                     uint32_t kmer_size, const abea_pair_t* __restrict__ pairs, const int32_t* __restrict__ n_pairs,
                     const abea_scalings_t* __restrict__ scalings_in, abea_index_pair_t* __restrict__ maps,
                     abea_scaling_result_t* __restrict__ results, int32_t min_num_events_to_rescale) {
@@ -244,15 +241,22 @@ abea_scaling_kernel(const abea_sread_t* __restrict__ sreads, int32_t n_reads, co
     out.num_m_state = 0;
     out.flags = 0;
     out.calibrated = 0;
-    if (np <= 0) { /* could not align (src/f5c.c:787-793) */
+    const int32_t K = rd.read_len - (int32_t)kmer_size + 1;
+    abea_index_pair_t* map = maps + rd.map_off;
+    if (np <= 0) { /* could not align (src/f5c.c:787-793): the reference allocates no map; here the read's region of
+                    * d_maps is set to "no events" so that no consumer ever sees an earlier batch's entries */
         out.flags = ABEA_FAILED_ALIGNMENT;
         if (lane == 0) results[r] = out;
+        for (int32_t ki = lane; ki < K; ki += 32) {
+            abea_index_pair_t e;
+            e.start = -1;
+            e.stop = -1;
+            map[ki] = e;
+        }
         return;
     }
-    const int32_t K = rd.read_len - (int32_t)kmer_size + 1;
     const abea_pair_t* p = pairs + rd.pair_off;
-    abea_index_pair_t* map = maps + rd.map_off;
-    const abea_event_t* ev = events + rd.ev_off;
+    const float* ev = means + rd.ev_off;
     const uint8_t* s = seq + rd.seq_off;
     scl_terms_t& T = terms[w];
 
@@ -327,7 +331,7 @@ abea_scaling_kernel(const abea_sread_t* __restrict__ sreads, int32_t n_reads, co
             ge[u] = 0.f;
             if (isM[u]) {
                 gm[u] = model[rank[u]];
-                ge[u] = ev[start[u]].mean;                         /* :709 */
+                ge[u] = ev[start[u]];                         /* :709 */
             }
         }
 #pragma unroll
@@ -379,7 +383,7 @@ abea_scaling_kernel(const abea_sread_t* __restrict__ sreads, int32_t n_reads, co
                 ge[u] = 0.f;
                 if (isM[u]) {
                     gm[u] = model[rank[u]];
-                    ge[u] = ev[start[u]].mean;
+                    ge[u] = ev[start[u]];
                 }
             }
 #pragma unroll

@@ -118,11 +118,15 @@ typedef struct {
  *
  *   seq      : concatenated read sequences, read i at seq[seq_ptr[i] .. seq_ptr[i]+read_len[i]) followed
  *              by one NUL (so seq_ptr advances by read_len+1, like the reference's read_ptr)
- *   events   : concatenated event tables, read i at events[event_ptr[i] .. +n_events[i]); NULL = the event tables the
- *              last abea_getevents left on the device (same reads, same order; n_events must repeat its counts,
+ *   events   : concatenated event tables, read i at events[event_ptr[i] .. +n_events[i]); NULL (with event_means NULL
+ *              as well) = the event tables the last abea_getevents left on the device (same reads, same order; n_events must repeat its counts,
  *              event_ptr is ignored) — raw signal in, alignment out, no event table crosses PCIe
  *   scalings : per read (from estimate_scalings_using_mom); NULL = estimate them on the device (abea_estimate_scalings)
  *   good     : per read, non-zero iff db->sig[i]->nsample > 0 (src/f5c.c:811); NULL = all good
+ *   event_means : optional flat array of the events' means alone, read i at event_means[event_ptr[i] .. +n_events[i]).
+ *              ABEA and the stages either side of it read nothing of an event but .mean (reference src/align.c:131,
+ *              src/align.cu:415), so a caller that holds (or extracts) the means ships 4 bytes per event instead of
+ *              the 24 of event_t. When it is not NULL it is used and `events` is ignored (and may be NULL).
  */
 typedef struct {
     int32_t n_reads;
@@ -134,6 +138,7 @@ typedef struct {
     const int32_t* n_events;
     const abea_scalings_t* scalings;
     const uint8_t* good;
+    const float* event_means;
 } abea_batch_t;
 
 #ifdef __cplusplus
