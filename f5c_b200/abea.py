@@ -33,6 +33,13 @@ class CSignals(ctypes.Structure):
                 ("digitisation", ctypes.c_void_p)]
 
 
+class CRagged(ctypes.Structure):
+    """ctypes image of abea_ragged_t (one pointer per read, as db_t holds a batch)."""
+    _fields_ = [("n_reads", ctypes.c_int32), ("seq", ctypes.c_void_p), ("read_len", ctypes.c_void_p),
+                ("events", ctypes.c_void_p), ("n_events", ctypes.c_void_p), ("scalings", ctypes.c_void_p),
+                ("good", ctypes.c_void_p), ("pairs", ctypes.c_void_p), ("n_pairs", ctypes.c_void_p)]
+
+
 class Timing(ctypes.Structure):
     """abea_timing_t"""
     _fields_ = [("pack_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("kmer_ms", ctypes.c_double),
@@ -42,7 +49,7 @@ class Timing(ctypes.Structure):
                 ("n_scheduled", ctypes.c_int32), ("n_wide", ctypes.c_int32), ("streamed", ctypes.c_int32),
                 ("n_bands", ctypes.c_int64), ("n_events", ctypes.c_int64), ("load_ms", ctypes.c_double),
                 ("mom_ms", ctypes.c_double), ("scaling_ms", ctypes.c_double), ("events_ms", ctypes.c_double),
-                ("n_samples", ctypes.c_int64)]
+                ("n_samples", ctypes.c_int64), ("ragged_ms", ctypes.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -63,6 +70,8 @@ def _bind(path: str):
     lib.abea_model_fill_log_stdv.argtypes = [vp, i64]
     lib.abea_model_fill_log_stdv.restype = None
     lib.abea_align_batch.argtypes = [vp, ctypes.POINTER(CBatch), vp, vp, vp, ctypes.POINTER(Timing)]
+    lib.abea_align_ragged.argtypes = [vp, ctypes.POINTER(CRagged), ctypes.c_int, ctypes.POINTER(Timing)]
+    lib.abea_scheduler_model.argtypes = [vp, vp]
     lib.abea_upload_batch.argtypes = [vp, ctypes.POINTER(CBatch), ctypes.POINTER(Timing)]
     lib.abea_run.argtypes = [vp, ctypes.POINTER(Timing)]
     lib.abea_download.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Timing)]
@@ -224,6 +233,47 @@ class AbeaContext:
         out = self.pinned_empty(a.shape, a.dtype)
         out[...] = a
         return out
+
+    def ragged_view(self, batch: ReadBatch):
+        """The batch as db_t holds it: per-read pointers into separately allocated sequences, event tables and pair
+        buffers (each read's arrays are copied out of the flat batch so that nothing is contiguous across reads).
+        Returns (CRagged, keep-alive list, per-read pair arrays, n_pairs)."""
+        n = batch.n_reads
+        seqs = [np.frombuffer(batch.read_seq(i) + b"\0", dtype=np.uint8).copy() for i in range(n)]
+        evs = [np.ascontiguousarray(batch.read_events(i)).copy() for i in range(n)]
+        cap = batch.pair_capacity()
+        outs = [np.zeros(int(cap[i]) + 1, dtype=PAIR_DTYPE) if batch.good[i] else None for i in range(n)]
+        P = ctypes.c_void_p * max(n, 1)
+        seq_p = P(*[s.ctypes.data for s in seqs])
+        ev_p = P(*[e.ctypes.data if len(e) else None for e in evs])
+        out_p = P(*[o.ctypes.data if o is not None else None for o in outs])
+        n_pairs = np.full(n, -7, dtype=np.int32)
+        read_len = np.ascontiguousarray(batch.read_len, dtype=np.int32)
+        n_events = np.ascontiguousarray(batch.n_events, dtype=np.int32)
+        sc = np.ascontiguousarray(batch.scalings)
+        good = np.ascontiguousarray(batch.good, dtype=np.uint8)
+        rg = CRagged(n, ctypes.addressof(seq_p), read_len.ctypes.data, ctypes.addressof(ev_p), n_events.ctypes.data,
+                     sc.ctypes.data, good.ctypes.data, ctypes.addressof(out_p), n_pairs.ctypes.data)
+        keep = [seqs, evs, seq_p, ev_p, out_p, read_len, n_events, sc, good]
+        return rg, keep, outs, n_pairs
+
+    def align_ragged(self, batch: ReadBatch, threads: int = 4, view=None) -> Alignment:
+        """abea_align_ragged on a db_t-like view of the batch; the result is gathered back into the flat capacity
+        layout so that it compares with align_batch."""
+        rg, keep, outs, n_pairs = view if view is not None else self.ragged_view(batch)
+        t = Timing()
+        self._check(self.lib.abea_align_ragged(self._h, ctypes.byref(rg), int(threads), ctypes.byref(t)), "abea_align_ragged")
+        pp = batch.pair_ptr()
+        pairs = np.zeros(int(batch.pair_capacity().sum()), dtype=PAIR_DTYPE)
+        for i in range(batch.n_reads):
+            if n_pairs[i] > 0:
+                pairs[int(pp[i]):int(pp[i]) + int(n_pairs[i])] = outs[i][:int(n_pairs[i])]
+        return Alignment(pairs, pp, n_pairs.copy(), t.as_dict())
+
+    def scheduler_model(self) -> dict:
+        m = np.zeros(4, dtype=np.float64)
+        self._check(self.lib.abea_scheduler_model(self._h, m.ctypes.data), "abea_scheduler_model")
+        return dict(cyc_wide=float(m[0]), cyc_narrow=float(m[1]), cyc_long=float(m[2]), cyc_trace=float(m[3]))
 
     def upload(self, batch: ReadBatch, with_scalings: bool = True, device_events: bool = False,
                means: np.ndarray | None = None) -> dict:

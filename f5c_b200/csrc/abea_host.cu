@@ -17,7 +17,13 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
+#include <sched.h>
 
 #ifndef ABEA_SIMT_EMU
 #include <cuda_runtime.h>
@@ -58,6 +64,65 @@ struct abea_hostbuf { /* pinned */
 typedef abea_devbuf DevBuf;
 typedef abea_hostbuf HostBuf;
 
+/* Host worker threads of abea_align_ragged: the packer / unpacker copies between the caller's ragged per-read arrays
+ * and the pinned staging run here, overlapped with the kernels (the reference does these copies on the one thread
+ * that calls align_cuda, before and after its kernels: src/f5c.cu:744-800, 1005-1030). */
+struct abea_pool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv, cv_done;
+    std::function<void(int)> job;
+    int gen = 0, pending = 0;
+    bool quit = false;
+    void ensure(int n) {
+        while ((int)th.size() < n) {
+            const int id = (int)th.size();
+            th.emplace_back([this, id]() {
+                int seen = 0;
+                for (;;) {
+                    std::function<void(int)> f;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [&]() { return quit || (gen != seen && id < active); });
+                        if (quit) return;
+                        seen = gen;
+                        f = job;
+                    }
+                    f(id);
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        if (--pending == 0) cv_done.notify_all();
+                    }
+                }
+            });
+        }
+    }
+    int active = 0;
+    void kick(int n, std::function<void(int)> f) { /* returns at once; wait() joins */
+        ensure(n);
+        {
+            std::lock_guard<std::mutex> lk(m);
+            job = std::move(f);
+            active = n;
+            pending = n;
+            gen++;
+        }
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&]() { return pending == 0; });
+    }
+    ~abea_pool() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit = true;
+        }
+        cv.notify_all();
+        for (std::thread& t : th) t.join();
+    }
+};
+
 struct abea_ctx {
     int device = 0;
     int sm_count = 0;
@@ -93,7 +158,6 @@ struct abea_ctx {
     int fill_ctas_per_sm = 1;  /* persistent narrow grid = sm_count * this (ABEA_FILL_CTAS_PER_SM) */
     int fill_warps_per_cta = 12; /* 4 primary + 8 secondary warps (ABEA_FILL_WARPS_PER_CTA, multiple of 4, <= 16; 12 measured best) */
     double long_alpha = 0.8;   /* ABEA_LONG_ALPHA: a read is "long" (runs alone on its sub-partition) above this share of the batch time */
-    int trace_ctas_per_sm = 4; /* ABEA_TRACE_CTAS_PER_SM */
     int sm_reserve = 0;        /* ABEA_SM_RESERVE: SMs left out of the narrow grid in addition to the wide CTAs' (when there are wide CTAs) */
     int sched_policy = 1;      /* ABEA_SCHED: 0 two-ended queue (secondary warps shortest-first), 1 longest-first for every warp */
 
@@ -106,6 +170,17 @@ struct abea_ctx {
     double load_crit = 1.0;    /* ABEA_LOAD_CRIT: need times of the makespan-setting reads (wide, long) are scaled by this */
     DevBuf d_ready, d_items;
     std::vector<abea_load_item_t> items;
+    std::vector<int32_t> finish_order; /* scheduled reads by the time the replayed schedule expects them to finish */
+    /* abea_align_ragged */
+    abea_pool pool;
+    HostBuf h_rseq, h_rmeans, h_rpairs, h_rnp, h_hostready, h_rmeta;
+    std::atomic<int> rag_items_ready{0};
+    /* Cycles per band of the three forms a read is filled in, cycles per traceback step and the band time of a fully
+     * loaded sub-partition: the scheduler's model of the kernels. Starting values measured on B200 at 1.965 GHz
+     * (profiles/); re-derived from the per-read clock64 counts of the batches that run (calibrate()). */
+    double cyc_wide = 400.0, cyc_narrow = 1000.0, cyc_long = 655.0, cyc_trace = 350.0;
+    int calib_mode = 1;        /* ABEA_CALIBRATE=0 keeps the starting values */
+    int calib_runs = 0;
     cudaStream_t load_stream = nullptr;
     cudaEvent_t ev_meta = nullptr, ev_loaded = nullptr, ev_load0 = nullptr;
     bool streaming = false;    /* the resident batch is being streamed in: its fill must wait on d_ready */
@@ -218,6 +293,22 @@ void launch_prepare(abea_ctx* c, int64_t check_events) {
         c->total_kmers, check_events);
 }
 
+/* The scheduler's thresholds, from its model of the kernels (abea_ctx::cyc_*).
+ * cyc_tput: band time of a sub-partition that runs its full share of narrow warps (warps per CTA / 4 of them). */
+double cyc_tput(const abea_ctx* c) { return c->cyc_narrow / std::max(1.0, (double)c->fill_warps_per_cta / 4.0); }
+double batch_cycles(const abea_ctx* c) { return (double)c->total_bands * cyc_tput(c) * 1.08 / ((double)c->sm_count * 4.0); }
+/* a narrow read is "long" when, sharing its sub-partition, it would take more than long_alpha of the time the whole
+ * batch needs at full throughput: it then runs alone on its sub-partition */
+int32_t long_threshold(const abea_ctx* c) {
+    const double shared = 0.5 * (c->cyc_narrow + c->cyc_long) * 0.945; /* ~780 at the starting values: two warps per sub-partition */
+    return (int32_t)std::min(2.0e9, std::max(1.0, c->long_alpha * batch_cycles(c) / shared));
+}
+/* a read goes to the wide kernel when it would outlast the whole batch even as a lone narrow warp */
+double wide_threshold(const abea_ctx* c, int64_t total_bands) {
+    const double cyc_batch = (double)total_bands * cyc_tput(c) * 1.08 / ((double)c->sm_count * 4.0);
+    return std::max(c->wide_min_bands, c->wide_alpha * 1.25 * cyc_batch / c->cyc_long);
+}
+
 /* see upload_impl */
 void build_load_order(abea_ctx* c) {
     const int64_t n = (int64_t)c->reads.size();
@@ -230,15 +321,14 @@ void build_load_order(abea_ctx* c) {
     const int64_t n_pri = 4 * blocks, n_sec = (int64_t)(wpc - 4) * blocks;
     /* cycles per band (wide CTA; narrow warp sharing its sub-partition; narrow warp alone on it = a "long" read) and
      * per traceback step. The longest reads set the makespan, so their pieces are asked for early rather than late. */
-    const double CYC_WIDE = 400.0, CYC_NARROW = 1000.0, CYC_LONG = 650.0, CYC_TRACE = 350.0;
-    const double cyc_batch = (double)c->total_bands * 360.0 / ((double)c->sm_count * 4.0);
-    const double long_thr = std::max(1.0, c->long_alpha * cyc_batch / 780.0); /* as in run_impl */
+    const double CYC_WIDE = c->cyc_wide, CYC_NARROW = c->cyc_narrow, CYC_LONG = c->cyc_long, CYC_TRACE = c->cyc_trace;
+    const double long_thr = (double)long_threshold(c); /* as in run_impl */
     auto rate = [&](int64_t r) {
         if (r < nw) return CYC_WIDE;
         const double nb = (double)c->reads[r].n_events + c->reads[r].n_kmers + 2;
         return nb > long_thr ? CYC_LONG : CYC_NARROW;
     };
-    std::vector<double> start((size_t)n, 0.0);
+    std::vector<double> start((size_t)n, 0.0), finish((size_t)n, 0.0);
     /* (time a warp becomes free, kind: 0 wide, 1 primary, 2 secondary); a min-heap */
     typedef std::pair<double, int> slot_t;
     std::vector<slot_t> heap;
@@ -266,6 +356,7 @@ void build_load_order(abea_ctx* c) {
         const double nb = (double)rd.n_events + rd.n_kmers + 2;
         start[r] = sl.first;
         sl.first += nb * rate(r) + (double)rd.n_events * CYC_TRACE;
+        finish[r] = sl.first;
         heap.push_back(sl);
         std::push_heap(heap.begin(), heap.end(), later);
     }
@@ -290,6 +381,42 @@ void build_load_order(abea_ctx* c) {
     c->items.clear();
     c->items.reserve(need.size());
     for (const need_t& x : need) c->items.push_back(abea_load_item_t{x.read, x.piece});
+    c->finish_order.resize((size_t)n);
+    for (int64_t r = 0; r < n; r++) c->finish_order[(size_t)r] = (int32_t)r;
+    std::stable_sort(c->finish_order.begin(), c->finish_order.end(), [&](int32_t x, int32_t y) { return finish[x] < finish[y]; });
+}
+
+/* Re-derive the scheduler's model from what the batch that has just run measured: every read reports the SM cycles of
+ * its fill and of its traceback (abea_result_t, in-kernel clock64), so the medians per form replace the constants a
+ * particular clock, SM count or kernel revision was tuned on. Only resident runs are used (a streamed read's cycles
+ * include its waits for PCIe); values are clamped to [1/2, 2] x the starting ones, and a class updates only when it has
+ * enough reads to have a meaningful median. */
+int calibrate(abea_ctx* c, int32_t long_thr) {
+    const size_t n = c->reads.size();
+    if (n < 256) return 0;
+    std::vector<abea_result_t> res(n);
+    CU(cudaMemcpyAsync(res.data(), c->d_results.p, n * sizeof(abea_result_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<double> wide, lng, shared, trace;
+    for (size_t j = 0; j < n; j++) {
+        const double nb = (double)c->reads[j].n_events + c->reads[j].n_kmers + 2;
+        if (nb < 512 || res[j].fill_cycles <= 0) continue;
+        const double per = (double)res[j].fill_cycles / nb;
+        if (res[j].wide) wide.push_back(per);
+        else if (nb > (double)long_thr) lng.push_back(per);
+        else shared.push_back(per);
+        if (res[j].n_aligned > 256 && res[j].trace_cycles > 0) trace.push_back((double)res[j].trace_cycles / res[j].n_aligned);
+    }
+    auto median = [](std::vector<double>& v) {
+        std::nth_element(v.begin(), v.begin() + v.size() / 2, v.end());
+        return v[v.size() / 2];
+    };
+    auto clampd = [](double x, double ref) { return std::min(2.0 * ref, std::max(0.5 * ref, x)); };
+    if (wide.size() >= 2) c->cyc_wide = clampd(median(wide), 400.0);
+    if (lng.size() >= 4) c->cyc_long = clampd(median(lng), 655.0);
+    if (shared.size() >= 64) c->cyc_narrow = clampd(median(shared), 1000.0);
+    if (trace.size() >= 64) c->cyc_trace = clampd(median(trace), 350.0);
+    return 0;
 }
 
 } // namespace
@@ -357,7 +484,7 @@ int abea_create(abea_ctx_t** out, int device) {
     if (const char* e = getenv("ABEA_FILL_CTAS_PER_SM")) c->fill_ctas_per_sm = std::max(1, atoi(e));
     if (const char* e = getenv("ABEA_FILL_WARPS_PER_CTA")) c->fill_warps_per_cta = std::min(ABEA_NARROW_WARPS_MAX, std::max(4, atoi(e) / 4 * 4));
     if (const char* e = getenv("ABEA_LONG_ALPHA")) c->long_alpha = atof(e);
-    if (const char* e = getenv("ABEA_TRACE_CTAS_PER_SM")) c->trace_ctas_per_sm = std::max(1, atoi(e));
+    if (const char* e = getenv("ABEA_CALIBRATE")) c->calib_mode = atoi(e);
     if (const char* e = getenv("ABEA_SCHED")) c->sched_policy = atoi(e) ? 1 : 0;
     if (const char* e = getenv("ABEA_SM_RESERVE")) c->sm_reserve = std::max(0, atoi(e));
     if (const char* e = getenv("ABEA_STREAM")) c->stream_mode = atoi(e);
@@ -448,9 +575,10 @@ int abea_set_model(abea_ctx_t* c, const abea_model_t* model, uint32_t kmer_size)
 
 /* ev_alias: device-side alias of the caller's pinned event array — batch->event_means when it is given, else
  * batch->events — (the batch is streamed in by abea_load_kernel while the fill runs), or NULL (the events go through
- * the copy engine before anything starts). host_ready: see abea_load_kernel. */
+ * the copy engine before anything starts). rag: the call comes from abea_align_ragged, whose worker threads fill the
+ * pinned array piece by piece in the order of the loader's work list while the loader runs (host_ready of abea_load_kernel). */
 static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alias, abea_timing_t* timing,
-                       const uint32_t* host_ready = nullptr) {
+                       bool rag = false) {
     if (!c || !b || b->n_reads < 0) return fail(c, ABEA_ERR_ARG, "bad batch");
     if (!c->have_model) return fail(c, ABEA_ERR_NOMODEL, "abea_set_model has not been called");
     CU(cudaSetDevice(c->device));
@@ -546,8 +674,7 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
      * finishes it sooner. cfg2 (log-normal sigma 0.5) has no such read; cfg3 (sigma 1.0) has a handful. */
     c->n_wide = 0;
     if (c->wide_mode && !c->reads.empty()) {
-        const double cyc_batch = (double)nb * 360.0 / ((double)c->sm_count * 4.0);
-        const double thr = std::max(c->wide_min_bands, c->wide_alpha * 1.25 * cyc_batch / 655.0);
+        const double thr = wide_threshold(c, nb);
         /* at most one wide CTA per SM: co-resident wide CTAs lose their advantage */
         /* a batch with fewer reads than SMs may run entirely wide; a larger one gives at most wide_cap SMs away */
         const int32_t cap = ((int32_t)c->reads.size() <= c->sm_count) ? c->sm_count : c->wide_cap;
@@ -648,6 +775,14 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         if (dev_reserve(c, c->d_items, c->items.size() * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
         if (host_reserve(c, c->h_items, c->items.size() * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
         memcpy(c->h_items.p, c->items.data(), c->items.size() * sizeof(abea_load_item_t));
+        const uint32_t* host_ready = nullptr;
+        if (rag) { /* one flag per work item, set by the packer threads; they start as soon as the list exists */
+            if (host_reserve(c, c->h_hostready, (c->items.size() + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
+            memset(c->h_hostready.p, 0, (c->items.size() + 1) * sizeof(uint32_t));
+            host_ready = (const uint32_t*)mapped_alias(c->h_hostready.p);
+            if (!host_ready) return fail(c, ABEA_ERR_CUDA, "pinned staging is not mapped into the device address space");
+            c->rag_items_ready.store(1, std::memory_order_release);
+        }
         t2 = now_ms();
         /* the loader's stream waits for the descriptors and the cleared counters, not for the k-mer kernel */
         CU(cudaStreamWaitEvent(c->load_stream, c->ev_meta, 0));
@@ -781,8 +916,7 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                 CU(cudaFuncSetAttribute((const void*)fill_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 /* a narrow read is "long" when, sharing its sub-partition (~780 cycles/band), it would take more than
                  * long_alpha of the time the whole batch needs at full throughput */
-                const double cyc_batch = (double)c->total_bands * 360.0 / ((double)c->sm_count * 4.0);
-                const int32_t long_thr = (int32_t)std::min(2.0e9, std::max(1.0, c->long_alpha * cyc_batch / 780.0));
+                const int32_t long_thr = long_threshold(c);
                 ABEA_LAUNCH_SMEM(fill_fast, blocks, 32 * wpc, smem, c->stream,
                     (const abea_read_t*)c->d_reads.p, n, (const float*)c->d_means.p, (const float4*)c->d_kparams.p,
                     (const uint32_t*)c->d_flags.p, (uint32_t*)c->d_trace.p, (abea_pair_t*)c->d_pairs.p,
@@ -819,6 +953,10 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
     c->ran = true;
     c->prepared = false;
     c->streaming = false; /* everything has landed: a further abea_run works on the resident copy */
+    if (c->calib_mode && !streaming && (c->calib_runs++ & 7) == 0) { /* the first resident run and every eighth after it */
+        const int rc = calibrate(c, long_threshold(c));
+        if (rc) return rc;
+    }
     c->results_on_device = true; /* a streamed-out run keeps the device copy too */
     if (streaming) {
         c->last.h2d_ms = ev_ms(c, EV_H2D0, EV_H2D1);
@@ -1223,7 +1361,17 @@ int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pair
         rc = abea_estimate_scalings(c, 0, nullptr, nullptr);
         if (rc) return rc;
     }
+    const bool was_streamed = c->streaming;
     rc = run_impl(c, fin_pairs, fin_np, nullptr);
+    if (rc == ABEA_ERR_CUDA && was_streamed && cudaGetLastError() == cudaSuccess) {
+        /* the stream from the caller's pinned buffer stalled (host contention, a tool slowing the loader down): the
+         * batch is intact in the caller's buffers, so run it once more through the copy engine before giving up */
+        rc = upload_impl(c, batch, nullptr, nullptr);
+        if (rc == ABEA_OK && c->need_scalings) rc = abea_estimate_scalings(c, 0, nullptr, nullptr);
+        if (rc == ABEA_OK) rc = run_impl(c, nullptr, nullptr, nullptr);
+        fin_pairs = nullptr;
+        fin_np = nullptr;
+    }
     if (rc) return rc;
     if (!fin_np) {
         rc = abea_download(c, pairs, pair_ptr, n_pairs, nullptr);
@@ -1234,6 +1382,175 @@ int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pair
         c->last.d2h_ms = 0.f;
         c->last.unpack_ms = 0.0;
         c->last.d2h_bytes = np * (int64_t)sizeof(abea_pair_t) + (int64_t)batch->n_reads * (int64_t)sizeof(int32_t);
+    }
+    if (timing) *timing = c->last;
+    return ABEA_OK;
+}
+
+/* ---- the ragged front door ------------------------------------------------------------------------------------ */
+
+int abea_scheduler_model(abea_ctx_t* c, double* cycles4) {
+    if (!c || !cycles4) return ABEA_ERR_ARG;
+    cycles4[0] = c->cyc_wide;
+    cycles4[1] = c->cyc_narrow;
+    cycles4[2] = c->cyc_long;
+    cycles4[3] = c->cyc_trace;
+    return ABEA_OK;
+}
+
+int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_timing_t* timing) {
+    if (!c || !r || r->n_reads < 0) return fail(c, ABEA_ERR_ARG, "bad batch");
+    if (!c->have_model) return fail(c, ABEA_ERR_NOMODEL, "abea_set_model has not been called");
+    const int32_t n = r->n_reads;
+    if (n > 0 && (!r->seq || !r->read_len || !r->events || !r->n_events || !r->scalings || !r->pairs || !r->n_pairs))
+        return fail(c, ABEA_ERR_ARG, "bad batch");
+    CU(cudaSetDevice(c->device));
+    const double t0 = now_ms();
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+
+    /* flat layout of the staging, caller's order */
+    if (host_reserve(c, c->h_rmeta, ((size_t)n + 1) * (3 * sizeof(int64_t) + 2 * sizeof(int32_t)))) return ABEA_ERR_CUDA;
+    int64_t* seq_ptr = (int64_t*)c->h_rmeta.p;
+    int64_t* event_ptr = seq_ptr + (n + 1);
+    int64_t* pair_ptr = event_ptr + (n + 1);
+    int32_t* n_events = (int32_t*)(pair_ptr + (n + 1));
+    int32_t* read_len = n_events + (n + 1);
+    int64_t sp = 0, ep = 0, pp = 0;
+    for (int32_t i = 0; i < n; i++) {
+        seq_ptr[i] = sp; event_ptr[i] = ep; pair_ptr[i] = pp;
+        read_len[i] = r->read_len[i];
+        n_events[i] = r->n_events[i] > 0 ? r->n_events[i] : 0;
+        sp += (int64_t)read_len[i] + 1; ep += n_events[i]; pp += (int64_t)n_events[i] + read_len[i];
+    }
+    if (host_reserve(c, c->h_rseq, (size_t)sp + 16)) return ABEA_ERR_CUDA;
+    if (host_reserve(c, c->h_rmeans, (size_t)ep * sizeof(float) + 64)) return ABEA_ERR_CUDA;
+    if (host_reserve(c, c->h_rpairs, (size_t)(pp + 1) * sizeof(abea_pair_t))) return ABEA_ERR_CUDA;
+    if (host_reserve(c, c->h_rnp, ((size_t)n + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
+    char* h_seq = (char*)c->h_rseq.p;
+    float* h_means = (float*)c->h_rmeans.p;
+    abea_pair_t* h_pairs = (abea_pair_t*)c->h_rpairs.p;
+    volatile int32_t* h_np = (volatile int32_t*)c->h_rnp.p;
+    for (int32_t i = 0; i < n; i++) h_np[i] = -1; /* "not done": the traceback stores the count when the list is out */
+
+    abea_batch_t b;
+    b.n_reads = n; b.seq = h_seq; b.seq_ptr = seq_ptr; b.read_len = read_len; b.events = nullptr;
+    b.event_ptr = event_ptr; b.n_events = n_events; b.scalings = r->scalings; b.good = r->good; b.event_means = h_means;
+
+    void* ev_alias = (c->stream_mode & 1) ? mapped_alias(h_means) : nullptr;
+    abea_pair_t* fin_pairs = (c->stream_mode & 2) ? (abea_pair_t*)mapped_alias(h_pairs) : nullptr;
+    int32_t* fin_np = fin_pairs ? (int32_t*)mapped_alias(c->h_rnp.p) : nullptr;
+    const bool overlap = ev_alias && fin_np && n > 0 && ep > 0;
+
+    /* workers: (1) sequences; (2) once the loader's work list exists, the means of its pieces in list order, each
+     * published to the loader through its flag; (3) the finished pair lists, in the order the reads are expected to
+     * finish, as their counts appear in the pinned count array */
+    std::atomic<int32_t> seq_next(0), seq_left(n), item_next(0), out_next(0);
+    std::atomic<int> abort_flag(0), all_packed(0);
+    c->rag_items_ready.store(0);
+    auto pack_read_means = [&](int32_t i, int32_t e0, int32_t e1) {
+        const abea_event_t* src = r->events[i];
+        float* dst = h_means + event_ptr[i];
+        for (int32_t e = e0; e < e1; e++) dst[e] = src[e].mean;
+    };
+    auto worker = [&](int) {
+        for (;;) { /* (1) */
+            const int32_t i0 = seq_next.fetch_add(16);
+            if (i0 >= n) break;
+            const int32_t i1 = std::min(n, i0 + 16);
+            for (int32_t i = i0; i < i1; i++) {
+                memcpy(h_seq + seq_ptr[i], r->seq[i], (size_t)read_len[i]);
+                h_seq[seq_ptr[i] + read_len[i]] = 0;
+                if (!overlap) pack_read_means(i, 0, n_events[i]);
+            }
+            seq_left.fetch_sub(i1 - i0);
+        }
+        if (!overlap) return;
+        while (!c->rag_items_ready.load(std::memory_order_acquire)) { /* (2) */
+            if (abort_flag.load()) return;
+            sched_yield();
+        }
+        volatile uint32_t* flags = (volatile uint32_t*)c->h_hostready.p;
+        const int32_t n_items = (int32_t)c->items.size();
+        const int64_t total_bytes = c->event_bytes, piece = c->load_piece_cur;
+        for (;;) {
+            const int32_t it = item_next.fetch_add(1);
+            if (it >= n_items) break;
+            const abea_load_item_t item = c->items[(size_t)it];
+            const abea_read_t& rd = c->reads[(size_t)item.read];
+            const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, total_bytes, piece, (int64_t)sizeof(float));
+            const int32_t e0 = (int32_t)abea_piece_first_event(g, item.piece, (int64_t)sizeof(float));
+            const int32_t e1 = item.piece + 1 < g.n_pieces ? (int32_t)abea_piece_first_event(g, item.piece + 1, (int64_t)sizeof(float)) : rd.n_events;
+            pack_read_means(rd.orig_index, e0, std::min(e1, rd.n_events));
+            std::atomic_thread_fence(std::memory_order_release);
+            flags[it] = 1u;
+        }
+        all_packed.fetch_add(1);
+        const int32_t n_sched = (int32_t)c->finish_order.size(); /* (3) */
+        for (;;) {
+            const int32_t j = out_next.fetch_add(1);
+            if (j >= n_sched) break;
+            const int32_t i = c->reads[(size_t)c->finish_order[(size_t)j]].orig_index;
+            int32_t np;
+            while ((np = h_np[i]) < 0) {
+                if (abort_flag.load()) return;
+                sched_yield();
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            r->n_pairs[i] = np;
+            if (np > 0 && r->pairs[i]) memcpy(r->pairs[i], h_pairs + pair_ptr[i], (size_t)np * sizeof(abea_pair_t));
+        }
+    };
+    c->pool.kick(threads, worker);
+    while (seq_left.load() > 0) sched_yield();
+    const double t1 = now_ms();
+
+    int rc = ABEA_OK;
+    if (overlap) {
+        rc = upload_impl(c, &b, ev_alias, nullptr, true);
+        if (rc == ABEA_OK && !c->streaming) rc = fail(c, ABEA_ERR_STATE, "ragged batch was not streamed");
+        if (rc == ABEA_OK) rc = run_impl(c, fin_pairs, fin_np, nullptr);
+        if (rc != ABEA_OK) abort_flag.store(1);
+        c->pool.wait();
+        if (rc != ABEA_OK && all_packed.load() == threads) {
+            /* e.g. a stalled stream: the batch is complete in the staging, run it once more through the copy engine */
+            rc = upload_impl(c, &b, nullptr, nullptr);
+            if (rc == ABEA_OK) rc = run_impl(c, nullptr, nullptr, nullptr);
+            if (rc == ABEA_OK) rc = abea_download(c, h_pairs, pair_ptr, (int32_t*)c->h_rnp.p, nullptr);
+            if (rc == ABEA_OK)
+                for (int32_t i = 0; i < n; i++) {
+                    r->n_pairs[i] = h_np[i];
+                    if (h_np[i] > 0 && r->pairs[i]) memcpy(r->pairs[i], h_pairs + pair_ptr[i], (size_t)h_np[i] * sizeof(abea_pair_t));
+                }
+        }
+        if (rc != ABEA_OK) return rc;
+        for (int32_t i = 0; i < n; i++) /* reads the filter kept out of the schedule */
+            if (c->sreads[(size_t)i].sched < 0) r->n_pairs[i] = 0;
+    } else {
+        c->pool.wait();
+        rc = upload_impl(c, &b, nullptr, nullptr);
+        if (rc == ABEA_OK) rc = run_impl(c, nullptr, nullptr, nullptr);
+        if (rc == ABEA_OK && n > 0) rc = abea_download(c, h_pairs, pair_ptr, (int32_t*)c->h_rnp.p, nullptr);
+        if (rc != ABEA_OK) return rc;
+        std::atomic<int32_t> nx(0);
+        c->pool.kick(threads, [&](int) {
+            for (;;) {
+                const int32_t i = nx.fetch_add(1);
+                if (i >= n) break;
+                r->n_pairs[i] = h_np[i];
+                if (h_np[i] > 0 && r->pairs[i]) memcpy(r->pairs[i], h_pairs + pair_ptr[i], (size_t)h_np[i] * sizeof(abea_pair_t));
+            }
+        });
+        c->pool.wait();
+    }
+    c->last.pack_ms += t1 - t0;
+    c->last.ragged_ms = now_ms() - t0;
+    if (overlap) {
+        int64_t np = 0;
+        for (int32_t i = 0; i < n; i++) np += r->n_pairs[i];
+        c->last.d2h_ms = 0.f;
+        c->last.unpack_ms = 0.0;
+        c->last.d2h_bytes = np * (int64_t)sizeof(abea_pair_t) + (int64_t)n * (int64_t)sizeof(int32_t);
     }
     if (timing) *timing = c->last;
     return ABEA_OK;

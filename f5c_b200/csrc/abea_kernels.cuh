@@ -325,10 +325,10 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
         if (it >= n_items) break;
         const abea_load_item_t item = items[it];
         const abea_read_t rd = reads[item.read];
-        if (host_ready) { /* the host packs reads in the order of this work list; normally it is far ahead */
+        if (host_ready) { /* the host packs the pieces in the order of this work list; normally it is far ahead */
             if (tid == 0) {
                 int spins = 0;
-                while (host_ready[item.read] == 0u) {
+                while (host_ready[it] == 0u) {
                     if (++spins > ABEA_WAIT_SPINS_MAX) {
                         *stalled = 1u;
                         break;
@@ -336,12 +336,16 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
 #ifndef ABEA_SIMT_EMU
                     __nanosleep(500);
 #else
-                    break;
+                    sched_yield(); /* the emulator runs this kernel on the caller's thread; the packers are real threads */
+                    spins = 0;
 #endif
                 }
             }
             __syncthreads();
         }
+        /* with a host that is still packing, a line shared with a neighbouring read may hold that read's means or not
+         * yet: only the read's own means are written (the neighbour's own pieces bring its) */
+        const bool own_only = host_ready != nullptr;
         const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, total_bytes, piece_min, esz);
         const int64_t a = g.a, b = g.b;
         const int64_t p0 = g.lo + (int64_t)item.piece * g.piece;
@@ -368,12 +372,16 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
                             if (mb >= a && mb < b && !abea_sane_level(x)) bad = true;
                         }
                     } else {
-                        ((uint4*)dst)[uj] = v[j];
                         const int64_t mb = uj << 4;
                         const uint32_t w4[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+                        const bool whole = (mb >= a) && (mb + 16 <= b);
+                        if (whole || !own_only) ((uint4*)dst)[uj] = v[j];
 #pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (mb + 4 * q >= a && mb + 4 * q < b && !abea_sane_level(__uint_as_float(w4[q]))) bad = true;
+                        for (int q = 0; q < 4; q++) {
+                            const bool mine = (mb + 4 * q >= a) && (mb + 4 * q < b);
+                            if (mine && !whole && own_only) dst[(mb >> 2) + q] = __uint_as_float(w4[q]);
+                            if (mine && !abea_sane_level(__uint_as_float(w4[q]))) bad = true;
+                        }
                     }
                 }
             }
@@ -382,8 +390,9 @@ abea_load_kernel(const abea_read_t* __restrict__ reads, const abea_load_item_t* 
             const int64_t f = (u1 << 2) + tid;
             if ((f << 2) < p1) {
                 const float x = ((const float*)src)[f];
-                dst[f] = x;
-                if ((f << 2) >= a && (f << 2) < b && !abea_sane_level(x)) bad = true;
+                const bool mine = ((f << 2) >= a) && ((f << 2) < b);
+                if (mine || !own_only) dst[f] = x;
+                if (mine && !abea_sane_level(x)) bad = true;
             }
         }
         if (bad) atomicAnd(&read_flags[item.read], ~ABEA_READ_FAST);

@@ -24,6 +24,7 @@
  * 701-735 have no counterpart), no load/memory "advisor" messages (:457-644), device memory grows on demand instead of
  * being pre-sized from cuda_mem_frac (:121-146).
  */
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -42,6 +43,8 @@ static_assert(sizeof(abea_event_t) == sizeof(event_t), "event_t layout differs f
 static_assert(sizeof(abea_model_t) == sizeof(model_t), "model_t layout differs (CACHED_LOG must be defined)");
 static_assert(sizeof(abea_scalings_t) == sizeof(scalings_t), "scalings_t layout differs");
 static_assert(sizeof(abea_pair_t) == sizeof(AlignedPair), "AlignedPair layout differs");
+static_assert(offsetof(abea_scalings_t, scale) == offsetof(scalings_t, scale) && offsetof(abea_scalings_t, shift) == offsetof(scalings_t, shift), "scalings_t field order differs");
+static_assert(offsetof(abea_event_t, mean) == offsetof(event_t, mean), "event_t.mean offset differs");
 static_assert(ABEA_BANDWIDTH == ALN_BANDWIDTH, "band width differs");
 static_assert(sizeof(abea_index_pair_t) == sizeof(index_pair_t), "index_pair_t layout differs");
 static_assert(ABEA_FAILED_CALIBRATION == FAILED_CALIBRATION && ABEA_FAILED_ALIGNMENT == FAILED_ALIGNMENT &&
@@ -66,6 +69,7 @@ struct dropin_data {
     abea_index_pair_t* maps; size_t map_cap;
     int64_t* map_ptr; size_t map_ptr_cap;
     const db_t* aligned_db; /* the batch whose pair lists are resident on the device */
+    const abea_event_t** rag_events; int32_t* rag_nev; uint8_t* rag_good; size_t rag_cap; /* align_cuda's per-read arrays */
     /* getevents_cuda staging */
     float* raw; size_t raw_cap;
     int64_t* raw_ptr; int32_t* n_samples; float* cal_off; float* cal_range; float* cal_dig; size_t sig_cap;
@@ -156,6 +160,7 @@ void free_cuda(core_t* core) {
                     d->n_pairs, d->scalings, d->good, d->sres, d->maps, d->map_ptr, d->raw, d->raw_ptr, d->n_samples,
                     d->cal_off, d->cal_range, d->cal_dig, d->ev_out};
     for (void* b : bufs) abea_host_free(b);
+    free(d->rag_events); free(d->rag_nev); free(d->rag_good);
     free(d);
     core->cuda = NULL;
 }
@@ -193,19 +198,42 @@ static void pack_db(dropin_data* d, const db_t* db, abea_batch_t& b, bool with_s
 void align_cuda(core_t* core, db_t* db) {
     dropin_data* d = (dropin_data*)core->cuda;
     double t0 = realtime();
-    abea_batch_t b;
-    pack_db(d, db, b, true, host_threads(core));
+    /* db_t is ragged (one malloc per read); the library takes it as it is and does the flattening on
+     * core->opt.num_thread threads while its kernels run (abea_align_ragged). Only the per-read pointer / count
+     * arrays are built here. */
+    const int32_t n = db->n_bam_rec;
+    if ((size_t)n > d->rag_cap) {
+        free(d->rag_events); free(d->rag_nev); free(d->rag_good);
+        d->rag_cap = (size_t)n + (size_t)n / 4 + 64;
+        d->rag_events = (const abea_event_t**)malloc(d->rag_cap * sizeof(abea_event_t*));
+        d->rag_nev = (int32_t*)malloc(d->rag_cap * sizeof(int32_t));
+        d->rag_good = (uint8_t*)malloc(d->rag_cap);
+        MALLOC_CHK(d->rag_events); MALLOC_CHK(d->rag_nev); MALLOC_CHK(d->rag_good);
+    }
+    for (int32_t i = 0; i < n; i++) {
+        d->rag_events[i] = (const abea_event_t*)db->et[i].event;
+        d->rag_nev[i] = (int32_t)db->et[i].n;
+        d->rag_good[i] = (db->sig[i] && db->sig[i]->nsample > 0) ? 1 : 0;   /* align_single, src/f5c.c:811 */
+    }
+    abea_ragged_t rg;
+    rg.n_reads = n;
+    rg.seq = (const char* const*)db->read;
+    rg.read_len = db->read_len;
+    rg.events = d->rag_events;
+    rg.n_events = d->rag_nev;
+    rg.scalings = (const abea_scalings_t*)db->scalings;
+    rg.good = d->rag_good;
+    rg.pairs = (abea_pair_t* const*)db->event_align_pairs;
+    rg.n_pairs = db->n_event_align_pairs;
     double t1 = realtime();
 
     abea_timing_t tm;
-    if (abea_align_batch(d->ctx, &b, d->pairs, d->pair_ptr, d->n_pairs, &tm)) die("align_cuda", "Cuda error", d->ctx);
+    if (abea_align_ragged(d->ctx, &rg, host_threads(core), &tm)) die("align_cuda", "Cuda error", d->ctx);
     d->aligned_db = db;
     double t2 = realtime();
 
-    copy_out(db, d->n_pairs, d->pair_ptr, d->pairs, host_threads(core));
-    double t3 = realtime();
-
-    /* the reference's timer split (src/f5c.h:457-466), printed by meth_main (src/meth_main.c:767-788) */
+    /* the reference's timer split (src/f5c.h:457-466), printed by meth_main (src/meth_main.c:767-788); packing and
+     * unpacking overlap the kernels here, so only what is not hidden behind them is charged to pre / postprocess */
     core->align_cuda_preprocess += (t1 - t0) + tm.pack_ms * 1e-3;
     core->align_cuda_memcpy += (tm.h2d_ms + tm.d2h_ms) * 1e-3;
     core->align_kernel_time += tm.kernel_ms * 1e-3;
@@ -213,7 +241,8 @@ void align_cuda(core_t* core, db_t* db) {
     core->align_core_kernel_time += tm.fill_ms * 1e-3;
     core->align_post_kernel_time += tm.trace_ms * 1e-3;
     core->align_cuda_total_kernel += tm.kernel_ms * 1e-3;
-    core->align_cuda_postprocess += (t3 - t2) + tm.unpack_ms * 1e-3;
+    const double rest = (t2 - t1) - (tm.pack_ms + tm.h2d_ms + tm.kernel_ms) * 1e-3;
+    core->align_cuda_postprocess += rest > 0 ? rest : 0;
     if (core->opt.verbosity > 1)
         fprintf(stderr, "[align_cuda] Load : GPU %d entries (%.1fM events), CPU 0 entries; kernels %.3f ms\n",
                 tm.n_scheduled, tm.n_events / 1e6, tm.kernel_ms);

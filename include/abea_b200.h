@@ -58,7 +58,7 @@ typedef struct {
     double h2d_ms;         /* device: sequence + event + descriptor copies */
     double kmer_ms;        /* device: abea_prepare_kernel (k-mer parameter cache + input validation) */
     double fill_ms;        /* device: band fill (narrow + wide kernels, concurrent) */
-    double trace_ms;       /* device: abea_traceback_kernel */
+    double trace_ms;       /* device: always ~0 — traceback + QC are fused into the fill kernels (kept for the reference's timer split) */
     double kernel_ms;      /* device: first kernel start to last kernel end */
     double d2h_ms;         /* device: result copies */
     double unpack_ms;      /* host: scatter into the caller's buffers */
@@ -75,6 +75,7 @@ typedef struct {
     double scaling_ms;       /* device: abea_scaling_kernel (abea_scaling_stage) */
     double events_ms;        /* device: abea_events_kernel (abea_getevents) */
     int64_t n_samples;       /* raw samples of the last abea_getevents */
+    double ragged_ms;        /* host: wall time of the last abea_align_ragged call, everything included */
 } abea_timing_t;
 
 /* Create a context on CUDA device `device` (cudaSetDevice is applied on every call). */
@@ -92,6 +93,14 @@ void abea_model_fill_log_stdv(abea_model_t* model, int64_t n);
 int abea_align_batch(abea_ctx_t* ctx, const abea_batch_t* batch, abea_pair_t* pairs, const int64_t* pair_ptr,
                      int32_t* n_pairs, abea_timing_t* timing);
 
+/* The whole path on the caller's RAGGED per-read arrays — the form db_t holds a batch in (db->read[i], db->et[i].event,
+ * db->event_align_pairs[i]; reference src/f5c.h:290-352) — so that the flattening the reference's align_cuda does on
+ * its calling thread before and after its kernels (src/f5c.cu:744-800, 1005-1030) overlaps the kernels instead:
+ * `threads` host threads extract the event means piece by piece into pinned staging in the order the loader kernel is
+ * going to ship them, and copy every read's pair list out to pairs[i] as soon as its count appears in the pinned count
+ * array (the traceback publishes it behind a system-scope fence). Same results as abea_align_batch. */
+int abea_align_ragged(abea_ctx_t* ctx, const abea_ragged_t* batch, int threads, abea_timing_t* timing);
+
 /* The same path in three separable phases. abea_run may be repeated on a resident batch (it re-zeroes its queues). */
 int abea_upload_batch(abea_ctx_t* ctx, const abea_batch_t* batch, abea_timing_t* timing);
 int abea_run(abea_ctx_t* ctx, abea_timing_t* timing);
@@ -102,8 +111,9 @@ int abea_download(abea_ctx_t* ctx, abea_pair_t* pairs, const int64_t* pair_ptr, 
  *
  * abea_getevents: getevents(nsample, rawptr, rna) (src/events.c:562-582) for every read of a batch of raw signals,
  * including event_single's conversion to picoamperes when the calibration arrays are given. n_events_out[i]
- * receives the number of events of read i (0 for signals shorter than 100 samples, which the reference asserts
- * on; -1 if a signal produced more than n_samples/2 + 1 boundaries, which no real signal does). The event tables stay
+ * receives the number of events of read i (0 for signals shorter than 100 samples; the reference itself aborts on
+ * any signal under 200 samples — nchunk == 1 in trim_raw_by_mad — and on zero-MAD signals, where this library
+ * returns the events the detector finds; -1 if a signal produced more than n_samples/2 + 1 boundaries, which no real signal does). The event tables stay
  * on the device until abea_getevents_download copies them to events[event_ptr[i] ..] — the caller sizes and lays
  * out that array from the counts (e.g. a prefix sum), which is the abea_batch_t.events / event_ptr of the alignment.
  * rna != 0 selects the RNA detector parameters (src/events.c:59-63).
@@ -154,6 +164,11 @@ int abea_read_cycles(abea_ctx_t* ctx, int64_t* fill_cycles, int64_t* trace_cycle
 /* When the fill of each read began: %globaltimer in microseconds (low 31 bits), -1 for reads that were not scheduled.
  * A profiling aid (how far the streaming loader is ahead of the fill). */
 int abea_read_starts(abea_ctx_t* ctx, int32_t* start_us);
+
+/* The scheduler's model of the kernels: cycles per band of a wide CTA, of a narrow warp sharing its sub-partition and
+ * of a narrow warp alone on it, and cycles per traceback step. Starts from values measured on B200 and is re-derived
+ * from the per-read cycle counts of resident runs (ABEA_CALIBRATE=0 keeps the starting values). */
+int abea_scheduler_model(abea_ctx_t* ctx, double* cycles4);
 
 /* Device-resident results of the last abea_run, for consumers that stay on the GPU (e.g. the NCCL gather of a
  * multi-GPU driver): *d_pairs points at the pairs in the canonical capacity layout (read i of the batch at the prefix

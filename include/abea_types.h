@@ -141,6 +141,23 @@ typedef struct {
     const float* event_means;
 } abea_batch_t;
 
+/* The same batch in the RAGGED form db_t holds it in (reference src/f5c.h:290-352): one pointer per read.
+ *   seq[i]     db->read[i] (read_len[i] bases)          events[i]  db->et[i].event (n_events[i] entries)
+ *   pairs[i]   db->event_align_pairs[i], caller-allocated with n_events[i] + read_len[i] entries (src/f5c.c:724-726),
+ *              may be NULL for reads that are not good
+ *   n_pairs    db->n_event_align_pairs, written for every read */
+typedef struct {
+    int32_t n_reads;
+    const char* const* seq;
+    const int32_t* read_len;
+    const abea_event_t* const* events;
+    const int32_t* n_events;
+    const abea_scalings_t* scalings;
+    const uint8_t* good;
+    abea_pair_t* const* pairs;
+    int32_t* n_pairs;
+} abea_ragged_t;
+
 #ifdef __cplusplus
 }
 #endif

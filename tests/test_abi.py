@@ -30,7 +30,7 @@ def test_types_match_reference_sizes():
     from f5c_b200 import batch
     assert batch.EVENT_DTYPE.itemsize == 24 and batch.MODEL_DTYPE.itemsize == 12
     assert batch.SCALINGS_DTYPE.itemsize == 16 and batch.PAIR_DTYPE.itemsize == 8
-    assert ctypes.sizeof(batch.CBatch) == 72
+    assert ctypes.sizeof(batch.CBatch) == 80   # abea_batch_t: 8 pointers + n_reads + event_means
 
 
 def test_no_cpu_fallback(built):

@@ -138,3 +138,23 @@ def test_smoke_entry_point_on_the_emulator(emu):
     both of its legs (alignment; raw signal -> events -> scalings -> alignment -> recalibration) stay runnable."""
     import __graft_entry__ as g
     g.smoke(lib_path=emu)
+
+
+@pytest.mark.parametrize("stream", ["3", "0"])
+@pytest.mark.parametrize("threads", [1, 3])
+def test_emulated_ragged_front_door(emu, monkeypatch, stream, threads):
+    """abea_align_ragged: the batch as db_t holds it (one allocation per read); packer threads publish the means piece
+    by piece to the loader, unpacker threads copy each pair list out when its count appears. Same answer as the flat
+    call, with and without the overlap (ABEA_STREAM=0: plain pack -> copy engine -> unpack)."""
+    monkeypatch.setenv("ABEA_STREAM", stream)
+    monkeypatch.setenv("ABEA_LOAD_PIECE_KB", "1")   # many pieces per read, so that the list order matters
+    k, m = models.load_model("r9")
+    for b in (synth.make_batch("r9", n_reads=7, mean_events=500, sigma=0.7, epk=1.8, seed=21), edge_batch()):
+        with AbeaContext(0, lib_path=emu) as ctx:
+            m = ctx.set_model(m, k)
+            got = ctx.align_ragged(b, threads=threads)
+            again = ctx.align_ragged(b, threads=threads)      # staging is reused
+        want = ol.port_align(b, m)
+        ol.assert_same_alignment(got, want, "ragged")
+        ol.assert_same_alignment(again, want, "ragged, second batch")
+        assert got.timing["streamed"] == int(stream)
