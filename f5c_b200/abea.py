@@ -72,6 +72,7 @@ def _bind(path: str):
     lib.abea_align_batch.argtypes = [vp, ctypes.POINTER(CBatch), vp, vp, vp, ctypes.POINTER(Timing)]
     lib.abea_align_ragged.argtypes = [vp, ctypes.POINTER(CRagged), ctypes.c_int, ctypes.POINTER(Timing)]
     lib.abea_scheduler_model.argtypes = [vp, vp]
+    lib.abea_compact_results.argtypes = [vp, vp, i64, ctypes.POINTER(i64)]
     lib.abea_upload_batch.argtypes = [vp, ctypes.POINTER(CBatch), ctypes.POINTER(Timing)]
     lib.abea_run.argtypes = [vp, ctypes.POINTER(Timing)]
     lib.abea_download.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Timing)]
@@ -377,6 +378,14 @@ class AbeaContext:
         self._check(self.lib.abea_device_results(self._h, ctypes.byref(dp), ctypes.byref(dn), ctypes.byref(cap),
                                                  ctypes.byref(n)), "abea_device_results")
         return dp.value, dn.value, cap.value, n.value
+
+    def compact_results(self, dst_ptr: int, dst_capacity: int) -> int:
+        """abea_compact_results: the last run's pair lists packed back to back into device memory at dst_ptr
+        (capacity in pairs); returns the number of pairs written."""
+        total = ctypes.c_int64()
+        self._check(self.lib.abea_compact_results(self._h, dst_ptr, int(dst_capacity), ctypes.byref(total)),
+                    "abea_compact_results")
+        return int(total.value)
 
     def read_stats(self, n_reads: int) -> dict:
         se = np.zeros(n_reads, dtype=np.float64)

@@ -168,7 +168,7 @@ struct abea_ctx {
     int64_t load_piece = 0;    /* ABEA_LOAD_PIECE_KB: smallest piece of a read the loader delivers (0: 2048 events) */
     int64_t load_piece_cur = ABEA_LOAD_PIECE_BYTES; /* the value in use for the batch being streamed */
     double load_crit = 1.0;    /* ABEA_LOAD_CRIT: need times of the makespan-setting reads (wide, long) are scaled by this */
-    DevBuf d_ready, d_items;
+    DevBuf d_ready, d_items, d_capptr, d_dense_off;
     std::vector<abea_load_item_t> items;
     std::vector<int32_t> finish_order; /* scheduled reads by the time the replayed schedule expects them to finish */
     /* abea_align_ragged */
@@ -531,7 +531,7 @@ void abea_destroy(abea_ctx_t* c) {
     cudaSetDevice(c->device);
     DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_means, &c->d_reads, &c->d_kparams,
                       &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags, &c->d_npairs,
-                      &c->d_ready, &c->d_items, &c->d_sreads, &c->d_scalings, &c->d_maps, &c->d_sres,
+                      &c->d_ready, &c->d_items, &c->d_capptr, &c->d_dense_off, &c->d_sreads, &c->d_scalings, &c->d_maps, &c->d_sres,
                       &c->d_raw, &c->d_sum, &c->d_sumsq, &c->d_ts1, &c->d_ts2, &c->d_peaks, &c->d_evcap, &c->d_sigs, &c->d_sigorder,
                       &c->d_nev, &c->d_evptr, &c->d_evout, &c->d_chunks, &c->d_spec, &c->d_fix, &c->d_spec_cnt, &c->d_fix_cnt,
                       &c->d_sync, &c->d_spec_end};
@@ -1090,6 +1090,36 @@ int abea_device_results(abea_ctx_t* c, const abea_pair_t** d_pairs, const int32_
     if (d_n_pairs) *d_n_pairs = (const int32_t*)c->d_npairs.p;
     if (total_pairs_capacity) *total_pairs_capacity = c->total_pair_cap;
     if (n_reads) *n_reads = c->n_batch_reads;
+    return ABEA_OK;
+}
+
+int abea_compact_results(abea_ctx_t* c, abea_pair_t* d_dst, int64_t dst_capacity, int64_t* total_pairs) {
+    if (!c || !total_pairs) return ABEA_ERR_ARG;
+    if (!c->ran || !c->results_on_device) return fail(c, ABEA_ERR_STATE, "abea_compact_results before abea_run");
+    CU(cudaSetDevice(c->device));
+    const int32_t n = c->n_batch_reads;
+    *total_pairs = 0;
+    if (n == 0) return ABEA_OK;
+    if (dev_reserve(c, c->d_capptr, ((size_t)n + 1) * sizeof(int64_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_dense_off, ((size_t)n + 1) * sizeof(int64_t))) return ABEA_ERR_CUDA;
+    if (host_reserve(c, c->h_items, ((size_t)n + 2) * sizeof(int64_t))) return ABEA_ERR_CUDA; /* pinned scratch */
+    memcpy(c->h_items.p, c->cap_ptr.data(), ((size_t)n + 1) * sizeof(int64_t));
+    CU(cudaMemcpyAsync(c->d_capptr.p, c->h_items.p, ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    ABEA_LAUNCH(abea_pair_offsets_kernel, 1, ABEA_SCAN_THREADS, c->stream, (const int32_t*)c->d_npairs.p, n,
+                (int64_t*)c->d_dense_off.p);
+    int64_t* h_total = (int64_t*)c->h_items.p + (n + 1);
+    CU(cudaMemcpyAsync(h_total, (const int64_t*)c->d_dense_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *total_pairs = *h_total;
+    if (*h_total > dst_capacity) return fail(c, ABEA_ERR_ARG, "dense buffer holds %lld pairs, %lld needed", (long long)dst_capacity, (long long)*h_total);
+    if (*h_total > 0) {
+        if (!d_dst) return fail(c, ABEA_ERR_ARG, "no destination");
+        const int blocks = std::max(1, std::min((n + 7) / 8, c->sm_count * 8));
+        ABEA_LAUNCH(abea_compact_pairs_kernel, blocks, 256, c->stream, (const abea_pair_t*)c->d_pairs.p,
+                    (const int64_t*)c->d_capptr.p, (const int32_t*)c->d_npairs.p, (const int64_t*)c->d_dense_off.p, n, d_dst);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+    }
     return ABEA_OK;
 }
 

@@ -1506,3 +1506,49 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
     }
 }
 
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Dense result list for consumers that move results between GPUs (the NCCL gather of a multi-GPU driver): the pair
+ * lists of a batch leave the alignment in the caller's capacity layout (read i at the prefix sum of E+L, n_pairs[i]
+ * of its E+L slots used); these two kernels pack them back to back. offsets[i] = sum of n_pairs[0..i), offsets[n] =
+ * the total: one block, each thread scans a contiguous slice, the slice sums are scanned through shared memory. */
+#define ABEA_SCAN_THREADS 1024
+__global__ void __launch_bounds__(ABEA_SCAN_THREADS)
+abea_pair_offsets_kernel(const int32_t* __restrict__ n_pairs, int32_t n, int64_t* __restrict__ offsets) {
+    __shared__ int64_t part[ABEA_SCAN_THREADS];
+    const int t = threadIdx.x;
+    const int32_t per = (n + ABEA_SCAN_THREADS - 1) / ABEA_SCAN_THREADS;
+    const int32_t i0 = t * per, i1 = (i0 + per < n) ? i0 + per : n;
+    int64_t sum = 0;
+    for (int32_t i = i0; i < i1; i++) sum += n_pairs[i] > 0 ? n_pairs[i] : 0;
+    part[t] = sum;
+    __syncthreads();
+    if (t == 0) { /* 1024 additions: not worth a parallel scan */
+        int64_t acc = 0;
+        for (int j = 0; j < ABEA_SCAN_THREADS; j++) {
+            const int64_t v = part[j];
+            part[j] = acc;
+            acc += v;
+        }
+        offsets[n] = acc;
+    }
+    __syncthreads();
+    int64_t acc = part[t];
+    for (int32_t i = i0; i < i1; i++) {
+        offsets[i] = acc;
+        acc += n_pairs[i] > 0 ? n_pairs[i] : 0;
+    }
+}
+
+/* one warp per read (grid-stride): dst[offsets[i] .. +n_pairs[i]) = pairs[cap_ptr[i] .. +n_pairs[i]) */
+__global__ void abea_compact_pairs_kernel(const abea_pair_t* __restrict__ pairs, const int64_t* __restrict__ cap_ptr,
+                                          const int32_t* __restrict__ n_pairs, const int64_t* __restrict__ offsets,
+                                          int32_t n, abea_pair_t* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int32_t warps = (int32_t)((gridDim.x * blockDim.x) >> 5);
+    for (int32_t i = (int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < n; i += warps) {
+        const int32_t np = n_pairs[i];
+        const abea_pair_t* src = pairs + cap_ptr[i];
+        abea_pair_t* d = dst + offsets[i];
+        for (int32_t j = lane; j < np; j += 32) d[j] = src[j];
+    }
+}

@@ -554,3 +554,65 @@ extern "C" double f5c_dropin_selftest_pack(const abea_batch_t* b, int threads, c
     free(db->read); free(db->read_len); free(db->et); free(db->event_align_pairs); free(db->n_event_align_pairs); free(db);
     return (t1 - t0) * 1e3;
 }
+
+/* Fifth door: what one call of align_cuda(core, db) costs on a real, ragged db_t (every read's sequence, event table
+ * and pair buffer its own allocation, as load_db / event_single leave them). The batch is built once; align_cuda is
+ * then called warmup + steps times on it and the wall time of each of the last `steps` calls is returned in ms_out —
+ * the `e2e_dropin` figure of bench.py. The last call's results come back flat for a parity check. */
+extern "C" int f5c_dropin_bench(const abea_batch_t* b, const abea_model_t* model, uint32_t kmer_size, int device,
+                                int num_thread, int warmup, int steps, double* ms_out, abea_pair_t* pairs,
+                                const int64_t* pair_ptr, int32_t* n_pairs) {
+    core_t* core = (core_t*)calloc(1, sizeof(core_t));
+    db_t* db = (db_t*)calloc(1, sizeof(db_t));
+    core->model = (model_t*)model;
+    core->kmer_size = kmer_size;
+    core->opt.cuda_dev_id = device;
+    core->opt.num_thread = num_thread;
+    const int32_t n = b->n_reads;
+    db->n_bam_rec = n;
+    db->capacity_bam_rec = n;
+    db->read = (char**)calloc(n, sizeof(char*));
+    db->read_len = (int32_t*)calloc(n, sizeof(int32_t));
+    db->et = (event_table*)calloc(n, sizeof(event_table));
+    db->scalings = (scalings_t*)calloc(n, sizeof(scalings_t));
+    db->sig = (signal_t**)calloc(n, sizeof(signal_t*));
+    db->event_align_pairs = (AlignedPair**)calloc(n, sizeof(AlignedPair*));
+    db->n_event_align_pairs = (int32_t*)calloc(n, sizeof(int32_t));
+    for (int32_t i = 0; i < n; i++) {
+        const int32_t L = b->read_len[i], E = b->n_events[i];
+        db->read[i] = (char*)malloc((size_t)L + 1);
+        memcpy(db->read[i], b->seq + b->seq_ptr[i], (size_t)L);
+        db->read[i][L] = 0;
+        db->read_len[i] = L;
+        db->et[i].n = (size_t)E;
+        db->et[i].end = (size_t)E;
+        db->et[i].event = (event_t*)malloc(sizeof(event_t) * (size_t)(E > 0 ? E : 1));
+        if (E > 0) memcpy(db->et[i].event, b->events + b->event_ptr[i], sizeof(event_t) * (size_t)E);
+        memcpy(&db->scalings[i], &b->scalings[i], sizeof(scalings_t));
+        db->sig[i] = (signal_t*)calloc(1, sizeof(signal_t));
+        db->sig[i]->nsample = (b->good && !b->good[i]) ? 0 : 1;
+        db->event_align_pairs[i] = db->sig[i]->nsample ? (AlignedPair*)malloc(sizeof(AlignedPair) * ((size_t)E + L)) : NULL;
+        db->sum_bases += L;
+    }
+    init_cuda(core);
+    for (int s = 0; s < warmup + steps; s++) {
+        for (int32_t i = 0; i < n; i++) db->n_event_align_pairs[i] = -3;
+        const double t0 = realtime();
+        align_cuda(core, db);
+        const double t1 = realtime();
+        if (s >= warmup) ms_out[s - warmup] = (t1 - t0) * 1e3;
+    }
+    for (int32_t i = 0; i < n; i++) {
+        n_pairs[i] = db->n_event_align_pairs[i];
+        if (n_pairs[i] > 0) memcpy(pairs + pair_ptr[i], db->event_align_pairs[i], (size_t)n_pairs[i] * sizeof(AlignedPair));
+        free(db->event_align_pairs[i]);
+        free(db->sig[i]);
+        free(db->read[i]);
+        free(db->et[i].event);
+    }
+    free_cuda(core);
+    free(db->read); free(db->read_len); free(db->et); free(db->scalings); free(db->sig);
+    free(db->event_align_pairs); free(db->n_event_align_pairs);
+    free(db); free(core);
+    return 0;
+}

@@ -78,9 +78,63 @@ def device_views(ctx):
     return pairs, counts
 
 
+class ResultExchange:
+    """The result exchange of the multi-GPU path (north_star: "NCCL over NVLink only for the final result gather").
+
+    Set up once per shard shape: every rank's read count and pair capacity are exchanged, rank 0 allocates one
+    receive buffer per peer and every rank one send buffer — nothing is allocated per step. A step then (1) packs the
+    rank's pair lists back to back on the device (abea_compact_results: 8 bytes per PAIR cross NVLink, not 8 bytes per
+    capacity slot), (2) gathers the exact pair totals and the per-read counts (padded to the largest shard) to rank 0,
+    and (3) moves every shard with one point-to-point transfer of exactly its size. On CUDA the tensors are device
+    memory and the backend is NCCL; with CPU tensors the same code runs over gloo against the CPU emulation build of
+    the library (tests/test_sharding_gloo.py)."""
+
+    def __init__(self, rank: int, world: int, n_reads: int, pair_capacity: int, device):
+        self.rank, self.world = rank, world
+        self.dev = torch.device(device)
+        self.n_reads, self.cap = int(n_reads), int(pair_capacity)
+        meta = torch.tensor([self.n_reads, self.cap], dtype=torch.int64, device=self.dev)
+        allm = [torch.zeros(2, dtype=torch.int64, device=self.dev) for _ in range(world)]
+        dist.all_gather(allm, meta)
+        self.meta = [tuple(int(v) for v in m.cpu().tolist()) for m in allm]
+        self.max_reads = max(m[0] for m in self.meta)
+        self.send = torch.empty((max(self.cap, 1), 2), dtype=torch.int32, device=self.dev)
+        self.counts = torch.zeros(self.max_reads + 2, dtype=torch.int32, device=self.dev)   # [total lo, total hi, counts...]
+        self.recv = self.recv_counts = None
+        if rank == 0:
+            self.recv = [self.send if r == 0 else torch.empty((max(self.meta[r][1], 1), 2), dtype=torch.int32, device=self.dev)
+                         for r in range(world)]
+            self.recv_counts = [torch.zeros(self.max_reads + 2, dtype=torch.int32, device=self.dev) for _ in range(world)]
+
+    def _counts_view(self, ctx):
+        dp, dn, cap, n = ctx.device_results()
+        if self.dev.type == "cuda":
+            return torch.as_tensor(_DevArray(dn, (max(n, 1),), "<i4"), device=self.dev)[:n]
+        import ctypes
+        return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_int32 * max(n, 1)).from_address(dn))[:n])
+
+    def gather(self, ctx):
+        """Returns on rank 0 a list of (n_pairs int32 [n_reads_r], dense pairs int32 [total_r, 2]) per rank; None elsewhere."""
+        total = ctx.compact_results(self.send.data_ptr(), self.send.shape[0])
+        self.counts[0] = total & 0x7fffffff
+        self.counts[1] = total >> 31
+        self.counts[2:2 + self.n_reads] = self._counts_view(ctx)
+        dist.gather(self.counts, self.recv_counts, dst=0)
+        if self.rank != 0:
+            if total:
+                dist.send(self.send[:total], dst=0)
+            return None
+        heads = torch.stack([c[:2] for c in self.recv_counts]).cpu().tolist()      # the one host sync of the exchange
+        sizes = [int(h[0]) | (int(h[1]) << 31) for h in heads]
+        reqs = [dist.irecv(self.recv[r][:sizes[r]], src=r) for r in range(1, self.world) if sizes[r]]
+        for q in reqs:
+            q.wait()
+        return [(self.recv_counts[r][2:2 + self.meta[r][0]], self.recv[r][:sizes[r]]) for r in range(self.world)]
+
+
 def gather_device_results(ctx, rank: int, world: int):
-    """NCCL gather of every rank's device-resident results (capacity layout) into rank 0's HBM — the only collective
-    of the path. Returns on rank 0 a list of (n_pairs, pairs) device tensors per rank; None elsewhere."""
+    """Round-1 form of the exchange, kept for comparison: gathers the CAPACITY layout padded to the largest shard and
+    allocates its buffers per call. ResultExchange replaces it."""
     pairs, counts = device_views(ctx)
     dev = pairs.device
     sizes = torch.tensor([counts.numel(), pairs.shape[0]], dtype=torch.int64, device=dev)

@@ -18,8 +18,11 @@ CONFIGS = {
     "cfg2": dict(model="r9", n_reads=4096, mean_events=4000, sigma=0.5, epk=1.8),
     "cfg3": dict(model="r10", n_reads=4096, mean_events=8000, sigma=1.0, epk=1.9),
     "cfg4": dict(model="rna004", n_reads=2048, mean_events=20000, sigma=0.5, epk=2.5),
-    "cfg5": dict(model="r10", n_reads=32768, mean_events=4000, sigma=0.5, epk=1.9),
+    # BASELINE configs[4] / the north_star target: R10.4.1, mean 4k events/read, 4096 reads PER GPU, read-sharded — the
+    # 32768-read batch of configs[4] is this config at world == 8; at world == N it is N x 4096 reads (weak scaling)
+    "cfg5": dict(model="r10", n_reads=4096, mean_events=4000, sigma=0.5, epk=1.9),
 }
+GLOBAL_READS_AT_8 = {"cfg5": 32768}
 
 
 def kmer_ranks_flat(bases: np.ndarray, k: int) -> np.ndarray:
@@ -145,7 +148,8 @@ def make_config(name: str, seed: int = 42, n_reads: int | None = None) -> ReadBa
 
 
 def make_config_shard(name: str, rank: int, world: int, seed: int = 42, reads_per_gpu: int | None = None) -> ReadBatch:
-    """Rank `rank`'s shard of a global batch of world*reads_per_gpu reads, partitioned read-wise.
+    """Rank `rank`'s shard of a global batch of world*reads_per_gpu reads, partitioned read-wise (CONFIGS[name]["n_reads"]
+    is the per-GPU count: cfg5 at world == 8 is the 32768-read batch of BASELINE configs[4]).
 
     Every rank draws the same global list of target lengths (one cheap log-normal draw), the list is split
     longest-first by estimated band count E*(1+1/epk), and the rank materialises only its own reads. With world == 1

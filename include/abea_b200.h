@@ -177,6 +177,12 @@ int abea_scheduler_model(abea_ctx_t* ctx, double* cycles4);
 int abea_device_results(abea_ctx_t* ctx, const abea_pair_t** d_pairs, const int32_t** d_n_pairs,
                         int64_t* total_pairs_capacity, int32_t* n_reads);
 
+/* The pair lists of the last run packed back to back in DEVICE memory the caller provides (e.g. the send buffer of an
+ * NCCL exchange): d_dst[0 .. *total_pairs) = read 0's pairs, read 1's pairs, ... in batch order; the per-read counts
+ * are *d_n_pairs of abea_device_results. dst_capacity is in pairs (the batch's sum of n_events+read_len always
+ * suffices). */
+int abea_compact_results(abea_ctx_t* ctx, abea_pair_t* d_dst, int64_t dst_capacity, int64_t* total_pairs);
+
 /* Pinned host memory for callers that want the H2D/D2H copies to run at full PCIe rate. */
 void* abea_host_alloc(size_t bytes);
 void abea_host_free(void* p);

@@ -154,3 +154,26 @@ def test_dropin_threaded_copies_roundtrip(threads):
     for i in range(b.n_reads):
         p, n = int(pp[i]), int(want.n_pairs[i])
         assert np.array_equal(pairs_rt[p:p + n], want.pairs[p:p + n])
+
+
+@needs_so
+@pytest.mark.gpu
+def test_dropin_bench_door_ragged_db(built):
+    """f5c_dropin_bench: align_cuda on a db_t whose reads are separate allocations (what load_db / event_single leave),
+    several calls on the same core, through abea_align_ragged with 4 host threads — the e2e_dropin leg of bench.py."""
+    lib = ctypes.CDLL(SO)
+    vp = ctypes.c_void_p
+    lib.f5c_dropin_bench.argtypes = [ctypes.POINTER(CBatch), vp, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, vp, vp, vp, vp]
+    for b, name in ((synth.make_config("cfg3", seed=64, n_reads=300), "r10"), (edge_batch(), "r9")):
+        k, m = models.load_model(name)
+        m = ol.full_model(m)
+        pairs = np.zeros(int(b.pair_capacity().sum()), dtype=PAIR_DTYPE)
+        n_pairs = np.full(b.n_reads, -1, dtype=np.int32)
+        pp = b.pair_ptr()
+        ms = np.zeros(3, dtype=np.float64)
+        cb = b.as_c()
+        assert lib.f5c_dropin_bench(ctypes.byref(cb), m.ctypes.data, k, 0, 4, 1, 3, ms.ctypes.data, pairs.ctypes.data,
+                                    pp.ctypes.data, n_pairs.ctypes.data) == 0
+        assert (ms > 0).all()
+        ol.assert_same_alignment(ol.AlignResult(b, pairs, n_pairs), ol.port_align(b, m), "drop-in bench door " + name)

@@ -55,6 +55,18 @@ def run_and_check(ctx, batch, model_name, what):
     ol.assert_same_alignment(gs, want, what + " (streamed)")
     st2 = ctx.read_stats(batch.n_reads)
     assert np.array_equal(st2["sum_emission"][sched], want.stats["sum_emission"][sched])
+    # the event means alone (abea_batch_t.event_means, 4 B per event over PCIe): pageable, then pinned and streamed
+    gm = ctx.align_batch(batch, means=batch.event_means())
+    ol.assert_same_alignment(gm, want, what + " (means)")
+    assert gm.timing["h2d_bytes"] < got.timing["h2d_bytes"] or batch.events.shape[0] == 0
+    out[0].view(np.uint8)[...] = 0x5A
+    gms = ctx.align_batch(pb, out, means=ctx.pin_array(batch.event_means()))
+    if batch.n_reads > 0 and int(batch.pair_capacity().sum()) > 0 and batch.events.shape[0] > 0:
+        assert gms.timing["streamed"] == 3
+    ol.assert_same_alignment(gms, want, what + " (means, streamed)")
+    # the batch as db_t holds it (abea_align_ragged): packed / unpacked by host threads while the kernels run
+    gr = ctx.align_ragged(batch, threads=4)
+    ol.assert_same_alignment(gr, want, what + " (ragged)")
     return got, want
 
 
@@ -202,3 +214,102 @@ def test_parity_against_reference_object_code(ctx):
     k, m = models.load_model("r10")
     m = ctx.set_model(m, k)
     ol.assert_same_alignment(align_db(ctx, b), ol.ref_align(b, m), "cfg3 vs reference")
+
+
+def full_size_check(ctx, cfg, n_longest, n_random, seed=42):
+    """A BASELINE config at FULL size and full batch composition: invariants on every read; the staged, the streamed
+    (pinned means) and the ragged path must agree on every read; the oracle on the longest reads (the ones that go
+    wide and set the time) plus a random sample."""
+    b = synth.make_config(cfg, seed=seed)
+    k, m = models.load_model(b.meta["model"])
+    m = ctx.set_model(m, k)
+    a = align_db(ctx, b)
+    assert (a.n_pairs > 0).mean() > 0.95
+    check_alignment_properties(b, a)
+    pb = ctx.pin_batch(b)
+    out = ctx.alloc_output(b, pinned=True)
+    s = ctx.align_batch(pb, out, means=ctx.pin_array(b.event_means()))      # the e2e path of bench.py
+    assert s.timing["streamed"] == 3 and s.timing["n_wide"] == a.timing["n_wide"]
+    assert np.array_equal(s.n_pairs, a.n_pairs)
+    for i in range(b.n_reads):
+        assert np.array_equal(s.read_pairs(i), a.read_pairs(i)), (cfg, "streamed", i)
+    rng = np.random.default_rng(seed + 5)
+    longest = np.argsort(b.n_events, kind="stable")[-n_longest:]
+    idx = np.concatenate([rng.choice(np.setdiff1d(np.arange(b.n_reads), longest), n_random, replace=False), longest])
+    want = ol.port_align(b.subset(idx), m)
+    for j, i in enumerate(idx):
+        assert int(a.n_pairs[i]) == int(want.n_pairs[j]), (cfg, i)
+        assert np.array_equal(a.read_pairs(int(i)), want.read_pairs(j)), (cfg, "oracle", i)
+    return b, a
+
+
+def test_full_size_cfg3_all_reads(ctx):
+    """BASELINE configs[2]: R10.4.1, 4096 reads, sigma 1.0 — its 160 k-event tail reads go wide."""
+    b, a = full_size_check(ctx, "cfg3", 16, 48)
+    assert a.timing["n_wide"] >= 2 and b.n_events.max() > 100000
+
+
+def test_full_size_cfg4_all_reads(ctx):
+    """BASELINE configs[3]: RNA004, 2048 reads, mean 20k events/read."""
+    b, a = full_size_check(ctx, "cfg4", 16, 48)
+    r = ctx.align_ragged(b, threads=8)
+    assert np.array_equal(r.n_pairs, a.n_pairs)
+    for i in range(b.n_reads):
+        assert np.array_equal(r.read_pairs(i), a.read_pairs(i)), ("ragged", i)
+
+
+def test_full_size_cfg5_target_config(ctx):
+    """The north_star target (BASELINE configs[4] per GPU): R10.4.1, 4096 reads, mean 4k events/read."""
+    full_size_check(ctx, "cfg5", 8, 56)
+
+
+def test_ecoli_all_112_reads_from_blow5(ctx):
+    """BASELINE configs[0] on the GPU, every read: the raw signals of tests/golden/ecoli/reads.blow5 (a copy of the
+    reference's test/ecoli_2kb_region fixture) through event detection, the scaling estimate, the alignment and the
+    recalibration, each stage against what the UNMODIFIED reference produced (tests/golden/ecoli_all.json)."""
+    import blow5
+    from f5c_b200.abea import scaling_db
+    from f5c_b200.batch import EVENT_DTYPE, SCALINGS_DTYPE
+    gold = json.load(open(os.path.join(HERE, "golden", "ecoli_all.json")))
+    f = blow5.Blow5(os.path.join(HERE, "golden", "ecoli", "reads.blow5"))
+    seqs = dict(blow5.read_fasta(os.path.join(HERE, "golden", "ecoli", "reads.fasta")))
+    recs = {}
+    for i in range(len(f)):
+        rid, dig, off, rng, sr, sig = f.read(i)
+        recs[rid] = (dig, off, rng, sig)
+    names = [r["name"] for r in gold["reads"]]
+    assert len(names) == 112
+    sig = [recs[n][3] for n in names]
+    n_samples = np.array([len(x) for x in sig], dtype=np.int32)
+    raw_ptr = np.zeros(len(sig), dtype=np.int64)
+    np.cumsum(n_samples[:-1], out=raw_ptr[1:])
+    raw = np.concatenate(sig).astype(np.float32)
+    cal = tuple(np.array([recs[n][j] for n in names], dtype=np.float32) for j in (1, 2, 0))   # offset, range, digitisation
+    k, m = models.load_model("r9")
+    ctx.set_model(m, k)
+    ev, ev_ptr, nev, _ = ctx.getevents(raw, raw_ptr, n_samples, cal)
+    assert [int(x) for x in nev] == [r["n_events"] for r in gold["reads"]]
+
+    def event_sha(e):
+        return sha(np.concatenate([e["start"].astype("<u8").view(np.uint8), e["length"].astype("<f4").view(np.uint8),
+                                   e["mean"].astype("<f4").view(np.uint8), e["stdv"].astype("<f4").view(np.uint8)]))
+    for i, r in enumerate(gold["reads"]):
+        assert event_sha(ev[int(ev_ptr[i]):int(ev_ptr[i]) + int(nev[i])]) == r["events_sha256"], ("events", r["name"])
+    b = ReadBatch.from_reads([seqs[n].encode() for n in names],
+                             [ev[int(ev_ptr[i]):int(ev_ptr[i]) + int(nev[i])] for i in range(len(names))],
+                             np.zeros(len(names), dtype=SCALINGS_DTYPE), k)
+    ctx.upload(b, with_scalings=False)
+    est, _ = ctx.estimate_scalings(b.n_reads)
+    assert [int(x) for x in est["shift"].view(np.uint32)] == [r["shift_bits"] for r in gold["reads"]]
+    assert [int(x) for x in est["scale"].view(np.uint32)] == [r["scale_bits"] for r in gold["reads"]]
+    ctx.run()
+    a = ctx.download(b)
+    assert [int(x) for x in a.n_pairs] == [r["n_pairs"] for r in gold["reads"]]
+    assert [sha(a.read_pairs(i)) for i in range(b.n_reads)] == [r["pairs_sha256"] for r in gold["reads"]]
+    sc = scaling_db(ctx, b)
+    for i, r in enumerate(gold["reads"]):
+        assert int(sc.results["flags"][i]) == r["flags"] and int(sc.results["n_event_alignment"][i]) == r["n_event_alignment"]
+        assert int(sc.results["scalings"]["shift"][i:i + 1].view(np.uint32)[0]) == r["recal_shift_bits"], r["name"]
+        assert int(sc.results["scalings"]["scale"][i:i + 1].view(np.uint32)[0]) == r["recal_scale_bits"], r["name"]
+        if r["map_sha256"] is not None:
+            assert sha(sc.read_map(i)) == r["map_sha256"], r["name"]

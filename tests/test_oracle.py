@@ -113,3 +113,37 @@ def test_transition_constants():
     assert lp_skip == np.log(1e-10) and lp_trim == np.log(0.01)
     assert abs(lp_stay - np.log(1 - 1 / (4000 / 2223 + 1))) < 1e-15
     assert abs(np.exp(lp_skip) + np.exp(lp_stay) + np.exp(lp_step) - 1.0) < 1e-12
+
+
+def test_port_reproduces_reference_on_all_112_ecoli_reads():
+    """BASELINE configs[0]: our restatement through every stage (getevents, estimate, align, scaling_single) on every read of
+    tests/golden/ecoli/reads.blow5 against what the UNMODIFIED reference produced (tests/golden/ecoli_all.json, written by
+    tests/golden/make_ecoli_all.py where the f5c tree is present). The GPU test of the same name checks the CUDA path."""
+    import hashlib, json
+    import blow5
+    from f5c_b200.batch import SCALINGS_DTYPE
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "ecoli_all.json")))
+    f = blow5.Blow5(os.path.join(here, "golden", "ecoli", "reads.blow5"))
+    seqs = dict(blow5.read_fasta(os.path.join(here, "golden", "ecoli", "reads.fasta")))
+    recs = {}
+    for i in range(len(f)):
+        rid, dig, off, rng, sr, sig = f.read(i)
+        recs[rid] = (dig, off, rng, sig)
+    k, m = models.load_model("r9")
+    m = ol.full_model(m)
+    evs, names = [], [r["name"] for r in gold["reads"]]
+    for n in names:
+        dig, off, rng, sig = recs[n]
+        pa = ((sig.astype(np.float32) + np.float32(off)) * np.float32(np.float32(rng) / np.float32(dig))).astype(np.float32)
+        evs.append(ol.port_getevents(pa))
+    assert [len(e) for e in evs] == [r["n_events"] for r in gold["reads"]]
+    b = ReadBatch.from_reads([seqs[n].encode() for n in names], evs, np.zeros(len(names), dtype=SCALINGS_DTYPE), k)
+    b.scalings[:] = ol.port_estimate_scalings(b, m)
+    assert [int(x) for x in b.scalings["shift"].view(np.uint32)] == [r["shift_bits"] for r in gold["reads"]]
+    a = ol.port_align(b, m)
+    assert [int(x) for x in a.n_pairs] == [r["n_pairs"] for r in gold["reads"]]
+    assert [sha(a.read_pairs(i)) for i in range(b.n_reads)] == [r["pairs_sha256"] for r in gold["reads"]]

@@ -31,9 +31,17 @@ def _worker(rank, world, port, out_path):
     with AbeaContext(0, lib_path=os.path.join(HERE, "simt", "libabea_emu.so")) as ctx:
         m = ctx.set_model(m, k)
         a = ctx.align_batch(b)
+        # the exchange bench.py uses over NCCL: device-side compaction + exact-size transfers into persistent buffers
+        from f5c_b200.dist import ResultExchange
+        ex = ResultExchange(rank, world, b.n_reads, int(b.pair_capacity().sum()), "cpu")
+        res2 = [ex.gather(ctx) for _ in range(2)][-1]     # twice: the buffers are reused
+        if rank == 0:
+            res2 = [(c.numpy().copy(), p.numpy().copy().reshape(-1).view(a.pairs.dtype)) for c, p in res2]
     res = gather_results(a.n_pairs, compact_pairs(a.pairs, a.pair_ptr, a.n_pairs), rank, world, "cpu")
     if rank == 0:
-        ok = len(res) == world
+        ok = len(res) == world and len(res2) == world
+        for r in range(world):
+            ok &= bool(np.array_equal(res[r][0], res2[r][0])) and bool(np.array_equal(res[r][1], res2[r][1]))
         total_reads = 0
         for r in range(world):
             br = synth.make_config_shard("tiny", r, world, seed=17)   # rank 0 can regenerate any shard to check it
