@@ -77,6 +77,7 @@ def _bind(path: str):
     lib.abea_run.argtypes = [vp, ctypes.POINTER(Timing)]
     lib.abea_download.argtypes = [vp, vp, vp, vp, ctypes.POINTER(Timing)]
     lib.abea_read_starts.argtypes = [vp, vp]
+    lib.abea_read_respec.argtypes = [vp, vp]
     lib.abea_read_stats.argtypes = [vp, vp, vp, vp, vp]
     lib.abea_read_cycles.argtypes = [vp, vp, vp, vp]
     lib.abea_device_results.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(i64),
@@ -365,6 +366,11 @@ class AbeaContext:
         wd = np.zeros(n_reads, dtype=np.int32)
         self._check(self.lib.abea_read_cycles(self._h, fc.ctypes.data, tc.ctypes.data, wd.ctypes.data), "abea_read_cycles")
         return dict(fill_cycles=fc, trace_cycles=tc, wide=wd)
+
+    def read_respec(self, n_reads: int) -> np.ndarray:
+        rs = np.zeros(n_reads, dtype=np.int32)
+        self._check(self.lib.abea_read_respec(self._h, rs.ctypes.data), "abea_read_respec")
+        return rs
 
     def read_starts(self, n_reads: int) -> np.ndarray:
         st = np.zeros(n_reads, dtype=np.int32)

@@ -180,6 +180,8 @@ struct abea_ctx {
      * (profiles/); re-derived from the per-read clock64 counts of the batches that run (calibrate()). */
     double cyc_wide = 400.0, cyc_narrow = 1000.0, cyc_long = 655.0, cyc_trace = 350.0;
     int calib_mode = 1;        /* ABEA_CALIBRATE=0 keeps the starting values */
+    int tb_mode = 1;           /* ABEA_TB: 1 segment-parallel traceback (a walk per lane), 0 the serial walk */
+    int tb_margin = 64;        /* ABEA_TB_MARGIN: bands a speculative walk starts above its segment */
     int calib_runs = 0;
     cudaStream_t load_stream = nullptr;
     cudaEvent_t ev_meta = nullptr, ev_loaded = nullptr, ev_load0 = nullptr;
@@ -485,6 +487,8 @@ int abea_create(abea_ctx_t** out, int device) {
     if (const char* e = getenv("ABEA_FILL_WARPS_PER_CTA")) c->fill_warps_per_cta = std::min(ABEA_NARROW_WARPS_MAX, std::max(4, atoi(e) / 4 * 4));
     if (const char* e = getenv("ABEA_LONG_ALPHA")) c->long_alpha = atof(e);
     if (const char* e = getenv("ABEA_CALIBRATE")) c->calib_mode = atoi(e);
+    if (const char* e = getenv("ABEA_TB")) c->tb_mode = atoi(e) & 3;
+    if (const char* e = getenv("ABEA_TB_MARGIN")) c->tb_margin = std::max(0, atoi(e));
     if (const char* e = getenv("ABEA_SCHED")) c->sched_policy = atoi(e) ? 1 : 0;
     if (const char* e = getenv("ABEA_SM_RESERVE")) c->sm_reserve = std::max(0, atoi(e));
     if (const char* e = getenv("ABEA_STREAM")) c->stream_mode = atoi(e);
@@ -858,6 +862,8 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
     io.n_pairs_final = fin_np;
     io.n_pairs_dev = (int32_t*)c->d_npairs.p;
     io.stalled = (uint32_t*)c->d_queue.p + 15; /* zeroed with the queue */
+    io.tb_mode = c->tb_mode;
+    io.tb_margin = c->tb_margin;
     if (!streaming) CU(cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
     CU(cudaMemsetAsync(c->d_npairs.p, 0, ((size_t)c->n_batch_reads + 1) * sizeof(int32_t), c->stream));
     if (!c->prepared) CU(cudaEventRecord(c->ev[EV_K0], c->stream));
@@ -1066,6 +1072,18 @@ int abea_read_cycles(abea_ctx_t* c, int64_t* fill_cycles, int64_t* trace_cycles,
         if (trace_cycles) trace_cycles[i] = res[j].trace_cycles;
         if (wide) wide[i] = res[j].wide;
     }
+    return ABEA_OK;
+}
+
+int abea_read_respec(abea_ctx_t* c, int32_t* respec) {
+    if (!c || !respec) return ABEA_ERR_ARG;
+    if (!c->ran) return fail(c, ABEA_ERR_STATE, "abea_read_respec before abea_run");
+    CU(cudaSetDevice(c->device));
+    const size_t n = c->reads.size();
+    std::vector<abea_result_t> res(n);
+    if (n) CU(cudaMemcpy(res.data(), c->d_results.p, n * sizeof(abea_result_t), cudaMemcpyDeviceToHost));
+    for (int32_t i = 0; i < c->n_batch_reads; i++) respec[i] = 0;
+    for (size_t j = 0; j < n; j++) respec[c->reads[j].orig_index] = res[j].respec;
     return ABEA_OK;
 }
 

@@ -68,6 +68,7 @@ struct abea_result_t {
     int32_t start_us;    /* %globaltimer (microseconds, low 31 bits) when the fill of this read began (for profiles/) */
     int32_t max_gap;
     int32_t wide;        /* 1 if the wide kernel filled this read */
+    int32_t respec;      /* parallel traceback: segments whose speculative entry cell was wrong and that were walked again */
     int64_t fill_cycles; /* SM clock cycles this read spent in the band fill ... */
     int64_t trace_cycles;/* ... and in traceback + QC (per-read latency, for profiles/) */
 };
@@ -202,6 +203,9 @@ struct abea_stream_t {
     int32_t* n_pairs_final;     /* [batch read] pair counts in the caller's mapped host buffer, or NULL */
     int32_t* n_pairs_dev;       /* [batch read] pair counts on the device (always written) */
     uint32_t* stalled;          /* set to 1 if a wait for streamed events gave up (the host reports an error) */
+    int32_t tb_mode;            /* 0: serial traceback (one walk per warp), 1: segment-parallel traceback (a walk per lane);
+                                 * bit 1 (tests): the parallel form always sums the emissions in order */
+    int32_t tb_margin;          /* bands a speculative walk starts above its segment */
 };
 
 /* default smallest work item of the loader: 2048 events, i.e. 48 KB of an AoS event table or 8 KB of a flat array of
@@ -710,6 +714,316 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
     }
 }
 
+/* ------------------------------------------------------------------------------------------------------------ */
+/* Segment-parallel traceback. The serial walk above is a chain of P dependent steps in which 31 lanes repeat what
+ * lane 0 does; for the longest read of a batch it is a third of the read's latency, and over a batch a fifth of all
+ * warp cycles. Here every LANE walks its own stretch of the path:
+ *
+ *   the band range [0, b_top] is cut into 32 segments; the lane of segment l does not know in which cell the path enters
+ *   it, so it starts `margin` bands ABOVE its segment in the middle of the band (offset 50 — the adaptive band keeps
+ *   the path near it) and walks down. Two backward walks that ever stand on the same cell stay together from there on,
+ *   and lattice paths built from the steps (-1,-1), (-1,0), (0,-1) cannot cross without sharing a cell, so a
+ *   speculative walk falls onto the true path after a few tens of bands (a detour from the best path costs an emission
+ *   mismatch per event or a skip at log 1e-10). Pass 1 records, per lane, the cell in which its walk enters the segment
+ *   (X), the cell in which it leaves it (Y) and the steps in between. Then the chain is verified: the true entry of the
+ *   top segment is the end cell; the true entry of segment l-1 is Y of segment l PROVIDED the walk of segment l has
+ *   met the true path before leaving the segment — which its lane checks by walking from the true entry side by side
+ *   with its own walk until the two stand on one cell (a few tens of steps; counted in abea_result_t.respec); only a
+ *   walk that leaves its segment still apart changes Y, and then the lanes below check again.
+ *   With the true entries and the step counts known, every pair's position in the output is
+ *   known, and pass 2 has each lane walk its segment once more from its true entry, writing the pairs where they
+ *   belong (ascending, at the front of the read's region: no reversal, no slide) and evaluating the emissions.
+ *
+ * The QC sum (reference src/align.c:476) is a double sum of float emissions in traceback order. Every term is a
+ * multiple of q = 2^(e_min - 23), e_min the smallest exponent among the terms; if sum |term| < 2^52 q, every partial
+ * sum of ANY grouping is exactly representable, no addition ever rounds, and the per-lane partial sums add up to the
+ * reference's value bit for bit. With the built-in models |emission| >= 0.97 (level_stdv >= 1.05), so this holds for
+ * every read; when it does not (a tiny emission next to a long read), the sum is redone in traceback order from the
+ * finished pair list, terms in parallel, additions in order.
+ * The result is the serial walk's, bit for bit: same pairs, same sum, same max_gap, same QC verdict.                  */
+
+struct abea_tbw_t { /* one lane's walker */
+    int32_t ce, ck;  /* current cell (event, k-mer); a negative coordinate = the walk has ended (src/align.c:454) */
+    int32_t eb;      /* event index of the lower-left cell of band ce + ck + 2 */
+};
+
+__device__ __forceinline__ int32_t abea_tbw_eb(const uint32_t* __restrict__ tr, int32_t b) {
+    return (int32_t)tr[(int64_t)(b >> 2) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES + (b & 3)];
+}
+
+/* one step back from a valid cell (ce, ck >= 0, so its band is >= 2); returns the cell's trace code */
+__device__ __forceinline__ uint32_t abea_tbw_step(abea_tbw_t& w, const uint32_t* __restrict__ tr) {
+    const int32_t b = w.ce + w.ck + 2;
+    const uint32_t* line = tr + (int64_t)(b >> 2) * ABEA_TRACE_GROUP_WORDS;
+    const int32_t o = w.eb - w.ce;
+    /* the two bands the walk can go to next, off the dependent chain */
+    const int32_t eb1 = abea_tbw_eb(tr, b - 1), eb2 = abea_tbw_eb(tr, b - 2);
+    const uint32_t tw = line[(o >> 2) & 31];
+    /* an out-of-band cell is undefined behaviour in the reference; stay in bounds */
+    const uint32_t from = ((uint32_t)o < (uint32_t)ABEA_W) ? ((tw >> (((b & 3) << 3) + 2 * (o & 3))) & 3u) : ABEA_FROM_D;
+    w.ce -= (from != ABEA_FROM_L) ? 1 : 0;
+    w.ck -= (from != ABEA_FROM_U) ? 1 : 0;
+    w.eb = (from == ABEA_FROM_D) ? eb2 : eb1;
+    return from;
+}
+
+/* walk while the cell is valid and its band is above `floor_band`; returns the number of steps */
+__device__ __forceinline__ int32_t abea_tbw_run(abea_tbw_t& w, const uint32_t* __restrict__ tr, int32_t floor_band) {
+    int32_t n = 0;
+    while ((w.ce | w.ck) >= 0 && w.ce + w.ck + 2 > floor_band) {
+        abea_tbw_step(w, tr);
+        n++;
+    }
+    return n;
+}
+
+__device__ __forceinline__ int32_t __reduce_add_sync_compat(int32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(ABEA_FULL, v, d);
+    return v;
+}
+
+template <bool FAST>
+__device__ __forceinline__ void abea_traceback_par(const abea_read_t& rd, int32_t ridx, int32_t end_event, int lane,
+                                                   const float* __restrict__ means, const float4* __restrict__ kparams,
+                                                   const uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs,
+                                                   abea_result_t* __restrict__ results, const abea_stream_t& io) {
+    const int32_t E = rd.n_events, K = rd.n_kmers;
+    const float* __restrict__ ev = means + rd.ev_off;
+    const float4* __restrict__ kpr = kparams + rd.kp_off;
+    const uint32_t* __restrict__ tr = trace + rd.trace_off;
+    abea_pair_t* out = pairs + rd.pair_off;
+    __syncwarp(); /* the trace lines written by the other lanes of this warp are visible */
+
+    const int32_t b_top = end_event + (K - 1) + 2;
+    int32_t S = (b_top + 32) >> 5; /* ceil((b_top + 1) / 32) */
+    if (S < 16) S = 16;
+    const int32_t l_top = b_top / S;
+    const int32_t margin = io.tb_margin;
+    const int32_t floor_b = lane * S - 1;      /* a lane's segment: bands (floor_b, top_b] */
+    const int32_t top_b = floor_b + S;
+
+    /* ---- pass 1: speculative entry X, steps n, exit Y ---- */
+    abea_tbw_t w;
+    w.ce = -1; w.ck = -1; w.eb = 0;
+    if (lane <= l_top) {
+        const int32_t s = top_b + margin;
+        if (lane == l_top || s >= b_top) { /* close enough to the end cell: walk from it, nothing to speculate on */
+            w.ce = end_event;
+            w.ck = K - 1;
+            w.eb = abea_tbw_eb(tr, b_top);
+        } else {
+            const int32_t eb = abea_tbw_eb(tr, s);
+            const int32_t ce = eb - ABEA_W / 2, ck = s - 2 - ce;
+            if (ce >= 0 && ce < E && ck >= 0 && ck < K) {
+                w.ce = ce;
+                w.ck = ck;
+                w.eb = eb;
+            }
+        }
+        abea_tbw_run(w, tr, top_b);
+    }
+    /* (ve, vk): the entry cell the lane's step count n and exit cell (ye, yk) are valid for — at first its own guess */
+    int32_t ve = w.ce, vk = w.ck;
+    int32_t n = abea_tbw_run(w, tr, floor_b);
+    int32_t ye = w.ce, yk = w.ck; /* where the walk leaves the segment: the entry of the segment below */
+    if (lane > l_top) n = 0;
+    __syncwarp();
+
+    /* ---- verify: the true entry of segment l is the exit of segment l + 1 (the top one starts at the end cell) ----
+     * A lane whose guess was not the true entry walks both paths side by side — always stepping the one that is higher
+     * up — until they stand on the same cell: from there on they are one path, so the exit stays and only the step
+     * count is corrected. That costs a few tens of steps. If they leave the segment apart, the exit changes and the lanes
+     * below look again; rounds repeat until nothing changes (one round, as a rule). */
+    int32_t respec = 0;
+    for (;;) {
+        const int32_t ue = __shfl_down_sync(ABEA_FULL, ye, 1), uk = __shfl_down_sync(ABEA_FULL, yk, 1);
+        bool changed = false;
+        if (lane < l_top && (ue != ve || uk != vk)) {
+            abea_tbw_t A, B;
+            A.ce = ue; A.ck = uk; A.eb = ((ue | uk) >= 0) ? abea_tbw_eb(tr, ue + uk + 2) : 0;
+            B.ce = ve; B.ck = vk; B.eb = ((ve | vk) >= 0) ? abea_tbw_eb(tr, ve + vk + 2) : 0;
+            int32_t sa = 0, sb = 0;
+            for (;;) {
+                if (A.ce == B.ce && A.ck == B.ck) break;
+                const int32_t ba = A.ce + A.ck + 2, bb = B.ce + B.ck + 2;
+                const bool la = (A.ce | A.ck) >= 0 && ba > floor_b, lb = (B.ce | B.ck) >= 0 && bb > floor_b;
+                if (!la && !lb) break;
+                if (la && (!lb || ba >= bb)) {
+                    abea_tbw_step(A, tr);
+                    sa++;
+                } else {
+                    abea_tbw_step(B, tr);
+                    sb++;
+                }
+            }
+            if (A.ce == B.ce && A.ck == B.ck) {
+                n = n - sb + sa; /* the rest of B's walk is A's */
+            } else {
+                n = sa;
+                ye = A.ce;
+                yk = A.ck;
+                changed = true;
+            }
+            ve = ue;
+            vk = uk;
+            respec++;
+        }
+        if (!__any_sync(ABEA_FULL, changed)) break;
+    }
+    const int32_t xe = ve, xk = vk;
+    const int32_t xeb = ((ve | vk) >= 0) ? abea_tbw_eb(tr, ve + vk + 2) : 0;
+    respec = __reduce_add_sync_compat(respec);
+
+    /* ---- positions: `before` = steps of the lanes above (earlier in traceback order) ---- */
+    int32_t incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int32_t v = __shfl_down_sync(ABEA_FULL, incl, d);
+        if (lane + d < 32) incl += v;
+    }
+    const int32_t total = __shfl_sync(ABEA_FULL, incl, 0);
+    const int32_t before = incl - n;
+
+    /* ---- pass 2: pairs, emissions, gap runs ---- */
+    double sum = 0.0, asum = 0.0;
+    uint32_t emin = 0xffu;                       /* smallest biased exponent among the non-zero emissions */
+    int32_t lead_run = 0, max_run = 0, run = 0;  /* runs of FROM_L: at the head of the segment, anywhere, at its tail */
+    bool all_l = true;
+    int32_t last_k = 0;
+    {
+        abea_tbw_t r;
+        r.ce = xe; r.ck = xk; r.eb = xeb;
+        int32_t pos = total - 1 - before;
+        for (int32_t j = 0; j < n; j++, pos--) {
+            abea_pair_t p;
+            p.ref_pos = r.ck;
+            p.read_pos = r.ce;
+            out[pos] = p;
+            last_k = r.ck;
+            const float lp = abea_emission_t<FAST>(ev[r.ce], kpr[r.ck]);
+            const uint32_t ex = (__float_as_uint(lp) >> 23) & 0xffu;
+            if (lp != 0.0f && ex < emin) emin = ex;
+            const double lpd = (double)lp;
+            sum = __dadd_rn(sum, lpd);
+            asum = __dadd_rn(asum, fabs(lpd));
+            const uint32_t from = abea_tbw_step(r, tr);
+            if (from == ABEA_FROM_L) {
+                run++;
+                if (run > max_run) max_run = run;
+            } else {
+                if (all_l) lead_run = run;
+                all_l = false;
+                run = 0;
+            }
+        }
+        if (all_l) lead_run = run;
+    }
+    __syncwarp();
+
+    /* ---- combine: gap runs across segment borders, traceback order = lanes descending ---- */
+    int32_t max_gap = 0, carry = 0;
+    for (int32_t l = l_top; l >= 0; l--) {
+        const int32_t ln = __shfl_sync(ABEA_FULL, n, l);
+        const int32_t llead = __shfl_sync(ABEA_FULL, lead_run, l), lmax = __shfl_sync(ABEA_FULL, max_run, l);
+        const int32_t ltail = __shfl_sync(ABEA_FULL, run, l);
+        const bool lall = __shfl_sync(ABEA_FULL, all_l ? 1 : 0, l) != 0;
+        if (ln == 0) continue;
+        if (lall) {
+            carry += ln;
+            if (carry > max_gap) max_gap = carry;
+        } else {
+            if (carry + llead > max_gap) max_gap = carry + llead;
+            if (lmax > max_gap) max_gap = lmax;
+            carry = ltail;
+        }
+    }
+    /* the last pair emitted (the lowest lane that has steps) */
+    const uint32_t have = __ballot_sync(ABEA_FULL, n > 0);
+    const int low = have ? (__ffs((int)have) - 1) : 0;
+    last_k = __shfl_sync(ABEA_FULL, last_k, low);
+
+    /* ---- the QC sum ---- */
+    double a_tot = asum;
+    uint32_t e_all = emin;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a_tot = __dadd_rn(a_tot, __shfl_xor_sync(ABEA_FULL, a_tot, d));
+        const uint32_t oe = __shfl_xor_sync(ABEA_FULL, e_all, d);
+        e_all = oe < e_all ? oe : e_all;
+    }
+    /* no addition rounds if sum|x| < 2^52 * 2^(e_min - 23) (one bit spare for the rounding of a_tot itself); e_all is
+     * biased by 127 and 0 means a denormal term: then the ordered sum below decides */
+    bool exact = false;
+    if (e_all == 0xffu) {
+        exact = true; /* every term is zero */
+    } else if (e_all > 0u) {
+        const int32_t lim_exp = (int32_t)e_all - 127 - 23 + 52; /* a_tot must stay below 2^lim_exp */
+        const double lim = (lim_exp > 1000) ? 1.0e300 : ((lim_exp < -1000) ? 0.0 : __hiloint2double((lim_exp + 1023) << 20, 0));
+        exact = a_tot < lim;
+    }
+    if (io.tb_mode & 2) exact = false; /* tests: always take the ordered sum */
+    if (exact) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum = __dadd_rn(sum, __shfl_xor_sync(ABEA_FULL, sum, d));
+    } else { /* traceback order = descending position in the finished list; terms in parallel, additions in order */
+        __syncwarp();
+        sum = 0.0;
+        for (int32_t t0 = 0; t0 < total; t0 += 32) {
+            const int32_t cnt = (total - t0 < 32) ? total - t0 : 32;
+            double lpd = 0.0;
+            if (lane < cnt) {
+                const abea_pair_t p = out[total - 1 - (t0 + lane)];
+                const float4 kp = kpr[p.ref_pos];
+                lpd = (double)abea_emission(ev[p.read_pos], kp.x, kp.y, kp.z);
+            }
+            for (int j = 0; j < cnt; j++) sum = __dadd_rn(sum, __shfl_sync(ABEA_FULL, lpd, j));
+        }
+    }
+
+    /* QC (reference src/align.c:526-543) */
+    const double avg = sum / (double)total;
+    const bool spanned = (total > 0) && (last_k == 0);
+    const bool fail = (avg < -5.0) || !spanned || (max_gap > 50);
+    const int32_t rs = respec;
+    if (lane == 0) {
+        results[ridx].sum_emission = sum;
+        results[ridx].n_aligned = total;
+        results[ridx].n_pairs = fail ? 0 : total;
+        results[ridx].max_gap = max_gap;
+        results[ridx].respec = rs;
+        io.n_pairs_dev[rd.orig_index] = fail ? 0 : total; /* db->n_event_align_pairs[i] */
+    }
+    /* the list already sits at the front of the read's region in d_pairs; a mapped caller buffer gets a coalesced copy */
+    __syncwarp();
+    if (io.pairs_final) {
+        abea_pair_t* fin = io.pairs_final + rd.pair_off;
+        if (!fail)
+            for (int32_t t = lane; t < total; t += 32) fin[t] = out[t];
+    }
+    if (io.n_pairs_final) {
+#ifndef ABEA_SIMT_EMU
+        __threadfence_system();
+#endif
+        __syncwarp();
+        if (lane == 0) *(volatile int32_t*)(io.n_pairs_final + rd.orig_index) = fail ? 0 : total;
+    }
+}
+
+/* the traceback of one read by the warp that filled it (warp 0 of a wide CTA) */
+template <bool FAST>
+__device__ __forceinline__ void abea_traceback(const abea_read_t& rd, int32_t ridx, int32_t end_event, uint32_t* ring, int lane,
+                                               const float* __restrict__ means, const float4* __restrict__ kparams,
+                                               const uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs,
+                                               abea_result_t* __restrict__ results, const abea_stream_t& io) {
+    if (io.tb_mode == 0) {
+        abea_traceback_read(rd, ridx, end_event, ring, lane, means, kparams, trace, pairs, results, io);
+        if (lane == 0) results[ridx].respec = 0;
+    } else {
+        abea_traceback_par<FAST>(rd, ridx, end_event, lane, means, kparams, trace, pairs, results, io);
+    }
+}
+
 /* One band of scores as held by a lane, with the two neighbour-lane cells next to its four ("halos"). */
 struct abea_band_t {
     double R[ABEA_CPL];
@@ -1107,7 +1421,7 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const f
          * is a serial chain too, and fusing it here takes it off the tail of the batch */
         __syncwarp();
         const long long t_fill = abea_clock();
-        abea_traceback_read(rd, ridx, end_event, tb_ring, lane, means, kparams, trace, pairs, results, io);
+        abea_traceback<FAST>(rd, ridx, end_event, tb_ring, lane, means, kparams, trace, pairs, results, io);
         if (lane == 0) {
             results[ridx].wide = 0;
             results[ridx].fill_cycles = t_fill - t_start;
@@ -1496,7 +1810,7 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                 results[ridx].end_event = end_event;
             }
             const long long t_fill = abea_clock();
-            abea_traceback_read(rd, ridx, end_event, (uint32_t*)sm.kp, lane, means, kparams, trace, pairs, results, io);
+            abea_traceback<FAST>(rd, ridx, end_event, (uint32_t*)sm.kp, lane, means, kparams, trace, pairs, results, io);
             if (lane == 0) {
                 results[ridx].wide = 1;
                 results[ridx].fill_cycles = t_fill - t_start;

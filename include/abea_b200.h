@@ -161,6 +161,9 @@ int abea_read_stats(abea_ctx_t* ctx, double* sum_emission, int32_t* n_aligned, i
  * the read; indexed like the batch, any pointer may be NULL. A profiling aid: it is how profiles/ shows what the
  * longest reads cost. */
 int abea_read_cycles(abea_ctx_t* ctx, int64_t* fill_cycles, int64_t* trace_cycles, int32_t* wide);
+/* Segment-parallel traceback: per read, how many of its (up to 32) segments were entered in another cell than the
+ * speculative walk had assumed and were walked again. A profiling aid (the choice of the margin, ABEA_TB_MARGIN). */
+int abea_read_respec(abea_ctx_t* ctx, int32_t* respec);
 /* When the fill of each read began: %globaltimer in microseconds (low 31 bits), -1 for reads that were not scheduled.
  * A profiling aid (how far the streaming loader is ahead of the fill). */
 int abea_read_starts(abea_ctx_t* ctx, int32_t* start_us);

@@ -158,3 +158,22 @@ def test_emulated_ragged_front_door(emu, monkeypatch, stream, threads):
         ol.assert_same_alignment(got, want, "ragged")
         ol.assert_same_alignment(again, want, "ragged, second batch")
         assert got.timing["streamed"] == int(stream)
+
+
+@pytest.mark.parametrize("tb,margin", [("0", "64"), ("1", "0"), ("1", "7"), ("1", "200"), ("3", "64")])
+def test_emulated_traceback_forms(emu, monkeypatch, tb, margin):
+    """The traceback in its three forms must give the same pairs, the same QC sum (bit for bit), the same max_gap:
+    ABEA_TB=0 the serial walk; 1 the segment-parallel walk (a walk per lane from a speculative entry cell, verified
+    against the true path) with margins from 0 (every segment mis-speculates and is corrected) to longer than the
+    reads (every lane walks from the end cell); 3 the parallel walk with the emissions summed in traceback order (the
+    path taken when the partial sums could round)."""
+    monkeypatch.setenv("ABEA_TB", tb)
+    monkeypatch.setenv("ABEA_TB_MARGIN", margin)
+    for wide in ("0", "1"):
+        monkeypatch.setenv("ABEA_WIDE", wide)
+        check(emu, synth.make_batch("r9", n_reads=5, mean_events=900, sigma=0.6, epk=1.8, seed=41), "r9", f"tb {tb}/{margin}")
+        check(emu, synth.make_batch("r9", n_reads=8, mean_events=130, sigma=0.8, epk=1.8, seed=42, min_len=20), "r9", "short")
+        check(emu, edge_batch(), "r9", "edge")
+    # skip-heavy reads: long runs of FROM_L cross segment borders (max_gap is assembled from per-lane runs)
+    monkeypatch.setenv("ABEA_WIDE", "0")
+    check(emu, synth.make_batch("r9", n_reads=4, mean_events=700, sigma=0.3, epk=1.8, seed=43, p_skip=0.35), "r9", "skips")
