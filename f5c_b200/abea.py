@@ -30,7 +30,13 @@ class CSignals(ctypes.Structure):
     """ctypes image of abea_signals_t."""
     _fields_ = [("n_reads", ctypes.c_int32), ("raw", ctypes.c_void_p), ("raw_ptr", ctypes.c_void_p),
                 ("n_samples", ctypes.c_void_p), ("offset", ctypes.c_void_p), ("range", ctypes.c_void_p),
-                ("digitisation", ctypes.c_void_p)]
+                ("digitisation", ctypes.c_void_p), ("raw_i16", ctypes.c_void_p)]
+
+
+class CBlow5(ctypes.Structure):
+    """ctypes image of abea_blow5_t."""
+    _fields_ = [("n_reads", ctypes.c_int32), ("bytes", ctypes.c_void_p), ("rec_ptr", ctypes.c_void_p),
+                ("rec_len", ctypes.c_void_p), ("record_method", ctypes.c_int32), ("signal_method", ctypes.c_int32)]
 
 
 class CRagged(ctypes.Structure):
@@ -49,7 +55,7 @@ class Timing(ctypes.Structure):
                 ("n_scheduled", ctypes.c_int32), ("n_wide", ctypes.c_int32), ("streamed", ctypes.c_int32),
                 ("n_bands", ctypes.c_int64), ("n_events", ctypes.c_int64), ("load_ms", ctypes.c_double),
                 ("mom_ms", ctypes.c_double), ("scaling_ms", ctypes.c_double), ("events_ms", ctypes.c_double),
-                ("n_samples", ctypes.c_int64), ("ragged_ms", ctypes.c_double)]
+                ("n_samples", ctypes.c_int64), ("ragged_ms", ctypes.c_double), ("blow5_ms", ctypes.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -84,6 +90,8 @@ def _bind(path: str):
                                         ctypes.POINTER(i32)]
     lib.abea_getevents.argtypes = [vp, ctypes.POINTER(CSignals), ctypes.c_int, vp, ctypes.POINTER(Timing)]
     lib.abea_getevents_download.argtypes = [vp, vp, vp]
+    lib.abea_getevents_blow5.argtypes = [vp, ctypes.POINTER(CBlow5), ctypes.c_int, vp, vp, ctypes.POINTER(Timing)]
+    lib.abea_raw_download.argtypes = [vp, vp, vp]
     lib.abea_estimate_scalings.argtypes = [vp, ctypes.c_int, vp, ctypes.POINTER(Timing)]
     lib.abea_scaling_stage.argtypes = [vp, i32, ctypes.POINTER(Timing)]
     lib.abea_scaling_download.argtypes = [vp, vp, vp, vp]
@@ -312,11 +320,15 @@ class AbeaContext:
         raw: float32 samples (ADC counts, or pA when calibration is None); calibration: (offset, range, digitisation)
         float32 arrays per read. Returns (events EVENT_DTYPE, event_ptr int64 [n], n_events int32 [n], timing)."""
         from .batch import EVENT_DTYPE
-        raw = np.ascontiguousarray(raw, dtype=np.float32)
         raw_ptr = np.ascontiguousarray(raw_ptr, dtype=np.int64)
         n_samples = np.ascontiguousarray(n_samples, dtype=np.int32)
         n = int(n_samples.shape[0])
-        cs = CSignals(n, raw.ctypes.data, raw_ptr.ctypes.data, n_samples.ctypes.data, None, None, None)
+        if np.asarray(raw).dtype == np.int16:   # the int16 front door: ADC counts as the file holds them
+            raw = np.ascontiguousarray(raw)
+            cs = CSignals(n, None, raw_ptr.ctypes.data, n_samples.ctypes.data, None, None, None, raw.ctypes.data)
+        else:
+            raw = np.ascontiguousarray(raw, dtype=np.float32)
+            cs = CSignals(n, raw.ctypes.data, raw_ptr.ctypes.data, n_samples.ctypes.data, None, None, None, None)
         keep = None
         if calibration is not None:
             keep = [np.ascontiguousarray(a, dtype=np.float32) for a in calibration]
@@ -335,6 +347,46 @@ class AbeaContext:
         self._check(self.lib.abea_getevents_download(self._h, events.ctypes.data if len(events) else None,
                                                      event_ptr.ctypes.data), "abea_getevents_download")
         return events, event_ptr, n_events, t.as_dict()
+
+    def getevents_blow5(self, payload: np.ndarray, rec_ptr, rec_len, record_method: int, signal_method: int,
+                        rna: bool = False):
+        """abea_getevents_blow5: BLOW5 records (their stored bytes, back to back in `payload`) -> event tables on the
+        device. Returns (n_events int32 [n], n_samples int32 [n], timing); follow with getevents_download-style calls
+        or upload(device_events=True)."""
+        payload = np.ascontiguousarray(payload, dtype=np.uint8)
+        rec_ptr = np.ascontiguousarray(rec_ptr, dtype=np.int64)
+        rec_len = np.ascontiguousarray(rec_len, dtype=np.int32)
+        n = int(rec_len.shape[0])
+        cb = CBlow5(n, payload.ctypes.data, rec_ptr.ctypes.data, rec_len.ctypes.data, int(record_method), int(signal_method))
+        n_events = np.zeros(n, dtype=np.int32)
+        n_samples = np.zeros(n, dtype=np.int32)
+        t = Timing()
+        self._check(self.lib.abea_getevents_blow5(self._h, ctypes.byref(cb), int(bool(rna)), n_events.ctypes.data,
+                                                  n_samples.ctypes.data, ctypes.byref(t)), "abea_getevents_blow5")
+        return n_events, n_samples, t.as_dict()
+
+    def events_download(self, n_events: np.ndarray):
+        """abea_getevents_download into a freshly laid out flat table: (events, event_ptr)."""
+        from .batch import EVENT_DTYPE
+        cnt = np.maximum(n_events, 0).astype(np.int64)
+        event_ptr = np.zeros(len(cnt), dtype=np.int64)
+        if len(cnt) > 1:
+            np.cumsum(cnt[:-1], out=event_ptr[1:])
+        events = np.zeros(int(cnt.sum()), dtype=EVENT_DTYPE)
+        self._check(self.lib.abea_getevents_download(self._h, events.ctypes.data if len(events) else None,
+                                                     event_ptr.ctypes.data), "abea_getevents_download")
+        return events, event_ptr
+
+    def raw_download(self, n_samples: np.ndarray):
+        """abea_raw_download: the float samples the last getevents worked on, (raw float32 flat, raw_ptr)."""
+        cnt = np.maximum(n_samples, 0).astype(np.int64)
+        raw_ptr = np.zeros(len(cnt), dtype=np.int64)
+        if len(cnt) > 1:
+            np.cumsum(cnt[:-1], out=raw_ptr[1:])
+        raw = np.zeros(int(cnt.sum()), dtype=np.float32)
+        self._check(self.lib.abea_raw_download(self._h, raw.ctypes.data if len(raw) else None, raw_ptr.ctypes.data),
+                    "abea_raw_download")
+        return raw, raw_ptr
 
     # -- the stages either side of the alignment ----------------------------------------------------------
     def estimate_scalings(self, n_reads: int, reverse_events: bool = False):

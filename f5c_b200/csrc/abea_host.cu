@@ -38,6 +38,7 @@
 #include "abea_kernels.cuh"
 #include "scaling_kernels.cuh"
 #include "events_kernels.cuh"
+#include "blow5_kernels.cuh"
 
 #define ABEA_VERSION_STR "abea-b200 0.1 (sm_100a)"
 
@@ -178,7 +179,7 @@ struct abea_ctx {
     /* Cycles per band of the three forms a read is filled in, cycles per traceback step and the band time of a fully
      * loaded sub-partition: the scheduler's model of the kernels. Starting values measured on B200 at 1.965 GHz
      * (profiles/); re-derived from the per-read clock64 counts of the batches that run (calibrate()). */
-    double cyc_wide = 400.0, cyc_narrow = 1000.0, cyc_long = 655.0, cyc_trace = 350.0;
+    double cyc_wide = 400.0, cyc_narrow = 1000.0, cyc_long = 655.0, cyc_trace = 40.0;
     int calib_mode = 1;        /* ABEA_CALIBRATE=0 keeps the starting values */
     int tb_mode = 1;           /* ABEA_TB: 1 segment-parallel traceback (a walk per lane), 0 the serial walk */
     int tb_margin = 64;        /* ABEA_TB_MARGIN: bands a speculative walk starts above its segment */
@@ -207,6 +208,8 @@ struct abea_ctx {
     std::vector<abea_sig_t> sigs;
     DevBuf d_raw, d_sum, d_sumsq, d_ts1, d_ts2, d_peaks, d_evcap, d_sigs, d_sigorder, d_nev, d_evptr, d_evout;
     DevBuf d_chunks, d_spec, d_fix, d_spec_cnt, d_fix_cnt, d_sync, d_spec_end;
+    DevBuf d_raw16, d_b5in, d_b5out, d_b5recs, d_b5len, d_b5status, d_b5hdr, d_b5rawoff; /* BLOW5 decode (blow5_kernels.cuh) */
+    HostBuf h_b5;
     int evt_chunk = 1024;            /* ABEA_EVT_CHUNK: samples per chunk of the speculative peak detector (multiple of 4) */
     std::vector<int32_t> nev;        /* event counts of the last abea_getevents */
     bool events_ready = false;
@@ -417,7 +420,7 @@ int calibrate(abea_ctx* c, int32_t long_thr) {
     if (wide.size() >= 2) c->cyc_wide = clampd(median(wide), 400.0);
     if (lng.size() >= 4) c->cyc_long = clampd(median(lng), 655.0);
     if (shared.size() >= 64) c->cyc_narrow = clampd(median(shared), 1000.0);
-    if (trace.size() >= 64) c->cyc_trace = clampd(median(trace), 350.0);
+    if (trace.size() >= 64) c->cyc_trace = std::min(700.0, std::max(2.0, median(trace))); /* 350 serial, a few tens segment-parallel */
     return 0;
 }
 
@@ -538,13 +541,16 @@ void abea_destroy(abea_ctx_t* c) {
                       &c->d_ready, &c->d_items, &c->d_capptr, &c->d_dense_off, &c->d_sreads, &c->d_scalings, &c->d_maps, &c->d_sres,
                       &c->d_raw, &c->d_sum, &c->d_sumsq, &c->d_ts1, &c->d_ts2, &c->d_peaks, &c->d_evcap, &c->d_sigs, &c->d_sigorder,
                       &c->d_nev, &c->d_evptr, &c->d_evout, &c->d_chunks, &c->d_spec, &c->d_fix, &c->d_spec_cnt, &c->d_fix_cnt,
-                      &c->d_sync, &c->d_spec_end};
+                      &c->d_sync, &c->d_spec_end, &c->d_raw16, &c->d_b5in, &c->d_b5out, &c->d_b5recs, &c->d_b5len, &c->d_b5status,
+                      &c->d_b5hdr, &c->d_b5rawoff};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->h_results.p) cudaFreeHost(c->h_results.p);
     if (c->h_pairs.p) cudaFreeHost(c->h_pairs.p);
     if (c->h_reads.p) cudaFreeHost(c->h_reads.p);
     if (c->h_items.p) cudaFreeHost(c->h_items.p);
+    for (HostBuf* hb : {&c->h_rseq, &c->h_rmeans, &c->h_rpairs, &c->h_rnp, &c->h_hostready, &c->h_rmeta, &c->h_b5})
+        if (hb->p) cudaFreeHost(hb->p);
     for (int i = 0; i < EV_COUNT; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -1143,9 +1149,13 @@ int abea_compact_results(abea_ctx_t* c, abea_pair_t* d_dst, int64_t dst_capacity
 
 /* ---- event detection ----------------------------------------------------------------------------------------- */
 
-int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_events_out, abea_timing_t* timing) {
+/* raw_kind: 0 the samples are s->raw (float, host); 1 they are s->raw_i16 (int16 ADC counts, host: half the bytes over
+ * PCIe, widened on the device as src/f5cio.c:461 does on the host); 2 they are already in d_raw at s->raw_ptr (put
+ * there by the BLOW5 decoder) */
+static int getevents_impl(abea_ctx_t* c, const abea_signals_t* s, int raw_kind, int rna, int32_t* n_events_out, abea_timing_t* timing) {
     if (!c || !s || s->n_reads < 0 || !n_events_out) return fail(c, ABEA_ERR_ARG, "bad signals");
-    if (s->n_reads > 0 && (!s->raw || !s->raw_ptr || !s->n_samples)) return fail(c, ABEA_ERR_ARG, "bad signals");
+    if (s->n_reads > 0 && (!s->raw_ptr || !s->n_samples)) return fail(c, ABEA_ERR_ARG, "bad signals");
+    if (s->n_reads > 0 && ((raw_kind == 0 && !s->raw) || (raw_kind == 1 && !s->raw_i16))) return fail(c, ABEA_ERR_ARG, "bad signals");
     if (s->offset && (!s->range || !s->digitisation)) return fail(c, ABEA_ERR_ARG, "offset without range / digitisation");
     CU(cudaSetDevice(c->device));
     c->events_ready = false;
@@ -1206,7 +1216,14 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
         CU(cudaMemcpyAsync(c->d_sigs.p, c->sigs.data(), (size_t)n * sizeof(abea_sig_t), cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->d_sigorder.p, order.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
         if (nck) CU(cudaMemcpyAsync(c->d_chunks.p, chunks.data(), nck * sizeof(abea_chunk_t), cudaMemcpyHostToDevice, c->stream));
-        if (raw_total > 0) CU(cudaMemcpyAsync(c->d_raw.p, s->raw, (size_t)raw_total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        if (raw_total > 0 && raw_kind == 0)
+            CU(cudaMemcpyAsync(c->d_raw.p, s->raw, (size_t)raw_total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        if (raw_total > 0 && raw_kind == 1) {
+            if (dev_reserve(c, c->d_raw16, (size_t)(raw_total + 1) * sizeof(int16_t))) return ABEA_ERR_CUDA;
+            CU(cudaMemcpyAsync(c->d_raw16.p, s->raw_i16, (size_t)raw_total * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
+            const int blocks = (int)std::min<int64_t>((raw_total + 255) / 256, (int64_t)c->sm_count * 16);
+            ABEA_LAUNCH(abea_i16_to_f32_kernel, blocks, 256, c->stream, (const int16_t*)c->d_raw16.p, (float*)c->d_raw.p, raw_total);
+        }
     }
     CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
     abea_det_param_t P;
@@ -1246,6 +1263,164 @@ int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_e
     c->last.h2d_ms = ev_ms(c, EV_H2D0, EV_H2D1);
     c->last.n_samples = raw_total;
     if (timing) *timing = c->last;
+    return ABEA_OK;
+}
+
+int abea_getevents(abea_ctx_t* c, const abea_signals_t* s, int rna, int32_t* n_events_out, abea_timing_t* timing) {
+    if (!s) return fail(c, ABEA_ERR_ARG, "bad signals");
+    return getevents_impl(c, s, (s->raw == nullptr && s->raw_i16 != nullptr) ? 1 : 0, rna, n_events_out, timing);
+}
+
+/* BLOW5 records in, event tables out: what read_slow5_single + event_single do per read on the host —
+ * slow5lib's record decompression, record parsing and signal decompression (slow5_press.c:921-1010, 1118-1170;
+ * slow5.c:2840-2930), the widening to float (src/f5cio.c:461), the conversion to pA and getevents (src/f5c.c:684-703)
+ * — for a whole batch on the device. The file's own bytes cross PCIe; the raw signal never exists on the host. */
+int abea_getevents_blow5(abea_ctx_t* c, const abea_blow5_t* f, int rna, int32_t* n_events_out, int32_t* n_samples_out,
+                         abea_timing_t* timing) {
+    if (!c || !f || f->n_reads < 0 || !n_events_out) return fail(c, ABEA_ERR_ARG, "bad records");
+    const int32_t n = f->n_reads;
+    if (n > 0 && (!f->bytes || !f->rec_ptr || !f->rec_len)) return fail(c, ABEA_ERR_ARG, "bad records");
+    if (f->record_method != B5_REC_NONE && f->record_method != B5_REC_ZLIB)
+        return fail(c, ABEA_ERR_ARG, "record compression %d is not supported (none and zlib are)", f->record_method);
+    if (f->signal_method != B5_SIG_NONE && f->signal_method != B5_SIG_SVB_ZD)
+        return fail(c, ABEA_ERR_ARG, "signal compression %d is not supported (none and svb-zd are)", f->signal_method);
+    CU(cudaSetDevice(c->device));
+    const double t0 = now_ms();
+    int64_t total_in = 0;
+    for (int32_t i = 0; i < n; i++) {
+        if (f->rec_len[i] < 0 || f->rec_ptr[i] < 0) return fail(c, ABEA_ERR_ARG, "bad record %d", i);
+        total_in = std::max(total_in, f->rec_ptr[i] + (int64_t)f->rec_len[i]);
+    }
+    if (dev_reserve(c, c->d_b5in, (size_t)total_in + 16)) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_b5recs, ((size_t)n + 1) * sizeof(abea_b5rec_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_b5len, ((size_t)n + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_b5status, ((size_t)n + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_b5hdr, ((size_t)n + 1) * sizeof(abea_b5hdr_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_b5rawoff, ((size_t)n + 1) * sizeof(int64_t))) return ABEA_ERR_CUDA;
+    const size_t hb = ((size_t)n + 1) * (sizeof(abea_b5rec_t) + sizeof(abea_b5hdr_t) + 2 * sizeof(int32_t) + sizeof(int64_t));
+    if (host_reserve(c, c->h_b5, hb)) return ABEA_ERR_CUDA;
+    abea_b5hdr_t* h_hdr = (abea_b5hdr_t*)c->h_b5.p;
+    abea_b5rec_t* h_recs = (abea_b5rec_t*)(h_hdr + (n + 1));
+    int64_t* h_rawoff = (int64_t*)(h_recs + (n + 1));
+    int32_t* h_len = (int32_t*)(h_rawoff + (n + 1));
+    int32_t* h_status = h_len + (n + 1);
+    CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
+    if (total_in > 0) CU(cudaMemcpyAsync(c->d_b5in.p, f->bytes, (size_t)total_in, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
+    CU(cudaEventRecord(c->ev[EV_D2H0], c->stream)); /* reused as "decode starts" */
+    const uint8_t* d_data = (const uint8_t*)c->d_b5in.p;
+    if (f->record_method == B5_REC_ZLIB && n > 0) {
+        /* a record's inflated size is not stored: guess generously (a raw signal deflates to ~60 %), let the kernel
+         * report an overflow, and retry with more — up to DEFLATE's own ceiling of 1032 : 1 */
+        const size_t smem = (size_t)B5_INFLATE_THREADS * sizeof(b5_tables_t);
+        CU(cudaFuncSetAttribute((const void*)abea_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        for (int64_t mult = 4;; mult *= 4) {
+            int64_t off = 0;
+            for (int32_t i = 0; i < n; i++) {
+                h_recs[i].in_off = f->rec_ptr[i];
+                h_recs[i].in_len = f->rec_len[i];
+                const int64_t cap = std::min<int64_t>(((int64_t)f->rec_len[i] * std::min<int64_t>(mult, 1032) + 4096 + 15) & ~(int64_t)15, 0x7ffffff0);
+                h_recs[i].out_off = off;
+                h_recs[i].out_cap = (int32_t)cap;
+                off += cap;
+            }
+            if (dev_reserve(c, c->d_b5out, (size_t)off + 16)) return ABEA_ERR_CUDA;
+            CU(cudaMemcpyAsync(c->d_b5recs.p, h_recs, (size_t)n * sizeof(abea_b5rec_t), cudaMemcpyHostToDevice, c->stream));
+            ABEA_LAUNCH_SMEM(abea_inflate_kernel, (n + B5_INFLATE_THREADS - 1) / B5_INFLATE_THREADS, B5_INFLATE_THREADS, smem, c->stream,
+                             (const abea_b5rec_t*)c->d_b5recs.p, n, (const uint8_t*)c->d_b5in.p, (uint8_t*)c->d_b5out.p,
+                             (int32_t*)c->d_b5len.p, (int32_t*)c->d_b5status.p);
+            CU(cudaMemcpyAsync(h_status, c->d_b5status.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(c->stream));
+            bool overflow = false;
+            for (int32_t i = 0; i < n; i++) {
+                if (h_status[i] == B5_ERR_DATA) return fail(c, ABEA_ERR_ARG, "record %d: malformed zlib stream", i);
+                overflow |= (h_status[i] == B5_ERR_OVERFLOW);
+            }
+            if (!overflow) break;
+            if (mult >= 1032) return fail(c, ABEA_ERR_ARG, "a record inflates beyond DEFLATE's maximum ratio");
+        }
+        d_data = (const uint8_t*)c->d_b5out.p;
+    } else if (n > 0) {
+        for (int32_t i = 0; i < n; i++) {
+            h_recs[i].in_off = f->rec_ptr[i];
+            h_recs[i].in_len = f->rec_len[i];
+            h_recs[i].out_off = f->rec_ptr[i];
+            h_recs[i].out_cap = f->rec_len[i];
+            h_len[i] = f->rec_len[i];
+        }
+        CU(cudaMemcpyAsync(c->d_b5recs.p, h_recs, (size_t)n * sizeof(abea_b5rec_t), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_b5len.p, h_len, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    std::vector<int32_t> ns((size_t)n, 0);
+    std::vector<int64_t> raw_ptr((size_t)n, 0);
+    std::vector<float> cal_off((size_t)n, 0.f), cal_range((size_t)n, 1.f), cal_dig((size_t)n, 1.f);
+    int64_t raw_total = 0;
+    if (n > 0) {
+        ABEA_LAUNCH(abea_blow5_parse_kernel, (n + 127) / 128, 128, c->stream, (const abea_b5rec_t*)c->d_b5recs.p, n, d_data,
+                    (const int32_t*)c->d_b5len.p, (const int32_t*)nullptr, f->signal_method, (abea_b5hdr_t*)c->d_b5hdr.p);
+        CU(cudaMemcpyAsync(h_hdr, c->d_b5hdr.p, (size_t)n * sizeof(abea_b5hdr_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+        for (int32_t i = 0; i < n; i++) {
+            if (h_hdr[i].status != B5_OK) return fail(c, ABEA_ERR_ARG, "record %d: malformed BLOW5 record", i);
+            ns[i] = h_hdr[i].n_samples;
+            raw_ptr[i] = raw_total;
+            h_rawoff[i] = raw_total;
+            raw_total += ns[i];
+            cal_dig[i] = (float)h_hdr[i].digitisation; /* the narrowing of read_slow5_single, src/f5cio.c:455-458 */
+            cal_off[i] = (float)h_hdr[i].offset;
+            cal_range[i] = (float)h_hdr[i].range;
+        }
+        if (dev_reserve(c, c->d_raw, (size_t)(raw_total + 1) * sizeof(float))) return ABEA_ERR_CUDA;
+        CU(cudaMemcpyAsync(c->d_b5rawoff.p, h_rawoff, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        ABEA_LAUNCH(abea_blow5_signal_kernel, (n + B5_SIG_WARPS - 1) / B5_SIG_WARPS, 32 * B5_SIG_WARPS, c->stream,
+                    (const abea_b5rec_t*)c->d_b5recs.p, n, d_data, (const abea_b5hdr_t*)c->d_b5hdr.p,
+                    (const int64_t*)c->d_b5rawoff.p, f->signal_method, (float*)c->d_raw.p, (int32_t*)c->d_b5status.p);
+        CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
+        CU(cudaMemcpyAsync(h_status, c->d_b5status.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+        for (int32_t i = 0; i < n; i++)
+            if (h_status[i] != B5_OK) return fail(c, ABEA_ERR_ARG, "record %d: malformed compressed signal", i);
+    } else {
+        CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    const float decode_ms = ev_ms(c, EV_D2H0, EV_D2H1);
+    const float in_ms = ev_ms(c, EV_H2D0, EV_H2D1);
+    if (n_samples_out)
+        for (int32_t i = 0; i < n; i++) n_samples_out[i] = ns[i];
+    abea_signals_t s;
+    memset(&s, 0, sizeof(s));
+    s.n_reads = n;
+    s.raw_ptr = raw_ptr.data();
+    s.n_samples = ns.data();
+    s.offset = cal_off.data();
+    s.range = cal_range.data();
+    s.digitisation = cal_dig.data();
+    const int rc = getevents_impl(c, &s, 2, rna, n_events_out, nullptr);
+    if (rc) return rc;
+    c->last.blow5_ms = decode_ms;
+    c->last.h2d_ms = in_ms;
+    c->last.h2d_bytes = total_in;
+    c->last.pack_ms = now_ms() - t0;
+    if (timing) *timing = c->last;
+    return ABEA_OK;
+}
+
+/* The float samples the last abea_getevents / abea_getevents_blow5 worked on (ADC counts as widened from int16, or
+ * whatever the caller handed over), read i at raw[raw_ptr[i] ..]: lets a test compare the device-side decoders. */
+int abea_raw_download(abea_ctx_t* c, float* raw, const int64_t* raw_ptr) {
+    if (!c || !raw_ptr) return fail(c, ABEA_ERR_ARG, "bad output");
+    if (!c->events_ready) return fail(c, ABEA_ERR_STATE, "abea_raw_download before abea_getevents");
+    CU(cudaSetDevice(c->device));
+    for (size_t i = 0; i < c->sigs.size(); i++)
+        if (c->sigs[i].n_samples > 0) {
+            if (!raw) return fail(c, ABEA_ERR_ARG, "bad output");
+            CU(cudaMemcpy(raw + raw_ptr[i], (const float*)c->d_raw.p + c->sigs[i].raw_off, (size_t)c->sigs[i].n_samples * sizeof(float),
+                          cudaMemcpyDeviceToHost));
+        }
     return ABEA_OK;
 }
 

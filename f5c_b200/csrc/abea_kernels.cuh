@@ -1248,9 +1248,16 @@ __device__ __forceinline__ bool abea_fill_step(abea_fill_ctx_t& cx, float* x, fl
  * so the STREAM instantiations keep the bound of 512 threads (124 registers). */
 #define ABEA_NARROW_BOUND(STREAM) ((STREAM) ? 32 * 16 : 32 * ABEA_NARROW_WARPS_MAX)
 
-__device__ __forceinline__ void abea_backoff() {
+/* A paused secondary warp must cost the warps that work next to it as little as possible: every poll is a dozen
+ * instructions through the same issue port (at a fixed 2 us request the polls were 6.5 % of all instructions issued,
+ * profiles/fill_narrow_opcode_mix_r01.txt — the hardware wakes a sleeper early), so the interval doubles up to
+ * ~32 us; a read that was waited for that long is a long one, and 32 us late is nothing against it. */
+__device__ __forceinline__ void abea_backoff(unsigned& ns) {
 #ifndef ABEA_SIMT_EMU
-    __nanosleep(2000);
+    __nanosleep(ns);
+    if (ns < 32768u) ns <<= 1;
+#else
+    (void)ns;
 #endif
 }
 
@@ -1295,11 +1302,12 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const f
 
     for (;;) {
         if (!primary) { /* let the long read on this sub-partition run alone */
+            unsigned ns = 1024u;
             for (;;) {
                 int busy = 0;
                 if (lane == 0) busy = atomicOr(&long_flag[slot], 0);
                 if (__shfl_sync(ABEA_FULL, busy, 0) == 0) break;
-                abea_backoff();
+                abea_backoff(ns);
             }
         }
         int32_t ridx = n_reads;

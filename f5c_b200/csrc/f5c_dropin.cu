@@ -293,6 +293,7 @@ void getevents_cuda(core_t* core, db_t* db) {
         if (d->n_samples[i]) memcpy(d->raw + d->raw_ptr[i], db->sig[i]->rawptr, (size_t)d->n_samples[i] * sizeof(float));
     });
     abea_signals_t sg;
+    memset(&sg, 0, sizeof(sg));
     sg.n_reads = n; sg.raw = d->raw; sg.raw_ptr = d->raw_ptr; sg.n_samples = d->n_samples;
     sg.offset = d->cal_off; sg.range = d->cal_range; sg.digitisation = d->cal_dig;
     if ((size_t)n > d->read_cap) { /* n_events / event_ptr staging is shared with align_cuda */

@@ -10,6 +10,8 @@
  *   abea_upload_batch / abea_run /  the three phases of align_cuda   src/f5c.cu:744-899 (pack + H2D),
  *   abea_download                   kept separable for measurement   :910-960 (kernels), :979-1030 (D2H + unpack)
  *   abea_model_fill_log_stdv        set_model's CACHED_LOG fill      src/model.c:179
+ *   abea_getevents_blow5            read_slow5_single's slow5lib     src/f5cio.c:421-470; slow5lib/src/slow5_press.c:921-1010,
+ *                                   calls + event_single's first half 1118-1170; slow5.c:2840-2930
  *   abea_getevents /                getevents (event detection) per  src/events.c:562-582, called by event_single
  *   abea_getevents_download         read + the pA conversion         src/f5c.c:692-703
  *   abea_estimate_scalings          estimate_scalings_using_mom      src/align.c:58-106, called per read by event_single
@@ -76,6 +78,7 @@ typedef struct {
     double events_ms;        /* device: abea_events_kernel (abea_getevents) */
     int64_t n_samples;       /* raw samples of the last abea_getevents */
     double ragged_ms;        /* host: wall time of the last abea_align_ragged call, everything included */
+    double blow5_ms;         /* device: BLOW5 record inflate + parse + signal decode (abea_getevents_blow5) */
 } abea_timing_t;
 
 /* Create a context on CUDA device `device` (cudaSetDevice is applied on every call). */
@@ -121,6 +124,18 @@ int abea_download(abea_ctx_t* ctx, abea_pair_t* pairs, const int64_t* pair_ptr, 
  * valid until the next abea_getevents). */
 int abea_getevents(abea_ctx_t* ctx, const abea_signals_t* signals, int rna, int32_t* n_events_out, abea_timing_t* timing);
 int abea_getevents_download(abea_ctx_t* ctx, abea_event_t* events, const int64_t* event_ptr);
+
+/* ---- BLOW5 records decoded on the device ----
+ * abea_getevents_blow5: abea_getevents for reads that are still BLOW5 records — the file's own bytes cross PCIe and
+ * slow5lib's reader side runs on the GPU: record decompression (zlib inflate, slow5lib/src/slow5_press.c:921-1010),
+ * record parsing (slow5.c:2840-2930), signal decompression (svb-zd, slow5_press.c:1118-1170), the widening to float
+ * and read_slow5_single's narrowing of the calibration to float (src/f5cio.c:455-461). n_samples_out (may be NULL)
+ * receives each read's sample count. Everything after that is abea_getevents: the event tables stay on the device for
+ * abea_getevents_download / abea_upload_batch(events == NULL). zstd records and ex-zd signals return ABEA_ERR_ARG.
+ * abea_raw_download: the float samples of the last abea_getevents / abea_getevents_blow5, for tests of the decoders. */
+int abea_getevents_blow5(abea_ctx_t* ctx, const abea_blow5_t* records, int rna, int32_t* n_events_out,
+                         int32_t* n_samples_out, abea_timing_t* timing);
+int abea_raw_download(abea_ctx_t* ctx, float* raw, const int64_t* raw_ptr);
 
 /* ---- the stages either side of the alignment; bit-identical to the reference's CPU code ----
  *

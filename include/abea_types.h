@@ -110,7 +110,24 @@ typedef struct {
     const float* offset;
     const float* range;
     const float* digitisation;
+    const int16_t* raw_i16; /* the ADC counts as the file holds them, used when raw == NULL: 2 bytes per sample cross PCIe
+                             * and the widening to float (src/f5cio.c:461) is done on the device */
 } abea_signals_t;
+
+/* BLOW5 records as they lie in the file (slow5lib v1.x binary format, slow5lib/src/slow5.c): the input of the
+ * device-side record decode. A host reader only walks the framing (uint64 size + payload per record).
+ *   bytes         : the records' payloads back to back (what follows each record's size field)
+ *   rec_ptr/len   : first byte and stored size of record i
+ *   record_method : 0 none, 1 zlib (the record-compression byte of the file header; zstd = 2 is not supported)
+ *   signal_method : 0 none, 1 svb-zd (the signal-compression byte, files >= v0.2.0; ex-zd = 2 is not supported) */
+typedef struct {
+    int32_t n_reads;
+    const uint8_t* bytes;
+    const int64_t* rec_ptr;
+    const int32_t* rec_len;
+    int32_t record_method;
+    int32_t signal_method;
+} abea_blow5_t;
 
 /* A ragged batch of reads in flat (CSR-style) form: what the reference's align_cuda packs db_t into
  * (src/f5c.cu:744-800) and what every implementation in this repo (CUDA path, oracle, _ref shim)

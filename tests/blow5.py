@@ -58,8 +58,12 @@ class Blow5:
         q = 2 + l
         rg, dig, off, rng, sr, n = struct.unpack("<IddddQ", rec[q:q + 44])
         q += 44
-        assert self.signal_method == 0, "signal compression is decoded on the device (tests use it as the subject, not here)"
-        sig = np.frombuffer(rec[q:q + 2 * n], dtype="<i2").copy()
+        if self.signal_method == 0:
+            sig = np.frombuffer(rec[q:q + 2 * n], dtype="<i2").copy()
+        elif self.signal_method == 1:     # svb-zd: len_raw_signal holds the BYTES of the compressed signal
+            sig = svb_zd_decode(rec[q:q + n])
+        else:
+            raise NotImplementedError("signal compression %d" % self.signal_method)
         return rid, dig, off, rng, sr, sig
 
     def __len__(self):
@@ -79,3 +83,24 @@ def read_fasta(path: str):
     if name is not None:
         out.append((name, "".join(buf)))
     return out
+
+
+def svb_zd_decode(buf: bytes) -> np.ndarray:
+    """Host restatement of slow5lib's svb-zd signal decompression (slow5_press.c:1118-1170, streamvbyte_decode.c,
+    streamvbyte_zigzag.c:34-40), numpy: [uint32 count][2-bit keys, 4 per byte: bytes-1][little-endian values]; value ->
+    zigzag decode -> running sum, truncated to int16."""
+    (count,) = struct.unpack("<I", buf[:4])
+    nkeys = (count + 3) // 4
+    keys = np.frombuffer(buf[4:4 + nkeys], dtype=np.uint8)
+    codes = ((keys[:, None] >> np.array([0, 2, 4, 6], dtype=np.uint8)) & 3).reshape(-1)[:count].astype(np.int64)
+    lens = codes + 1
+    offs = np.zeros(count, dtype=np.int64)
+    np.cumsum(lens[:-1], out=offs[1:])
+    data = np.frombuffer(buf[4 + nkeys:], dtype=np.uint8).astype(np.uint32)
+    data = np.concatenate([data, np.zeros(4, dtype=np.uint32)])
+    val = data[offs].copy()
+    for j in range(1, 4):
+        val |= np.where(lens > j, data[offs + j] << np.uint32(8 * j), np.uint32(0))
+    assert int(offs[-1] + lens[-1]) == len(buf) - 4 - nkeys if count else True
+    zz = (val >> np.uint32(1)).astype(np.int64) ^ -(val & np.uint32(1)).astype(np.int64)
+    return np.cumsum(zz).astype(np.int64).astype(np.int16) if count else np.zeros(0, dtype=np.int16)

@@ -139,6 +139,14 @@ static inline double __hiloint2double(int hi, int lo) {
 static inline int __double2hiint(double d) { return (int)(simt::pack(d) >> 32); }
 static inline int __double2loint(double d) { return (int)(simt::pack(d) & 0xffffffffu); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline unsigned __brev(unsigned x) {
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+    return (x >> 16) | (x << 16);
+}
+static inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }

@@ -1,0 +1,196 @@
+"""BLOW5 records decoded on the device (f5c_b200/csrc/blow5_kernels.cuh) and the int16 front door of the
+event detection. The checker is tests/blow5.py (Python's zlib + a numpy restatement of slow5lib's svb-zd) on fixtures
+written by the reference's own slow5lib (tests/golden/ecoli: a copy of test/ecoli_2kb_region/reads.blow5 — zlib, v0.1.0
+— and its first 8 records re-encoded with svb-zd signal compression by tests/golden/make_blow5_fixtures.py).
+The CPU tests run the product kernels on the SIMT emulator; the GPU tests run all 112 records and compare the events
+with the reference's golden event tables (tests/golden/ecoli_all.json)."""
+import hashlib
+import json
+import os
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+import blow5
+import oracle_lib as ol
+from f5c_b200 import models
+from f5c_b200.abea import AbeaContext, AbeaError
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "simt", "libabea_emu.so")
+ECOLI = os.path.join(HERE, "golden", "ecoli")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "simt")], stderr=subprocess.DEVNULL)
+    return EMU
+
+
+def payload_of(f: blow5.Blow5, idx):
+    """The stored bytes of the chosen records back to back + (rec_ptr, rec_len): what a host reader hands over after
+    walking the file's framing."""
+    chunks = [f.record_bytes(i) for i in idx]
+    rec_len = np.array([len(c) for c in chunks], dtype=np.int32)
+    rec_ptr = np.zeros(len(chunks), dtype=np.int64)
+    np.cumsum(rec_len[:-1].astype(np.int64), out=rec_ptr[1:])
+    return np.frombuffer(b"".join(chunks), dtype=np.uint8).copy(), rec_ptr, rec_len
+
+
+def check_decode(ctx, f, idx, f_truth=None, check_events=True):
+    f_truth = f_truth or f
+    payload, rec_ptr, rec_len = payload_of(f, idx)
+    nev, ns, t = ctx.getevents_blow5(payload, rec_ptr, rec_len, f.record_method, f.signal_method)
+    raw, raw_ptr = ctx.raw_download(ns)
+    ev, ev_ptr = ctx.events_download(nev)
+    for j, i in enumerate(idx):
+        rid, dig, off, rng, sr, sig = f_truth.read(i)
+        assert int(ns[j]) == len(sig), (i, "sample count")
+        got = raw[int(raw_ptr[j]):int(raw_ptr[j]) + int(ns[j])]
+        assert np.array_equal(got, sig.astype(np.float32)), (i, "decoded signal")
+        if check_events:
+            pa = ((sig.astype(np.float32) + np.float32(off)) * np.float32(np.float32(rng) / np.float32(dig))).astype(np.float32)
+            want = ol.port_getevents(pa)
+            assert int(nev[j]) == len(want), (i, "event count")
+            assert ol._events_equal(ev[int(ev_ptr[j]):int(ev_ptr[j]) + int(nev[j])], want), (i, "events")
+    return t
+
+
+def test_python_checker_reads_the_slow5lib_fixtures():
+    f0 = blow5.Blow5(os.path.join(ECOLI, "reads.blow5"))
+    assert len(f0) == 112 and f0.record_method == blow5.RECORD_ZLIB and f0.signal_method == 0
+    for name in ("ecoli8_zlib_svbzd.blow5", "ecoli8_none_svbzd.blow5"):
+        f = blow5.Blow5(os.path.join(ECOLI, name))
+        assert len(f) == 8 and f.signal_method == 1
+        for i in range(8):
+            a, b = f.read(i), f0.read(i)
+            assert a[0] == b[0] and a[1:5] == b[1:5] and np.array_equal(a[5], b[5])
+
+
+def test_emulated_inflate_and_events_zlib_records(emu):
+    """zlib records (dynamic Huffman blocks as slow5lib's deflate level writes them): two short reads on the emulator."""
+    f = blow5.Blow5(os.path.join(ECOLI, "reads.blow5"))
+    order = np.argsort([r[1] for r in f.records])
+    with AbeaContext(0, lib_path=emu) as ctx:
+        check_decode(ctx, f, [int(order[0]), int(order[1])])
+
+
+@pytest.mark.parametrize("name", ["ecoli8_zlib_svbzd.blow5", "ecoli8_none_svbzd.blow5"])
+def test_emulated_svbzd_signal_decode(emu, name):
+    f = blow5.Blow5(os.path.join(ECOLI, name))
+    order = np.argsort([r[1] for r in f.records])
+    with AbeaContext(0, lib_path=emu) as ctx:
+        check_decode(ctx, f, [int(order[0]), int(order[2])], check_events=False)
+
+
+def synth_records(levels, signals, rid=b"synthetic-read"):
+    """BLOW5 v0.1.0-style records (no signal compression) built here, deflated at the given zlib levels — level 0 gives
+    stored blocks, level 1 with Z_FIXED fixed-Huffman blocks."""
+    recs = []
+    for (level, strategy), sig in zip(levels, signals):
+        body = (np.uint16(len(rid) + 1).tobytes() + rid + b"\0" + np.uint32(0).tobytes() +
+                np.array([8192.0, 10.0, 1400.0, 4000.0], dtype="<f8").tobytes() + np.uint64(len(sig)).tobytes() +
+                sig.astype("<i2").tobytes() + b"aux-fields-are-skipped")
+        co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+        recs.append(co.compress(body) + co.flush())
+    return recs
+
+
+def test_emulated_inflate_block_types_and_errors(emu):
+    """Stored, fixed-Huffman and dynamic blocks, long matches (a constant stretch), an empty signal; a truncated stream
+    and a corrupted one must be reported, not decoded."""
+    rng = np.random.default_rng(3)
+    sigs = [rng.integers(300, 700, 900).astype(np.int16),
+            np.concatenate([np.full(700, 512, dtype=np.int16), rng.integers(-200, 900, 300).astype(np.int16)]),
+            (500 + 40 * np.sin(np.arange(1500) / 7.0) + rng.normal(0, 3, 1500)).astype(np.int16),
+            np.zeros(0, dtype=np.int16)]
+    levels = [(0, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_FIXED), (9, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY)]
+    recs = synth_records(levels, sigs)
+    rec_len = np.array([len(r) for r in recs], dtype=np.int32)
+    rec_ptr = np.zeros(len(recs), dtype=np.int64)
+    np.cumsum(rec_len[:-1].astype(np.int64), out=rec_ptr[1:])
+    payload = np.frombuffer(b"".join(recs), dtype=np.uint8).copy()
+    with AbeaContext(0, lib_path=emu) as ctx:
+        nev, ns, _ = ctx.getevents_blow5(payload, rec_ptr, rec_len, 1, 0)
+        assert [int(x) for x in ns] == [len(s) for s in sigs]
+        raw, raw_ptr = ctx.raw_download(ns)
+        for j, s in enumerate(sigs):
+            assert np.array_equal(raw[int(raw_ptr[j]):int(raw_ptr[j]) + len(s)], s.astype(np.float32)), j
+        bad = payload.copy()
+        with pytest.raises(AbeaError):
+            ctx.getevents_blow5(bad[:int(rec_len[0]) - 7], rec_ptr[:1], np.array([rec_len[0] - 7], dtype=np.int32), 1, 0)
+        bad[int(rec_ptr[2]) + 40: int(rec_ptr[2]) + 60] ^= 0x5A
+        with pytest.raises(AbeaError):
+            ctx.getevents_blow5(bad, rec_ptr, rec_len, 1, 0)
+        with pytest.raises(AbeaError):     # zstd records are not supported
+            ctx.getevents_blow5(payload, rec_ptr, rec_len, 3, 0)
+
+
+def test_emulated_int16_front_door(emu):
+    """abea_signals_t.raw_i16: ADC counts as int16 give the same event tables as the float samples."""
+    f = blow5.Blow5(os.path.join(ECOLI, "reads.blow5"))
+    order = np.argsort([r[1] for r in f.records])
+    recs = [f.read(int(order[j])) for j in (0, 1)]
+    sig = np.concatenate([r[5] for r in recs])
+    ns = np.array([len(r[5]) for r in recs], dtype=np.int32)
+    ptr = np.array([0, ns[0]], dtype=np.int64)
+    cal = tuple(np.array([r[j] for r in recs], dtype=np.float32) for j in (2, 3, 1))
+    with AbeaContext(0, lib_path=emu) as ctx:
+        e16, p16, n16, _ = ctx.getevents(sig, ptr, ns, cal)
+        e32, p32, n32, _ = ctx.getevents(sig.astype(np.float32), ptr, ns, cal)
+    assert np.array_equal(n16, n32) and e16.tobytes() == e32.tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gctx(built):
+    c = AbeaContext(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+def test_gpu_blow5_all_112_records_to_golden_events(gctx):
+    """BLOW5 bytes -> events on the GPU for every record of the ecoli fixture, against the UNMODIFIED reference's event
+    tables (tests/golden/ecoli_all.json: f5cref_getevents on slow5lib-decoded signals) and the Python-decoded signals."""
+    gold = {r["name"]: r for r in json.load(open(os.path.join(HERE, "golden", "ecoli_all.json")))["reads"]}
+    f = blow5.Blow5(os.path.join(ECOLI, "reads.blow5"))
+    idx = list(range(len(f)))
+    payload, rec_ptr, rec_len = payload_of(f, idx)
+    nev, ns, t = gctx.getevents_blow5(payload, rec_ptr, rec_len, f.record_method, f.signal_method)
+    raw, raw_ptr = gctx.raw_download(ns)
+    ev, ev_ptr = gctx.events_download(nev)
+
+    def event_sha(e):
+        return hashlib.sha256(np.concatenate([e["start"].astype("<u8").view(np.uint8), e["length"].astype("<f4").view(np.uint8),
+                                              e["mean"].astype("<f4").view(np.uint8), e["stdv"].astype("<f4").view(np.uint8)]).tobytes()).hexdigest()
+    for j in idx:
+        rid, dig, off, rng, sr, sig = f.read(j)
+        assert np.array_equal(raw[int(raw_ptr[j]):int(raw_ptr[j]) + int(ns[j])], sig.astype(np.float32)), rid
+        g = gold[rid]
+        assert int(ns[j]) == g["n_samples"] and int(nev[j]) == g["n_events"], rid
+        assert event_sha(ev[int(ev_ptr[j]):int(ev_ptr[j]) + int(nev[j])]) == g["events_sha256"], rid
+    assert t["blow5_ms"] > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["ecoli8_zlib_svbzd.blow5", "ecoli8_none_svbzd.blow5"])
+def test_gpu_blow5_svbzd(gctx, name):
+    f = blow5.Blow5(os.path.join(ECOLI, name))
+    check_decode(gctx, f, list(range(len(f))))
+
+
+@pytest.mark.gpu
+def test_gpu_int16_front_door_pinned(gctx):
+    f = blow5.Blow5(os.path.join(ECOLI, "reads.blow5"))
+    recs = [f.read(i) for i in range(0, 112, 7)]
+    sig = np.concatenate([r[5] for r in recs])
+    ns = np.array([len(r[5]) for r in recs], dtype=np.int32)
+    ptr = np.zeros(len(recs), dtype=np.int64)
+    np.cumsum(ns[:-1].astype(np.int64), out=ptr[1:])
+    cal = tuple(np.array([r[j] for r in recs], dtype=np.float32) for j in (2, 3, 1))
+    e16, p16, n16, _ = gctx.getevents(gctx.pin_array(sig), ptr, ns, cal)
+    e32, p32, n32, _ = gctx.getevents(sig.astype(np.float32), ptr, ns, cal)
+    assert np.array_equal(n16, n32) and e16.tobytes() == e32.tobytes()

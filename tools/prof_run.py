@@ -27,4 +27,11 @@ print("  fill cycles/band ", np.round(cyc["fill_cycles"][order] / nb[order], 1).
 print("  trace cycles/step", np.round(cyc["trace_cycles"][order] / ev[order], 1).tolist())
 sel = np.argsort(nb)[len(nb)//2 - 3: len(nb)//2 + 3]
 print("median reads: fill cycles/band", np.round(cyc["fill_cycles"][sel] / nb[sel], 1).tolist(), " trace cycles/step", np.round(cyc["trace_cycles"][sel] / ev[sel], 1).tolist())
+try:
+    rs = ctx.read_respec(b.n_reads)
+    print("traceback: segments re-checked per read: mean %.2f max %d; reads with any %d of %d; margin %s; mode %s" % (
+        rs.mean(), rs.max(), int((rs > 0).sum()), b.n_reads, os.environ.get("ABEA_TB_MARGIN", "default"), os.environ.get("ABEA_TB", "default")))
+except Exception as e:
+    print("respec n/a", e)
+print("scheduler model", ctx.scheduler_model())
 print("sum fill Mcycles", cyc["fill_cycles"].sum() / 1e6, "sum trace Mcycles", cyc["trace_cycles"].sum() / 1e6, "max fill+trace Mcycles", (cyc["fill_cycles"] + cyc["trace_cycles"]).max() / 1e6)
