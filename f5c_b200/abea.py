@@ -92,6 +92,7 @@ def _bind(path: str):
     lib.abea_getevents_download.argtypes = [vp, vp, vp]
     lib.abea_getevents_blow5.argtypes = [vp, ctypes.POINTER(CBlow5), ctypes.c_int, vp, vp, ctypes.POINTER(Timing)]
     lib.abea_raw_download.argtypes = [vp, vp, vp]
+    lib.abea_write_pairs.argtypes = [ctypes.c_char_p, ctypes.c_int, i32, vp, vp, vp, vp, vp]
     lib.abea_estimate_scalings.argtypes = [vp, ctypes.c_int, vp, ctypes.POINTER(Timing)]
     lib.abea_scaling_stage.argtypes = [vp, i32, ctypes.POINTER(Timing)]
     lib.abea_scaling_download.argtypes = [vp, vp, vp, vp]
@@ -466,3 +467,18 @@ def scaling_db(ctx: AbeaContext, batch: ReadBatch,
     align left on the device: postalign + recalibrate_model + the read flags."""
     t = ctx.scaling_stage(min_num_events_to_rescale)
     return ctx.scaling_download(batch, t)
+
+
+def write_pairs(path: str, names, aln: Alignment, flags: np.ndarray | None = None, append: bool = False, lib_path: str | None = None):
+    """abea_write_pairs: the reference's --print-banded-aln dump (src/f5c.c:989-1006) of an Alignment."""
+    lib = load_library(lib_path)
+    n = len(names)
+    arr = (ctypes.c_char_p * max(n, 1))(*[s.encode() if isinstance(s, str) else s for s in names])
+    pairs = np.ascontiguousarray(aln.pairs)
+    pp = np.ascontiguousarray(aln.pair_ptr, dtype=np.int64)
+    npairs = np.ascontiguousarray(aln.n_pairs, dtype=np.int32)
+    fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint32)
+    rc = lib.abea_write_pairs(path.encode(), int(append), n, ctypes.cast(arr, ctypes.c_void_p), npairs.ctypes.data,
+                              pairs.ctypes.data, pp.ctypes.data, None if fl is None else fl.ctypes.data)
+    if rc != 0:
+        raise AbeaError(f"abea_write_pairs failed ({rc})")

@@ -1610,6 +1610,25 @@ int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pair
     return ABEA_OK;
 }
 
+/* The reference's --print-banded-aln dump (src/f5c.c:989-1006), for diffing this path against an f5c run: per read
+ * that did not fail the alignment,  ">name\tN_ALGN_PAIR:n\t{ref_pos,read_pos}\n"  then "{k,e}\t" per pair and "\n". */
+int abea_write_pairs(const char* path, int append, int32_t n_reads, const char* const* names, const int32_t* n_pairs,
+                     const abea_pair_t* pairs, const int64_t* pair_ptr, const uint32_t* read_stat_flag) {
+    if (!path || n_reads < 0 || (n_reads > 0 && (!names || !n_pairs || !pair_ptr))) return ABEA_ERR_ARG;
+    FILE* fp = strcmp(path, "-") == 0 ? stdout : fopen(path, append ? "a" : "w");
+    if (!fp) return ABEA_ERR_ARG;
+    for (int32_t i = 0; i < n_reads; i++) {
+        if (read_stat_flag && (read_stat_flag[i] & ABEA_FAILED_ALIGNMENT)) continue;
+        fprintf(fp, ">%s\tN_ALGN_PAIR:%d\t{ref_pos,read_pos}\n", names[i], (int)n_pairs[i]);
+        const abea_pair_t* p = pairs + pair_ptr[i];
+        for (int32_t j = 0; j < n_pairs[i]; j++) fprintf(fp, "{%d,%d}\t", p[j].ref_pos, p[j].read_pos);
+        fprintf(fp, "\n");
+    }
+    if (fp != stdout) fclose(fp);
+    else fflush(fp);
+    return ABEA_OK;
+}
+
 /* ---- the ragged front door ------------------------------------------------------------------------------------ */
 
 int abea_scheduler_model(abea_ctx_t* c, double* cycles4) {

@@ -201,6 +201,12 @@ int abea_device_results(abea_ctx_t* ctx, const abea_pair_t** d_pairs, const int3
  * suffices). */
 int abea_compact_results(abea_ctx_t* ctx, abea_pair_t* d_dst, int64_t dst_capacity, int64_t* total_pairs);
 
+/* The reference's --print-banded-aln dump (src/f5c.c:989-1006) of a batch's pair lists, byte for byte the text f5c
+ * prints, so that this path can be diffed against an f5c run: reads whose read_stat_flag has ABEA_FAILED_ALIGNMENT are
+ * skipped (read_stat_flag may be NULL: none is). path "-" = stdout. Host-side formatting only. */
+int abea_write_pairs(const char* path, int append, int32_t n_reads, const char* const* names, const int32_t* n_pairs,
+                     const abea_pair_t* pairs, const int64_t* pair_ptr, const uint32_t* read_stat_flag);
+
 /* Pinned host memory for callers that want the H2D/D2H copies to run at full PCIe rate. */
 void* abea_host_alloc(size_t bytes);
 void abea_host_free(void* p);

@@ -194,3 +194,57 @@ def test_gpu_int16_front_door_pinned(gctx):
     e16, p16, n16, _ = gctx.getevents(gctx.pin_array(sig), ptr, ns, cal)
     e32, p32, n32, _ = gctx.getevents(sig.astype(np.float32), ptr, ns, cal)
     assert np.array_equal(n16, n32) and e16.tobytes() == e32.tobytes()
+
+
+def banded_aln_text(names, aln, flags):
+    """The text of the reference's --print-banded-aln block (src/f5c.c:989-1006), formatted independently in Python."""
+    out = []
+    for i, nm in enumerate(names):
+        if flags is not None and (int(flags[i]) & 0x002):
+            continue
+        out.append(">%s\tN_ALGN_PAIR:%d\t{ref_pos,read_pos}\n" % (nm, int(aln.n_pairs[i])))
+        p = aln.read_pairs(i)
+        out.append("".join("{%d,%d}\t" % (int(a), int(b)) for a, b in zip(p["ref_pos"], p["read_pos"])) + "\n")
+    return "".join(out)
+
+
+def test_pair_dump_matches_reference_format(emu, tmp_path):
+    """abea_write_pairs on the oracle's pair lists of a few synthetic reads (one failing QC, one flagged as failed)."""
+    from f5c_b200 import synth
+    from f5c_b200.abea import write_pairs
+    from edge_cases import edge_batch
+    b = edge_batch()
+    k, m = models.load_model("r9")
+    want = ol.port_align(b, ol.full_model(m))
+    names = ["read/%d" % i for i in range(b.n_reads)]
+    flags = np.where(want.n_pairs > 0, 0, 2).astype(np.uint32)
+    path = str(tmp_path / "aln.txt")
+    write_pairs(path, names, want, flags, lib_path=emu)
+    assert open(path).read() == banded_aln_text(names, want, flags)
+    write_pairs(path, names, want, None, lib_path=emu)
+    assert open(path).read() == banded_aln_text(names, want, None)
+
+
+@pytest.mark.gpu
+def test_gpu_blow5_to_banded_aln_dump(built, tmp_path):
+    """tools/blow5_eventalign_dump.py: BLOW5 + FASTA -> the --print-banded-aln text, every stage on the GPU; every read's
+    pair list in the text must be the one the UNMODIFIED reference produced (tests/golden/ecoli_all.json)."""
+    import sys
+    from f5c_b200.batch import PAIR_DTYPE
+    out = str(tmp_path / "dump.txt")
+    subprocess.check_call([sys.executable, os.path.join(os.path.dirname(HERE), "tools", "blow5_eventalign_dump.py"),
+                           os.path.join(ECOLI, "reads.blow5"), os.path.join(ECOLI, "reads.fasta"), out])
+    gold = {r["name"]: r for r in json.load(open(os.path.join(HERE, "golden", "ecoli_all.json")))["reads"]}
+    lines = open(out).read().split("\n")
+    seen = 0
+    for hdr, body in zip(lines[0::2], lines[1::2]):
+        if not hdr:
+            continue
+        name, npair, _ = hdr[1:].split("\t")
+        n = int(npair.split(":")[1])
+        toks = [t for t in body.split("\t") if t]
+        assert len(toks) == n == gold[name]["n_pairs"], name
+        arr = np.array([tuple(int(x) for x in t[1:-1].split(",")) for t in toks], dtype=PAIR_DTYPE)
+        assert hashlib.sha256(arr.tobytes()).hexdigest() == gold[name]["pairs_sha256"], name
+        seen += 1
+    assert seen == sum(1 for r in gold.values() if not (r["flags"] & 2))
