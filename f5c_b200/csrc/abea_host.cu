@@ -677,11 +677,12 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         nb += NB;
         ne += r.n_events;
     }
-    /* The longest reads go to the wide kernel (one CTA of 4 warps per read). Measured on B200 (profiles/README.md):
-     * a narrow warp alone on its SM sub-partition needs ~655 cycles per band, a wide CTA alone on its SM ~490, and
-     * when SMs are shared the wide form has no advantage. So a read is made wide only when it would outlast the whole
-     * batch even as a lone narrow warp — it is going to run (nearly) alone at the end anyway, and then the wide form
-     * finishes it sooner. cfg2 (log-normal sigma 0.5) has no such read; cfg3 (sigma 1.0) has a handful. */
+    /* The longest reads go to the wide kernel (one CTA of 4 warps per read). Measured on B200 (profiles/): a narrow
+     * warp alone on its SM sub-partition needs ~650 cycles per band, a wide CTA alone on its SM ~400 (cyc_long /
+     * cyc_wide of the scheduler's model, re-measured per batch), and when SMs are shared the wide form has no
+     * advantage. So a read is made wide only when it would outlast the whole batch even as a lone narrow warp — it is
+     * going to run (nearly) alone at the end anyway, and then the wide form finishes it sooner. The target config
+     * (log-normal sigma 0.5) sends 6-8 reads wide; cfg3 (sigma 1.0) and cfg4 fill the cap of SMs / 4. */
     c->n_wide = 0;
     if (c->wide_mode && !c->reads.empty()) {
         const double thr = wide_threshold(c, nb);
@@ -885,14 +886,14 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
         launches++;
         {
             /* The longest n_wide reads: one CTA of 4 warps each (wide kernel) on a second stream, beside the persistent
-             * narrow warps (4 CTAs of 4 warps per SM, each warp pulls reads longest-first). The FAST instantiations
-             * take the reads whose inputs passed validation, the EXACT ones the rest (normally none). */
+             * narrow CTAs (one CTA of 12 warps per remaining SM, each warp pulls reads longest-first). The FAST
+             * instantiations take the reads whose inputs passed validation, the EXACT ones the rest (normally none). */
             const int32_t nw = c->n_wide;
             if (nw > 0) {
                 CU(cudaEventRecord(c->ev_fork, c->stream));
                 CU(cudaStreamWaitEvent(c->wide_stream, c->ev_fork, 0));
                 int wblocks = std::min(c->sm_count, (int)nw);
-                /* A wide CTA is only faster than a lone narrow warp when it has its SM to itself (measured: 495
+                /* A wide CTA is only faster than a lone narrow warp when it has its SM to itself (measured: 400
                  * cycles/band alone, 800 beside a narrow CTA). It therefore asks for so much dynamic shared memory
                  * that no narrow CTA fits on the same SM. Tiny batches (every read wide) do not need the exclusion. */
                 const size_t excl = (n > nw) ? (size_t)160 * 1024 : 0;

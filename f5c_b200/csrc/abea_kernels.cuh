@@ -8,8 +8,11 @@
  *                            range check of all inputs that selects the fast or the exact arithmetic per read
  *   abea_fill_kernel         one WARP per read, 4 band cells per lane, whole band state in registers; neighbours
  *                            through warp shuffles; 2-bit packed trace, one coalesced 128-B store per 4 bands;
- *                            last-column arg-max folded into the fill; persistent warps pulling reads longest-first
- *   abea_traceback_kernel    one warp per read walking the packed trace, pairs written in ascending order
+ *                            last-column arg-max folded into the fill; persistent warps pulling reads longest-first;
+ *                            traceback + QC of a read fused in, by the warp that filled it (abea_traceback_par:
+ *                            128 walks per warp over 128 stretches of the path, speculative entries verified)
+ *   abea_fill_wide_kernel    one CTA of four warps per read, one band cell per lane, for the reads that set the makespan
+ *   abea_load_kernel         streams a pinned host batch in, in the order the fill will ask for it
  *
  * Arithmetic contract (bit-exact against the reference CPU align(), src/align.c:180-559):
  * emission in float with explicit round-to-nearest intrinsics (no FMA contraction), the three transition sums in
@@ -767,14 +770,38 @@ __device__ __forceinline__ uint32_t abea_tbw_step(abea_tbw_t& w, const uint32_t*
     return from;
 }
 
-/* walk while the cell is valid and its band is above `floor_band`; returns the number of steps */
-__device__ __forceinline__ int32_t abea_tbw_run(abea_tbw_t& w, const uint32_t* __restrict__ tr, int32_t floor_band) {
-    int32_t n = 0;
-    while ((w.ce | w.ck) >= 0 && w.ce + w.ck + 2 > floor_band) {
-        abea_tbw_step(w, tr);
-        n++;
+/* K walkers per lane, stepped together: a step is one round trip to the trace (L2 latency under load, the lanes of a
+ * warp read 32 different lines), so what a lane's time is made of is round trips, and K independent walks in flight
+ * cost one. The loads of all K walkers are issued before any is used; a walker that is not `act` re-reads band 2 of
+ * the read (always there) and keeps its state. */
+#define ABEA_TB_K 4
+__device__ __forceinline__ void abea_tbw_step_all(abea_tbw_t (&w)[ABEA_TB_K], const bool (&act)[ABEA_TB_K],
+                                                  const uint32_t* __restrict__ tr, uint32_t (&from)[ABEA_TB_K]) {
+    uint32_t tw[ABEA_TB_K];
+    int32_t e1[ABEA_TB_K], e2[ABEA_TB_K], bb[ABEA_TB_K], oo[ABEA_TB_K];
+#pragma unroll
+    for (int k = 0; k < ABEA_TB_K; k++) {
+        const int32_t b = act[k] ? (w[k].ce + w[k].ck + 2) : 2;
+        const int32_t o = act[k] ? (w[k].eb - w[k].ce) : 0;
+        bb[k] = b;
+        oo[k] = o;
+        tw[k] = tr[(int64_t)(b >> 2) * ABEA_TRACE_GROUP_WORDS + ((o >> 2) & 31)];
+        e1[k] = abea_tbw_eb(tr, b - 1);
+        e2[k] = abea_tbw_eb(tr, b - 2);
     }
-    return n;
+#pragma unroll
+    for (int k = 0; k < ABEA_TB_K; k++) {
+        const uint32_t f = ((uint32_t)oo[k] < (uint32_t)ABEA_W) ? ((tw[k] >> (((bb[k] & 3) << 3) + 2 * (oo[k] & 3))) & 3u) : ABEA_FROM_D;
+        from[k] = f;
+        if (act[k]) {
+            w[k].ce -= (f != ABEA_FROM_L) ? 1 : 0;
+            w[k].ck -= (f != ABEA_FROM_U) ? 1 : 0;
+            w[k].eb = (f == ABEA_FROM_D) ? e2[k] : e1[k];
+        }
+    }
+}
+__device__ __forceinline__ bool abea_tbw_above(const abea_tbw_t& w, int32_t floor_band) {
+    return (w.ce | w.ck) >= 0 && w.ce + w.ck + 2 > floor_band;
 }
 
 __device__ __forceinline__ int32_t __reduce_add_sync_compat(int32_t v) {
@@ -788,146 +815,277 @@ __device__ __forceinline__ void abea_traceback_par(const abea_read_t& rd, int32_
                                                    const float* __restrict__ means, const float4* __restrict__ kparams,
                                                    const uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs,
                                                    abea_result_t* __restrict__ results, const abea_stream_t& io) {
-    const int32_t E = rd.n_events, K = rd.n_kmers;
+    constexpr int K = ABEA_TB_K;
+    const int32_t E = rd.n_events, NK = rd.n_kmers;
     const float* __restrict__ ev = means + rd.ev_off;
     const float4* __restrict__ kpr = kparams + rd.kp_off;
     const uint32_t* __restrict__ tr = trace + rd.trace_off;
     abea_pair_t* out = pairs + rd.pair_off;
     __syncwarp(); /* the trace lines written by the other lanes of this warp are visible */
 
-    const int32_t b_top = end_event + (K - 1) + 2;
-    int32_t S = (b_top + 32) >> 5; /* ceil((b_top + 1) / 32) */
+    /* 32 K segments of S bands: segment s = lane * K + k covers bands (s S - 1, (s + 1) S - 1]; a higher segment is
+     * earlier in traceback order */
+    const int32_t b_top = end_event + (NK - 1) + 2;
+    int32_t S = (b_top + 32 * K) / (32 * K); /* ceil((b_top + 1) / (32 K)) */
     if (S < 16) S = 16;
-    const int32_t l_top = b_top / S;
+    const int32_t s_top = b_top / S;
     const int32_t margin = io.tb_margin;
-    const int32_t floor_b = lane * S - 1;      /* a lane's segment: bands (floor_b, top_b] */
-    const int32_t top_b = floor_b + S;
+    const int32_t eb_top = abea_tbw_eb(tr, b_top);
 
-    /* ---- pass 1: speculative entry X, steps n, exit Y ---- */
-    abea_tbw_t w;
-    w.ce = -1; w.ck = -1; w.eb = 0;
-    if (lane <= l_top) {
-        const int32_t s = top_b + margin;
-        if (lane == l_top || s >= b_top) { /* close enough to the end cell: walk from it, nothing to speculate on */
-            w.ce = end_event;
-            w.ck = K - 1;
-            w.eb = abea_tbw_eb(tr, b_top);
-        } else {
-            const int32_t eb = abea_tbw_eb(tr, s);
-            const int32_t ce = eb - ABEA_W / 2, ck = s - 2 - ce;
-            if (ce >= 0 && ce < E && ck >= 0 && ck < K) {
-                w.ce = ce;
-                w.ck = ck;
-                w.eb = eb;
-            }
-        }
-        abea_tbw_run(w, tr, top_b);
-    }
-    /* (ve, vk): the entry cell the lane's step count n and exit cell (ye, yk) are valid for — at first its own guess */
-    int32_t ve = w.ce, vk = w.ck;
-    int32_t n = abea_tbw_run(w, tr, floor_b);
-    int32_t ye = w.ce, yk = w.ck; /* where the walk leaves the segment: the entry of the segment below */
-    if (lane > l_top) n = 0;
-    __syncwarp();
-
-    /* ---- verify: the true entry of segment l is the exit of segment l + 1 (the top one starts at the end cell) ----
-     * A lane whose guess was not the true entry walks both paths side by side — always stepping the one that is higher
-     * up — until they stand on the same cell: from there on they are one path, so the exit stays and only the step
-     * count is corrected. That costs a few tens of steps. If they leave the segment apart, the exit changes and the lanes
-     * below look again; rounds repeat until nothing changes (one round, as a rule). */
-    int32_t respec = 0;
-    for (;;) {
-        const int32_t ue = __shfl_down_sync(ABEA_FULL, ye, 1), uk = __shfl_down_sync(ABEA_FULL, yk, 1);
-        bool changed = false;
-        if (lane < l_top && (ue != ve || uk != vk)) {
-            abea_tbw_t A, B;
-            A.ce = ue; A.ck = uk; A.eb = ((ue | uk) >= 0) ? abea_tbw_eb(tr, ue + uk + 2) : 0;
-            B.ce = ve; B.ck = vk; B.eb = ((ve | vk) >= 0) ? abea_tbw_eb(tr, ve + vk + 2) : 0;
-            int32_t sa = 0, sb = 0;
-            for (;;) {
-                if (A.ce == B.ce && A.ck == B.ck) break;
-                const int32_t ba = A.ce + A.ck + 2, bb = B.ce + B.ck + 2;
-                const bool la = (A.ce | A.ck) >= 0 && ba > floor_b, lb = (B.ce | B.ck) >= 0 && bb > floor_b;
-                if (!la && !lb) break;
-                if (la && (!lb || ba >= bb)) {
-                    abea_tbw_step(A, tr);
-                    sa++;
-                } else {
-                    abea_tbw_step(B, tr);
-                    sb++;
+    /* ---- pass 1: speculative entry, steps, exit of every segment ---- */
+    abea_tbw_t w[K];
+    int32_t floor_b[K], n[K], ve[K], vk[K], ye[K], yk[K];
+    bool act[K];
+    uint32_t from[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const int32_t sg = lane * K + k;
+        floor_b[k] = sg * S - 1;
+        n[k] = 0;
+        w[k].ce = -1; w[k].ck = -1; w[k].eb = 0;
+        if (sg <= s_top) {
+            const int32_t st = floor_b[k] + S + margin;
+            if (sg == s_top || st >= b_top) { /* close enough to the end cell: walk from it, nothing to speculate on */
+                w[k].ce = end_event;
+                w[k].ck = NK - 1;
+                w[k].eb = eb_top;
+            } else {
+                const int32_t eb = abea_tbw_eb(tr, st);
+                const int32_t ce = eb - ABEA_W / 2, ck = st - 2 - ce;
+                if (ce >= 0 && ce < E && ck >= 0 && ck < NK) {
+                    w[k].ce = ce;
+                    w[k].ck = ck;
+                    w[k].eb = eb;
                 }
             }
-            if (A.ce == B.ce && A.ck == B.ck) {
-                n = n - sb + sa; /* the rest of B's walk is A's */
-            } else {
-                n = sa;
-                ye = A.ce;
-                yk = A.ck;
-                changed = true;
+        }
+    }
+    for (;;) { /* down to the segment's top band */
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            act[k] = abea_tbw_above(w[k], floor_b[k] + S);
+            any = any || act[k];
+        }
+        if (!any) break;
+        abea_tbw_step_all(w, act, tr, from);
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) { /* (ve, vk): the entry cell the segment's step count and exit cell are valid for */
+        ve[k] = w[k].ce;
+        vk[k] = w[k].ck;
+    }
+    for (;;) { /* through the segment */
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            act[k] = abea_tbw_above(w[k], floor_b[k]);
+            any = any || act[k];
+            n[k] += act[k] ? 1 : 0;
+        }
+        if (!any) break;
+        abea_tbw_step_all(w, act, tr, from);
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        ye[k] = w[k].ce;
+        yk[k] = w[k].ck;
+        if (lane * K + k > s_top) n[k] = 0;
+    }
+    __syncwarp();
+
+    /* ---- verify: the true entry of segment s is the exit of segment s + 1 (the top one starts at the end cell) ----
+     * A segment whose guess was not the true entry walks both paths side by side — always stepping the one that is
+     * higher up — until they stand on the same cell: from there on they are one path, so the exit stays and only the
+     * step count is corrected. That costs a few tens of steps. If they leave the segment apart, the exit changes and
+     * the segments below look again; rounds repeat until nothing changes (one round, as a rule). */
+    int32_t respec = 0;
+    for (;;) {
+        const int32_t ne0 = __shfl_down_sync(ABEA_FULL, ye[0], 1), nk0 = __shfl_down_sync(ABEA_FULL, yk[0], 1);
+        abea_tbw_t A[K], B[K];
+        int32_t sa[K], sb[K], ue[K], uk[K];
+        bool need[K], fin[K];
+        bool any_need = false;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            ue[k] = (k + 1 < K) ? ye[(k + 1 < K) ? k + 1 : k] : ne0;
+            uk[k] = (k + 1 < K) ? yk[(k + 1 < K) ? k + 1 : k] : nk0;
+            need[k] = (lane * K + k < s_top) && (ue[k] != ve[k] || uk[k] != vk[k]);
+            any_need = any_need || need[k];
+            fin[k] = !need[k];
+            sa[k] = sb[k] = 0;
+            A[k].ce = ue[k]; A[k].ck = uk[k]; A[k].eb = 0;
+            B[k].ce = ve[k]; B[k].ck = vk[k]; B[k].eb = 0;
+            if (need[k]) {
+                if ((ue[k] | uk[k]) >= 0) A[k].eb = abea_tbw_eb(tr, ue[k] + uk[k] + 2);
+                if ((ve[k] | vk[k]) >= 0) B[k].eb = abea_tbw_eb(tr, ve[k] + vk[k] + 2);
             }
-            ve = ue;
-            vk = uk;
-            respec++;
+        }
+        bool changed = false;
+        if (any_need) {
+            for (;;) {
+                abea_tbw_t W[K];
+                bool stepA[K];
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    act[k] = false;
+                    stepA[k] = false;
+                    W[k] = A[k];
+                    if (!fin[k]) {
+                        if (A[k].ce == B[k].ce && A[k].ck == B[k].ck) {
+                            fin[k] = true;
+                        } else {
+                            const bool la = abea_tbw_above(A[k], floor_b[k]), lb = abea_tbw_above(B[k], floor_b[k]);
+                            if (!la && !lb) {
+                                fin[k] = true;
+                            } else {
+                                stepA[k] = la && (!lb || A[k].ce + A[k].ck >= B[k].ce + B[k].ck);
+                                W[k] = stepA[k] ? A[k] : B[k];
+                                act[k] = true;
+                                any = true;
+                            }
+                        }
+                    }
+                }
+                if (!any) break;
+                abea_tbw_step_all(W, act, tr, from);
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    if (act[k]) {
+                        if (stepA[k]) { A[k] = W[k]; sa[k]++; } else { B[k] = W[k]; sb[k]++; }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (need[k]) {
+                    if (A[k].ce == B[k].ce && A[k].ck == B[k].ck) {
+                        n[k] = n[k] - sb[k] + sa[k]; /* the rest of B's walk is A's */
+                    } else {
+                        n[k] = sa[k];
+                        ye[k] = A[k].ce;
+                        yk[k] = A[k].ck;
+                        changed = true;
+                    }
+                    ve[k] = ue[k];
+                    vk[k] = uk[k];
+                    respec++;
+                }
+            }
         }
         if (!__any_sync(ABEA_FULL, changed)) break;
     }
-    const int32_t xe = ve, xk = vk;
-    const int32_t xeb = ((ve | vk) >= 0) ? abea_tbw_eb(tr, ve + vk + 2) : 0;
     respec = __reduce_add_sync_compat(respec);
 
-    /* ---- positions: `before` = steps of the lanes above (earlier in traceback order) ---- */
-    int32_t incl = n;
+    /* ---- positions: steps of all segments above (earlier in traceback order) ---- */
+    int32_t lane_n = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) lane_n += n[k];
+    int32_t incl = lane_n;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int32_t v = __shfl_down_sync(ABEA_FULL, incl, d);
         if (lane + d < 32) incl += v;
     }
     const int32_t total = __shfl_sync(ABEA_FULL, incl, 0);
-    const int32_t before = incl - n;
+    int32_t pos[K];
+    {
+        int32_t before = incl - lane_n; /* the lanes above */
+#pragma unroll
+        for (int k = K - 1; k >= 0; k--) {
+            pos[k] = total - 1 - before;
+            before += n[k];
+        }
+    }
 
     /* ---- pass 2: pairs, emissions, gap runs ---- */
     double sum = 0.0, asum = 0.0;
-    uint32_t emin = 0xffu;                       /* smallest biased exponent among the non-zero emissions */
-    int32_t lead_run = 0, max_run = 0, run = 0;  /* runs of FROM_L: at the head of the segment, anywhere, at its tail */
-    bool all_l = true;
-    int32_t last_k = 0;
-    {
-        abea_tbw_t r;
-        r.ce = xe; r.ck = xk; r.eb = xeb;
-        int32_t pos = total - 1 - before;
-        for (int32_t j = 0; j < n; j++, pos--) {
-            abea_pair_t p;
-            p.ref_pos = r.ck;
-            p.read_pos = r.ce;
-            out[pos] = p;
-            last_k = r.ck;
-            const float lp = abea_emission_t<FAST>(ev[r.ce], kpr[r.ck]);
-            const uint32_t ex = (__float_as_uint(lp) >> 23) & 0xffu;
-            if (lp != 0.0f && ex < emin) emin = ex;
-            const double lpd = (double)lp;
-            sum = __dadd_rn(sum, lpd);
-            asum = __dadd_rn(asum, fabs(lpd));
-            const uint32_t from = abea_tbw_step(r, tr);
-            if (from == ABEA_FROM_L) {
-                run++;
-                if (run > max_run) max_run = run;
-            } else {
-                if (all_l) lead_run = run;
-                all_l = false;
-                run = 0;
+    uint32_t emin = 0xffu;                             /* smallest biased exponent among the non-zero emissions */
+    int32_t lead_run[K], max_run[K], run[K], last_kk[K]; /* runs of FROM_L: at the head of a segment, anywhere, at its tail */
+    bool all_l[K];
+    int32_t nmax = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        w[k].ce = ve[k];
+        w[k].ck = vk[k];
+        w[k].eb = (n[k] > 0) ? abea_tbw_eb(tr, ve[k] + vk[k] + 2) : 0;
+        lead_run[k] = max_run[k] = run[k] = 0;
+        last_kk[k] = 0;
+        all_l[k] = true;
+        nmax = n[k] > nmax ? n[k] : nmax;
+    }
+    for (int32_t j = 0; j < nmax; j++) {
+        float x[K];
+        float4 kp[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            act[k] = j < n[k];
+            const int32_t e = act[k] ? w[k].ce : 0, q = act[k] ? w[k].ck : 0;
+            x[k] = ev[e];
+            kp[k] = kpr[q];
+            if (act[k]) {
+                abea_pair_t p;
+                p.ref_pos = w[k].ck;
+                p.read_pos = w[k].ce;
+                out[pos[k] - j] = p;
+                last_kk[k] = w[k].ck;
             }
         }
-        if (all_l) lead_run = run;
+        abea_tbw_step_all(w, act, tr, from);
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (act[k]) {
+                const float lp = abea_emission_t<FAST>(x[k], kp[k]);
+                const uint32_t ex = (__float_as_uint(lp) >> 23) & 0xffu;
+                if (lp != 0.0f && ex < emin) emin = ex;
+                const double lpd = (double)lp;
+                sum = __dadd_rn(sum, lpd);
+                asum = __dadd_rn(asum, fabs(lpd));
+                if (from[k] == ABEA_FROM_L) {
+                    run[k]++;
+                    if (run[k] > max_run[k]) max_run[k] = run[k];
+                } else {
+                    if (all_l[k]) lead_run[k] = run[k];
+                    all_l[k] = false;
+                    run[k] = 0;
+                }
+            }
+        }
     }
+    /* a lane's segments in traceback order (k descending) as one stretch: steps, leading / longest / trailing run */
+    int32_t L_n = 0, L_lead = 0, L_max = 0, L_tail = 0, L_lastk = 0;
+    bool L_all = true, L_has = false;
+#pragma unroll
+    for (int k = K - 1; k >= 0; k--) {
+        if (n[k] > 0) {
+            if (all_l[k]) {
+                L_tail += n[k];
+                if (L_all) L_lead = L_tail;
+                if (L_tail > L_max) L_max = L_tail;
+            } else {
+                const int32_t joined = L_tail + lead_run[k];
+                if (L_all) L_lead = joined;
+                if (joined > L_max) L_max = joined;
+                if (max_run[k] > L_max) L_max = max_run[k];
+                L_tail = run[k];
+                L_all = false;
+            }
+            L_n += n[k];
+            L_lastk = last_kk[k];
+            L_has = true;
+        }
+    }
+    (void)L_has;
     __syncwarp();
 
-    /* ---- combine: gap runs across segment borders, traceback order = lanes descending ---- */
+    /* ---- combine across lanes, traceback order = lanes descending ---- */
     int32_t max_gap = 0, carry = 0;
-    for (int32_t l = l_top; l >= 0; l--) {
-        const int32_t ln = __shfl_sync(ABEA_FULL, n, l);
-        const int32_t llead = __shfl_sync(ABEA_FULL, lead_run, l), lmax = __shfl_sync(ABEA_FULL, max_run, l);
-        const int32_t ltail = __shfl_sync(ABEA_FULL, run, l);
-        const bool lall = __shfl_sync(ABEA_FULL, all_l ? 1 : 0, l) != 0;
+    for (int32_t l = 31; l >= 0; l--) {
+        const int32_t ln = __shfl_sync(ABEA_FULL, L_n, l);
+        const int32_t llead = __shfl_sync(ABEA_FULL, L_lead, l), lmax = __shfl_sync(ABEA_FULL, L_max, l);
+        const int32_t ltail = __shfl_sync(ABEA_FULL, L_tail, l);
+        const bool lall = __shfl_sync(ABEA_FULL, L_all ? 1 : 0, l) != 0;
         if (ln == 0) continue;
         if (lall) {
             carry += ln;
@@ -939,9 +1097,9 @@ __device__ __forceinline__ void abea_traceback_par(const abea_read_t& rd, int32_
         }
     }
     /* the last pair emitted (the lowest lane that has steps) */
-    const uint32_t have = __ballot_sync(ABEA_FULL, n > 0);
+    const uint32_t have = __ballot_sync(ABEA_FULL, L_n > 0);
     const int low = have ? (__ffs((int)have) - 1) : 0;
-    last_k = __shfl_sync(ABEA_FULL, last_k, low);
+    const int32_t last_k = __shfl_sync(ABEA_FULL, L_lastk, low);
 
     /* ---- the QC sum ---- */
     double a_tot = asum;
@@ -959,8 +1117,7 @@ __device__ __forceinline__ void abea_traceback_par(const abea_read_t& rd, int32_
         exact = true; /* every term is zero */
     } else if (e_all > 0u) {
         const int32_t lim_exp = (int32_t)e_all - 127 - 23 + 52; /* a_tot must stay below 2^lim_exp */
-        const double lim = (lim_exp > 1000) ? 1.0e300 : ((lim_exp < -1000) ? 0.0 : __hiloint2double((lim_exp + 1023) << 20, 0));
-        exact = a_tot < lim;
+        exact = a_tot < __hiloint2double((lim_exp + 1023) << 20, 0);
     }
     if (io.tb_mode & 2) exact = false; /* tests: always take the ordered sum */
     if (exact) {
@@ -1446,8 +1603,9 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const f
  * register windows to slide). Warp w owns offsets 28w..28w+27 (warp 3: 84..99), so that four lanes form one word of
  * the same 128-B trace line layout the narrow kernel writes. Events and k-mer parameters of the whole band window live
  * in shared-memory rings (256 entries, 64-entry chunks staged by cp.async) and are simply re-addressed every band.
- * Warps exchange their two boundary cells and the two cells of Suzuki's rule through shared memory, one
- * __syncthreads per band, double-buffered by band parity. Arithmetic is the same templates as the narrow kernel.   */
+ * Every lane publishes its cell of the band to a shared-memory copy (double-buffered by band parity); neighbours and
+ * the two cells of Suzuki's rule are read from it behind a split-phase mbarrier (below). Arithmetic is the same
+ * templates as the narrow kernel.                                                                                  */
 
 /* Split-phase CTA barrier (mbarrier in shared memory): a warp ARRIVES as soon as its boundary cells of the band are
  * published and WAITS only when it needs the other warps' cells at the top of the next band; everything in between

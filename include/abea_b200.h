@@ -59,7 +59,7 @@ typedef struct {
     double pack_ms;        /* host: descriptors, scheduling order */
     double h2d_ms;         /* device: sequence + event + descriptor copies */
     double kmer_ms;        /* device: abea_prepare_kernel (k-mer parameter cache + input validation) */
-    double fill_ms;        /* device: band fill (narrow + wide kernels, concurrent) */
+    double fill_ms;        /* device: band fill + fused traceback / QC (narrow + wide kernels, concurrent) */
     double trace_ms;       /* device: always ~0 — traceback + QC are fused into the fill kernels (kept for the reference's timer split) */
     double kernel_ms;      /* device: first kernel start to last kernel end */
     double d2h_ms;         /* device: result copies */
