@@ -172,6 +172,12 @@ struct abea_ctx {
     DevBuf d_ready, d_items, d_capptr, d_dense_off;
     std::vector<abea_load_item_t> items;
     std::vector<int32_t> finish_order; /* scheduled reads by the time the replayed schedule expects them to finish */
+    std::vector<double> sched_start, sched_finish; /* scratch of build_load_order, kept across batches */
+    struct sched_slot_t { double t; int kind; };
+    std::vector<sched_slot_t> sched_heap;
+    struct sched_need_t { int32_t read, piece, bucket; };
+    std::vector<sched_need_t> sched_need;
+    std::vector<int32_t> sched_count;
     /* abea_align_ragged */
     abea_pool pool;
     HostBuf h_rseq, h_rmeans, h_rpairs, h_rnp, h_hostready, h_rmeta;
@@ -315,7 +321,7 @@ double wide_threshold(const abea_ctx* c, int64_t total_bands) {
 }
 
 /* see upload_impl */
-void build_load_order(abea_ctx* c) {
+void build_load_order(abea_ctx* c, bool want_finish_order) {
     const int64_t n = (int64_t)c->reads.size();
     const int nw = c->n_wide;
     const int wpc = c->fill_warps_per_cta;
@@ -333,62 +339,94 @@ void build_load_order(abea_ctx* c) {
         const double nb = (double)c->reads[r].n_events + c->reads[r].n_kmers + 2;
         return nb > long_thr ? CYC_LONG : CYC_NARROW;
     };
-    std::vector<double> start((size_t)n, 0.0), finish((size_t)n, 0.0);
-    /* (time a warp becomes free, kind: 0 wide, 1 primary, 2 secondary); a min-heap */
-    typedef std::pair<double, int> slot_t;
-    std::vector<slot_t> heap;
+    std::vector<double>& start = c->sched_start;
+    std::vector<double>& finish = c->sched_finish;
+    start.assign((size_t)n, 0.0);
+    finish.assign((size_t)n, 0.0);
+    /* (time a warp becomes free, kind: 0 wide, 1 primary, 2 secondary) in a binary min-heap that is updated in place:
+     * the slot at the root takes the next read and sinks (this runs on the critical path of every streamed batch) */
+    typedef abea_ctx::sched_slot_t slot_t;
+    std::vector<slot_t>& heap = c->sched_heap;
+    heap.clear();
     /* at t = 0 the three kinds ask in this order of urgency; the tiny offsets only order the first requests: the
      * reads that set the makespan first, and primary and secondary warps served alternately after that */
-    for (int i = 0; i < std::min<int64_t>(nw, c->sm_count); i++) heap.push_back(slot_t(0.0, 0));
-    for (int64_t i = 0; i < n_pri; i++) heap.push_back(slot_t(1e-3 * (double)i / (double)n_pri, 1));
-    for (int64_t i = 0; i < n_sec; i++) heap.push_back(slot_t(1.5e-3 * (double)i / (double)std::max<int64_t>(1, n_sec), 2));
-    auto later = [](const slot_t& x, const slot_t& y) { return x.first > y.first; };
-    std::make_heap(heap.begin(), heap.end(), later);
+    for (int i = 0; i < std::min<int64_t>(nw, c->sm_count); i++) heap.push_back(slot_t{0.0, 0});
+    for (int64_t i = 0; i < n_pri; i++) heap.push_back(slot_t{1e-3 * (double)i / (double)n_pri, 1});
+    for (int64_t i = 0; i < n_sec; i++) heap.push_back(slot_t{1.5e-3 * (double)i / (double)std::max<int64_t>(1, n_sec), 2});
+    std::make_heap(heap.begin(), heap.end(), [](const slot_t& x, const slot_t& y) { return x.t > y.t; });
+    auto sift_down = [&]() {
+        const size_t hn = heap.size();
+        size_t i = 0;
+        const slot_t v = heap[0];
+        for (;;) {
+            size_t l = 2 * i + 1;
+            if (l >= hn) break;
+            if (l + 1 < hn && heap[l + 1].t < heap[l].t) l++;
+            if (!(heap[l].t < v.t)) break;
+            heap[i] = heap[l];
+            i = l;
+        }
+        heap[i] = v;
+    };
     int64_t w = 0, h = nw, t = n - 1;
+    double t_max = 0.0;
     while ((w < nw || h <= t) && !heap.empty()) {
-        std::pop_heap(heap.begin(), heap.end(), later);
-        slot_t sl = heap.back();
-        heap.pop_back();
-        int64_t r;
-        if (sl.second == 0) {
-            if (w >= nw) continue;
-            r = w++;
-        } else {
-            if (h > t) continue;
-            r = (sl.second == 1 || c->sched_policy == 1) ? h++ : t--;
+        slot_t& sl = heap[0];
+        int64_t r = -1;
+        if (sl.kind == 0) {
+            if (w < nw) r = w++;
+        } else if (h <= t) {
+            r = (sl.kind == 1 || c->sched_policy == 1) ? h++ : t--;
+        }
+        if (r < 0) { /* nothing left for this kind of slot: it leaves the heap */
+            heap[0] = heap.back();
+            heap.pop_back();
+            if (!heap.empty()) sift_down();
+            continue;
         }
         const abea_read_t& rd = c->reads[r];
         const double nb = (double)rd.n_events + rd.n_kmers + 2;
-        start[r] = sl.first;
-        sl.first += nb * rate(r) + (double)rd.n_events * CYC_TRACE;
-        finish[r] = sl.first;
-        heap.push_back(sl);
-        std::push_heap(heap.begin(), heap.end(), later);
+        start[r] = sl.t;
+        sl.t += nb * rate(r) + (double)rd.n_events * CYC_TRACE;
+        finish[r] = sl.t;
+        if (sl.t > t_max) t_max = sl.t;
+        sift_down();
     }
-    struct need_t { double t; int32_t read, piece; };
-    std::vector<need_t> need;
+    /* every (read, piece) with the time the fill first touches it: event e when the read is about e/E of the way through
+     * its bands. Ordered by that time with a counting sort over 8192 time buckets (the order inside a bucket — 1/8192 of
+     * the batch — does not matter to a heuristic; a comparison sort of the ~10^4 items was most of this function). */
+    typedef abea_ctx::sched_need_t need_t;
+    std::vector<need_t>& need = c->sched_need;
+    need.clear();
     const int64_t esz = c->load_aos ? (int64_t)sizeof(abea_event_t) : (int64_t)sizeof(float);
-    need.reserve((size_t)n + (size_t)(c->event_bytes / c->load_piece_cur) + 8);
+    const int NBUCKET = 8192;
+    const double to_bucket = t_max > 0.0 ? (double)(NBUCKET - 1) / t_max : 0.0;
+    std::vector<int32_t>& count = c->sched_count;
+    count.assign((size_t)NBUCKET + 1, 0);
     for (int64_t r = 0; r < n; r++) {
         const abea_read_t& rd = c->reads[r];
         const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, c->event_bytes, c->load_piece_cur, esz);
         const double nb = (double)rd.n_events + rd.n_kmers + 2;
         const double rt = rate(r);
         const double fill = nb * rt * (rt < CYC_NARROW ? c->load_crit : 1.0);
+        const double per_byte = fill / (double)(g.b - g.a); /* time per byte of the read's own range */
         for (int32_t q = 0; q < g.n_pieces; q++) {
-            /* the fill touches event e when it is about e/E of the way through the read's bands */
-            const double frac = (double)abea_piece_first_event(g, q, esz) / (double)rd.n_events;
-            need.push_back(need_t{start[r] + frac * fill, (int32_t)r, q});
+            const int64_t off = g.lo + (int64_t)q * g.piece - g.a; /* first byte of the piece, relative to the read's first */
+            const double tq = start[r] + (off > 0 ? (double)off * per_byte : 0.0);
+            int bk = (int)(tq * to_bucket);
+            bk = bk < 0 ? 0 : (bk >= NBUCKET ? NBUCKET - 1 : bk);
+            need.push_back(need_t{(int32_t)r, q, bk});
+            count[(size_t)bk + 1]++;
         }
     }
-    /* nearly sorted already (reads in schedule order, pieces ascending): a merge sort is the fast one here */
-    std::stable_sort(need.begin(), need.end(), [](const need_t& x, const need_t& y) { return x.t < y.t; });
-    c->items.clear();
-    c->items.reserve(need.size());
-    for (const need_t& x : need) c->items.push_back(abea_load_item_t{x.read, x.piece});
-    c->finish_order.resize((size_t)n);
-    for (int64_t r = 0; r < n; r++) c->finish_order[(size_t)r] = (int32_t)r;
-    std::stable_sort(c->finish_order.begin(), c->finish_order.end(), [&](int32_t x, int32_t y) { return finish[x] < finish[y]; });
+    for (int i = 0; i < NBUCKET; i++) count[(size_t)i + 1] += count[(size_t)i];
+    c->items.resize(need.size());
+    for (const need_t& x : need) c->items[(size_t)count[(size_t)x.bucket]++] = abea_load_item_t{x.read, x.piece};
+    if (want_finish_order) {
+        c->finish_order.resize((size_t)n);
+        for (int64_t r = 0; r < n; r++) c->finish_order[(size_t)r] = (int32_t)r;
+        std::stable_sort(c->finish_order.begin(), c->finish_order.end(), [&](int32_t x, int32_t y) { return finish[x] < finish[y]; });
+    }
 }
 
 /* Re-derive the scheduler's model from what the batch that has just run measured: every read reports the SM cycles of
@@ -511,7 +549,12 @@ int abea_create(abea_ctx_t** out, int device) {
      * loader had finished. */
     {
         cudaError_t e = cudaSuccess;
-        const int carve = 100; /* percent of the maximum: cudaSharedmemCarveoutMaxShared */
+        /* ABEA_CARVEOUT: percent of the maximum shared memory asked for by the kernels that share SMs with the narrow
+         * fill (its CTA needs 64 KB; what is left of the 256 KB is L1, which the traceback's scattered reads and the
+         * cp.async staging live in). The wide kernel keeps 100: it claims its SM through 160 KB of shared memory. */
+        int carve = 35; /* 80 KB: measured 10.04 ms (100) -> 9.75 (60) -> 9.71 (35) on the target config, traceback steps of
+                         * median reads 190 -> 110 cycles (profiles/read_cycles_partd_r02_*) */
+        if (const char* e = getenv("ABEA_CARVEOUT")) carve = std::min(100, std::max(30, atoi(e)));
         if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_load_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_load_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_extract_means_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
@@ -520,8 +563,8 @@ int abea_create(abea_ctx_t** out, int device) {
                                (const void*)abea_fill_kernel<true, true>,       (const void*)abea_fill_kernel<false, true>,
                                (const void*)abea_fill_wide_kernel<true, false>, (const void*)abea_fill_wide_kernel<false, false>,
                                (const void*)abea_fill_wide_kernel<true, true>,  (const void*)abea_fill_wide_kernel<false, true>};
-        for (const void* f : fills)
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        for (int i = 0; i < 8; i++)
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fills[i], cudaFuncAttributePreferredSharedMemoryCarveout, i < 4 ? carve : 100);
         if (e != cudaSuccess) {
             delete c;
             return ABEA_ERR_CUDA;
@@ -782,7 +825,8 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
          * each piece is first touched. That is predicted by replaying the schedule with nominal rates (cycles per
          * band measured on B200, profiles/README.md): wide CTAs take reads [0, n_wide) in order, primary warps pull
          * from the head of the longest-first order, secondary warps from the tail. */
-        build_load_order(c);
+        const double t_enq = now_ms();
+        build_load_order(c, rag);
         if (dev_reserve(c, c->d_items, c->items.size() * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
         if (host_reserve(c, c->h_items, c->items.size() * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
         memcpy(c->h_items.p, c->items.data(), c->items.size() * sizeof(abea_load_item_t));
@@ -795,6 +839,9 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
             c->rag_items_ready.store(1, std::memory_order_release);
         }
         t2 = now_ms();
+        if (getenv("ABEA_TIME_PACK"))
+            fprintf(stderr, "[abea pack] descriptors+sort %.3f ms, reserve+enqueue+prepare %.3f ms, load order %.3f ms (%zu items)\n",
+                    t1 - t0, t_enq - t1, t2 - t_enq, c->items.size());
         /* the loader's stream waits for the descriptors and the cleared counters, not for the k-mer kernel */
         CU(cudaStreamWaitEvent(c->load_stream, c->ev_meta, 0));
         CU(cudaMemcpyAsync(c->d_items.p, c->h_items.p, c->items.size() * sizeof(abea_load_item_t),
@@ -1313,7 +1360,7 @@ int abea_getevents_blow5(abea_ctx_t* c, const abea_blow5_t* f, int rna, int32_t*
     if (f->record_method == B5_REC_ZLIB && n > 0) {
         /* a record's inflated size is not stored: guess generously (a raw signal deflates to ~60 %), let the kernel
          * report an overflow, and retry with more — up to DEFLATE's own ceiling of 1032 : 1 */
-        const size_t smem = (size_t)B5_INFLATE_THREADS * sizeof(b5_tables_t);
+        const size_t smem = (size_t)B5_INFLATE_WARPS * sizeof(b5_tables_t);
         CU(cudaFuncSetAttribute((const void*)abea_inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         for (int64_t mult = 4;; mult *= 4) {
             int64_t off = 0;
@@ -1327,7 +1374,7 @@ int abea_getevents_blow5(abea_ctx_t* c, const abea_blow5_t* f, int rna, int32_t*
             }
             if (dev_reserve(c, c->d_b5out, (size_t)off + 16)) return ABEA_ERR_CUDA;
             CU(cudaMemcpyAsync(c->d_b5recs.p, h_recs, (size_t)n * sizeof(abea_b5rec_t), cudaMemcpyHostToDevice, c->stream));
-            ABEA_LAUNCH_SMEM(abea_inflate_kernel, (n + B5_INFLATE_THREADS - 1) / B5_INFLATE_THREADS, B5_INFLATE_THREADS, smem, c->stream,
+            ABEA_LAUNCH_SMEM(abea_inflate_kernel, (n + B5_INFLATE_WARPS - 1) / B5_INFLATE_WARPS, 32 * B5_INFLATE_WARPS, smem, c->stream,
                              (const abea_b5rec_t*)c->d_b5recs.p, n, (const uint8_t*)c->d_b5in.p, (uint8_t*)c->d_b5out.p,
                              (int32_t*)c->d_b5len.p, (int32_t*)c->d_b5status.p);
             CU(cudaMemcpyAsync(h_status, c->d_b5status.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -181,7 +181,8 @@ __global__ void abea_prepare_kernel(const abea_read_t* __restrict__ reads, int32
         kp.z = __fsub_rn(-0.918938f, m.level_log_stdv);               /* src/align.c:111-113 */
         kp.w = __frcp_rn(m.level_stdv);
         kparams[idx] = kp;
-        if (!(abea_sane_level(kp.x) && abea_sane_stdv(kp.y))) atomicAnd(&read_flags[r], ~ABEA_READ_FAST);
+        /* kp.z <= 0: every emission is <= 0, so every band score is negative (abea_cell_once relies on the sign) */
+        if (!(abea_sane_level(kp.x) && abea_sane_stdv(kp.y) && kp.z <= 0.0f)) atomicAnd(&read_flags[r], ~ABEA_READ_FAST);
     }
     /* events of scheduled reads, in schedule order (evs_off = running sum of n_events) */
     for (int64_t idx = tid; idx < total_events; idx += stride) {
@@ -506,6 +507,32 @@ __device__ __forceinline__ void abea_cell_dd(double lpd, double up, double left,
     score = isL ? rl : m;
     from = isL ? ABEA_FROM_L : (isU ? ABEA_FROM_U : ABEA_FROM_D);
 }
+/* The same cell with ONE rounding (narrow kernel, FAST reads). Rounding is monotone, so the cell's score is the rounded
+ * MAXIMUM of the three unrounded sums, and a candidate ties with (or is) that maximum after rounding exactly when it
+ * lies in the score's rounding interval, i.e. is not below its lower end lb = |R| + half a float ulp (inclusive when R's
+ * last float mantissa bit is even: round-to-nearest-even). For a NEGATIVE float-valued double that is an integer
+ * operation on the low word: bit 29 is the float's last mantissa bit, bit 28 half an ulp. Every cell score of a FAST
+ * read is negative or -inf (abea_prepare_kernel admits a read only if all its emission constants -0.918938 - log stdv
+ * are <= 0; transitions and the trim penalty are logs of probabilities); for -inf, lb is a NaN and the unordered
+ * compares below give the reference's answer, L. Ties resolve L > U > D as in the reference (src/align.c:386-392).
+ * 20 instructions instead of 28 per cell, 9 instead of 13 on the FP64 pipe; the rounding itself goes through the
+ * conversion unit (2 F2F). tools/validate_fast_arith.c checks it against the three-rounding form (10^9 cells, a fifth
+ * of them with tied rounded candidates). */
+__device__ __forceinline__ void abea_cell_once(double lpd, double up, double left, double diag, double lp_step,
+                                               double lp_stay, double lp_skip, double& score, uint32_t& from) {
+    const double d = __dadd_rn(__dadd_rn(diag, lp_step), lpd);
+    const double u = __dadd_rn(__dadd_rn(up, lp_stay), lpd);
+    const double l = __dadd_rn(left, lp_skip);
+    const double m2 = (u >= d) ? u : d;
+    const double m3 = (l >= m2) ? l : m2;
+    const double R = (double)__double2float_rn(m3);
+    const uint32_t lo = (uint32_t)__double2loint(R);
+    const double lb = __hiloint2double(__double2hiint(R), (int)(lo + 0x10000000u - ((lo >> 29) & 1u)));
+    const bool isL = !(l < lb), isU = !(u < lb);
+    score = R;
+    from = isL ? ABEA_FROM_L : (isU ? ABEA_FROM_U : ABEA_FROM_D);
+}
+
 template <bool FAST>
 __device__ __forceinline__ void abea_cell_d(float lp, double up, double left, double diag, double lp_step,
                                             double lp_stay, double lp_skip, double& score, uint32_t& from) {
@@ -770,17 +797,29 @@ __device__ __forceinline__ uint32_t abea_tbw_step(abea_tbw_t& w, const uint32_t*
     return from;
 }
 
+__device__ __forceinline__ void abea_prefetch_l1(const void* p) {
+#ifndef ABEA_SIMT_EMU
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 /* K walkers per lane, stepped together: a step is one round trip to the trace (L2 latency under load, the lanes of a
  * warp read 32 different lines), so what a lane's time is made of is round trips, and K independent walks in flight
  * cost one. The loads of all K walkers are issued before any is used; a walker that is not `act` re-reads band 2 of
- * the read (always there) and keeps its state. */
-#define ABEA_TB_K 4
-__device__ __forceinline__ void abea_tbw_step_all(abea_tbw_t (&w)[ABEA_TB_K], const bool (&act)[ABEA_TB_K],
-                                                  const uint32_t* __restrict__ tr, uint32_t (&from)[ABEA_TB_K]) {
-    uint32_t tw[ABEA_TB_K];
-    int32_t e1[ABEA_TB_K], e2[ABEA_TB_K], bb[ABEA_TB_K], oo[ABEA_TB_K];
+ * the read (always there) and keeps its state. K = 4 for the reads of the wide kernel (alone on their SM, bound by the
+ * round trips: 95 -> 46-70 cycles per traceback step); K = 1 for the narrow warps, whose steps compete with eleven
+ * other warps for issue slots and load wavefronts (with K = 4 the extra walks cost more than the round trips they
+ * save: measured 10.3 -> 11.2 ms on the target config, profiles/read_cycles_partc_k4_r02_*). */
+#define ABEA_TB_K4_MIN_BANDS 16384
+template <int K>
+__device__ __forceinline__ void abea_tbw_step_all(abea_tbw_t (&w)[K], const bool (&act)[K],
+                                                  const uint32_t* __restrict__ tr, uint32_t (&from)[K]) {
+    uint32_t tw[K];
+    int32_t e1[K], e2[K], bb[K], oo[K];
 #pragma unroll
-    for (int k = 0; k < ABEA_TB_K; k++) {
+    for (int k = 0; k < K; k++) {
         const int32_t b = act[k] ? (w[k].ce + w[k].ck + 2) : 2;
         const int32_t o = act[k] ? (w[k].eb - w[k].ce) : 0;
         bb[k] = b;
@@ -788,9 +827,13 @@ __device__ __forceinline__ void abea_tbw_step_all(abea_tbw_t (&w)[ABEA_TB_K], co
         tw[k] = tr[(int64_t)(b >> 2) * ABEA_TRACE_GROUP_WORDS + ((o >> 2) & 31)];
         e1[k] = abea_tbw_eb(tr, b - 1);
         e2[k] = abea_tbw_eb(tr, b - 2);
+        /* the line the walk reaches four bands further down, at the word it is most likely to need there (the offset
+         * drifts by at most one per band) and at the band event indices: in L1 by the time the walk gets to it */
+        abea_prefetch_l1(tr + (int64_t)((b >= 6 ? b - 4 : 2) >> 2) * ABEA_TRACE_GROUP_WORDS + ((o >> 2) & 31));
+        abea_prefetch_l1(tr + (int64_t)((b >= 6 ? b - 4 : 2) >> 2) * ABEA_TRACE_GROUP_WORDS + ABEA_LANES);
     }
 #pragma unroll
-    for (int k = 0; k < ABEA_TB_K; k++) {
+    for (int k = 0; k < K; k++) {
         const uint32_t f = ((uint32_t)oo[k] < (uint32_t)ABEA_W) ? ((tw[k] >> (((bb[k] & 3) << 3) + 2 * (oo[k] & 3))) & 3u) : ABEA_FROM_D;
         from[k] = f;
         if (act[k]) {
@@ -810,12 +853,11 @@ __device__ __forceinline__ int32_t __reduce_add_sync_compat(int32_t v) {
     return v;
 }
 
-template <bool FAST>
+template <bool FAST, int K>
 __device__ __forceinline__ void abea_traceback_par(const abea_read_t& rd, int32_t ridx, int32_t end_event, int lane,
                                                    const float* __restrict__ means, const float4* __restrict__ kparams,
                                                    const uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs,
                                                    abea_result_t* __restrict__ results, const abea_stream_t& io) {
-    constexpr int K = ABEA_TB_K;
     const int32_t E = rd.n_events, NK = rd.n_kmers;
     const float* __restrict__ ev = means + rd.ev_off;
     const float4* __restrict__ kpr = kparams + rd.kp_off;
@@ -1024,6 +1066,8 @@ __device__ __forceinline__ void abea_traceback_par(const abea_read_t& rd, int32_
             const int32_t e = act[k] ? w[k].ce : 0, q = act[k] ? w[k].ck : 0;
             x[k] = ev[e];
             kp[k] = kpr[q];
+            abea_prefetch_l1(ev + (e >= 12 ? e - 12 : 0)); /* the walk moves down both arrays a step at a time */
+            abea_prefetch_l1(kpr + (q >= 6 ? q - 6 : 0));
             if (act[k]) {
                 abea_pair_t p;
                 p.ref_pos = w[k].ck;
@@ -1168,7 +1212,7 @@ __device__ __forceinline__ void abea_traceback_par(const abea_read_t& rd, int32_
 }
 
 /* the traceback of one read by the warp that filled it (warp 0 of a wide CTA) */
-template <bool FAST>
+template <bool FAST, int K>
 __device__ __forceinline__ void abea_traceback(const abea_read_t& rd, int32_t ridx, int32_t end_event, uint32_t* ring, int lane,
                                                const float* __restrict__ means, const float4* __restrict__ kparams,
                                                const uint32_t* __restrict__ trace, abea_pair_t* __restrict__ pairs,
@@ -1177,7 +1221,7 @@ __device__ __forceinline__ void abea_traceback(const abea_read_t& rd, int32_t ri
         abea_traceback_read(rd, ridx, end_event, ring, lane, means, kparams, trace, pairs, results, io);
         if (lane == 0) results[ridx].respec = 0;
     } else {
-        abea_traceback_par<FAST>(rd, ridx, end_event, lane, means, kparams, trace, pairs, results, io);
+        abea_traceback_par<FAST, K>(rd, ridx, end_event, lane, means, kparams, trace, pairs, results, io);
     }
 }
 
@@ -1235,7 +1279,8 @@ __device__ __forceinline__ void abea_band_cells(const float* x, const float4* kp
         else if (!RIGHT && !PREV_RIGHT) diag = (c > 0) ? B.R[c > 0 ? c - 1 : 0] : B.lo;
         else diag = B.R[c];
         float lp = abea_emission_t<FAST>(x[c], kp[c]);
-        abea_cell_d<FAST>(lp, up, left, diag, lp_step, lp_stay, lp_skip, Rn[c], fr[c]);
+        if (FAST) abea_cell_once((double)lp, up, left, diag, lp_step, lp_stay, lp_skip, Rn[c], fr[c]);
+        else abea_cell_d<FAST>(lp, up, left, diag, lp_step, lp_stay, lp_skip, Rn[c], fr[c]);
     }
 }
 
@@ -1586,7 +1631,12 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const f
          * is a serial chain too, and fusing it here takes it off the tail of the batch */
         __syncwarp();
         const long long t_fill = abea_clock();
-        abea_traceback<FAST>(rd, ridx, end_event, tb_ring, lane, means, kparams, trace, pairs, results, io);
+        /* four walks per lane pay off once the stretches are long (RNA reads of 20 k events: 39.4 -> 35.7 ms at cfg4);
+         * on reads of a few thousand bands the margins of 128 short stretches cost more than the round trips saved */
+        if (cx.NB >= ABEA_TB_K4_MIN_BANDS)
+            abea_traceback<FAST, 4>(rd, ridx, end_event, tb_ring, lane, means, kparams, trace, pairs, results, io);
+        else
+            abea_traceback<FAST, 1>(rd, ridx, end_event, tb_ring, lane, means, kparams, trace, pairs, results, io);
         if (lane == 0) {
             results[ridx].wide = 0;
             results[ridx].fill_cycles = t_fill - t_start;
@@ -1976,7 +2026,7 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                 results[ridx].end_event = end_event;
             }
             const long long t_fill = abea_clock();
-            abea_traceback<FAST>(rd, ridx, end_event, (uint32_t*)sm.kp, lane, means, kparams, trace, pairs, results, io);
+            abea_traceback<FAST, 4>(rd, ridx, end_event, (uint32_t*)sm.kp, lane, means, kparams, trace, pairs, results, io);
             if (lane == 0) {
                 results[ridx].wide = 1;
                 results[ridx].fill_cycles = t_fill - t_start;

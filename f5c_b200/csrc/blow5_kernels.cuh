@@ -7,11 +7,14 @@
  * len_raw_signal, raw_signal) -> signal decompression (svb-zd: slow5_press.c:1118-1170, streamvbyte_decode.c,
  * streamvbyte_zigzag.c:34-40) -> the int16 -> float widening of src/f5cio.c:461.
  *
- *   abea_inflate_kernel        one THREAD per record: a complete DEFLATE decoder (RFC 1951: stored, fixed and dynamic
- *                              Huffman blocks) behind the zlib wrapper (RFC 1950). Records are independent streams, a
- *                              stream is bit-serial, so the parallelism is across records. Huffman tables live in shared
- *                              memory, one set per thread: a 10-bit direct table for literal/length codes, an 8-bit one
- *                              for distance codes, canonical count/symbol arrays for the (rare) longer codes.
+ *   abea_inflate_kernel        one WARP per record, lane 0 decoding: a complete DEFLATE decoder (RFC 1951: stored,
+ *                              fixed and dynamic Huffman blocks) behind the zlib wrapper (RFC 1950). Records are
+ *                              independent streams, a stream is bit-serial, so the parallelism is across records — and
+ *                              a record gets a warp of its own because 32 decoders in one warp are 32 different control
+ *                              flows (first version, one thread per record: 565 ms per 1792 records, every branch
+ *                              divergent). Huffman tables live in shared memory, one set per warp: a 10-bit direct
+ *                              table for literal/length codes, an 8-bit one for distance codes, canonical count/symbol
+ *                              arrays for the (rare) longer codes.
  *   abea_blow5_parse_kernel    one thread per record: the fixed fields in front of the signal (unaligned loads).
  *   abea_blow5_signal_kernel   one WARP per record: int16 samples (or svb-zd: 2-bit keys -> byte counts -> warp scan ->
  *                              values -> zigzag -> warp scan of the deltas) widened to the float samples the event
@@ -32,7 +35,7 @@
 #define B5_ERR_DATA 1     /* malformed stream / record */
 #define B5_ERR_OVERFLOW 2 /* the output capacity was too small (the host retries with more) */
 
-#define B5_INFLATE_THREADS 32
+#define B5_INFLATE_WARPS 8   /* records per CTA */
 #define B5_LIT_BITS 10
 #define B5_DIST_BITS 8
 
@@ -156,8 +159,8 @@ __device__ __forceinline__ int b5_decode(b5_bits_t& b, const uint16_t* tab, int 
     return b5_decode_slow(b, cnt, sym);
 }
 
-/* One thread inflates one zlib stream (slow5lib: inflate() on the whole record, slow5_press.c:921-1010). */
-__global__ void __launch_bounds__(B5_INFLATE_THREADS)
+/* Lane 0 of a warp inflates one zlib stream (slow5lib: inflate() on the whole record, slow5_press.c:921-1010). */
+__global__ void __launch_bounds__(32 * B5_INFLATE_WARPS)
 abea_inflate_kernel(const abea_b5rec_t* __restrict__ recs, int32_t n, const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
                     int32_t* __restrict__ out_len, int32_t* __restrict__ status) {
 #ifdef ABEA_SIMT_EMU
@@ -166,9 +169,9 @@ abea_inflate_kernel(const abea_b5rec_t* __restrict__ recs, int32_t n, const uint
     extern __shared__ __align__(16) unsigned char b5_dyn_smem[];
     unsigned char* dyn = b5_dyn_smem;
 #endif
-    const int32_t r = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
-    if (r >= n) return;
-    b5_tables_t& T = ((b5_tables_t*)dyn)[threadIdx.x];
+    const int32_t r = (int32_t)(blockIdx.x * B5_INFLATE_WARPS + (threadIdx.x >> 5));
+    if (r >= n || (threadIdx.x & 31) != 0) return;
+    b5_tables_t& T = ((b5_tables_t*)dyn)[threadIdx.x >> 5];
     const abea_b5rec_t rec = recs[r];
     uint8_t* o = out + rec.out_off;
     const int64_t cap = rec.out_cap;

@@ -123,10 +123,95 @@ static int test_rounding(long trials) {
     return bad != 0;
 }
 
+/* (3) one DP cell with ONE rounding (abea_cell_once): the reference rounds the three candidate sums to float and compares
+ *     the floats, ties L > U > D (src/align.c:378-392). Rounding is monotone, so the cell's score is RN(max of the three
+ *     unrounded sums); a candidate ties with (or is) the maximum exactly when it lies in the rounding interval of that
+ *     score, i.e. at or above its lower end lb — |R| + half an ulp of float, inclusive when R's last mantissa bit is even
+ *     — which for a NEGATIVE float-valued double R is an integer operation on its low word. All cell scores of a FAST
+ *     read are negative (every emission constant -0.918938 - log stdv is <= 0: checked per read) or -inf. */
+static void cell_ref(double lpd, double up, double left, double diag, double lp_step, double lp_stay, double lp_skip,
+                     double* score, int* from) {
+    volatile double d0 = diag + lp_step, u0 = up + lp_stay;
+    volatile float sd = (float)(d0 + lpd), su = (float)(u0 + lpd), sl = (float)(left + lp_skip);
+    float mx = sd;
+    int f = 0;
+    if (su > mx) mx = su;
+    if (mx == su) f = 1;
+    if (sl > mx) mx = sl;
+    if (mx == sl) f = 2;
+    *score = (double)mx;
+    *from = f;
+}
+static void cell_once(double lpd, double up, double left, double diag, double lp_step, double lp_stay, double lp_skip,
+                      double* score, int* from) {
+    volatile double d0 = diag + lp_step, u0 = up + lp_stay;
+    volatile double d = d0 + lpd, u = u0 + lpd, l = left + lp_skip;
+    double m2 = (u >= d) ? u : d;
+    double m3 = (l >= m2) ? l : m2;
+    double R = (double)(float)m3;
+    uint64_t rb = bits_from_d(R);
+    uint32_t lo = (uint32_t)rb;
+    uint32_t lb_lo = lo + 0x10000000u - ((lo >> 29) & 1u);
+    double lb = d_from_bits((rb & 0xffffffff00000000ull) | lb_lo);
+    int isL = !(l < lb), isU = !(u < lb);
+    *score = R;
+    *from = isL ? 2 : (isU ? 1 : 0);
+}
+static double neg_score(void) { /* a float-valued double: a negative band score, now and then -inf */
+    uint64_t r = rnd();
+    if ((r & 0x3f) == 0) return -INFINITY;
+    return (double)(-fabsf(rnd_float(-4, 17)));
+}
+static int test_cell_once(long trials) {
+    long bad = 0, ties = 0;
+    for (long i = 0; i < trials; i++) {
+        uint64_t r = rnd();
+        double lp_step = -fabs((double)rnd_float(-4, 2)) + (double)rnd_float(-45, -30);
+        double lp_stay = -fabs((double)rnd_float(-5, 2)) + (double)rnd_float(-45, -30);
+        double lp_skip = log(1e-10);
+        double lpd = (double)(-fabsf(rnd_float(-1, 9)));
+        double diag = neg_score(), up = neg_score(), left = neg_score();
+        switch (r & 7) { /* force near-ties between the candidates: they decide `from` */
+        case 0: case 1: { /* up such that u' is within a few float ulps of d' */
+            double d = (diag + lp_step) + lpd;
+            if (isfinite(d)) {
+                float t = (float)(d - lp_stay - lpd);
+                up = (double)f_from_bits(bits_from_f(t) + (uint32_t)((r >> 8) & 7) - 3u);
+            }
+            break; }
+        case 2: case 3: { /* left such that l' is within a few ulps of max(d', u') */
+            double d = (diag + lp_step) + lpd, u = (up + lp_stay) + lpd;
+            double m = d > u ? d : u;
+            if (isfinite(m)) {
+                float t = (float)(m - lp_skip);
+                left = (double)f_from_bits(bits_from_f(t) + (uint32_t)((r >> 8) & 7) - 3u);
+            }
+            break; }
+        case 4: if ((r >> 8) & 1) diag = -INFINITY; if ((r >> 9) & 1) up = -INFINITY; if ((r >> 10) & 1) left = -INFINITY; break;
+        default: break;
+        }
+        double s0, s1;
+        int f0, f1;
+        cell_ref(lpd, up, left, diag, lp_step, lp_stay, lp_skip, &s0, &f0);
+        cell_once(lpd, up, left, diag, lp_step, lp_stay, lp_skip, &s1, &f1);
+        {
+            volatile float sd = (float)((diag + lp_step) + lpd), su = (float)((up + lp_stay) + lpd), sl = (float)(left + lp_skip);
+            if (sd == su || su == sl || sd == sl) ties++;
+        }
+        if (bits_from_d(s0) != bits_from_d(s1) || f0 != f1) {
+            if (bad < 10) fprintf(stderr, "cell mismatch: diag=%a up=%a left=%a lp=%a: ref (%a,%d) once (%a,%d)\n", diag, up, left, lpd, s0, f0, s1, f1);
+            bad++;
+        }
+    }
+    printf("cell (one rounding): %ld trials, %ld with tied rounded candidates, %ld mismatches\n", trials, ties, bad);
+    return bad != 0;
+}
+
 int main(int argc, char** argv) {
     long m = argc > 1 ? atol(argv[1]) : 100;
     int rc = 0;
     rc |= test_emission(m * 1000000L);
     rc |= test_rounding(m * 1000000L);
+    rc |= test_cell_once(m * 1000000L);
     return rc;
 }
