@@ -110,7 +110,7 @@ _LIBS = {}
 
 
 def load_library(path: str | None = None):
-    path = path or LIB_PATH
+    path = path or os.environ.get("ABEA_LIB") or LIB_PATH   # ABEA_LIB: an experimental build of the same library (tools/)
     if path not in _LIBS:
         _LIBS[path] = _bind(path)
     return _LIBS[path]

@@ -187,6 +187,7 @@ struct abea_ctx {
      * (profiles/); re-derived from the per-read clock64 counts of the batches that run (calibrate()). */
     double cyc_wide = 400.0, cyc_narrow = 1000.0, cyc_long = 655.0, cyc_trace = 40.0;
     int calib_mode = 1;        /* ABEA_CALIBRATE=0 keeps the starting values */
+    size_t wide_excl_bytes = (size_t)160 * 1024; /* dynamic shared memory a wide CTA asks for to have its SM to itself */
     int tb_mode = 1;           /* ABEA_TB: 1 segment-parallel traceback (a walk per lane), 0 the serial walk */
     int tb_margin = 64;        /* ABEA_TB_MARGIN: bands a speculative walk starts above its segment */
     int calib_runs = 0;
@@ -543,18 +544,21 @@ int abea_create(abea_ctx_t** out, int device) {
         delete c;
         return ABEA_ERR_CUDA;
     }
-    /* Every kernel asks for the same (largest) shared-memory carve-out. An SM cannot change its L1/shared split while
-     * CTAs are resident, so a loader or prepare CTA running with a small carve-out would keep the persistent fill
-     * CTAs (64 KB / 160 KB of shared memory) off its SM until it exits — measured: the fill started only when the
-     * loader had finished. */
+    /* Every kernel asks for the SAME shared-memory carve-out. An SM cannot change its L1/shared split while CTAs are
+     * resident, so kernels with different preferences keep each other off an SM until the other's CTAs have left —
+     * measured twice: a loader CTA with a small carve-out held the persistent fill CTAs back until the loader had
+     * finished (round 1), and loader CTAs at 35 % held the wide CTAs (then still at 100 %) back, so that the longest
+     * reads started when the stream had ended (align_cuda 16.1 ms instead of 13.4; profiles/dropin_breakdown_r02.txt).
+     * ABEA_CARVEOUT: percent of the maximum shared memory. The narrow CTA needs 64 KB; what is left of the SM's 256 KB
+     * is L1, which the traceback's scattered reads and the cp.async staging live in: measured 10.04 ms (100 %) ->
+     * 9.75 (60 %) -> 9.71 (35 %, i.e. the 100 KB configuration) on the target config, traceback steps of median reads
+     * 190 -> 110 cycles (profiles/read_cycles_partd_r02_*). A wide CTA claims its SM by asking for so much dynamic
+     * shared memory that neither a narrow CTA nor a second wide one fits beside it (wide_excl_bytes). */
     {
         cudaError_t e = cudaSuccess;
-        /* ABEA_CARVEOUT: percent of the maximum shared memory asked for by the kernels that share SMs with the narrow
-         * fill (its CTA needs 64 KB; what is left of the 256 KB is L1, which the traceback's scattered reads and the
-         * cp.async staging live in). The wide kernel keeps 100: it claims its SM through 160 KB of shared memory. */
-        int carve = 35; /* 80 KB: measured 10.04 ms (100) -> 9.75 (60) -> 9.71 (35) on the target config, traceback steps of
-                         * median reads 190 -> 110 cycles (profiles/read_cycles_partd_r02_*) */
+        int carve = 35;
         if (const char* e = getenv("ABEA_CARVEOUT")) carve = std::min(100, std::max(30, atoi(e)));
+        c->wide_excl_bytes = carve < 60 ? (size_t)64 * 1024 : (size_t)160 * 1024;
         if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_load_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_load_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(abea_extract_means_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
@@ -564,7 +568,7 @@ int abea_create(abea_ctx_t** out, int device) {
                                (const void*)abea_fill_wide_kernel<true, false>, (const void*)abea_fill_wide_kernel<false, false>,
                                (const void*)abea_fill_wide_kernel<true, true>,  (const void*)abea_fill_wide_kernel<false, true>};
         for (int i = 0; i < 8; i++)
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(fills[i], cudaFuncAttributePreferredSharedMemoryCarveout, i < 4 ? carve : 100);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fills[i], cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) {
             delete c;
             return ABEA_ERR_CUDA;
@@ -943,7 +947,7 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                 /* A wide CTA is only faster than a lone narrow warp when it has its SM to itself (measured: 400
                  * cycles/band alone, 800 beside a narrow CTA). It therefore asks for so much dynamic shared memory
                  * that no narrow CTA fits on the same SM. Tiny batches (every read wide) do not need the exclusion. */
-                const size_t excl = (n > nw) ? (size_t)160 * 1024 : 0;
+                const size_t excl = (n > nw) ? c->wide_excl_bytes : 0;
                 /* the STREAM instantiations chase the loader (abea_wait_landed_events); the others assume a resident batch */
                 auto wide_fast = streaming ? abea_fill_wide_kernel<true, true> : abea_fill_wide_kernel<true, false>;
                 auto wide_exact = streaming ? abea_fill_wide_kernel<false, true> : abea_fill_wide_kernel<false, false>;
@@ -1743,7 +1747,16 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
         float* dst = h_means + event_ptr[i];
         for (int32_t e = e0; e < e1; e++) dst[e] = src[e].mean;
     };
-    auto worker = [&](int) {
+    double t_packed[64] = {0};
+    std::atomic<int> kernels_done(0);
+    const bool rag_late_copy = getenv("ABEA_RAG_LATE_COPY") != nullptr;
+    const int rag_poll_us = getenv("ABEA_RAG_POLL_US") ? atoi(getenv("ABEA_RAG_POLL_US")) : 0;
+    auto rag_pause = [](int us) {
+        if (us <= 0) { sched_yield(); return; }
+        struct timespec ts = {0, (long)us * 1000L};
+        nanosleep(&ts, nullptr);
+    };
+    auto worker = [&](int tid_) {
         for (;;) { /* (1) */
             const int32_t i0 = seq_next.fetch_add(16);
             if (i0 >= n) break;
@@ -1758,7 +1771,7 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
         if (!overlap) return;
         while (!c->rag_items_ready.load(std::memory_order_acquire)) { /* (2) */
             if (abort_flag.load()) return;
-            sched_yield();
+            rag_pause(0);
         }
         volatile uint32_t* flags = (volatile uint32_t*)c->h_hostready.p;
         const int32_t n_items = (int32_t)c->items.size();
@@ -1776,6 +1789,9 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
             flags[it] = 1u;
         }
         all_packed.fetch_add(1);
+        t_packed[tid_ & 63] = now_ms();
+        if (rag_late_copy) /* experiment: no copy-out while the kernels run */
+            while (!kernels_done.load() && !abort_flag.load()) rag_pause(50);
         const int32_t n_sched = (int32_t)c->finish_order.size(); /* (3) */
         for (;;) {
             const int32_t j = out_next.fetch_add(1);
@@ -1784,7 +1800,7 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
             int32_t np;
             while ((np = h_np[i]) < 0) {
                 if (abort_flag.load()) return;
-                sched_yield();
+                rag_pause(rag_poll_us);
             }
             std::atomic_thread_fence(std::memory_order_acquire);
             r->n_pairs[i] = np;
@@ -1801,7 +1817,15 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
         if (rc == ABEA_OK && !c->streaming) rc = fail(c, ABEA_ERR_STATE, "ragged batch was not streamed");
         if (rc == ABEA_OK) rc = run_impl(c, fin_pairs, fin_np, nullptr);
         if (rc != ABEA_OK) abort_flag.store(1);
+        kernels_done.store(1);
+        const double t_run = now_ms();
         c->pool.wait();
+        if (getenv("ABEA_TIME_PACK")) {
+            double tp = 0;
+            for (int i = 0; i < threads && i < 64; i++) tp = std::max(tp, t_packed[i]);
+            fprintf(stderr, "[abea ragged] layout+seq %.3f ms, kernels done at %.3f ms, means packed at %.3f ms, unpacked at %.3f ms (%d threads, %zu items)\n",
+                    t1 - t0, t_run - t0, tp - t0, now_ms() - t0, threads, c->items.size());
+        }
         if (rc != ABEA_OK && all_packed.load() == threads) {
             /* e.g. a stalled stream: the batch is complete in the staging, run it once more through the copy engine */
             rc = upload_impl(c, &b, nullptr, nullptr);

@@ -181,8 +181,7 @@ __global__ void abea_prepare_kernel(const abea_read_t* __restrict__ reads, int32
         kp.z = __fsub_rn(-0.918938f, m.level_log_stdv);               /* src/align.c:111-113 */
         kp.w = __frcp_rn(m.level_stdv);
         kparams[idx] = kp;
-        /* kp.z <= 0: every emission is <= 0, so every band score is negative (abea_cell_once relies on the sign) */
-        if (!(abea_sane_level(kp.x) && abea_sane_stdv(kp.y) && kp.z <= 0.0f)) atomicAnd(&read_flags[r], ~ABEA_READ_FAST);
+        if (!(abea_sane_level(kp.x) && abea_sane_stdv(kp.y))) atomicAnd(&read_flags[r], ~ABEA_READ_FAST);
     }
     /* events of scheduled reads, in schedule order (evs_off = running sum of n_events) */
     for (int64_t idx = tid; idx < total_events; idx += stride) {
@@ -507,36 +506,40 @@ __device__ __forceinline__ void abea_cell_dd(double lpd, double up, double left,
     score = isL ? rl : m;
     from = isL ? ABEA_FROM_L : (isU ? ABEA_FROM_U : ABEA_FROM_D);
 }
-/* The same cell with ONE rounding (narrow kernel, FAST reads). Rounding is monotone, so the cell's score is the rounded
- * MAXIMUM of the three unrounded sums, and a candidate ties with (or is) that maximum after rounding exactly when it
- * lies in the score's rounding interval, i.e. is not below its lower end lb = |R| + half a float ulp (inclusive when R's
- * last float mantissa bit is even: round-to-nearest-even). For a NEGATIVE float-valued double that is an integer
- * operation on the low word: bit 29 is the float's last mantissa bit, bit 28 half an ulp. Every cell score of a FAST
- * read is negative or -inf (abea_prepare_kernel admits a read only if all its emission constants -0.918938 - log stdv
- * are <= 0; transitions and the trim penalty are logs of probabilities); for -inf, lb is a NaN and the unordered
- * compares below give the reference's answer, L. Ties resolve L > U > D as in the reference (src/align.c:386-392).
- * 20 instructions instead of 28 per cell, 9 instead of 13 on the FP64 pipe; the rounding itself goes through the
- * conversion unit (2 F2F). tools/validate_fast_arith.c checks it against the three-rounding form (10^9 cells, a fifth
- * of them with tied rounded candidates). */
-__device__ __forceinline__ void abea_cell_once(double lpd, double up, double left, double diag, double lp_step,
-                                               double lp_stay, double lp_skip, double& score, uint32_t& from) {
-    const double d = __dadd_rn(__dadd_rn(diag, lp_step), lpd);
-    const double u = __dadd_rn(__dadd_rn(up, lp_stay), lpd);
-    const double l = __dadd_rn(left, lp_skip);
-    const double m2 = (u >= d) ? u : d;
-    const double m3 = (l >= m2) ? l : m2;
-    const double R = (double)__double2float_rn(m3);
-    const uint32_t lo = (uint32_t)__double2loint(R);
-    const double lb = __hiloint2double(__double2hiint(R), (int)(lo + 0x10000000u - ((lo >> 29) & 1u)));
-    const bool isL = !(l < lb), isU = !(u < lb);
-    score = R;
-    from = isL ? ABEA_FROM_L : (isU ? ABEA_FROM_U : ABEA_FROM_D);
+/* The cell as the narrow kernel computes it: the three sums in double, each narrowed to float by the hardware
+ * conversion (cvt.rn.f32.f64 — on sm_100 the DOWN conversion runs at the FP64 pipe's rate, 2 warp-ops/clk/SM; it is the
+ * UP conversion that crawls through the XU pipe at 0.5, profiles/microbench_r01.txt), then the reference's own float
+ * logic (src/align.c:386-392): the score is the float maximum, `from` is L if the left candidate equals it, else U if
+ * the up candidate does, else D — ties L > U > D. One up-conversion turns the score into the float-valued double the
+ * next bands add to. 15 instructions per cell (5 DADD, 3 + 1 F2F, 2 FMNMX, 2 FSETP, 2 SEL) against 28 for the form that
+ * rounds inside the FP64 pipe (abea_cell_dd<true>, still the wide kernel's: its per-band latency chain is shorter
+ * without the conversions) — the opcode mixes are in profiles/fill_narrow_opcode_mix_*_r02.txt. No range assumption:
+ * these ARE the reference's operations. */
+__device__ __forceinline__ void abea_cell_f32(double lpd, double up, double left, double diag, double lp_step,
+                                              double lp_stay, double lp_skip, double& score, uint32_t& from) {
+    const float sd = __double2float_rn(__dadd_rn(__dadd_rn(diag, lp_step), lpd));
+    const float su = __double2float_rn(__dadd_rn(__dadd_rn(up, lp_stay), lpd));
+    const float sl = __double2float_rn(__dadd_rn(left, lp_skip));
+    const float m = fmaxf(fmaxf(sd, su), sl); /* no NaN ever: the candidates are finite or -inf */
+    score = (double)m;
+    from = (sl == m) ? ABEA_FROM_L : ((su == m) ? ABEA_FROM_U : ABEA_FROM_D);
 }
 
 template <bool FAST>
 __device__ __forceinline__ void abea_cell_d(float lp, double up, double left, double diag, double lp_step,
                                             double lp_stay, double lp_skip, double& score, uint32_t& from) {
     abea_cell_dd<FAST>((double)lp, up, left, diag, lp_step, lp_stay, lp_skip, score, from);
+}
+
+/* the wide kernel's cell: ABEA_WIDE_CELL_F32 selects the float-maximum form for an experiment build */
+template <bool FAST>
+__device__ __forceinline__ void abea_wide_cell(double lpd, double up, double left, double diag, double lp_step,
+                                               double lp_stay, double lp_skip, double& score, uint32_t& from) {
+#ifdef ABEA_WIDE_CELL_F32
+    abea_cell_f32(lpd, up, left, diag, lp_step, lp_stay, lp_skip, score, from);
+#else
+    abea_cell_dd<FAST>(lpd, up, left, diag, lp_step, lp_stay, lp_skip, score, from);
+#endif
 }
 
 /* cp.async helpers (LDGSTS on sm_100a); the CPU emulator copies synchronously */
@@ -1279,7 +1282,7 @@ __device__ __forceinline__ void abea_band_cells(const float* x, const float4* kp
         else if (!RIGHT && !PREV_RIGHT) diag = (c > 0) ? B.R[c > 0 ? c - 1 : 0] : B.lo;
         else diag = B.R[c];
         float lp = abea_emission_t<FAST>(x[c], kp[c]);
-        if (FAST) abea_cell_once((double)lp, up, left, diag, lp_step, lp_stay, lp_skip, Rn[c], fr[c]);
+        if (FAST) abea_cell_f32((double)lp, up, left, diag, lp_step, lp_stay, lp_skip, Rn[c], fr[c]);
         else abea_cell_d<FAST>(lp, up, left, diag, lp_step, lp_stay, lp_skip, Rn[c], fr[c]);
     }
 }
@@ -1442,7 +1445,9 @@ __device__ __forceinline__ bool abea_fill_step(abea_fill_ctx_t& cx, float* x, fl
  * read longer than long_thr bands, they wait between reads — so the reads that set the makespan run alone on their
  * sub-partition (~655 instead of ~780 cycles per band, profiles/README.md) at the cost of idling a few of the 592
  * sub-partitions' second slots. queue[0] counts pulls, queue[1] the head, queue[2] the tail. */
+#ifndef ABEA_NARROW_WARPS_MAX
 #define ABEA_NARROW_WARPS_MAX 12
+#endif
 /* Register budget. A resident batch: the CTA's 12 warps may use the whole register file (launch bound 384 threads ->
  * 162 registers, 8 % fewer instructions than at 124: cfg2 11.08 -> 10.81 ms). A streamed batch: the CTAs of
  * abea_load_kernel must fit on the same SMs BESIDE the persistent narrow CTAs (with 162 x 384 registers taken they do
@@ -1804,8 +1809,8 @@ __device__ __forceinline__ void abea_wide_step(abea_wide_ctx_t& cx, abea_wide_sm
             cx.kchunk_hi += 1;
             abea_wide_stage(&sm, cx.ev, cx.kpr, -1, cx.kchunk_hi, cx.E, cx.K, tid);
         }
-        if (cx.prev_right) abea_cell_dd<FAST>(cx.lpd_rt, A.hi, A.R, B.hi, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
-        else abea_cell_dd<FAST>(cx.lpd_rt, A.hi, A.R, B.R, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+        if (cx.prev_right) abea_wide_cell<FAST>(cx.lpd_rt, A.hi, A.R, B.hi, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+        else abea_wide_cell<FAST>(cx.lpd_rt, A.hi, A.R, B.R, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
     } else {
         cx.eb += 1;
         cx.x_cur = cx.x_dn;
@@ -1820,8 +1825,8 @@ __device__ __forceinline__ void abea_wide_step(abea_wide_ctx_t& cx, abea_wide_sm
             }
             abea_wide_stage(&sm, cx.ev, cx.kpr, cx.echunk_hi, -1, cx.E, cx.K, tid);
         }
-        if (cx.prev_right) abea_cell_dd<FAST>(cx.lpd_dn, A.R, A.lo, B.R, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
-        else abea_cell_dd<FAST>(cx.lpd_dn, A.R, A.lo, B.lo, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+        if (cx.prev_right) abea_wide_cell<FAST>(cx.lpd_dn, A.R, A.lo, B.R, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
+        else abea_wide_cell<FAST>(cx.lpd_dn, A.R, A.lo, B.lo, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
     }
     cx.prev_right = right;
 
