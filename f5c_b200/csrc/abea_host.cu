@@ -172,6 +172,12 @@ struct abea_ctx {
     DevBuf d_ready, d_items, d_capptr, d_dense_off;
     std::vector<abea_load_item_t> items;
     std::vector<int32_t> finish_order; /* scheduled reads by the time the replayed schedule expects them to finish */
+    int32_t n_items = 0;        /* entries of `items` in use */
+    int32_t n_first_items = 0;  /* of those, the first wave's first pieces: shipped before the rest of the list exists */
+    bool pending_order = false; /* the rest of the list is still to be built and shipped (finish_load_order) */
+    bool rag_mode = false;
+    const void* ev_alias_cur = nullptr;
+    std::atomic<int> rag_items_final{0};
     std::vector<double> sched_start, sched_finish; /* scratch of build_load_order, kept across batches */
     struct sched_slot_t { double t; int kind; };
     std::vector<sched_slot_t> sched_heap;
@@ -411,7 +417,7 @@ void build_load_order(abea_ctx* c, bool want_finish_order) {
         const double rt = rate(r);
         const double fill = nb * rt * (rt < CYC_NARROW ? c->load_crit : 1.0);
         const double per_byte = fill / (double)(g.b - g.a); /* time per byte of the read's own range */
-        for (int32_t q = 0; q < g.n_pieces; q++) {
+        for (int32_t q = (r < c->n_first_items) ? 1 : 0; q < g.n_pieces; q++) {
             const int64_t off = g.lo + (int64_t)q * g.piece - g.a; /* first byte of the piece, relative to the read's first */
             const double tq = start[r] + (off > 0 ? (double)off * per_byte : 0.0);
             int bk = (int)(tq * to_bucket);
@@ -421,8 +427,11 @@ void build_load_order(abea_ctx* c, bool want_finish_order) {
         }
     }
     for (int i = 0; i < NBUCKET; i++) count[(size_t)i + 1] += count[(size_t)i];
-    c->items.resize(need.size());
-    for (const need_t& x : need) c->items[(size_t)count[(size_t)x.bucket]++] = abea_load_item_t{x.read, x.piece};
+    /* the first pieces of the first wave are already in the list (and on their way): the rest follows them */
+    const size_t base = (size_t)c->n_first_items;
+    if (c->items.size() < base + need.size()) c->items.resize(base + need.size());
+    for (const need_t& x : need) c->items[base + (size_t)count[(size_t)x.bucket]++] = abea_load_item_t{x.read, x.piece};
+    c->n_items = (int32_t)(base + need.size());
     if (want_finish_order) {
         c->finish_order.resize((size_t)n);
         for (int64_t r = 0; r < n; r++) c->finish_order[(size_t)r] = (int32_t)r;
@@ -461,6 +470,49 @@ int calibrate(abea_ctx* c, int32_t long_thr) {
     if (shared.size() >= 64) c->cyc_narrow = clampd(median(shared), 1000.0);
     if (trace.size() >= 64) c->cyc_trace = std::min(700.0, std::max(2.0, median(trace))); /* 350 serial, a few tens segment-parallel */
     return 0;
+}
+
+/* items [first, first + count) of the loader's work list on the loader's stream; `slot`: its counter in d_queue */
+int launch_loader(abea_ctx* c, int32_t first, int32_t count, int slot) {
+    if (count <= 0) return ABEA_OK;
+    const int blocks = (int)std::min<int64_t>((int64_t)count, (int64_t)c->load_ctas);
+    const uint32_t* host_ready = c->rag_mode ? (const uint32_t*)mapped_alias(c->h_hostready.p) + first : nullptr;
+    if (c->load_aos)
+        ABEA_LAUNCH(abea_load_kernel<true>, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
+                    (const abea_load_item_t*)c->d_items.p + first, count, (const uint4*)c->ev_alias_cur,
+                    (float*)c->d_means.p, c->event_bytes, (uint32_t*)c->d_flags.p, (uint32_t*)c->d_ready.p,
+                    (int32_t*)c->d_queue.p + slot, c->load_piece_cur, (const volatile uint32_t*)host_ready,
+                    (uint32_t*)c->d_queue.p + 15);
+    else
+        ABEA_LAUNCH(abea_load_kernel<false>, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
+                    (const abea_load_item_t*)c->d_items.p + first, count, (const uint4*)c->ev_alias_cur,
+                    (float*)c->d_means.p, c->event_bytes, (uint32_t*)c->d_flags.p, (uint32_t*)c->d_ready.p,
+                    (int32_t*)c->d_queue.p + slot, c->load_piece_cur, (const volatile uint32_t*)host_ready,
+                    (uint32_t*)c->d_queue.p + 15);
+    CU(cudaGetLastError());
+    return ABEA_OK;
+}
+
+/* the rest of the loader's work list, built while the GPU is already filling the first wave (see upload_impl) */
+int finish_load_order(abea_ctx* c) {
+    const double t0 = now_ms();
+    build_load_order(c, c->rag_mode);
+    const int32_t rest = c->n_items - c->n_first_items;
+    if (rest > 0) {
+        memcpy((abea_load_item_t*)c->h_items.p + c->n_first_items, c->items.data() + c->n_first_items, (size_t)rest * sizeof(abea_load_item_t));
+        CU(cudaMemcpyAsync((abea_load_item_t*)c->d_items.p + c->n_first_items, (abea_load_item_t*)c->h_items.p + c->n_first_items,
+                           (size_t)rest * sizeof(abea_load_item_t), cudaMemcpyHostToDevice, c->load_stream));
+    }
+    if (c->rag_mode) {
+        c->rag_items_ready.store(c->n_items, std::memory_order_release);
+        c->rag_items_final.store(1, std::memory_order_release);
+    }
+    const int rc = launch_loader(c, c->n_first_items, rest, 13);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_loaded, c->load_stream));
+    c->pending_order = false;
+    if (getenv("ABEA_TIME_PACK")) fprintf(stderr, "[abea pack] rest of the load order %.3f ms (%d items), behind the fill launches\n", now_ms() - t0, rest);
+    return ABEA_OK;
 }
 
 } // namespace
@@ -826,45 +878,55 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         c->prepared = true;
         /* Work list of the loader: every (read, piece) in the order the fill is expected to NEED it. The fill starts
          * a read when its first piece has landed and then chases the loader piece by piece, so what matters is when
-         * each piece is first touched. That is predicted by replaying the schedule with nominal rates (cycles per
-         * band measured on B200, profiles/README.md): wide CTAs take reads [0, n_wide) in order, primary warps pull
-         * from the head of the longest-first order, secondary warps from the tail. */
+         * each piece is first touched. That is predicted by replaying the schedule with the scheduler's model of the
+         * kernels (build_load_order) — half a millisecond of host work. The FIRST pieces of the reads the first wave
+         * of warps starts with need no prediction: they go out at once, with a loader launch of their own, and the
+         * rest of the list is built and shipped after the fill kernels have been launched (finish_load_order). */
         const double t_enq = now_ms();
-        build_load_order(c, rag);
-        if (dev_reserve(c, c->d_items, c->items.size() * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
-        if (host_reserve(c, c->h_items, c->items.size() * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
-        memcpy(c->h_items.p, c->items.data(), c->items.size() * sizeof(abea_load_item_t));
+        {
+            const int wpc = c->fill_warps_per_cta;
+            const int nw = c->n_wide;
+            const int wide_sms = nw > 0 ? std::min(c->sm_count, nw + c->sm_reserve) : 0;
+            int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((int64_t)(c->sm_count - wide_sms) * c->fill_ctas_per_sm,
+                                                                    ((int64_t)n_sched - nw + wpc - 1) / wpc));
+            c->n_first_items = (int32_t)std::min<int64_t>((int64_t)n_sched, (int64_t)nw + blocks * wpc);
+        }
+        const size_t max_items = (size_t)n_sched * 2 + (size_t)(c->event_bytes / c->load_piece_cur) + 8;
+        if (c->items.size() < max_items) c->items.resize(max_items);
+        for (int32_t r = 0; r < c->n_first_items; r++) c->items[(size_t)r] = abea_load_item_t{r, 0};
+        c->n_items = c->n_first_items;
+        if (dev_reserve(c, c->d_items, max_items * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
+        if (host_reserve(c, c->h_items, max_items * sizeof(abea_load_item_t))) return ABEA_ERR_CUDA;
+        memcpy(c->h_items.p, c->items.data(), (size_t)c->n_first_items * sizeof(abea_load_item_t));
         const uint32_t* host_ready = nullptr;
-        if (rag) { /* one flag per work item, set by the packer threads; they start as soon as the list exists */
-            if (host_reserve(c, c->h_hostready, (c->items.size() + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
-            memset(c->h_hostready.p, 0, (c->items.size() + 1) * sizeof(uint32_t));
+        c->rag_mode = rag;
+        if (rag) { /* one flag per work item, set by the packer threads; they start as soon as a part of the list exists */
+            if (host_reserve(c, c->h_hostready, (max_items + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
+            memset(c->h_hostready.p, 0, (max_items + 1) * sizeof(uint32_t));
             host_ready = (const uint32_t*)mapped_alias(c->h_hostready.p);
             if (!host_ready) return fail(c, ABEA_ERR_CUDA, "pinned staging is not mapped into the device address space");
-            c->rag_items_ready.store(1, std::memory_order_release);
+            c->rag_items_final.store(0, std::memory_order_relaxed);
+            c->rag_items_ready.store(c->n_first_items, std::memory_order_release);
         }
         t2 = now_ms();
         if (getenv("ABEA_TIME_PACK"))
-            fprintf(stderr, "[abea pack] descriptors+sort %.3f ms, reserve+enqueue+prepare %.3f ms, load order %.3f ms (%zu items)\n",
-                    t1 - t0, t_enq - t1, t2 - t_enq, c->items.size());
+            fprintf(stderr, "[abea pack] descriptors+sort %.3f ms, reserve+enqueue+prepare %.3f ms, first wave list %.3f ms (%d items)\n",
+                    t1 - t0, t_enq - t1, t2 - t_enq, c->n_first_items);
         /* the loader's stream waits for the descriptors and the cleared counters, not for the k-mer kernel */
         CU(cudaStreamWaitEvent(c->load_stream, c->ev_meta, 0));
-        CU(cudaMemcpyAsync(c->d_items.p, c->h_items.p, c->items.size() * sizeof(abea_load_item_t),
+        CU(cudaMemcpyAsync(c->d_items.p, c->h_items.p, (size_t)c->n_first_items * sizeof(abea_load_item_t),
                            cudaMemcpyHostToDevice, c->load_stream));
         CU(cudaEventRecord(c->ev_load0, c->load_stream));
-        const int blocks = (int)std::min<size_t>(c->items.size(), (size_t)c->load_ctas);
-        if (c->load_aos)
-            ABEA_LAUNCH(abea_load_kernel<true>, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
-                        (const abea_load_item_t*)c->d_items.p, (int32_t)c->items.size(), (const uint4*)ev_alias,
-                        (float*)c->d_means.p, c->event_bytes, (uint32_t*)c->d_flags.p, (uint32_t*)c->d_ready.p,
-                        (int32_t*)c->d_queue.p + 12, c->load_piece_cur, (const volatile uint32_t*)host_ready,
-                        (uint32_t*)c->d_queue.p + 15);
-        else
-            ABEA_LAUNCH(abea_load_kernel<false>, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
-                        (const abea_load_item_t*)c->d_items.p, (int32_t)c->items.size(), (const uint4*)ev_alias,
-                        (float*)c->d_means.p, c->event_bytes, (uint32_t*)c->d_flags.p, (uint32_t*)c->d_ready.p,
-                        (int32_t*)c->d_queue.p + 12, c->load_piece_cur, (const volatile uint32_t*)host_ready,
-                        (uint32_t*)c->d_queue.p + 15);
-        CU(cudaEventRecord(c->ev_loaded, c->load_stream));
+        c->ev_alias_cur = ev_alias;
+        int rc_l = launch_loader(c, 0, c->n_first_items, 12);
+        if (rc_l) return rc_l;
+        c->pending_order = true;
+#ifdef ABEA_SIMT_EMU /* the emulator runs a kernel to completion at its launch: the whole list must be in before the fill */
+        {
+            const int rc_f = finish_load_order(c);
+            if (rc_f) return rc_f;
+        }
+#endif
         c->streaming = true;
     } else if (have_means) {
         if (n_ev_total)
@@ -999,8 +1061,12 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
         CU(cudaEventRecord(c->ev[EV_K2], c->stream));
     }
     if (streaming) {
+        if (c->pending_order) { /* the fill kernels are launched and working on the first wave: now the rest of the list */
+            const int rc = finish_load_order(c);
+            if (rc) return rc;
+        }
         CU(cudaStreamWaitEvent(c->stream, c->ev_loaded, 0));
-        launches++;
+        launches += 2;
     }
     CU(cudaEventRecord(c->ev[EV_K3], c->stream));
     uint32_t stalled = 0;
@@ -1769,16 +1835,21 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
             seq_left.fetch_sub(i1 - i0);
         }
         if (!overlap) return;
-        while (!c->rag_items_ready.load(std::memory_order_acquire)) { /* (2) */
+        while (c->rag_items_ready.load(std::memory_order_acquire) <= 0) { /* (2) */
             if (abort_flag.load()) return;
             rag_pause(0);
         }
         volatile uint32_t* flags = (volatile uint32_t*)c->h_hostready.p;
-        const int32_t n_items = (int32_t)c->items.size();
         const int64_t total_bytes = c->event_bytes, piece = c->load_piece_cur;
         for (;;) {
             const int32_t it = item_next.fetch_add(1);
-            if (it >= n_items) break;
+            bool none_left = false;
+            while (it >= c->rag_items_ready.load(std::memory_order_acquire)) { /* the list grows once (finish_load_order) */
+                if (c->rag_items_final.load(std::memory_order_acquire) && it >= c->rag_items_ready.load(std::memory_order_acquire)) { none_left = true; break; }
+                if (abort_flag.load()) return;
+                rag_pause(0);
+            }
+            if (none_left) break;
             const abea_load_item_t item = c->items[(size_t)it];
             const abea_read_t& rd = c->reads[(size_t)item.read];
             const abea_load_geom_t g = abea_load_geom(rd.ev_off, rd.n_events, total_bytes, piece, (int64_t)sizeof(float));
@@ -1824,7 +1895,7 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
             double tp = 0;
             for (int i = 0; i < threads && i < 64; i++) tp = std::max(tp, t_packed[i]);
             fprintf(stderr, "[abea ragged] layout+seq %.3f ms, kernels done at %.3f ms, means packed at %.3f ms, unpacked at %.3f ms (%d threads, %zu items)\n",
-                    t1 - t0, t_run - t0, tp - t0, now_ms() - t0, threads, c->items.size());
+                    t1 - t0, t_run - t0, tp - t0, now_ms() - t0, threads, (size_t)c->n_items);
         }
         if (rc != ABEA_OK && all_packed.load() == threads) {
             /* e.g. a stalled stream: the batch is complete in the staging, run it once more through the copy engine */
