@@ -166,6 +166,7 @@ struct abea_ctx {
      * the fill asks for them, pair lists written to the caller's mapped buffer by the traceback */
     int stream_mode = 3;       /* ABEA_STREAM: bit 0 events in, bit 1 pair lists out; 0: always stage through the copy engine */
     int load_ctas = 64;        /* ABEA_LOAD_CTAS */
+    int load_ctas_rag = 296;   /* ABEA_LOAD_CTAS_RAG: loader CTAs when the host packs while the loader runs (2 per SM) */
     int64_t load_piece = 0;    /* ABEA_LOAD_PIECE_KB: smallest piece of a read the loader delivers (0: 2048 events) */
     int64_t load_piece_cur = ABEA_LOAD_PIECE_BYTES; /* the value in use for the batch being streamed */
     double load_crit = 1.0;    /* ABEA_LOAD_CRIT: need times of the makespan-setting reads (wide, long) are scaled by this */
@@ -475,7 +476,12 @@ int calibrate(abea_ctx* c, int32_t long_thr) {
 /* items [first, first + count) of the loader's work list on the loader's stream; `slot`: its counter in d_queue */
 int launch_loader(abea_ctx* c, int32_t first, int32_t count, int slot) {
     if (count <= 0) return ABEA_OK;
-    const int blocks = (int)std::min<int64_t>((int64_t)count, (int64_t)c->load_ctas);
+    /* A loader CTA has one item in flight. When the items are gated by the host packers (ragged front door) an item's
+     * latency includes the poll of its flag over PCIe and the host's memory system is busy with the packers: 64 CTAs
+     * then bound the batch (align_cuda 12.6 ms; 12.1 with 148, 11.6 with 296; profiles/dropin_experiments_r02.txt),
+     * while with everything already in pinned memory 64 are the fastest (10.47 / 10.60 / 10.71 ms). */
+    const int ctas = c->rag_mode ? c->load_ctas_rag : c->load_ctas;
+    const int blocks = (int)std::min<int64_t>((int64_t)count, (int64_t)ctas);
     const uint32_t* host_ready = c->rag_mode ? (const uint32_t*)mapped_alias(c->h_hostready.p) + first : nullptr;
     if (c->load_aos)
         ABEA_LAUNCH(abea_load_kernel<true>, blocks, ABEA_LOAD_THREADS, c->load_stream, (const abea_read_t*)c->d_reads.p,
@@ -586,7 +592,9 @@ int abea_create(abea_ctx_t** out, int device) {
     if (const char* e = getenv("ABEA_SCHED")) c->sched_policy = atoi(e) ? 1 : 0;
     if (const char* e = getenv("ABEA_SM_RESERVE")) c->sm_reserve = std::max(0, atoi(e));
     if (const char* e = getenv("ABEA_STREAM")) c->stream_mode = atoi(e);
-    if (const char* e = getenv("ABEA_LOAD_CTAS")) c->load_ctas = std::max(1, atoi(e));
+    c->load_ctas_rag = 2 * c->sm_count;
+    if (const char* e = getenv("ABEA_LOAD_CTAS")) c->load_ctas = c->load_ctas_rag = std::max(1, atoi(e));
+    if (const char* e = getenv("ABEA_LOAD_CTAS_RAG")) c->load_ctas_rag = std::max(1, atoi(e));
     if (const char* e = getenv("ABEA_LOAD_PIECE_KB")) c->load_piece = (int64_t)std::max(1, atoi(e)) * 1024;
     if (const char* e = getenv("ABEA_LOAD_CRIT")) c->load_crit = atof(e);
     if (const char* e = getenv("ABEA_EVT_CHUNK")) c->evt_chunk = std::max(8, atoi(e) / 4 * 4);
