@@ -522,12 +522,15 @@ def main():
             ctx.close()
             ctx = None
             line["configs"] = other_configs(lambda: AbeaContext(local_rank), a, peak, cores)
-        print(json.dumps(line), flush=True)
     if ctx is not None:
         ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:   # last thing written, on a line of its own (NCCL and torch print to the same pipe under torchrun)
+        sys.stderr.flush()
+        sys.stdout.write("\n" + json.dumps(line) + "\n")
+        sys.stdout.flush()
 
 
 def reference_arm(a, rank, world):

@@ -121,14 +121,16 @@ class ResultExchange:
         self.counts[2:2 + self.n_reads] = self._counts_view(ctx)
         dist.gather(self.counts, self.recv_counts, dst=0)
         if self.rank != 0:
-            if total:
-                dist.send(self.send[:total], dst=0)
+            if total:   # one grouped point-to-point operation per shard (ncclGroupStart / ncclSend / ncclGroupEnd)
+                for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, self.send[:total], 0)]):
+                    q.wait()
             return None
         heads = torch.stack([c[:2] for c in self.recv_counts]).cpu().tolist()      # the one host sync of the exchange
         sizes = [int(h[0]) | (int(h[1]) << 31) for h in heads]
-        reqs = [dist.irecv(self.recv[r][:sizes[r]], src=r) for r in range(1, self.world) if sizes[r]]
-        for q in reqs:
-            q.wait()
+        ops = [dist.P2POp(dist.irecv, self.recv[r][:sizes[r]], r) for r in range(1, self.world) if sizes[r]]
+        if ops:
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
         return [(self.recv_counts[r][2:2 + self.meta[r][0]], self.recv[r][:sizes[r]]) for r in range(self.world)]
 
 
