@@ -468,7 +468,10 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms_max / a.steps, "nccl_gather_ms_per_step": gather_ms / a.steps,
                     "load_ms_max_over_ranks": load_ms_max,
-                    "call": "abea_align_batch (C ABI) with pinned host buffers: event means 4 B/event in, pair lists out",
+                    "call": "abea_align_batch (C ABI) with pinned host buffers: event means 4 B/event in; pair lists out as "
+                            "path codes (first pair + 2 bits per step) that the library's host threads expand into the "
+                            "caller's buffer while the kernels run (ABEA_STREAM bit 2; d2h bytes are what crossed PCIe)",
+                    "host_threads": ctx.host_threads(),
                     "last_step_parts_ms_rank0": e2e_parts,
                     "last_step_output_equals_resident_result_all_ranks": e2e_ok_all},
             "gpu_launches": int(launches + e2e_launches),

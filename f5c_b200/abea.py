@@ -102,6 +102,7 @@ def _bind(path: str):
     lib.abea_host_free.argtypes = [vp]
     lib.abea_host_free.restype = None
     lib.abea_device_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p]
+    lib.abea_host_threads.argtypes = [vp, ctypes.c_int]
     lib.abea_version.restype = ctypes.c_char_p
     return lib
 
@@ -197,6 +198,10 @@ class AbeaContext:
         name = ctypes.create_string_buffer(256)
         self.lib.abea_device_info(self._h, ctypes.byref(n), name)
         return n.value, name.value.decode()
+
+    def host_threads(self, threads: int = -1) -> int:
+        """Threads align_batch expands path codes with (abea_host_threads); a negative value only queries."""
+        return int(self.lib.abea_host_threads(self._h, int(threads)))
 
     # -- pinned host memory ----------------------------------------------------------------------------
     def pinned_empty(self, shape, dtype) -> np.ndarray:

@@ -164,7 +164,9 @@ struct abea_ctx {
 
     /* streaming (abea_align_batch with pinned host buffers): events pulled over PCIe by abea_load_kernel in the order
      * the fill asks for them, pair lists written to the caller's mapped buffer by the traceback */
-    int stream_mode = 3;       /* ABEA_STREAM: bit 0 events in, bit 1 pair lists out; 0: always stage through the copy engine */
+    int stream_mode = 5;       /* ABEA_STREAM: bit 0 events streamed in; pair lists out: bit 2 as path codes expanded by host
+                                * threads (wins), bit 1 written whole into the caller's mapped buffer; 0: copy engine both ways */
+    int host_threads = 8;      /* ABEA_HOST_THREADS: threads of abea_align_batch that expand path codes (0: no codes) */
     int load_ctas = 64;        /* ABEA_LOAD_CTAS */
     int load_ctas_rag = 296;   /* ABEA_LOAD_CTAS_RAG: loader CTAs when the host packs while the loader runs (2 per SM) */
     int64_t load_piece = 0;    /* ABEA_LOAD_PIECE_KB: smallest piece of a read the loader delivers (0: 2048 events) */
@@ -188,6 +190,7 @@ struct abea_ctx {
     /* abea_align_ragged */
     abea_pool pool;
     HostBuf h_rseq, h_rmeans, h_rpairs, h_rnp, h_hostready, h_rmeta;
+    HostBuf h_codes, h_fnp;    /* path codes and per-read counts written by the traceback (mapped) */
     std::atomic<int> rag_items_ready{0};
     /* Cycles per band of the three forms a read is filled in, cycles per traceback step and the band time of a fully
      * loaded sub-partition: the scheduler's model of the kernels. Starting values measured on B200 at 1.965 GHz
@@ -327,6 +330,30 @@ double wide_threshold(const abea_ctx* c, int64_t total_bands) {
     const double cyc_batch = (double)total_bands * cyc_tput(c) * 1.08 / ((double)c->sm_count * 4.0);
     return std::max(c->wide_min_bands, c->wide_alpha * 1.25 * cyc_batch / c->cyc_long);
 }
+
+/* A pair list from its path codes (abea_code_t, abea_kernels.cuh): the first pair, then one step per bit. */
+void decode_codes(const abea_code_t* w, int32_t n, abea_pair_t* dst) {
+    if (n <= 0) return;
+    int32_t k = (int32_t)w[0].a, e = (int32_t)w[0].b;
+    dst[0].ref_pos = k;
+    dst[0].read_pos = e;
+    int32_t j = 1;
+    for (const abea_code_t* q = w + 1; j < n; q++) {
+        uint32_t mk = q->a, me = q->b;
+        const int32_t lim = std::min<int32_t>(32, n - j);
+        for (int32_t t = 0; t < lim; t++) {
+            k += (int32_t)(mk & 1u);
+            e += (int32_t)(me & 1u);
+            mk >>= 1;
+            me >>= 1;
+            dst[j].ref_pos = k;
+            dst[j].read_pos = e;
+            j++;
+        }
+    }
+}
+int64_t code_words(int64_t total_pair_cap, int32_t n_reads) { return (total_pair_cap >> 5) + 2 * (int64_t)n_reads + 2; }
+int64_t code_bytes_used(int32_t np) { return np > 0 ? (int64_t)(1 + (np - 1 + 31) / 32) * (int64_t)sizeof(abea_code_t) : 0; }
 
 /* see upload_impl */
 void build_load_order(abea_ctx* c, bool want_finish_order) {
@@ -592,6 +619,13 @@ int abea_create(abea_ctx_t** out, int device) {
     if (const char* e = getenv("ABEA_SCHED")) c->sched_policy = atoi(e) ? 1 : 0;
     if (const char* e = getenv("ABEA_SM_RESERVE")) c->sm_reserve = std::max(0, atoi(e));
     if (const char* e = getenv("ABEA_STREAM")) c->stream_mode = atoi(e);
+    {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        int cpus = (sched_getaffinity(0, sizeof(set), &set) == 0) ? CPU_COUNT(&set) : 1;
+        c->host_threads = std::max(1, std::min(8, cpus));
+    }
+    if (const char* e = getenv("ABEA_HOST_THREADS")) c->host_threads = std::min(64, std::max(0, atoi(e)));
     c->load_ctas_rag = 2 * c->sm_count;
     if (const char* e = getenv("ABEA_LOAD_CTAS")) c->load_ctas = c->load_ctas_rag = std::max(1, atoi(e));
     if (const char* e = getenv("ABEA_LOAD_CTAS_RAG")) c->load_ctas_rag = std::max(1, atoi(e));
@@ -656,7 +690,7 @@ void abea_destroy(abea_ctx_t* c) {
     if (c->h_pairs.p) cudaFreeHost(c->h_pairs.p);
     if (c->h_reads.p) cudaFreeHost(c->h_reads.p);
     if (c->h_items.p) cudaFreeHost(c->h_items.p);
-    for (HostBuf* hb : {&c->h_rseq, &c->h_rmeans, &c->h_rpairs, &c->h_rnp, &c->h_hostready, &c->h_rmeta, &c->h_b5})
+    for (HostBuf* hb : {&c->h_rseq, &c->h_rmeans, &c->h_rpairs, &c->h_rnp, &c->h_hostready, &c->h_rmeta, &c->h_b5, &c->h_codes, &c->h_fnp})
         if (hb->p) cudaFreeHost(hb->p);
     for (int i = 0; i < EV_COUNT; i++)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -669,6 +703,12 @@ void abea_destroy(abea_ctx_t* c) {
     if (c->wide_stream) cudaStreamDestroy(c->wide_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
+}
+
+int abea_host_threads(abea_ctx_t* c, int threads) {
+    if (!c) return ABEA_ERR_ARG;
+    if (threads >= 0) c->host_threads = std::min(64, threads);
+    return c->host_threads;
 }
 
 int abea_device_info(abea_ctx_t* c, int* sm_count, char* name) {
@@ -974,7 +1014,8 @@ int abea_upload_batch(abea_ctx_t* c, const abea_batch_t* b, abea_timing_t* timin
 
 /* fin_pairs / fin_np: device-side aliases of the caller's pinned output buffers (canonical layout), or NULL: the
  * lists stay in d_pairs / d_npairs for abea_download. */
-static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea_timing_t* timing) {
+static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea_timing_t* timing,
+                    abea_code_t* fin_codes = nullptr) {
     if (!c) return ABEA_ERR_ARG;
     if (!c->uploaded) return fail(c, ABEA_ERR_STATE, "abea_run before abea_upload_batch");
     if (c->need_scalings)
@@ -988,6 +1029,7 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
     io.ready = streaming ? (const uint32_t*)c->d_ready.p : nullptr;
     io.pairs_final = fin_pairs;
     io.n_pairs_final = fin_np;
+    io.codes_final = fin_codes;
     io.n_pairs_dev = (int32_t*)c->d_npairs.p;
     io.stalled = (uint32_t*)c->d_queue.p + 15; /* zeroed with the queue */
     io.tb_mode = c->tb_mode;
@@ -1102,6 +1144,7 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
         if (cudaEventElapsedTime(&ms, c->ev_load0, c->ev_loaded) == cudaSuccess) c->last.load_ms = ms;
     }
     if (fin_pairs) c->last.streamed |= 2;
+    if (fin_codes) c->last.streamed |= 4;
     c->last.kmer_ms = ev_ms(c, EV_K0, EV_K1);
     c->last.fill_ms = ev_ms(c, EV_K1, EV_K2);
     c->last.trace_ms = ev_ms(c, EV_K2, EV_K3);
@@ -1696,22 +1739,74 @@ int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pair
     if (rc) return rc;
     abea_pair_t* fin_pairs = nullptr;
     int32_t* fin_np = nullptr;
-    if ((c->stream_mode & 2) && batch->n_reads > 0 && c->total_pair_cap > 0) {
+    abea_code_t* fin_codes = nullptr;
+    const int32_t n = batch->n_reads;
+    /* Pair lists out. (a) As path codes: the traceback writes 8 bytes per 32 pairs into the context's pinned staging and
+     * publishes each read's count behind them; host threads expand the lists into the caller's buffer — pinned or not,
+     * any pair_ptr layout — while the kernels are still running. (b) Whole, into the caller's mapped buffer. (c) Through
+     * the copy engine after the kernels (abea_download). */
+    if ((c->stream_mode & 4) && c->host_threads > 0 && n > 0 && c->total_pair_cap > 0 && pairs) {
+        if (host_reserve(c, c->h_codes, (size_t)code_words(c->total_pair_cap, n) * sizeof(abea_code_t))) return ABEA_ERR_CUDA;
+        if (host_reserve(c, c->h_fnp, ((size_t)n + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
+        fin_codes = (abea_code_t*)mapped_alias(c->h_codes.p);
+        fin_np = (int32_t*)mapped_alias(c->h_fnp.p);
+        if (!fin_codes || !fin_np) fin_codes = nullptr, fin_np = nullptr;
+    }
+    if (!fin_codes && (c->stream_mode & 2) && n > 0 && c->total_pair_cap > 0) {
         bool canonical = true;
-        for (int32_t i = 0; i < batch->n_reads && canonical; i++) canonical = (pair_ptr[i] == c->cap_ptr[i]);
+        for (int32_t i = 0; i < n && canonical; i++) canonical = (pair_ptr[i] == c->cap_ptr[i]);
         if (canonical) {
             fin_pairs = (abea_pair_t*)mapped_alias(pairs);
             fin_np = (int32_t*)mapped_alias(n_pairs);
             if (!fin_pairs || !fin_np) fin_pairs = nullptr, fin_np = nullptr;
         }
     }
-    if (fin_np) memset(n_pairs, 0, (size_t)batch->n_reads * sizeof(int32_t)); /* reads that are not scheduled */
+    if (fin_np) memset(n_pairs, 0, (size_t)n * sizeof(int32_t)); /* reads that are not scheduled */
     if (c->need_scalings) { /* batch->scalings == NULL: method-of-moments estimate on the device first */
         rc = abea_estimate_scalings(c, 0, nullptr, nullptr);
         if (rc) return rc;
     }
+    std::atomic<int> abort_flag(0);
+    std::atomic<int64_t> code_bytes(0);
+    if (fin_codes) {
+        volatile int32_t* h_np = (volatile int32_t*)c->h_fnp.p;
+        for (int32_t i = 0; i < n; i++) h_np[i] = -1; /* "not done": the traceback stores the count when the codes are out */
+        const abea_code_t* h_codes = (const abea_code_t*)c->h_codes.p;
+        const int T = c->host_threads;
+        /* scheduled read j belongs to thread j % T (the schedule is longest-first, so the shares are even); a thread
+         * keeps sweeping its reads for counts that have appeared — no prediction of the finishing order is needed */
+        c->pool.kick(T, [&, h_np, h_codes, T](int tid) {
+            std::vector<int32_t> mine;
+            for (int32_t j = tid; j < (int32_t)c->reads.size(); j += T) mine.push_back(c->reads[(size_t)j].orig_index);
+            int64_t bytes = 0;
+            while (!mine.empty()) {
+                bool any = false;
+                for (size_t q = 0; q < mine.size();) {
+                    const int32_t i = mine[q];
+                    const int32_t np = h_np[i];
+                    if (np < 0) { q++; continue; }
+                    std::atomic_thread_fence(std::memory_order_acquire);
+                    n_pairs[i] = np;
+                    if (np > 0) decode_codes(h_codes + abea_code_offset(c->cap_ptr[(size_t)i], i), np, pairs + pair_ptr[i]);
+                    bytes += code_bytes_used(np);
+                    mine[q] = mine.back();
+                    mine.pop_back();
+                    any = true;
+                }
+                if (!any) {
+                    if (abort_flag.load()) return;
+                    sched_yield();
+                }
+            }
+            code_bytes.fetch_add(bytes);
+        });
+    }
     const bool was_streamed = c->streaming;
-    rc = run_impl(c, fin_pairs, fin_np, nullptr);
+    rc = run_impl(c, fin_pairs, fin_np, nullptr, fin_codes);
+    if (fin_codes) {
+        if (rc != ABEA_OK) abort_flag.store(1);
+        c->pool.wait();
+    }
     if (rc == ABEA_ERR_CUDA && was_streamed && cudaGetLastError() == cudaSuccess) {
         /* the stream from the caller's pinned buffer stalled (host contention, a tool slowing the loader down): the
          * batch is intact in the caller's buffers, so run it once more through the copy engine before giving up */
@@ -1720,6 +1815,7 @@ int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pair
         if (rc == ABEA_OK) rc = run_impl(c, nullptr, nullptr, nullptr);
         fin_pairs = nullptr;
         fin_np = nullptr;
+        fin_codes = nullptr;
     }
     if (rc) return rc;
     if (!fin_np) {
@@ -1727,10 +1823,10 @@ int abea_align_batch(abea_ctx_t* c, const abea_batch_t* batch, abea_pair_t* pair
         if (rc) return rc;
     } else {
         int64_t np = 0;
-        for (int32_t i = 0; i < batch->n_reads; i++) np += n_pairs[i];
+        for (int32_t i = 0; i < n; i++) np += n_pairs[i];
         c->last.d2h_ms = 0.f;
         c->last.unpack_ms = 0.0;
-        c->last.d2h_bytes = np * (int64_t)sizeof(abea_pair_t) + (int64_t)batch->n_reads * (int64_t)sizeof(int32_t);
+        c->last.d2h_bytes = (fin_codes ? code_bytes.load() : np * (int64_t)sizeof(abea_pair_t)) + (int64_t)n * (int64_t)sizeof(int32_t);
     }
     if (timing) *timing = c->last;
     return ABEA_OK;
@@ -1793,11 +1889,16 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
     }
     if (host_reserve(c, c->h_rseq, (size_t)sp + 16)) return ABEA_ERR_CUDA;
     if (host_reserve(c, c->h_rmeans, (size_t)ep * sizeof(float) + 64)) return ABEA_ERR_CUDA;
-    if (host_reserve(c, c->h_rpairs, (size_t)(pp + 1) * sizeof(abea_pair_t))) return ABEA_ERR_CUDA;
+    /* pair lists come back as path codes (stream_mode bit 2: 8 bytes per 32 pairs) or whole (bit 1); the staging for
+     * whole lists is also what the copy-engine fall-backs below download into */
+    const bool want_codes = (c->stream_mode & 4) != 0;
+    if (want_codes && host_reserve(c, c->h_codes, (size_t)code_words(pp, n) * sizeof(abea_code_t))) return ABEA_ERR_CUDA;
+    if (!want_codes && host_reserve(c, c->h_rpairs, (size_t)(pp + 1) * sizeof(abea_pair_t))) return ABEA_ERR_CUDA;
     if (host_reserve(c, c->h_rnp, ((size_t)n + 1) * sizeof(int32_t))) return ABEA_ERR_CUDA;
     char* h_seq = (char*)c->h_rseq.p;
     float* h_means = (float*)c->h_rmeans.p;
-    abea_pair_t* h_pairs = (abea_pair_t*)c->h_rpairs.p;
+    abea_pair_t* h_pairs = (abea_pair_t*)c->h_rpairs.p; /* re-read after a late reservation (fall-backs) */
+    const abea_code_t* h_codes = (const abea_code_t*)c->h_codes.p;
     volatile int32_t* h_np = (volatile int32_t*)c->h_rnp.p;
     for (int32_t i = 0; i < n; i++) h_np[i] = -1; /* "not done": the traceback stores the count when the list is out */
 
@@ -1806,8 +1907,9 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
     b.event_ptr = event_ptr; b.n_events = n_events; b.scalings = r->scalings; b.good = r->good; b.event_means = h_means;
 
     void* ev_alias = (c->stream_mode & 1) ? mapped_alias(h_means) : nullptr;
-    abea_pair_t* fin_pairs = (c->stream_mode & 2) ? (abea_pair_t*)mapped_alias(h_pairs) : nullptr;
-    int32_t* fin_np = fin_pairs ? (int32_t*)mapped_alias(c->h_rnp.p) : nullptr;
+    abea_code_t* fin_codes = want_codes ? (abea_code_t*)mapped_alias(c->h_codes.p) : nullptr;
+    abea_pair_t* fin_pairs = (!want_codes && (c->stream_mode & 2)) ? (abea_pair_t*)mapped_alias(h_pairs) : nullptr;
+    int32_t* fin_np = (fin_pairs || fin_codes) ? (int32_t*)mapped_alias(c->h_rnp.p) : nullptr;
     const bool overlap = ev_alias && fin_np && n > 0 && ep > 0;
 
     /* workers: (1) sequences; (2) once the loader's work list exists, the means of its pieces in list order, each
@@ -1883,7 +1985,10 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
             }
             std::atomic_thread_fence(std::memory_order_acquire);
             r->n_pairs[i] = np;
-            if (np > 0 && r->pairs[i]) memcpy(r->pairs[i], h_pairs + pair_ptr[i], (size_t)np * sizeof(abea_pair_t));
+            if (np > 0 && r->pairs[i]) {
+                if (fin_codes) decode_codes(h_codes + abea_code_offset(pair_ptr[i], i), np, r->pairs[i]);
+                else memcpy(r->pairs[i], h_pairs + pair_ptr[i], (size_t)np * sizeof(abea_pair_t));
+            }
         }
     };
     c->pool.kick(threads, worker);
@@ -1894,7 +1999,7 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
     if (overlap) {
         rc = upload_impl(c, &b, ev_alias, nullptr, true);
         if (rc == ABEA_OK && !c->streaming) rc = fail(c, ABEA_ERR_STATE, "ragged batch was not streamed");
-        if (rc == ABEA_OK) rc = run_impl(c, fin_pairs, fin_np, nullptr);
+        if (rc == ABEA_OK) rc = run_impl(c, fin_pairs, fin_np, nullptr, fin_codes);
         if (rc != ABEA_OK) abort_flag.store(1);
         kernels_done.store(1);
         const double t_run = now_ms();
@@ -1909,6 +2014,8 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
             /* e.g. a stalled stream: the batch is complete in the staging, run it once more through the copy engine */
             rc = upload_impl(c, &b, nullptr, nullptr);
             if (rc == ABEA_OK) rc = run_impl(c, nullptr, nullptr, nullptr);
+            if (rc == ABEA_OK && host_reserve(c, c->h_rpairs, (size_t)(pp + 1) * sizeof(abea_pair_t))) rc = ABEA_ERR_CUDA;
+            h_pairs = (abea_pair_t*)c->h_rpairs.p;
             if (rc == ABEA_OK) rc = abea_download(c, h_pairs, pair_ptr, (int32_t*)c->h_rnp.p, nullptr);
             if (rc == ABEA_OK)
                 for (int32_t i = 0; i < n; i++) {
@@ -1923,6 +2030,8 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
         c->pool.wait();
         rc = upload_impl(c, &b, nullptr, nullptr);
         if (rc == ABEA_OK) rc = run_impl(c, nullptr, nullptr, nullptr);
+        if (rc == ABEA_OK && host_reserve(c, c->h_rpairs, (size_t)(pp + 1) * sizeof(abea_pair_t))) rc = ABEA_ERR_CUDA;
+        h_pairs = (abea_pair_t*)c->h_rpairs.p;
         if (rc == ABEA_OK && n > 0) rc = abea_download(c, h_pairs, pair_ptr, (int32_t*)c->h_rnp.p, nullptr);
         if (rc != ABEA_OK) return rc;
         std::atomic<int32_t> nx(0);
@@ -1943,7 +2052,10 @@ int abea_align_ragged(abea_ctx_t* c, const abea_ragged_t* r, int threads, abea_t
         for (int32_t i = 0; i < n; i++) np += r->n_pairs[i];
         c->last.d2h_ms = 0.f;
         c->last.unpack_ms = 0.0;
-        c->last.d2h_bytes = np * (int64_t)sizeof(abea_pair_t) + (int64_t)n * (int64_t)sizeof(int32_t);
+        int64_t cb = 0;
+        if (fin_codes)
+            for (int32_t i = 0; i < n; i++) cb += code_bytes_used(r->n_pairs[i]);
+        c->last.d2h_bytes = (fin_codes ? cb : np * (int64_t)sizeof(abea_pair_t)) + (int64_t)n * (int64_t)sizeof(int32_t);
     }
     if (timing) *timing = c->last;
     return ABEA_OK;

@@ -200,10 +200,26 @@ __global__ void abea_prepare_kernel(const abea_read_t* __restrict__ reads, int32
  * waits on before it touches the read. The results go the other way without a copy either: the last step of the
  * traceback writes the finished pair list to the caller's mapped buffer. With ready == NULL and pairs_final ==
  * pairs the kernels run on data that is already resident (abea_upload_batch / abea_run / abea_download). */
+/* Path codes: a finished pair list in 1/32 of its size. The list is a monotone lattice path — consecutive pairs differ
+ * by (+1,+1), (0,+1) or (+1,0) in (ref_pos, read_pos), the traceback's D / U / L steps read forwards (reference
+ * src/align.c:452-499) — so the first pair and one bit per coordinate per step say everything: word 0 of a read's
+ * region holds the first pair, word 1 + j the steps 32 j .. 32 j + 31 as two bit planes (bit t of `a`: ref_pos advances
+ * at step 32 j + t; bit t of `b`: read_pos does). 8 bytes cross PCIe for 32 pairs instead of 256, and host threads that
+ * would otherwise only copy the list expand it while the kernels are still running (abea_host.cu: decode_codes).
+ * Read i's region starts at word (pair_off >> 5) + 2 i of the buffer: 1 + ceil((E+L-1)/32) words always fit before the
+ * next read's. */
+struct abea_code_t {
+    uint32_t a, b;
+};
+__host__ __device__ __forceinline__ int64_t abea_code_offset(int64_t pair_off, int32_t batch_index) {
+    return (pair_off >> 5) + 2 * (int64_t)batch_index;
+}
+
 struct abea_stream_t {
     const uint32_t* ready;      /* [scheduled read] pieces of its events landed so far; NULL: everything is resident */
     abea_pair_t* pairs_final;   /* the caller's mapped host buffer (canonical layout), or NULL: the lists stay in d_pairs only */
     int32_t* n_pairs_final;     /* [batch read] pair counts in the caller's mapped host buffer, or NULL */
+    abea_code_t* codes_final;   /* mapped host buffer of path codes (below), or NULL */
     int32_t* n_pairs_dev;       /* [batch read] pair counts on the device (always written) */
     uint32_t* stalled;          /* set to 1 if a wait for streamed events gave up (the host reports an error) */
     int32_t tb_mode;            /* 0: serial traceback (one walk per warp), 1: segment-parallel traceback (a walk per lane);
@@ -622,6 +638,40 @@ __device__ __forceinline__ double abea_tb_flush(double sum, int cnt, int lane, i
     return sum;
 }
 
+/* The path codes of a finished list (out[0 .. total), ascending, written by lanes of this warp; the caller has
+ * synchronised the warp): 32 steps per trip — two coalesced loads, two ballots — and one coalesced store of 32 words
+ * every 32 trips. */
+__device__ __forceinline__ void abea_emit_codes(abea_code_t* __restrict__ dst, const abea_pair_t* __restrict__ out,
+                                                int32_t total, int lane) {
+    if (total <= 0) return;
+    if (lane == 0) {
+        abea_code_t h;
+        h.a = (uint32_t)out[0].ref_pos;
+        h.b = (uint32_t)out[0].read_pos;
+        dst[0] = h;
+    }
+    const int32_t steps = total - 1;
+    abea_code_t keep;
+    keep.a = keep.b = 0u;
+    int32_t j = 0;
+    for (int32_t t0 = 0; t0 < steps; t0 += 32, j++) {
+        const int32_t t = t0 + lane;
+        int dk = 0, de = 0;
+        if (t < steps) {
+            const abea_pair_t p = out[t], q = out[t + 1];
+            dk = q.ref_pos != p.ref_pos;
+            de = q.read_pos != p.read_pos;
+        }
+        const uint32_t mk = __ballot_sync(ABEA_FULL, dk), me = __ballot_sync(ABEA_FULL, de);
+        if ((j & 31) == lane) {
+            keep.a = mk;
+            keep.b = me;
+        }
+        if ((j & 31) == 31) dst[1 + (j & ~31) + lane] = keep;
+    }
+    if ((j & 31) != 0 && lane < (j & 31)) dst[1 + (j & ~31) + lane] = keep;
+}
+
 /* Traceback + QC of one read by one warp. `ring` is the warp's 4 KB shared-memory ring (32 trace lines). The trace
  * lines were written by lanes of this warp or CTA; the caller has synchronised (__syncwarp / __syncthreads). */
 __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32_t ridx, int32_t end_event, uint32_t* ring,
@@ -734,6 +784,10 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
             }
             __syncwarp();
         }
+    }
+    if (io.codes_final && !fail) {
+        __syncwarp();
+        abea_emit_codes(io.codes_final + abea_code_offset(rd.pair_off, rd.orig_index), out, n, lane);
     }
     /* the count in the caller's buffer doubles as the read's "done" flag: it is written after the list, behind a
      * system-scope fence, so a host thread that sees a count >= 0 may copy the list out while other reads are still
@@ -1205,6 +1259,7 @@ __device__ __forceinline__ void abea_traceback_par(const abea_read_t& rd, int32_
         if (!fail)
             for (int32_t t = lane; t < total; t += 32) fin[t] = out[t];
     }
+    if (io.codes_final && !fail) abea_emit_codes(io.codes_final + abea_code_offset(rd.pair_off, rd.orig_index), out, total, lane);
     if (io.n_pairs_final) {
 #ifndef ABEA_SIMT_EMU
         __threadfence_system();
@@ -1212,6 +1267,24 @@ __device__ __forceinline__ void abea_traceback_par(const abea_read_t& rd, int32_
         __syncwarp();
         if (lane == 0) *(volatile int32_t*)(io.n_pairs_final + rd.orig_index) = fail ? 0 : total;
     }
+}
+
+/* A streamed read filled by the FAST instantiation may have lost its FAST bit while it was being filled: the loader
+ * clears the bit when an out-of-range event mean passes through it, BEFORE it publishes that piece, and the fill has
+ * consumed every piece by now — so the bit is final here. Such a read is filled again, last, by the EXACT instantiation,
+ * which overwrites every result; but a host thread takes a read's list the moment its count appears in the mapped
+ * count array, so the first, invalid result must never be published there. */
+template <bool FAST, bool STREAM>
+__device__ __forceinline__ abea_stream_t abea_publishable(const abea_stream_t& io, const uint32_t* flag) {
+    abea_stream_t r = io;
+    if (FAST && STREAM) {
+        if ((abea_ld_acquire_u32(flag) & ABEA_READ_FAST) == 0u) {
+            r.pairs_final = nullptr;
+            r.n_pairs_final = nullptr;
+            r.codes_final = nullptr;
+        }
+    }
+    return r;
 }
 
 /* the traceback of one read by the warp that filled it (warp 0 of a wide CTA) */
@@ -1638,10 +1711,11 @@ abea_fill_kernel(const abea_read_t* __restrict__ reads, int32_t n_reads, const f
         const long long t_fill = abea_clock();
         /* four walks per lane pay off once the stretches are long (RNA reads of 20 k events: 39.4 -> 35.7 ms at cfg4);
          * on reads of a few thousand bands the margins of 128 short stretches cost more than the round trips saved */
+        const abea_stream_t io_r = abea_publishable<FAST, STREAM>(io, read_flags + ridx);
         if (cx.NB >= ABEA_TB_K4_MIN_BANDS)
-            abea_traceback<FAST, 4>(rd, ridx, end_event, tb_ring, lane, means, kparams, trace, pairs, results, io);
+            abea_traceback<FAST, 4>(rd, ridx, end_event, tb_ring, lane, means, kparams, trace, pairs, results, io_r);
         else
-            abea_traceback<FAST, 1>(rd, ridx, end_event, tb_ring, lane, means, kparams, trace, pairs, results, io);
+            abea_traceback<FAST, 1>(rd, ridx, end_event, tb_ring, lane, means, kparams, trace, pairs, results, io_r);
         if (lane == 0) {
             results[ridx].wide = 0;
             results[ridx].fill_cycles = t_fill - t_start;
@@ -2031,7 +2105,8 @@ abea_fill_wide_kernel(const abea_read_t* __restrict__ reads, int32_t n_wide, con
                 results[ridx].end_event = end_event;
             }
             const long long t_fill = abea_clock();
-            abea_traceback<FAST, 4>(rd, ridx, end_event, (uint32_t*)sm.kp, lane, means, kparams, trace, pairs, results, io);
+            abea_traceback<FAST, 4>(rd, ridx, end_event, (uint32_t*)sm.kp, lane, means, kparams, trace, pairs, results,
+                                    abea_publishable<FAST, STREAM>(io, read_flags + ridx));
             if (lane == 0) {
                 results[ridx].wide = 1;
                 results[ridx].fill_cycles = t_fill - t_start;

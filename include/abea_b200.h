@@ -26,7 +26,7 @@
  * src/align.c:180-559): for every read i, n_pairs[i] is the number of aligned pairs after QC (0 for bad reads,
  * over-segmented reads with events/base >= 15, and QC failures) and pairs[pair_ptr[i] .. +n_pairs[i]) holds them in
  * ascending order, bit-identical to the reference. The caller sizes read i's region to n_events[i]+read_len[i]
- * pairs (src/f5c.c:724-726). No read is ever sent to a CPU fallback (the reference's if_on_gpu heuristic,
+ * pairs (src/f5c.c:724-726); a region's slots past n_pairs[i] are left as they were. No read is ever sent to a CPU fallback (the reference's if_on_gpu heuristic,
  * src/f5c.cu:440-452, has no counterpart).
  *
  * Errors: functions return 0 on success or a negative abea_status; abea_last_error() gives the message. The
@@ -69,7 +69,8 @@ typedef struct {
     int32_t kernel_launches; /* kernels of this library launched by the call */
     int32_t n_scheduled;     /* reads that passed the eligibility filter */
     int32_t n_wide;          /* of those, reads filled by the wide (4 warps per read) kernel */
-    int32_t streamed;        /* bit 0: events streamed in by abea_load_kernel; bit 1: pair lists written straight to the caller's buffer */
+    int32_t streamed;        /* bit 0: events streamed in by abea_load_kernel; bit 1: pair lists written whole to the caller's mapped
+                              * buffer; bit 2: pair lists out as path codes expanded by host threads */
     int64_t n_bands;         /* sum of NB over scheduled reads */
     int64_t n_events;        /* sum of E over scheduled reads (the metric's numerator) */
     double load_ms;          /* device: abea_load_kernel, first CTA start to last piece landed (streaming only) */
@@ -206,6 +207,13 @@ int abea_compact_results(abea_ctx_t* ctx, abea_pair_t* d_dst, int64_t dst_capaci
  * skipped (read_stat_flag may be NULL: none is). path "-" = stdout. Host-side formatting only. */
 int abea_write_pairs(const char* path, int append, int32_t n_reads, const char* const* names, const int32_t* n_pairs,
                      const abea_pair_t* pairs, const int64_t* pair_ptr, const uint32_t* read_stat_flag);
+
+/* Host threads abea_align_batch uses to expand the pair lists, which leave the device as path codes (the first pair of
+ * a list and two bits per step: 8 bytes per 32 pairs over PCIe instead of 256) while the kernels are still running.
+ * threads >= 0 sets the number (0: no path codes — the lists are written whole into a pinned caller buffer, or copied
+ * back by the copy engine); threads < 0 only queries. Returns the value in force. Default: min(8, CPUs of the calling
+ * process); ABEA_HOST_THREADS overrides the default. abea_align_ragged has its own `threads` argument. */
+int abea_host_threads(abea_ctx_t* ctx, int threads);
 
 /* Pinned host memory for callers that want the H2D/D2H copies to run at full PCIe rate. */
 void* abea_host_alloc(size_t bytes);

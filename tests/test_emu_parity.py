@@ -62,16 +62,17 @@ def test_emulated_kernels_match_oracle(emu, monkeypatch, name, kw, wide):
         assert got.timing["n_wide"] == 0
 
 
-@pytest.mark.parametrize("stream", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("stream", ["0", "1", "2", "3", "4", "5", "7"])
 @pytest.mark.parametrize("wide", ["0", "1"])
 def test_emulated_edge_cases(emu, monkeypatch, wide, stream):
-    """stream=1: events through abea_load_kernel (which also range-checks them: read 0 has an event that must send it
-    to the exact instantiation), pair lists written to the caller's buffer by the traceback; stream=0: staged copies."""
+    """ABEA_STREAM bit 0: events through abea_load_kernel (which also range-checks them: read 0 has an event that must
+    send it to the exact instantiation); bit 1: pair lists written whole to the caller's buffer by the traceback; bit 2
+    (wins over bit 1): pair lists as path codes, expanded by host threads; 0: staged copies."""
     monkeypatch.setenv("ABEA_WIDE", wide)
     monkeypatch.setenv("ABEA_STREAM", stream)
     b = edge_batch()
     got = check(emu, b, "r9", "edge")
-    assert (got.timing["streamed"] & 2) == (int(stream) & 2)
+    assert (got.timing["streamed"] & 6) == (4 if int(stream) & 4 else int(stream) & 2)
     if b.events.ctypes.data % 16 == 0:
         assert (got.timing["streamed"] & 1) == (int(stream) & 1)
     assert got.n_pairs[1] == 0 and got.n_pairs[3] == 0 and got.n_pairs[4] == 0
@@ -140,7 +141,7 @@ def test_smoke_entry_point_on_the_emulator(emu):
     g.smoke(lib_path=emu)
 
 
-@pytest.mark.parametrize("stream", ["3", "0"])
+@pytest.mark.parametrize("stream", ["5", "3", "0"])
 @pytest.mark.parametrize("threads", [1, 3])
 def test_emulated_ragged_front_door(emu, monkeypatch, stream, threads):
     """abea_align_ragged: the batch as db_t holds it (one allocation per read); packer threads publish the means piece
@@ -158,6 +159,30 @@ def test_emulated_ragged_front_door(emu, monkeypatch, stream, threads):
         ol.assert_same_alignment(got, want, "ragged")
         ol.assert_same_alignment(again, want, "ragged, second batch")
         assert got.timing["streamed"] == int(stream)
+
+
+@pytest.mark.parametrize("tb", ["1", "0"])
+def test_emulated_path_codes(emu, monkeypatch, tb):
+    """Pair lists leave the device as path codes (first pair + two bit planes per 32 steps) and host threads expand them:
+    lists long enough for several 32-word stores plus a tail, from both traceback forms, with 1 and 3 threads; with 0
+    threads the lists are copied back whole. 8 bytes per 32 pairs cross the boundary."""
+    monkeypatch.setenv("ABEA_TB", tb)
+    b = synth.make_batch("r9", n_reads=5, mean_events=2600, sigma=0.5, epk=1.8, seed=77)
+    k, m = models.load_model("r9")
+    with AbeaContext(0, lib_path=emu) as ctx:
+        m = ctx.set_model(m, k)
+        want = ol.port_align(b, m)
+        assert int(want.n_pairs.max()) > 3 * 1024 + 40
+        for threads in (1, 3):
+            assert ctx.host_threads(threads) == threads
+            got = ctx.align_batch(b)
+            ol.assert_same_alignment(got, want, f"path codes, {threads} threads")
+            assert got.timing["streamed"] & 4
+            assert got.timing["d2h_bytes"] < int(want.n_pairs.sum()) * 8 // 16
+        assert ctx.host_threads(0) == 0 and ctx.host_threads() == 0
+        got = ctx.align_batch(b)
+        ol.assert_same_alignment(got, want, "whole lists")
+        assert (got.timing["streamed"] & 4) == 0 and got.timing["d2h_bytes"] >= int(want.n_pairs.sum()) * 8
 
 
 @pytest.mark.parametrize("tb,margin", [("0", "64"), ("1", "0"), ("1", "7"), ("1", "200"), ("3", "64")])
