@@ -316,6 +316,12 @@ def main():
     batch = synth.make_config_shard(a.config, rank, world, seed=a.seed, reads_per_gpu=a.reads_per_gpu)
     k, model = models.load_model(batch.meta["model"])
     ctx = AbeaContext(local_rank)
+    # host threads that expand the path codes: the box's CPUs are shared by the ranks of this node (one process per GPU),
+    # so a rank takes its share minus the thread that drives the GPU (the library's own default, min(8, CPUs), is for a
+    # process that has the box to itself); ABEA_HOST_THREADS overrides
+    if "ABEA_HOST_THREADS" not in os.environ:
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        ctx.host_threads(max(1, min(8, len(os.sched_getaffinity(0)) // max(1, local_world) - 1)))
     model = ctx.set_model(model, k)
     sm_count, dev_name = ctx.device_info()
     pinned = ctx.pin_batch(batch)

@@ -10,6 +10,7 @@
  */
 #include <math.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -331,7 +332,9 @@ double wide_threshold(const abea_ctx* c, int64_t total_bands) {
     return std::max(c->wide_min_bands, c->wide_alpha * 1.25 * cyc_batch / c->cyc_long);
 }
 
-/* A pair list from its path codes (abea_code_t, abea_kernels.cuh): the first pair, then one step per bit. */
+/* A pair list from its path codes (abea_code_t, abea_kernels.cuh): the first pair, then one step per bit. Measured: a
+ * host core expands ~0.8 G pairs/s, bound by writing the list to memory — a 256-entry table of four-step running sums
+ * with 64-bit packed pairs and non-temporal stores were both slower than this loop (profiles/path_codes_r02.txt). */
 void decode_codes(const abea_code_t* w, int32_t n, abea_pair_t* dst) {
     if (n <= 0) return;
     int32_t k = (int32_t)w[0].a, e = (int32_t)w[0].b;
@@ -767,6 +770,12 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         if (ee > n_ev_total) n_ev_total = ee;
     }
 
+    /* the bases do not depend on the schedule: their copy is enqueued first and crosses PCIe while this thread builds the
+     * descriptors and the schedule (0.4 ms per 4096 reads) */
+    CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
+    if (dev_reserve(c, c->d_seq, (size_t)seq_bytes + 16)) return ABEA_ERR_CUDA;
+    if (seq_bytes) CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
+
     /* canonical output layout: read i owns pairs [cap_ptr[i], cap_ptr[i] + E_i + L_i) (reference src/f5c.c:724-726) */
     c->cap_ptr.assign((size_t)b->n_reads + 1, 0);
     for (int32_t i = 0; i < b->n_reads; i++)
@@ -877,7 +886,6 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
     c->scaled = false;
     double t1 = now_ms();
 
-    if (dev_reserve(c, c->d_seq, (size_t)seq_bytes + 16)) return ABEA_ERR_CUDA;
     /* the alignment reads event means only (reference src/align.cu:415): they live in d_means, indexed like the source
      * (the caller's event_ptr space, or the capacity layout of abea_getevents). An AoS table that goes through the copy
      * engine is staged in d_events and its means are extracted on the device. */
@@ -905,7 +913,6 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
     c->results_on_device = false;
     double t2 = t1;
     c->prepared = false;
-    CU(cudaEventRecord(c->ev[EV_H2D0], c->stream));
     if (n_sched) { /* descriptors through pinned staging: a pageable source would make the copy synchronous */
         if (host_reserve(c, c->h_reads, n_sched * sizeof(abea_read_t))) return ABEA_ERR_CUDA;
         memcpy(c->h_reads.p, c->reads.data(), n_sched * sizeof(abea_read_t));
@@ -915,7 +922,6 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
         /* Everything the k-mer parameter kernel needs goes first, and the kernel with it: the host then works out
          * the loader's order while the GPU is busy with that. */
         if (dev_reserve(c, c->d_ready, ABEA_READY_WORDS * (n_sched + 1) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
-        if (seq_bytes) CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemsetAsync(c->d_queue.p, 0, 64, c->stream));
         CU(cudaMemsetAsync(c->d_flags.p, 0x01, n_sched * sizeof(uint32_t), c->stream));
         CU(cudaMemsetAsync(c->d_ready.p, 0, ABEA_READY_WORDS * n_sched * sizeof(uint32_t), c->stream));
@@ -989,8 +995,6 @@ static int upload_impl(abea_ctx_t* c, const abea_batch_t* b, const void* ev_alia
             ABEA_LAUNCH(abea_extract_means_kernel, blocks, 256, c->stream, src_tab, (float*)c->d_means.p, n_means);
         }
     }
-    if (seq_bytes && !c->streaming)
-        CU(cudaMemcpyAsync(c->d_seq.p, b->seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaEventRecord(c->ev[EV_H2D1], c->stream));
     if (!c->streaming) CU(cudaStreamSynchronize(c->stream));
     c->uploaded = true;
