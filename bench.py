@@ -319,9 +319,12 @@ def main():
     # host threads that expand the path codes: the box's CPUs are shared by the ranks of this node (one process per GPU),
     # so a rank takes its share minus the thread that drives the GPU (the library's own default, min(8, CPUs), is for a
     # process that has the box to itself); ABEA_HOST_THREADS overrides
+    # A host core expands ~0.8 G pairs/s, so fewer than four threads cannot keep up with the kernels
+    # (profiles/path_codes_r02.txt): a rank whose share is smaller has the traceback write whole lists instead (0 threads)
     if "ABEA_HOST_THREADS" not in os.environ:
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-        ctx.host_threads(max(1, min(8, len(os.sched_getaffinity(0)) // max(1, local_world) - 1)))
+        share = len(os.sched_getaffinity(0)) // max(1, local_world) - 1
+        ctx.host_threads(min(8, share) if share >= 4 else 0)
     model = ctx.set_model(model, k)
     sm_count, dev_name = ctx.device_info()
     pinned = ctx.pin_batch(batch)
@@ -398,7 +401,7 @@ def main():
     # ---- end to end through the C ABI with host buffers (+ NCCL result exchange for N > 1) ------------------------
     exch = None
     if world > 1:
-        exch = ResultExchange(rank, world, batch.n_reads, int(batch.pair_capacity().sum()), torch.device("cuda", local_rank))
+        exch = ResultExchange(rank, world, batch.pair_capacity(), torch.device("cuda", local_rank))
     gathered = None
 
     def e2e_step():
@@ -474,9 +477,11 @@ def main():
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms_max / a.steps, "nccl_gather_ms_per_step": gather_ms / a.steps,
                     "load_ms_max_over_ranks": load_ms_max,
-                    "call": "abea_align_batch (C ABI) with pinned host buffers: event means 4 B/event in; pair lists out as "
-                            "path codes (first pair + 2 bits per step) that the library's host threads expand into the "
-                            "caller's buffer while the kernels run (ABEA_STREAM bit 2; d2h bytes are what crossed PCIe)",
+                    "call": "abea_align_batch (C ABI) with pinned host buffers: event means 4 B/event in; pair lists out "
+                            + ("as path codes (first pair + 2 bits per step) that the library's host threads expand into the "
+                               "caller's buffer while the kernels run" if (r.timing["streamed"] & 4) else
+                               "whole, written by the traceback into the caller's mapped buffer (too few host CPUs per "
+                               "rank for the code expansion)") + "; d2h bytes are what crossed PCIe",
                     "host_threads": ctx.host_threads(),
                     "last_step_parts_ms_rank0": e2e_parts,
                     "last_step_output_equals_resident_result_all_ranks": e2e_ok_all},

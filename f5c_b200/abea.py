@@ -103,6 +103,8 @@ def _bind(path: str):
     lib.abea_host_free.restype = None
     lib.abea_device_info.argtypes = [vp, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p]
     lib.abea_host_threads.argtypes = [vp, ctypes.c_int]
+    lib.abea_device_codes.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+    lib.abea_expand_codes.argtypes = [vp, vp, vp, vp, i32, vp, i64, vp, ctypes.POINTER(i64)]
     lib.abea_version.restype = ctypes.c_char_p
     return lib
 
@@ -449,6 +451,23 @@ class AbeaContext:
         total = ctypes.c_int64()
         self._check(self.lib.abea_compact_results(self._h, dst_ptr, int(dst_capacity), ctypes.byref(total)),
                     "abea_compact_results")
+        return int(total.value)
+
+    def device_codes(self):
+        """(codes_ptr, n_words) of the last run's pair lists as path codes (abea_device_codes), a raw device address."""
+        dp, n = ctypes.c_void_p(), ctypes.c_int64()
+        self._check(self.lib.abea_device_codes(self._h, ctypes.byref(dp), ctypes.byref(n)), "abea_device_codes")
+        return dp.value, n.value
+
+    def expand_codes(self, codes_ptr: int, n_pairs_ptr: int, cap_ptr: np.ndarray, dst_ptr: int, dst_capacity: int,
+                     total_ptr: int = 0, sync: bool = False) -> int:
+        """abea_expand_codes: path codes + counts (device addresses) -> dense pair lists at dst_ptr (device). cap_ptr is
+        the int64 capacity prefix sum of the reads the codes describe (host). Returns the total when sync, else -1."""
+        cp = np.ascontiguousarray(cap_ptr, dtype=np.int64)
+        total = ctypes.c_int64(-1)
+        self._check(self.lib.abea_expand_codes(self._h, codes_ptr, n_pairs_ptr, cp.ctypes.data, int(cp.shape[0] - 1), dst_ptr,
+                                               int(dst_capacity), total_ptr or None, ctypes.byref(total) if sync else None),
+                    "abea_expand_codes")
         return int(total.value)
 
     def read_stats(self, n_reads: int) -> dict:

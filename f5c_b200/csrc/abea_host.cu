@@ -140,6 +140,8 @@ struct abea_ctx {
 
     /* resident batch */
     DevBuf d_seq, d_events, d_means, d_reads, d_kparams, d_trace, d_pairs, d_results, d_queue, d_flags, d_npairs;
+    DevBuf d_codes;                   /* path codes of the last run's pair lists (abea_code_t), for abea_device_codes */
+    DevBuf d_xcap, d_xoff;            /* abea_expand_codes: a peer's capacity prefix sums, dense offsets */
     std::vector<int64_t> cap_ptr;     /* canonical pair_ptr of the caller's batch: prefix sum of E+L over ALL reads */
     HostBuf h_results, h_pairs, h_reads, h_items; /* pinned staging */
     bool prepared = false;            /* abea_prepare_kernel of the resident batch was already launched by the upload */
@@ -165,8 +167,9 @@ struct abea_ctx {
 
     /* streaming (abea_align_batch with pinned host buffers): events pulled over PCIe by abea_load_kernel in the order
      * the fill asks for them, pair lists written to the caller's mapped buffer by the traceback */
-    int stream_mode = 5;       /* ABEA_STREAM: bit 0 events streamed in; pair lists out: bit 2 as path codes expanded by host
-                                * threads (wins), bit 1 written whole into the caller's mapped buffer; 0: copy engine both ways */
+    int stream_mode = 7;       /* ABEA_STREAM: bit 0 events streamed in; pair lists out: bit 2 as path codes expanded by host
+                                * threads (wins when there are host threads), bit 1 written whole into the caller's mapped
+                                * buffer; 0: copy engine both ways */
     int host_threads = 8;      /* ABEA_HOST_THREADS: threads of abea_align_batch that expand path codes (0: no codes) */
     int load_ctas = 64;        /* ABEA_LOAD_CTAS */
     int load_ctas_rag = 296;   /* ABEA_LOAD_CTAS_RAG: loader CTAs when the host packs while the loader runs (2 per SM) */
@@ -680,7 +683,7 @@ int abea_create(abea_ctx_t** out, int device) {
 void abea_destroy(abea_ctx_t* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    DevBuf* bufs[] = {&c->d_model, &c->d_seq, &c->d_events, &c->d_means, &c->d_reads, &c->d_kparams,
+    DevBuf* bufs[] = {&c->d_codes, &c->d_xcap, &c->d_xoff, &c->d_model, &c->d_seq, &c->d_events, &c->d_means, &c->d_reads, &c->d_kparams,
                       &c->d_trace, &c->d_pairs, &c->d_results, &c->d_queue, &c->d_flags, &c->d_npairs,
                       &c->d_ready, &c->d_items, &c->d_capptr, &c->d_dense_off, &c->d_sreads, &c->d_scalings, &c->d_maps, &c->d_sres,
                       &c->d_raw, &c->d_sum, &c->d_sumsq, &c->d_ts1, &c->d_ts2, &c->d_peaks, &c->d_evcap, &c->d_sigs, &c->d_sigorder,
@@ -1034,6 +1037,11 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
     io.pairs_final = fin_pairs;
     io.n_pairs_final = fin_np;
     io.codes_final = fin_codes;
+    io.codes_dev = nullptr;
+    if (c->n_batch_reads > 0 && c->total_pair_cap > 0) {
+        if (dev_reserve(c, c->d_codes, (size_t)code_words(c->total_pair_cap, c->n_batch_reads) * sizeof(abea_code_t))) return ABEA_ERR_CUDA;
+        io.codes_dev = (abea_code_t*)c->d_codes.p;
+    }
     io.n_pairs_dev = (int32_t*)c->d_npairs.p;
     io.stalled = (uint32_t*)c->d_queue.p + 15; /* zeroed with the queue */
     io.tb_mode = c->tb_mode;
@@ -1316,6 +1324,42 @@ int abea_compact_results(abea_ctx_t* c, abea_pair_t* d_dst, int64_t dst_capacity
                     (const int64_t*)c->d_capptr.p, (const int32_t*)c->d_npairs.p, (const int64_t*)c->d_dense_off.p, n, d_dst);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(c->stream));
+    }
+    return ABEA_OK;
+}
+
+int abea_device_codes(abea_ctx_t* c, const abea_code_t** d_codes, int64_t* n_words) {
+    if (!c) return ABEA_ERR_ARG;
+    if (!c->ran || !c->results_on_device) return fail(c, ABEA_ERR_STATE, "abea_device_codes before abea_run");
+    if (d_codes) *d_codes = (const abea_code_t*)c->d_codes.p;
+    if (n_words) *n_words = (c->n_batch_reads > 0 && c->total_pair_cap > 0) ? code_words(c->total_pair_cap, c->n_batch_reads) : 0;
+    return ABEA_OK;
+}
+
+int abea_expand_codes(abea_ctx_t* c, const abea_code_t* d_codes, const int32_t* d_n_pairs, const int64_t* cap_ptr,
+                      int32_t n_reads, abea_pair_t* d_dst, int64_t dst_capacity, int64_t* d_total, int64_t* total_pairs) {
+    if (!c || n_reads < 0 || (n_reads > 0 && (!d_codes || !d_n_pairs || !cap_ptr))) return fail(c, ABEA_ERR_ARG, "bad codes");
+    CU(cudaSetDevice(c->device));
+    if (total_pairs) *total_pairs = 0;
+    if (n_reads == 0) return ABEA_OK;
+    if (cap_ptr[n_reads] > dst_capacity) /* a list never has more pairs than capacity slots */
+        return fail(c, ABEA_ERR_ARG, "dense buffer holds %lld pairs, up to %lld needed", (long long)dst_capacity, (long long)cap_ptr[n_reads]);
+    if (!d_dst) return fail(c, ABEA_ERR_ARG, "no destination");
+    if (dev_reserve(c, c->d_xcap, ((size_t)n_reads + 1) * sizeof(int64_t))) return ABEA_ERR_CUDA;
+    if (dev_reserve(c, c->d_xoff, ((size_t)n_reads + 1) * sizeof(int64_t))) return ABEA_ERR_CUDA;
+    /* pageable source: the copy is staged by the runtime before the call returns (the caller may reuse cap_ptr) */
+    CU(cudaMemcpyAsync(c->d_xcap.p, cap_ptr, ((size_t)n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    ABEA_LAUNCH(abea_pair_offsets_kernel, 1, ABEA_SCAN_THREADS, c->stream, d_n_pairs, n_reads, (int64_t*)c->d_xoff.p);
+    const int blocks = std::max(1, std::min((n_reads + 7) / 8, c->sm_count * 8));
+    ABEA_LAUNCH(abea_expand_codes_kernel, blocks, 256, c->stream, d_codes, (const int64_t*)c->d_xcap.p, d_n_pairs,
+                (const int64_t*)c->d_xoff.p, n_reads, d_dst);
+    CU(cudaGetLastError());
+    if (d_total) CU(cudaMemcpyAsync(d_total, (const int64_t*)c->d_xoff.p + n_reads, sizeof(int64_t), cudaMemcpyDeviceToDevice, c->stream));
+    if (total_pairs) {
+        if (host_reserve(c, c->h_items, 64)) return ABEA_ERR_CUDA;
+        CU(cudaMemcpyAsync(c->h_items.p, (const int64_t*)c->d_xoff.p + n_reads, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        *total_pairs = *(const int64_t*)c->h_items.p;
     }
     return ABEA_OK;
 }

@@ -208,9 +208,7 @@ __global__ void abea_prepare_kernel(const abea_read_t* __restrict__ reads, int32
  * would otherwise only copy the list expand it while the kernels are still running (abea_host.cu: decode_codes).
  * Read i's region starts at word (pair_off >> 5) + 2 i of the buffer: 1 + ceil((E+L-1)/32) words always fit before the
  * next read's. */
-struct abea_code_t {
-    uint32_t a, b;
-};
+typedef abea_code_word_t abea_code_t; /* include/abea_types.h */
 __host__ __device__ __forceinline__ int64_t abea_code_offset(int64_t pair_off, int32_t batch_index) {
     return (pair_off >> 5) + 2 * (int64_t)batch_index;
 }
@@ -220,6 +218,7 @@ struct abea_stream_t {
     abea_pair_t* pairs_final;   /* the caller's mapped host buffer (canonical layout), or NULL: the lists stay in d_pairs only */
     int32_t* n_pairs_final;     /* [batch read] pair counts in the caller's mapped host buffer, or NULL */
     abea_code_t* codes_final;   /* mapped host buffer of path codes (below), or NULL */
+    abea_code_t* codes_dev;     /* the same codes in device memory (what a multi-GPU driver exchanges), or NULL */
     int32_t* n_pairs_dev;       /* [batch read] pair counts on the device (always written) */
     uint32_t* stalled;          /* set to 1 if a wait for streamed events gave up (the host reports an error) */
     int32_t tb_mode;            /* 0: serial traceback (one walk per warp), 1: segment-parallel traceback (a walk per lane);
@@ -641,14 +640,19 @@ __device__ __forceinline__ double abea_tb_flush(double sum, int cnt, int lane, i
 /* The path codes of a finished list (out[0 .. total), ascending, written by lanes of this warp; the caller has
  * synchronised the warp): 32 steps per trip — two coalesced loads, two ballots — and one coalesced store of 32 words
  * every 32 trips. */
-__device__ __forceinline__ void abea_emit_codes(abea_code_t* __restrict__ dst, const abea_pair_t* __restrict__ out,
+__device__ __forceinline__ void abea_put_code(abea_code_t* a, abea_code_t* b, int64_t i, const abea_code_t& v) {
+    if (a) a[i] = v;
+    if (b) b[i] = v;
+}
+/* dst_a / dst_b: the read's region in the mapped host buffer and / or in the device buffer (either may be NULL) */
+__device__ __forceinline__ void abea_emit_codes(abea_code_t* dst_a, abea_code_t* dst_b, const abea_pair_t* __restrict__ out,
                                                 int32_t total, int lane) {
-    if (total <= 0) return;
+    if (total <= 0 || (!dst_a && !dst_b)) return;
     if (lane == 0) {
         abea_code_t h;
         h.a = (uint32_t)out[0].ref_pos;
         h.b = (uint32_t)out[0].read_pos;
-        dst[0] = h;
+        abea_put_code(dst_a, dst_b, 0, h);
     }
     const int32_t steps = total - 1;
     abea_code_t keep;
@@ -667,9 +671,14 @@ __device__ __forceinline__ void abea_emit_codes(abea_code_t* __restrict__ dst, c
             keep.a = mk;
             keep.b = me;
         }
-        if ((j & 31) == 31) dst[1 + (j & ~31) + lane] = keep;
+        if ((j & 31) == 31) abea_put_code(dst_a, dst_b, 1 + (j & ~31) + lane, keep);
     }
-    if ((j & 31) != 0 && lane < (j & 31)) dst[1 + (j & ~31) + lane] = keep;
+    if ((j & 31) != 0 && lane < (j & 31)) abea_put_code(dst_a, dst_b, 1 + (j & ~31) + lane, keep);
+}
+__device__ __forceinline__ void abea_emit_codes_io(const abea_stream_t& io, const abea_read_t& rd, const abea_pair_t* out,
+                                                   int32_t total, int lane) {
+    const int64_t off = abea_code_offset(rd.pair_off, rd.orig_index);
+    abea_emit_codes(io.codes_final ? io.codes_final + off : nullptr, io.codes_dev ? io.codes_dev + off : nullptr, out, total, lane);
 }
 
 /* Traceback + QC of one read by one warp. `ring` is the warp's 4 KB shared-memory ring (32 trace lines). The trace
@@ -785,9 +794,9 @@ __device__ __forceinline__ void abea_traceback_read(const abea_read_t& rd, int32
             __syncwarp();
         }
     }
-    if (io.codes_final && !fail) {
+    if (!fail) {
         __syncwarp();
-        abea_emit_codes(io.codes_final + abea_code_offset(rd.pair_off, rd.orig_index), out, n, lane);
+        abea_emit_codes_io(io, rd, out, n, lane);
     }
     /* the count in the caller's buffer doubles as the read's "done" flag: it is written after the list, behind a
      * system-scope fence, so a host thread that sees a count >= 0 may copy the list out while other reads are still
@@ -1259,7 +1268,7 @@ __device__ __forceinline__ void abea_traceback_par(const abea_read_t& rd, int32_
         if (!fail)
             for (int32_t t = lane; t < total; t += 32) fin[t] = out[t];
     }
-    if (io.codes_final && !fail) abea_emit_codes(io.codes_final + abea_code_offset(rd.pair_off, rd.orig_index), out, total, lane);
+    if (!fail) abea_emit_codes_io(io, rd, out, total, lane);
     if (io.n_pairs_final) {
 #ifndef ABEA_SIMT_EMU
         __threadfence_system();
@@ -2160,5 +2169,41 @@ __global__ void abea_compact_pairs_kernel(const abea_pair_t* __restrict__ pairs,
         const abea_pair_t* src = pairs + cap_ptr[i];
         abea_pair_t* d = dst + offsets[i];
         for (int32_t j = lane; j < np; j += 32) d[j] = src[j];
+    }
+}
+
+/* Path codes back to a dense pair list on the device (the receiving end of the multi-GPU exchange, or any consumer
+ * that was handed codes): one warp per read, 32 steps per trip — lane t's pair is the base of the word plus the number
+ * of set bits below bit t+1 in each plane. dst[offsets[i] .. +n_pairs[i]) = read i's pairs. */
+__global__ void abea_expand_codes_kernel(const abea_code_t* __restrict__ codes, const int64_t* __restrict__ cap_ptr,
+                                         const int32_t* __restrict__ n_pairs, const int64_t* __restrict__ offsets,
+                                         int32_t n, abea_pair_t* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int32_t warps = (int32_t)((gridDim.x * blockDim.x) >> 5);
+    for (int32_t i = (int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < n; i += warps) {
+        const int32_t np = n_pairs[i];
+        if (np <= 0) continue;
+        const abea_code_t* w = codes + abea_code_offset(cap_ptr[i], i);
+        abea_pair_t* d = dst + offsets[i];
+        int32_t k = (int32_t)w[0].a, e = (int32_t)w[0].b;
+        if (lane == 0) {
+            abea_pair_t p;
+            p.ref_pos = k;
+            p.read_pos = e;
+            d[0] = p;
+        }
+        const uint32_t below = 0xffffffffu >> (31 - lane); /* bits 0..lane */
+        for (int32_t j0 = 1; j0 < np; j0 += 32) {
+            const abea_code_t c = w[1 + ((j0 - 1) >> 5)];
+            const int32_t j = j0 + lane;
+            if (j < np) {
+                abea_pair_t p;
+                p.ref_pos = k + __popc(c.a & below);
+                p.read_pos = e + __popc(c.b & below);
+                d[j] = p;
+            }
+            k += __popc(c.a);
+            e += __popc(c.b);
+        }
     }
 }

@@ -81,57 +81,88 @@ def device_views(ctx):
 class ResultExchange:
     """The result exchange of the multi-GPU path (north_star: "NCCL over NVLink only for the final result gather").
 
-    Set up once per shard shape: every rank's read count and pair capacity are exchanged, rank 0 allocates one
-    receive buffer per peer and every rank one send buffer — nothing is allocated per step. A step then (1) packs the
-    rank's pair lists back to back on the device (abea_compact_results: 8 bytes per PAIR cross NVLink, not 8 bytes per
-    capacity slot), (2) gathers the exact pair totals and the per-read counts (padded to the largest shard) to rank 0,
-    and (3) moves every shard with one point-to-point transfer of exactly its size. On CUDA the tensors are device
-    memory and the backend is NCCL; with CPU tensors the same code runs over gloo against the CPU emulation build of
-    the library (tests/test_sharding_gloo.py)."""
+    What moves between the GPUs is each rank's pair lists as PATH CODES (abea_device_codes: the first pair of a list and
+    two bits per step, 8 bytes per 32 pairs) plus the per-read counts: 1/32 of the pairs' bytes, and the size of a
+    rank's code buffer is a function of its shard's shape alone, so nothing has to be agreed per step — no compaction,
+    no size exchange, no host synchronisation before the transfer. Set up once per shard shape: every rank's read count,
+    capacity and capacity prefix sums go to rank 0, which allocates one receive buffer per peer and one dense pair
+    buffer per shard — nothing is allocated per step. A step is one grouped point-to-point operation (ncclGroupStart /
+    ncclSend | ncclRecv x 2 per peer / ncclGroupEnd) and, on rank 0, one expansion kernel per shard
+    (abea_expand_codes) that leaves every shard's pair lists back to back in rank 0's HBM. On CUDA the tensors are
+    device memory and the backend is NCCL; with CPU tensors the same code runs over gloo against the CPU emulation build
+    of the library (tests/test_sharding_gloo.py)."""
 
-    def __init__(self, rank: int, world: int, n_reads: int, pair_capacity: int, device):
+    def __init__(self, rank: int, world: int, pair_capacity, device):
         self.rank, self.world = rank, world
         self.dev = torch.device(device)
-        self.n_reads, self.cap = int(n_reads), int(pair_capacity)
-        meta = torch.tensor([self.n_reads, self.cap], dtype=torch.int64, device=self.dev)
-        allm = [torch.zeros(2, dtype=torch.int64, device=self.dev) for _ in range(world)]
+        cap = np.ascontiguousarray(pair_capacity, dtype=np.int64)
+        self.n_reads = int(cap.shape[0])
+        self.cap_ptr = np.zeros(self.n_reads + 1, dtype=np.int64)
+        np.cumsum(cap, out=self.cap_ptr[1:])
+        self.cap = int(self.cap_ptr[-1])
+        self.n_words = (self.cap >> 5) + 2 * self.n_reads + 2 if (self.n_reads and self.cap) else 0
+        meta = torch.tensor([self.n_reads, self.cap, self.n_words], dtype=torch.int64, device=self.dev)
+        allm = [torch.zeros(3, dtype=torch.int64, device=self.dev) for _ in range(world)]
         dist.all_gather(allm, meta)
         self.meta = [tuple(int(v) for v in m.cpu().tolist()) for m in allm]
-        self.max_reads = max(m[0] for m in self.meta)
-        self.send = torch.empty((max(self.cap, 1), 2), dtype=torch.int32, device=self.dev)
-        self.counts = torch.zeros(self.max_reads + 2, dtype=torch.int32, device=self.dev)   # [total lo, total hi, counts...]
-        self.recv = self.recv_counts = None
+        max_reads = max(m[0] for m in self.meta)
+        cp = torch.zeros(max_reads + 1, dtype=torch.int64, device=self.dev)
+        cp[:self.n_reads + 1] = torch.from_numpy(self.cap_ptr).to(self.dev)
+        cps = [torch.zeros_like(cp) for _ in range(world)] if rank == 0 else None
+        dist.gather(cp, cps, dst=0)
+        self.peer_cap_ptr = self.recv_codes = self.recv_counts = self.dense = self.totals = None
         if rank == 0:
-            self.recv = [self.send if r == 0 else torch.empty((max(self.meta[r][1], 1), 2), dtype=torch.int32, device=self.dev)
-                         for r in range(world)]
-            self.recv_counts = [torch.zeros(self.max_reads + 2, dtype=torch.int32, device=self.dev) for _ in range(world)]
+            self.peer_cap_ptr = [cps[r][:self.meta[r][0] + 1].cpu().numpy().copy() for r in range(world)]
+            self.recv_codes = [None if r == 0 else torch.zeros((max(self.meta[r][2], 1), 2), dtype=torch.int32, device=self.dev)
+                               for r in range(world)]
+            self.recv_counts = [None if r == 0 else torch.zeros(max(self.meta[r][0], 1), dtype=torch.int32, device=self.dev)
+                                for r in range(world)]
+            self.dense = [torch.empty((max(self.meta[r][1], 1), 2), dtype=torch.int32, device=self.dev) for r in range(world)]
+            self.totals = torch.zeros(world, dtype=torch.int64, device=self.dev)
 
-    def _counts_view(self, ctx):
-        dp, dn, cap, n = ctx.device_results()
+    def _view(self, ptr: int, shape, n_elems_guard: int):
+        """A tensor over library-owned memory (device memory on CUDA, host memory under the CPU emulation build)."""
+        if n_elems_guard <= 0 or not ptr:
+            return torch.zeros(shape, dtype=torch.int32, device=self.dev)[:0]
         if self.dev.type == "cuda":
-            return torch.as_tensor(_DevArray(dn, (max(n, 1),), "<i4"), device=self.dev)[:n]
+            return torch.as_tensor(_DevArray(ptr, shape, "<i4"), device=self.dev)
         import ctypes
-        return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_int32 * max(n, 1)).from_address(dn))[:n])
+        n = int(np.prod(shape))
+        return torch.from_numpy(np.ctypeslib.as_array((ctypes.c_int32 * n).from_address(ptr)).reshape(shape))
 
     def gather(self, ctx):
         """Returns on rank 0 a list of (n_pairs int32 [n_reads_r], dense pairs int32 [total_r, 2]) per rank; None elsewhere."""
-        total = ctx.compact_results(self.send.data_ptr(), self.send.shape[0])
-        self.counts[0] = total & 0x7fffffff
-        self.counts[1] = total >> 31
-        self.counts[2:2 + self.n_reads] = self._counts_view(ctx)
-        dist.gather(self.counts, self.recv_counts, dst=0)
+        _dp, dn, _cap, n = ctx.device_results()
+        dc, n_words = ctx.device_codes()
+        assert n == self.n_reads and n_words == self.n_words, "the batch does not have the shape this exchange was set up for"
+        counts = self._view(dn, (max(n, 1),), n)
+        codes = self._view(dc, (max(n_words, 1), 2), n_words)
         if self.rank != 0:
-            if total:   # one grouped point-to-point operation per shard (ncclGroupStart / ncclSend / ncclGroupEnd)
-                for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, self.send[:total], 0)]):
+            if n_words:   # one grouped point-to-point operation per shard
+                for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, codes, 0), dist.P2POp(dist.isend, counts, 0)]):
                     q.wait()
             return None
-        heads = torch.stack([c[:2] for c in self.recv_counts]).cpu().tolist()      # the one host sync of the exchange
-        sizes = [int(h[0]) | (int(h[1]) << 31) for h in heads]
-        ops = [dist.P2POp(dist.irecv, self.recv[r][:sizes[r]], r) for r in range(1, self.world) if sizes[r]]
+        ops = []
+        for r in range(1, self.world):
+            if self.meta[r][2]:
+                ops += [dist.P2POp(dist.irecv, self.recv_codes[r], r), dist.P2POp(dist.irecv, self.recv_counts[r], r)]
         if ops:
             for q in dist.batch_isend_irecv(ops):
                 q.wait()
-        return [(self.recv_counts[r][2:2 + self.meta[r][0]], self.recv[r][:sizes[r]]) for r in range(self.world)]
+        if self.dev.type == "cuda":
+            torch.cuda.current_stream(self.dev).synchronize()   # the library's kernels run on the context's own stream
+        out_counts = []
+        last = max((r for r in range(self.world) if self.meta[r][2]), default=-1)
+        for r in range(self.world):
+            c_r = counts if r == 0 else self.recv_counts[r][:self.meta[r][0]]
+            out_counts.append(c_r)
+            if not self.meta[r][2]:
+                continue
+            k_r = codes if r == 0 else self.recv_codes[r]
+            ctx.expand_codes(k_r.data_ptr(), c_r.data_ptr(), self.peer_cap_ptr[r], self.dense[r].data_ptr(), self.meta[r][1],
+                             total_ptr=self.totals[r:r + 1].data_ptr(), sync=(r == last))
+        sizes = self.totals.cpu().tolist()       # the one host read of the exchange (after the last expansion has finished)
+        return [(out_counts[r], self.dense[r][:int(sizes[r]) if self.meta[r][2] else 0]) for r in range(self.world)]
 
 
 def gather_device_results(ctx, rank: int, world: int):

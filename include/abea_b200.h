@@ -202,6 +202,24 @@ int abea_device_results(abea_ctx_t* ctx, const abea_pair_t** d_pairs, const int3
  * suffices). */
 int abea_compact_results(abea_ctx_t* ctx, abea_pair_t* d_dst, int64_t dst_capacity, int64_t* total_pairs);
 
+/* The same results as PATH CODES, 1/32 of the size — what a multi-GPU driver should move between GPUs. A pair list is a
+ * monotone lattice path, so its first pair and one bit per coordinate per step describe it: read i (batch order) owns the
+ * words [(P_i >> 5) + 2 i, ...) of *d_codes, P_i = the prefix sum of n_events+read_len (the capacity layout of
+ * abea_device_results); word 0 = {first ref_pos, first read_pos}, word 1 + j = steps 32 j .. 32 j + 31 as two bit planes
+ * (bit t of `a`: ref_pos advances at that step; bit t of `b`: read_pos does). Only the first 1 + ceil((n_pairs[i] - 1) / 32)
+ * words of a read with n_pairs[i] > 0 are defined. *n_words = the buffer's size, a function of the batch shape alone
+ * ((sum of n_events+read_len >> 5) + 2 n_reads + 2), so a peer can be sent the whole buffer without a size exchange.
+ * Valid until the next abea_run / abea_upload_batch / abea_destroy on this context. */
+int abea_device_codes(abea_ctx_t* ctx, const abea_code_word_t** d_codes, int64_t* n_words);
+
+/* Path codes back to dense pair lists, on this context's device: d_codes / d_n_pairs (device memory, e.g. received from
+ * a peer) describe n_reads reads whose capacity prefix sums are cap_ptr[0 .. n_reads] (HOST memory); d_dst[0 .. total)
+ * receives read 0's pairs, read 1's pairs, ... back to back. dst_capacity (in pairs) must be at least cap_ptr[n_reads].
+ * The total is written to *d_total (device memory, may be NULL) and, if total_pairs is not NULL, returned to the host
+ * (which synchronises the context's stream; with NULL the call only enqueues work). */
+int abea_expand_codes(abea_ctx_t* ctx, const abea_code_word_t* d_codes, const int32_t* d_n_pairs, const int64_t* cap_ptr,
+                      int32_t n_reads, abea_pair_t* d_dst, int64_t dst_capacity, int64_t* d_total, int64_t* total_pairs);
+
 /* The reference's --print-banded-aln dump (src/f5c.c:989-1006) of a batch's pair lists, byte for byte the text f5c
  * prints, so that this path can be diffed against an f5c run: reads whose read_stat_flag has ABEA_FAILED_ALIGNMENT are
  * skipped (read_stat_flag may be NULL: none is). path "-" = stdout. Host-side formatting only. */

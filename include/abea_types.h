@@ -175,6 +175,12 @@ typedef struct {
     int32_t* n_pairs;
 } abea_ragged_t;
 
+/* One word of a pair list's path codes (abea_device_codes in abea_b200.h): the first word of a read holds its first
+ * pair, every further word 32 steps as two bit planes. */
+typedef struct {
+    uint32_t a, b;
+} abea_code_word_t;
+
 #ifdef __cplusplus
 }
 #endif

@@ -179,6 +179,17 @@ def test_emulated_path_codes(emu, monkeypatch, tb):
             ol.assert_same_alignment(got, want, f"path codes, {threads} threads")
             assert got.timing["streamed"] & 4
             assert got.timing["d2h_bytes"] < int(want.n_pairs.sum()) * 8 // 16
+        # the same codes stay in device memory for consumers on the GPU (the multi-GPU exchange): expanded back to dense
+        # lists by abea_expand_codes they are the compacted pair lists (under the emulator device memory is host memory)
+        from f5c_b200.dist import compact_pairs
+        _dp, dn, cap, n = ctx.device_results()
+        dc, n_words = ctx.device_codes()
+        cap_ptr = np.concatenate([[0], np.cumsum(b.pair_capacity().astype(np.int64))])
+        assert n == b.n_reads and cap == cap_ptr[-1] and n_words == (cap >> 5) + 2 * n + 2
+        dense = np.zeros((int(cap), 2), dtype=np.int32)
+        total = ctx.expand_codes(dc, dn, cap_ptr, dense.ctypes.data, int(cap), sync=True)
+        assert total == int(want.n_pairs.sum())
+        assert np.array_equal(dense[:total].reshape(-1).view(want.pairs.dtype), compact_pairs(want.pairs, want.pair_ptr, want.n_pairs))
         assert ctx.host_threads(0) == 0 and ctx.host_threads() == 0
         got = ctx.align_batch(b)
         ol.assert_same_alignment(got, want, "whole lists")

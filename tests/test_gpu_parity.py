@@ -259,8 +259,21 @@ def test_full_size_cfg4_all_reads(ctx):
 
 
 def test_full_size_cfg5_target_config(ctx):
-    """The north_star target (BASELINE configs[4] per GPU): R10.4.1, 4096 reads, mean 4k events/read."""
-    full_size_check(ctx, "cfg5", 8, 56)
+    """The north_star target (BASELINE configs[4] per GPU): R10.4.1, 4096 reads, mean 4k events/read. Also what a
+    multi-GPU driver exchanges: the run's path codes in device memory (abea_device_codes), expanded on the device
+    (abea_expand_codes), are the pair lists back to back."""
+    import torch
+    from f5c_b200.dist import compact_pairs
+    b, a = full_size_check(ctx, "cfg5", 8, 56)
+    _dp, dn, cap, n = ctx.device_results()
+    dc, n_words = ctx.device_codes()
+    cap_ptr = np.concatenate([[0], np.cumsum(b.pair_capacity().astype(np.int64))])
+    assert n == b.n_reads and cap == cap_ptr[-1] and n_words == (cap >> 5) + 2 * n + 2
+    dense = torch.zeros((int(cap), 2), dtype=torch.int32, device="cuda")
+    total = ctx.expand_codes(dc, dn, cap_ptr, dense.data_ptr(), int(cap), sync=True)
+    assert total == int(a.n_pairs.sum())
+    got = dense[:total].cpu().numpy().reshape(-1).view(a.pairs.dtype)
+    assert np.array_equal(got, compact_pairs(a.pairs, a.pair_ptr, a.n_pairs))
 
 
 def test_ecoli_all_112_reads_from_blow5(ctx):

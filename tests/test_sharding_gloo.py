@@ -31,9 +31,9 @@ def _worker(rank, world, port, out_path):
     with AbeaContext(0, lib_path=os.path.join(HERE, "simt", "libabea_emu.so")) as ctx:
         m = ctx.set_model(m, k)
         a = ctx.align_batch(b)
-        # the exchange bench.py uses over NCCL: device-side compaction + exact-size transfers into persistent buffers
+        # the exchange bench.py uses over NCCL: path codes + counts into persistent buffers, expanded on rank 0
         from f5c_b200.dist import ResultExchange
-        ex = ResultExchange(rank, world, b.n_reads, int(b.pair_capacity().sum()), "cpu")
+        ex = ResultExchange(rank, world, b.pair_capacity(), "cpu")
         res2 = [ex.gather(ctx) for _ in range(2)][-1]     # twice: the buffers are reused
         if rank == 0:
             res2 = [(c.numpy().copy(), p.numpy().copy().reshape(-1).view(a.pairs.dtype)) for c, p in res2]

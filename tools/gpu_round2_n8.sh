@@ -1,10 +1,16 @@
 #!/bin/bash
-# the multi-GPU line as the driver launches it (our arm only)
+# the multi-GPU line as the driver launches it (our arm only). With arguments "N ab": A/B of the two output forms.
 mkdir -p gpurun_out
 N=${1:-8}
-nproc; free -g | head -2
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/ro_bench_n$N.json 2> gpurun_out/ro_bench_n$N.err
-tail -3 gpurun_out/ro_bench_n$N.err | cut -c1-300
+nproc
+run() { tag=$1; shift; env "$@" timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 10 --warmup 3 $EXTRA > gpurun_out/ro_bench_n${N}_$tag.json 2> gpurun_out/ro_bench_n${N}_$tag.err
 python -c "
 import json
-d=json.loads(open('gpurun_out/ro_bench_n$N.json').read().strip().splitlines()[-1]); print('N=$N value %.3e'%d['value'], 'dev ms %.3f'%d['ms_per_step'], 'e2e %.3e'%d['e2e']['value'], 'e2e ms %.3f'%d['e2e']['ms_per_step'], 'gather ms %.3f'%d['e2e']['nccl_gather_ms_per_step'], 'load_ms max %.2f'%d['e2e']['load_ms_max_over_ranks'], d.get('parity_gathered_shard'), d['e2e']['last_step_output_equals_resident_result_all_ranks'], d['e2e']['last_step_parts_ms_rank0'], d['clocks'])"
+d=json.loads(open('gpurun_out/ro_bench_n${N}_$tag.json').read().strip().splitlines()[-1]); print('$tag N=$N value %.3e'%d['value'], 'dev ms %.3f'%d['ms_per_step'], 'e2e %.3e'%d['e2e']['value'], 'e2e ms %.3f'%d['e2e']['ms_per_step'], 'gather ms %.3f'%d['e2e']['nccl_gather_ms_per_step'], 'load_ms max %.2f'%d['e2e']['load_ms_max_over_ranks'], 'threads', d['e2e'].get('host_threads'), d.get('parity_gathered_shard'), d['e2e']['last_step_output_equals_resident_result_all_ranks'], d['e2e']['last_step_parts_ms_rank0'])"; }
+if [ "$2" = ab ]; then
+  EXTRA="--no-extras"
+  run default X=1
+  run codes3 ABEA_HOST_THREADS=3
+else
+  run default X=1
+fi
