@@ -432,6 +432,7 @@ def main():
     clocks = sampler.stop() if sampler else None   # sampled across both timed regions (and the stage timings between them)
     e2e_parts = {kk: r.timing[kk] for kk in ("pack_ms", "h2d_ms", "load_ms", "kernel_ms", "d2h_ms", "unpack_ms")}
     e2e_parts["streamed"] = r.timing["streamed"]
+    e2e_parts["n_wide"] = r.timing["n_wide"]
     # what the last timed e2e step left in the caller's pinned buffers must be what the resident runs produced
     e2e_same_as_resident = bool(np.array_equal(out[2], n_pairs_local) and all(
         np.array_equal(out[0][int(out[1][i]):int(out[1][i]) + int(out[2][i])], res.read_pairs(i)) for i in range(batch.n_reads)))

@@ -199,7 +199,7 @@ struct abea_ctx {
     /* Cycles per band of the three forms a read is filled in, cycles per traceback step and the band time of a fully
      * loaded sub-partition: the scheduler's model of the kernels. Starting values measured on B200 at 1.965 GHz
      * (profiles/); re-derived from the per-read clock64 counts of the batches that run (calibrate()). */
-    double cyc_wide = 400.0, cyc_narrow = 1000.0, cyc_long = 655.0, cyc_trace = 40.0;
+    double cyc_wide = 400.0, cyc_narrow = 856.0, cyc_long = 626.0, cyc_trace = 100.0; /* measured on B200 with this revision of the kernels (profiles/read_cycles_final_r02_cfg5.txt) */
     int calib_mode = 1;        /* ABEA_CALIBRATE=0 keeps the starting values */
     size_t wide_excl_bytes = (size_t)160 * 1024; /* dynamic shared memory a wide CTA asks for to have its SM to itself */
     int tb_mode = 1;           /* ABEA_TB: 1 segment-parallel traceback (a walk per lane), 0 the serial walk */
@@ -326,13 +326,18 @@ double batch_cycles(const abea_ctx* c) { return (double)c->total_bands * cyc_tpu
 /* a narrow read is "long" when, sharing its sub-partition, it would take more than long_alpha of the time the whole
  * batch needs at full throughput: it then runs alone on its sub-partition */
 int32_t long_threshold(const abea_ctx* c) {
-    const double shared = 0.5 * (c->cyc_narrow + c->cyc_long) * 0.945; /* ~780 at the starting values: two warps per sub-partition */
+    /* The two thresholds below were tuned by sweeps (profiles/sweep_*): on the target config a read is long above
+     * 15.4 k bands and wide above 23.0 k. Their constants (0.904, 1.40) are what reproduces those optima from the
+     * MEASURED cycle counts, so that the thresholds do not move when the model is re-derived from a batch's own counts
+     * (round 2 found them tuned against stale start values: after the first calibration 18 reads went wide instead of
+     * 6 and the step took 8.47 instead of 8.12 ms). */
+    const double shared = 0.5 * (c->cyc_narrow + c->cyc_long) * 0.904; /* two warps per sub-partition */
     return (int32_t)std::min(2.0e9, std::max(1.0, c->long_alpha * batch_cycles(c) / shared));
 }
 /* a read goes to the wide kernel when it would outlast the whole batch even as a lone narrow warp */
 double wide_threshold(const abea_ctx* c, int64_t total_bands) {
     const double cyc_batch = (double)total_bands * cyc_tput(c) * 1.08 / ((double)c->sm_count * 4.0);
-    return std::max(c->wide_min_bands, c->wide_alpha * 1.25 * cyc_batch / c->cyc_long);
+    return std::max(c->wide_min_bands, c->wide_alpha * 1.40 * cyc_batch / c->cyc_long);
 }
 
 /* A pair list from its path codes (abea_code_t, abea_kernels.cuh): the first pair, then one step per bit. Measured: a
@@ -500,8 +505,8 @@ int calibrate(abea_ctx* c, int32_t long_thr) {
     };
     auto clampd = [](double x, double ref) { return std::min(2.0 * ref, std::max(0.5 * ref, x)); };
     if (wide.size() >= 2) c->cyc_wide = clampd(median(wide), 400.0);
-    if (lng.size() >= 4) c->cyc_long = clampd(median(lng), 655.0);
-    if (shared.size() >= 64) c->cyc_narrow = clampd(median(shared), 1000.0);
+    if (lng.size() >= 4) c->cyc_long = clampd(median(lng), 626.0);
+    if (shared.size() >= 64) c->cyc_narrow = clampd(median(shared), 856.0);
     if (trace.size() >= 64) c->cyc_trace = std::min(700.0, std::max(2.0, median(trace))); /* 350 serial, a few tens segment-parallel */
     return 0;
 }
@@ -1102,7 +1107,7 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
                 auto fill_exact = streaming ? abea_fill_kernel<false, true> : abea_fill_kernel<false, false>;
                 CU(cudaFuncSetAttribute((const void*)fill_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 CU(cudaFuncSetAttribute((const void*)fill_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                /* a narrow read is "long" when, sharing its sub-partition (~780 cycles/band), it would take more than
+                /* a narrow read is "long" when, sharing its sub-partition (~670 cycles/band at two warps), it would take more than
                  * long_alpha of the time the whole batch needs at full throughput */
                 const int32_t long_thr = long_threshold(c);
                 ABEA_LAUNCH_SMEM(fill_fast, blocks, 32 * wpc, smem, c->stream,

@@ -15,13 +15,23 @@ k, m = models.load_model(b.meta["model"])
 ctx = AbeaContext(0); ctx.set_model(m, k)
 pb = ctx.pin_batch(b)
 out = ctx.alloc_output(b, pinned=True)
+means = ctx.pin_array(b.event_means()) if os.environ.get("E2E_MEANS", "1") != "0" else None   # 4 B per event in (the bench's leg)
+if os.environ.get("E2E_RESIDENT"):      # the same batch resident: upload once, time abea_run alone
+    ctx.upload(pb, means=means)
+    for _ in range(3):
+        ctx.run()
 for _ in range(3):
-    r = ctx.align_batch(pb, out)
+    r = ctx.align_batch(pb, out, means=means)
 ts = []
 for _ in range(iters):
     t0 = time.perf_counter()
-    r = ctx.align_batch(pb, out)
+    r = ctx.align_batch(pb, out, means=means)
     ts.append((time.perf_counter() - t0) * 1e3)
+if os.environ.get("E2E_RESIDENT"):
+    ctx.upload(pb, means=means)
+    for _ in range(3):
+        tr = ctx.run()
+    print("resident run kernel_ms %.3f" % tr["kernel_ms"])
 ev = b.events_aligned()
 t = r.timing
 print(cfg, "STREAM", os.environ.get("ABEA_STREAM", "3"), "LOAD_CTAS", os.environ.get("ABEA_LOAD_CTAS", "-"),
@@ -31,6 +41,7 @@ print(cfg, "STREAM", os.environ.get("ABEA_STREAM", "3"), "LOAD_CTAS", os.environ
 
 if os.environ.get("E2E_STARTS"):
     st = ctx.read_starts(b.n_reads).astype(np.int64)
+    print("timeline of the", "resident run" if os.environ.get("E2E_RESIDENT") else "last streamed call")
     cyc = ctx.read_cycles(b.n_reads)
     ok = st >= 0
     t0_ = st[ok].min()
@@ -39,6 +50,10 @@ if os.environ.get("E2E_STARTS"):
     order = np.argsort(-b.n_bands)
     print("start ms of the 12 longest reads:", np.round(rel[order[:12]], 2).tolist())
     print("  their duration ms:", np.round(dur[order[:12]], 2).tolist())
+    print("  wide:", cyc["wide"][order[:12]].tolist(), " fill cycles/band:", np.round(cyc["fill_cycles"][order[:12]] / b.n_bands[order[:12]], 0).tolist(),
+          " n_wide", (tr if os.environ.get("E2E_RESIDENT") else t)["n_wide"], " model", ctx.scheduler_model())
+    o2 = order[12:40]
+    print("  LPT ranks 12-40: wide", int(cyc["wide"][o2].sum()), "fill cycles/band min/med/max %.0f %.0f %.0f" % tuple(np.percentile(cyc["fill_cycles"][o2] / b.n_bands[o2], [0, 50, 100])))
     el = order[ok[order]]
     for lo, hi in ((0, 148), (148, 592), (592, 1500), (1500, 3000), (3000, len(el))):
         seg = el[lo:hi]
