@@ -279,7 +279,10 @@ def e2e_dropin(batch, model, k, device, threads, steps, warmup, want, sample_n):
          "call": "align_cuda(core_t*, db_t*) of libf5c_abea_dropin.so on a ragged db_t (per-read malloc'd sequences, event tables "
                  "and pair buffers); timed per call with the reference's realtime()",
          "h2d_bytes_per_step": int(4 * batch.n_events.astype(np.int64).sum() + batch.seq.shape[0]),
-         "d2h_bytes_per_step": int(8 * n_pairs.astype(np.int64).sum() + 4 * batch.n_reads)}
+         # the lists cross PCIe as path codes (one 8-byte word for the first pair + one per 32 steps) unless ABEA_STREAM says otherwise
+         "d2h_bytes_per_step": int((8 * (1 + (np.maximum(n_pairs.astype(np.int64) - 1, 0) + 31) // 32) * (n_pairs > 0)).sum()
+                                   + 4 * batch.n_reads) if (int(os.environ.get("ABEA_STREAM", "7")) & 4)
+                               else int(8 * n_pairs.astype(np.int64).sum() + 4 * batch.n_reads)}
     if want is not None:
         d["parity_on_cpu_sample"] = bool(same_pairs(pairs, pp, n_pairs, want, range(sample_n)))
     return d, pairs, n_pairs

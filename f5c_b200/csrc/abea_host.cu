@@ -140,7 +140,8 @@ struct abea_ctx {
 
     /* resident batch */
     DevBuf d_seq, d_events, d_means, d_reads, d_kparams, d_trace, d_pairs, d_results, d_queue, d_flags, d_npairs;
-    DevBuf d_codes;                   /* path codes of the last run's pair lists (abea_code_t), for abea_device_codes */
+    DevBuf d_codes;                   /* path codes of the last run's pair lists (abea_code_t), made on demand by abea_device_codes */
+    bool codes_current = false;       /* d_codes describes the last run */
     DevBuf d_xcap, d_xoff;            /* abea_expand_codes: a peer's capacity prefix sums, dense offsets */
     std::vector<int64_t> cap_ptr;     /* canonical pair_ptr of the caller's batch: prefix sum of E+L over ALL reads */
     HostBuf h_results, h_pairs, h_reads, h_items; /* pinned staging */
@@ -1042,11 +1043,7 @@ static int run_impl(abea_ctx_t* c, abea_pair_t* fin_pairs, int32_t* fin_np, abea
     io.pairs_final = fin_pairs;
     io.n_pairs_final = fin_np;
     io.codes_final = fin_codes;
-    io.codes_dev = nullptr;
-    if (c->n_batch_reads > 0 && c->total_pair_cap > 0) {
-        if (dev_reserve(c, c->d_codes, (size_t)code_words(c->total_pair_cap, c->n_batch_reads) * sizeof(abea_code_t))) return ABEA_ERR_CUDA;
-        io.codes_dev = (abea_code_t*)c->d_codes.p;
-    }
+    c->codes_current = false;
     io.n_pairs_dev = (int32_t*)c->d_npairs.p;
     io.stalled = (uint32_t*)c->d_queue.p + 15; /* zeroed with the queue */
     io.tb_mode = c->tb_mode;
@@ -1336,8 +1333,24 @@ int abea_compact_results(abea_ctx_t* c, abea_pair_t* d_dst, int64_t dst_capacity
 int abea_device_codes(abea_ctx_t* c, const abea_code_t** d_codes, int64_t* n_words) {
     if (!c) return ABEA_ERR_ARG;
     if (!c->ran || !c->results_on_device) return fail(c, ABEA_ERR_STATE, "abea_device_codes before abea_run");
+    CU(cudaSetDevice(c->device));
+    const int32_t n = c->n_batch_reads;
+    const int64_t words = (n > 0 && c->total_pair_cap > 0) ? code_words(c->total_pair_cap, n) : 0;
+    if (words > 0 && !c->codes_current) { /* one warp per read over the lists in d_pairs; once per run */
+        if (dev_reserve(c, c->d_codes, (size_t)words * sizeof(abea_code_t))) return ABEA_ERR_CUDA;
+        if (dev_reserve(c, c->d_capptr, ((size_t)n + 1) * sizeof(int64_t))) return ABEA_ERR_CUDA;
+        if (host_reserve(c, c->h_items, ((size_t)n + 2) * sizeof(int64_t))) return ABEA_ERR_CUDA; /* pinned scratch */
+        memcpy(c->h_items.p, c->cap_ptr.data(), ((size_t)n + 1) * sizeof(int64_t));
+        CU(cudaMemcpyAsync(c->d_capptr.p, c->h_items.p, ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        const int blocks = std::max(1, std::min((n + 7) / 8, c->sm_count * 8));
+        ABEA_LAUNCH(abea_pairs_to_codes_kernel, blocks, 256, c->stream, (const abea_pair_t*)c->d_pairs.p,
+                    (const int64_t*)c->d_capptr.p, (const int32_t*)c->d_npairs.p, n, (abea_code_t*)c->d_codes.p);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->stream));
+        c->codes_current = true;
+    }
     if (d_codes) *d_codes = (const abea_code_t*)c->d_codes.p;
-    if (n_words) *n_words = (c->n_batch_reads > 0 && c->total_pair_cap > 0) ? code_words(c->total_pair_cap, c->n_batch_reads) : 0;
+    if (n_words) *n_words = words;
     return ABEA_OK;
 }
 

@@ -218,7 +218,6 @@ struct abea_stream_t {
     abea_pair_t* pairs_final;   /* the caller's mapped host buffer (canonical layout), or NULL: the lists stay in d_pairs only */
     int32_t* n_pairs_final;     /* [batch read] pair counts in the caller's mapped host buffer, or NULL */
     abea_code_t* codes_final;   /* mapped host buffer of path codes (below), or NULL */
-    abea_code_t* codes_dev;     /* the same codes in device memory (what a multi-GPU driver exchanges), or NULL */
     int32_t* n_pairs_dev;       /* [batch read] pair counts on the device (always written) */
     uint32_t* stalled;          /* set to 1 if a wait for streamed events gave up (the host reports an error) */
     int32_t tb_mode;            /* 0: serial traceback (one walk per warp), 1: segment-parallel traceback (a walk per lane);
@@ -678,7 +677,7 @@ __device__ __forceinline__ void abea_emit_codes(abea_code_t* dst_a, abea_code_t*
 __device__ __forceinline__ void abea_emit_codes_io(const abea_stream_t& io, const abea_read_t& rd, const abea_pair_t* out,
                                                    int32_t total, int lane) {
     const int64_t off = abea_code_offset(rd.pair_off, rd.orig_index);
-    abea_emit_codes(io.codes_final ? io.codes_final + off : nullptr, io.codes_dev ? io.codes_dev + off : nullptr, out, total, lane);
+    abea_emit_codes(io.codes_final ? io.codes_final + off : nullptr, nullptr, out, total, lane);
 }
 
 /* Traceback + QC of one read by one warp. `ring` is the warp's 4 KB shared-memory ring (32 trace lines). The trace
@@ -2169,6 +2168,19 @@ __global__ void abea_compact_pairs_kernel(const abea_pair_t* __restrict__ pairs,
         const abea_pair_t* src = pairs + cap_ptr[i];
         abea_pair_t* d = dst + offsets[i];
         for (int32_t j = lane; j < np; j += 32) d[j] = src[j];
+    }
+}
+
+/* The path codes of a whole batch from the pair lists the traceback left in d_pairs (capacity layout): one warp per read.
+ * This is how abea_device_codes produces them — on demand, off every read's critical path (emitting them from the
+ * traceback cost the longest read of a batch 9 cycles per step: cfg3 38.6 -> 39.1 ms). */
+__global__ void abea_pairs_to_codes_kernel(const abea_pair_t* __restrict__ pairs, const int64_t* __restrict__ cap_ptr,
+                                           const int32_t* __restrict__ n_pairs, int32_t n, abea_code_t* __restrict__ codes) {
+    const int lane = threadIdx.x & 31;
+    const int32_t warps = (int32_t)((gridDim.x * blockDim.x) >> 5);
+    for (int32_t i = (int32_t)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); i < n; i += warps) {
+        const int32_t np = n_pairs[i];
+        if (np > 0) abea_emit_codes(nullptr, codes + abea_code_offset(cap_ptr[i], i), pairs + cap_ptr[i], np, lane);
     }
 }
 

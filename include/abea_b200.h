@@ -209,7 +209,8 @@ int abea_compact_results(abea_ctx_t* ctx, abea_pair_t* d_dst, int64_t dst_capaci
  * (bit t of `a`: ref_pos advances at that step; bit t of `b`: read_pos does). Only the first 1 + ceil((n_pairs[i] - 1) / 32)
  * words of a read with n_pairs[i] > 0 are defined. *n_words = the buffer's size, a function of the batch shape alone
  * ((sum of n_events+read_len >> 5) + 2 n_reads + 2), so a peer can be sent the whole buffer without a size exchange.
- * Valid until the next abea_run / abea_upload_batch / abea_destroy on this context. */
+ * The codes are made by the first call after a run (one kernel over the pair lists, one warp per read; the call
+ * synchronises the context's stream). Valid until the next abea_run / abea_upload_batch / abea_destroy on this context. */
 int abea_device_codes(abea_ctx_t* ctx, const abea_code_word_t** d_codes, int64_t* n_words);
 
 /* Path codes back to dense pair lists, on this context's device: d_codes / d_n_pairs (device memory, e.g. received from

@@ -14,9 +14,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:abea_fill_kernel -c 1 -s 2 -f -o gpurun_out/fill_$TAG python tools/prof_run.py cfg5 - 3 > gpurun_out/ncu_$TAG.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:abea_fill_wide -c 1 -s 2 -f -o gpurun_out/wide_$TAG python tools/prof_run.py cfg5 - 3 >> gpurun_out/ncu_$TAG.log 2>&1
 for tool in memcheck racecheck synccheck; do timeout 900 compute-sanitizer --tool $tool python tools/sanitize_run.py > gpurun_out/sanitizer_${tool}_$TAG.log 2>&1; tail -3 gpurun_out/sanitizer_${tool}_$TAG.log; done
-for m in 1 2; do ABEA_STREAM=$m timeout 300 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_${TAG}_stream$m.json; done
+for m in 3 4; do ABEA_STREAM=$m timeout 300 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_${TAG}_stream$m.json; done
 for c in cfg5 cfg3 cfg4; do timeout 300 python tools/prof_run.py $c - 3 > gpurun_out/prof_${TAG}_$c.txt 2>&1; done
 cat gpurun_out/tests_$TAG.log; tail -2 gpurun_out/smoke_$TAG.log; cut -c1-400 gpurun_out/bench_$TAG.json; cut -c1-200 gpurun_out/bench_${TAG}_ref.json
-for m in 1 2; do python -c "
+for m in 3 4; do python -c "
 import json
 d=json.load(open('gpurun_out/bench_${TAG}_stream$m.json')); print('ABEA_STREAM=$m e2e ms %.3f'%d['e2e']['ms_per_step'], d['e2e']['last_step_parts_ms_rank0'])"; done
