@@ -65,6 +65,14 @@ with AbeaContext(0) as ctx:
     total = ctx.compact_results(dd.data_ptr(), dd.shape[0])
     assert total == int(a.n_pairs.sum())
     print("ok scaling stages + compaction", total)
+    # the lists as path codes in device memory (abea_pairs_to_codes_kernel) and back (abea_expand_codes_kernel)
+    _dp, dn, cap, n = ctx.device_results()
+    dc, n_words = ctx.device_codes()
+    cap_ptr = np.concatenate([[0], np.cumsum(b.pair_capacity().astype(np.int64))])
+    d2 = torch.zeros((int(cap), 2), dtype=torch.int32, device="cuda")
+    total2 = ctx.expand_codes(dc, dn, cap_ptr, d2.data_ptr(), int(cap), sync=True)
+    assert total2 == total and bool(torch.equal(d2[:total2], dd[:total]))
+    print("ok device codes + expansion", total2, n_words)
     f = blow5.Blow5(os.path.join(ROOT, "tests", "golden", "ecoli", "ecoli8_zlib_svbzd.blow5"))
     order = np.argsort([r[1] for r in f.records])[:3]
     chunks = [f.record_bytes(int(i)) for i in order]
