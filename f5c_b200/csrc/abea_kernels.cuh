@@ -198,8 +198,9 @@ __global__ void abea_prepare_kernel(const abea_read_t* __restrict__ reads, int32
  * abea_load_kernel read the events straight out of the caller's pinned buffer over PCIe — in the order the fill
  * warps are going to ask for them — and publish a per-read counter of landed pieces that a fill warp (or wide CTA)
  * waits on before it touches the read. The results go the other way without a copy either: the last step of the
- * traceback writes the finished pair list to the caller's mapped buffer. With ready == NULL and pairs_final ==
- * pairs the kernels run on data that is already resident (abea_upload_batch / abea_run / abea_download). */
+ * traceback writes the finished pair list — as path codes (below), or whole — to mapped host memory and publishes the
+ * read's count behind it. With ready == NULL and no *_final pointer the kernels run on data that is already resident
+ * and leave their results in device memory only (abea_upload_batch / abea_run / abea_download). */
 /* Path codes: a finished pair list in 1/32 of its size. The list is a monotone lattice path — consecutive pairs differ
  * by (+1,+1), (0,+1) or (+1,0) in (ref_pos, read_pos), the traceback's D / U / L steps read forwards (reference
  * src/align.c:452-499) — so the first pair and one bit per coordinate per step say everything: word 0 of a read's

@@ -101,8 +101,9 @@ int abea_align_batch(abea_ctx_t* ctx, const abea_batch_t* batch, abea_pair_t* pa
  * db->event_align_pairs[i]; reference src/f5c.h:290-352) — so that the flattening the reference's align_cuda does on
  * its calling thread before and after its kernels (src/f5c.cu:744-800, 1005-1030) overlaps the kernels instead:
  * `threads` host threads extract the event means piece by piece into pinned staging in the order the loader kernel is
- * going to ship them, and copy every read's pair list out to pairs[i] as soon as its count appears in the pinned count
- * array (the traceback publishes it behind a system-scope fence). Same results as abea_align_batch. */
+ * going to ship them, and expand every read's pair list from its path codes (8 bytes per 32 pairs over PCIe, see
+ * abea_host_threads) into pairs[i] as soon as its count appears in the pinned count array (the traceback publishes it
+ * behind a system-scope fence). Same results as abea_align_batch. */
 int abea_align_ragged(abea_ctx_t* ctx, const abea_ragged_t* batch, int threads, abea_timing_t* timing);
 
 /* The same path in three separable phases. abea_run may be repeated on a resident batch (it re-zeroes its queues). */
