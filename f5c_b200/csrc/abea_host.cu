@@ -230,7 +230,7 @@ struct abea_ctx {
     std::vector<abea_sig_t> sigs;
     DevBuf d_raw, d_sum, d_sumsq, d_ts1, d_ts2, d_peaks, d_evcap, d_sigs, d_sigorder, d_nev, d_evptr, d_evout;
     DevBuf d_chunks, d_spec, d_fix, d_spec_cnt, d_fix_cnt, d_sync, d_spec_end;
-    DevBuf d_raw16, d_b5in, d_b5out, d_b5recs, d_b5len, d_b5status, d_b5hdr, d_b5rawoff; /* BLOW5 decode (blow5_kernels.cuh) */
+    DevBuf d_raw16, d_b5in, d_b5out, d_b5recs, d_b5len, d_b5status, d_b5hdr, d_b5rawoff, d_b5ex; /* BLOW5 decode (blow5_kernels.cuh) */
     HostBuf h_b5;
     int evt_chunk = 1024;            /* ABEA_EVT_CHUNK: samples per chunk of the speculative peak detector (multiple of 4) */
     std::vector<int32_t> nev;        /* event counts of the last abea_getevents */
@@ -1517,8 +1517,8 @@ int abea_getevents_blow5(abea_ctx_t* c, const abea_blow5_t* f, int rna, int32_t*
     if (n > 0 && (!f->bytes || !f->rec_ptr || !f->rec_len)) return fail(c, ABEA_ERR_ARG, "bad records");
     if (f->record_method != B5_REC_NONE && f->record_method != B5_REC_ZLIB)
         return fail(c, ABEA_ERR_ARG, "record compression %d is not supported (none and zlib are)", f->record_method);
-    if (f->signal_method != B5_SIG_NONE && f->signal_method != B5_SIG_SVB_ZD)
-        return fail(c, ABEA_ERR_ARG, "signal compression %d is not supported (none and svb-zd are)", f->signal_method);
+    if (f->signal_method != B5_SIG_NONE && f->signal_method != B5_SIG_SVB_ZD && f->signal_method != B5_SIG_EX_ZD)
+        return fail(c, ABEA_ERR_ARG, "signal compression %d is not supported (none, svb-zd and ex-zd are)", f->signal_method);
     CU(cudaSetDevice(c->device));
     const double t0 = now_ms();
     int64_t total_in = 0;
@@ -1609,9 +1609,14 @@ int abea_getevents_blow5(abea_ctx_t* c, const abea_blow5_t* f, int rna, int32_t*
         }
         if (dev_reserve(c, c->d_raw, (size_t)(raw_total + 1) * sizeof(float))) return ABEA_ERR_CUDA;
         CU(cudaMemcpyAsync(c->d_b5rawoff.p, h_rawoff, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        uint32_t* ex_scratch = nullptr; /* ex-zd: positions and values of a record's exceptions, at most one per sample */
+        if (f->signal_method == B5_SIG_EX_ZD) {
+            if (dev_reserve(c, c->d_b5ex, (size_t)(2 * raw_total + 2) * sizeof(uint32_t))) return ABEA_ERR_CUDA;
+            ex_scratch = (uint32_t*)c->d_b5ex.p;
+        }
         ABEA_LAUNCH(abea_blow5_signal_kernel, (n + B5_SIG_WARPS - 1) / B5_SIG_WARPS, 32 * B5_SIG_WARPS, c->stream,
                     (const abea_b5rec_t*)c->d_b5recs.p, n, d_data, (const abea_b5hdr_t*)c->d_b5hdr.p,
-                    (const int64_t*)c->d_b5rawoff.p, f->signal_method, (float*)c->d_raw.p, (int32_t*)c->d_b5status.p);
+                    (const int64_t*)c->d_b5rawoff.p, f->signal_method, (float*)c->d_raw.p, (int32_t*)c->d_b5status.p, ex_scratch);
         CU(cudaEventRecord(c->ev[EV_D2H1], c->stream));
         CU(cudaMemcpyAsync(h_status, c->d_b5status.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaGetLastError());

@@ -16,9 +16,12 @@
  *                              table for literal/length codes, an 8-bit one for distance codes, canonical count/symbol
  *                              arrays for the (rare) longer codes.
  *   abea_blow5_parse_kernel    one thread per record: the fixed fields in front of the signal (unaligned loads).
- *   abea_blow5_signal_kernel   one WARP per record: int16 samples (or svb-zd: 2-bit keys -> byte counts -> warp scan ->
- *                              values -> zigzag -> warp scan of the deltas) widened to the float samples the event
- *                              detection kernels read.
+ *   abea_blow5_signal_kernel   one WARP per record: int16 samples, or svb-zd (2-bit keys -> byte counts -> warp scan ->
+ *                              values -> zigzag -> warp scan of the deltas), or ex-zd (slow5_press.c:1262-1842: one byte
+ *                              per zigzag delta, the deltas above 255 kept aside as "exceptions" whose positions and
+ *                              values are two streamvbyte streams; every lane finds by binary search how many
+ *                              exceptions lie before its sample), widened to the float samples the event detection
+ *                              kernels read.
  *
  * Integer / byte work throughout: results are bit-identical to slow5lib's by construction (tests/test_blow5.py checks
  * against Python's zlib and a restatement of svb-zd, on files written by slow5lib itself).
@@ -30,6 +33,7 @@
 #define B5_REC_ZLIB 1
 #define B5_SIG_NONE 0
 #define B5_SIG_SVB_ZD 1
+#define B5_SIG_EX_ZD 2
 
 #define B5_OK 0
 #define B5_ERR_DATA 1     /* malformed stream / record */
@@ -326,6 +330,16 @@ __global__ void abea_blow5_parse_kernel(const abea_b5rec_t* __restrict__ recs, i
                     h.sig_bytes = (int64_t)(2 * lrs);
                     h.n_samples = (int32_t)lrs;
                     if (lrs > 0x3fffffffull || q + h.sig_bytes > len) h.status = B5_ERR_DATA;
+                } else if (signal_method == B5_SIG_EX_ZD) {
+                    /* ex-zd v0 (slow5_press.c:1721-1842): u8 version, u64 samples, u8 shift, then ex_zd_press_16's stream */
+                    h.sig_bytes = (int64_t)lrs;
+                    if (lrs < 16 || lrs > 0x7fffffffull || q + h.sig_bytes > len || p[q] != 0) {
+                        h.status = B5_ERR_DATA;
+                    } else {
+                        const uint64_t cnt = b5_le(p + q + 1, 8);
+                        h.n_samples = (int32_t)cnt;
+                        if (cnt < 1 || cnt > 0x3fffffffull || p[q + 9] > 5) h.status = B5_ERR_DATA;
+                    }
                 } else {
                     h.sig_bytes = (int64_t)lrs;
                     if (lrs < 4 || lrs > 0x7fffffffull || q + h.sig_bytes > len) {
@@ -343,6 +357,148 @@ __global__ void abea_blow5_parse_kernel(const abea_b5rec_t* __restrict__ recs, i
     hdr[r] = h;
 }
 
+/* streamvbyte (slow5lib's __slow5_streamvbyte_decode: (count+3)/4 key bytes, then 1..4 data bytes per value) by one warp
+ * into out[0 .. count): tiles of 128 values, each lane one key byte = four values, a warp scan of the per-lane byte counts
+ * gives where each lane's data starts. `len` = the stream's stored size; false when it does not hold exactly count values. */
+__device__ __forceinline__ bool b5_svb_decode_warp(const uint8_t* __restrict__ in, int64_t len, int64_t count,
+                                                   uint32_t* __restrict__ out, int lane) {
+    const int64_t nkeys = (count + 3) / 4;
+    if (nkeys > len) return false;
+    const uint8_t* keys = in;
+    const uint8_t* dat = in + nkeys;
+    const int64_t dat_len = len - nkeys;
+    int64_t dpos = 0;
+    for (int64_t k0 = 0; k0 < nkeys; k0 += 32) {
+        const int64_t ki = k0 + lane;
+        const uint32_t key = ki < nkeys ? keys[ki] : 0u;
+        int nv = 0;
+        if (ki < nkeys) {
+            const int64_t left = count - 4 * ki;
+            nv = left >= 4 ? 4 : (int)left;
+        }
+        int bl[4], mybytes = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            bl[q] = (q < nv) ? (int)((key >> (2 * q)) & 3u) + 1 : 0;
+            mybytes += bl[q];
+        }
+        int incl = mybytes;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(ABEA_FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const int tile_bytes = __shfl_sync(ABEA_FULL, incl, 31);
+        if (dpos + tile_bytes > dat_len) return false;
+        int64_t my = dpos + (incl - mybytes);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t v = 0;
+            for (int t = 0; t < bl[q]; t++) v |= (uint32_t)dat[my + t] << (8 * t);
+            my += bl[q];
+            if (q < nv) out[4 * ki + q] = v;
+        }
+        dpos += tile_bytes;
+    }
+    return dpos == dat_len;
+}
+
+/* ex-zd (slow5_press.c:1262-1842: ex_press / ex_depress over the zigzag deltas of the samples, shifted right by q when
+ * every sample has q trailing zero bits) by one warp. Stream: u8 version = 0, u64 n, u8 q, u16 first zigzag delta, u32
+ * number of exceptions (zigzag deltas above 255), their positions (strictly increasing, stored as streamvbyte of
+ * position[i] - position[i-1] - 1) and their values minus 256 (streamvbyte) — both behind a u32 byte count, or inline as
+ * two u32 when there is exactly one — and then one byte for every zigzag delta that is not an exception, in order.
+ * `ex` = 2 * n words of scratch for the exception positions and values. */
+__device__ __forceinline__ bool b5_exzd_decode_warp(const uint8_t* __restrict__ p, int64_t len, int32_t n, uint32_t* __restrict__ ex,
+                                                    float* __restrict__ dst, int lane) {
+    if (len < 16) return false;
+    const int qs = (int)p[9];
+    const uint32_t first = (uint32_t)b5_le(p + 10, 2);
+    const int64_t nex = (int64_t)b5_le(p + 12, 4);
+    const int64_t nz = (int64_t)n - 1; /* zigzag deltas after the first */
+    if (nex > nz) return false;
+    int64_t off = 16;
+    uint32_t* ex_pos = ex;
+    uint32_t* ex_val = ex + n;
+    if (nex > 1) {
+        if (off + 4 > len) return false;
+        const int64_t pos_len = (int64_t)b5_le(p + off, 4);
+        off += 4;
+        if (off + pos_len + 4 > len) return false;
+        if (!b5_svb_decode_warp(p + off, pos_len, nex, ex_pos, lane)) return false;
+        off += pos_len;
+        const int64_t val_len = (int64_t)b5_le(p + off, 4);
+        off += 4;
+        if (off + val_len > len) return false;
+        if (!b5_svb_decode_warp(p + off, val_len, nex, ex_val, lane)) return false;
+        off += val_len;
+        __syncwarp();
+        /* position[i] = sum of the stored differences up to i, plus i (undelta_inplace_increasing_u32) */
+        uint32_t carry = 0;
+        for (int64_t i0 = 0; i0 < nex; i0 += 32) {
+            const int64_t i = i0 + lane;
+            uint32_t v = i < nex ? ex_pos[i] + (i > 0 ? 1u : 0u) : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(ABEA_FULL, incl, d);
+                if (lane >= d) incl += u;
+            }
+            if (i < nex) ex_pos[i] = carry + incl;
+            carry += __shfl_sync(ABEA_FULL, incl, 31);
+        }
+        __syncwarp();
+    } else if (nex == 1) {
+        if (off + 8 > len) return false;
+        if (lane == 0) {
+            ex_pos[0] = (uint32_t)b5_le(p + off, 4);
+            ex_val[0] = (uint32_t)b5_le(p + off + 4, 4);
+        }
+        off += 8;
+        __syncwarp();
+    }
+    const uint8_t* bytes = p + off;
+    if (len - off != nz - nex) return false; /* ex_depress consumes exactly one byte per non-exception */
+    /* sample 0, then tiles of 32 deltas: lane t of a tile decodes delta i (the i-th value after the first), which is an
+     * exception iff it is the r-th one's position, r = the number of exceptions before i (binary search); else it is byte
+     * i - r. The running sum wraps at 16 bits like the reference's int16 arithmetic (unzigdelta_u16_16). */
+    int32_t prev = (int32_t)(int16_t)((first >> 1) ^ (0u - (first & 1u)));
+    if (lane == 0) dst[0] = (float)(int16_t)((uint32_t)prev << qs);
+    bool bad = false;
+    for (int64_t i0 = 0; i0 < nz; i0 += 32) {
+        const int64_t i = i0 + lane;
+        int32_t z = 0;
+        if (i < nz) {
+            int64_t lo = 0, hi = nex; /* first exception whose position is >= i */
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if ((int64_t)ex_pos[mid] < i) lo = mid + 1;
+                else hi = mid;
+            }
+            uint32_t zd;
+            if (lo < nex && (int64_t)ex_pos[lo] == i) {
+                zd = ex_val[lo] + 256u;
+                if (zd > 0xffffu) bad = true;
+            } else {
+                zd = bytes[i - lo];
+            }
+            z = (int32_t)(int16_t)((zd >> 1) ^ (0u - (zd & 1u)));
+        }
+        int32_t incl = z;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int32_t u = __shfl_up_sync(ABEA_FULL, incl, d);
+            if (lane >= d) incl += u;
+        }
+        if (i < nz) dst[i + 1] = (float)(int16_t)((uint32_t)(int16_t)(prev + incl) << qs);
+        prev += __shfl_sync(ABEA_FULL, incl, 31);
+    }
+    /* the exceptions' positions must be strictly increasing and inside the signal */
+    for (int64_t j = lane; j < nex; j += 32)
+        if ((int64_t)ex_pos[j] >= nz || (j > 0 && ex_pos[j] <= ex_pos[j - 1])) bad = true;
+    return !__any_sync(ABEA_FULL, bad);
+}
+
 /* The signal of one record by one warp, widened to float at raw[raw_off[r] ..] (src/f5cio.c:461). svb-zd: tiles of
  * 128 values — each lane takes one key byte = four values: 2-bit codes give their byte counts, a warp scan of the
  * per-lane byte counts gives where each lane's data starts, the values are zigzag-decoded deltas and a second warp
@@ -351,7 +507,7 @@ __global__ void abea_blow5_parse_kernel(const abea_b5rec_t* __restrict__ recs, i
 __global__ void __launch_bounds__(32 * B5_SIG_WARPS)
 abea_blow5_signal_kernel(const abea_b5rec_t* __restrict__ recs, int32_t n, const uint8_t* __restrict__ data,
                          const abea_b5hdr_t* __restrict__ hdr, const int64_t* __restrict__ raw_off, int32_t signal_method,
-                         float* __restrict__ raw, int32_t* __restrict__ sig_status) {
+                         float* __restrict__ raw, int32_t* __restrict__ sig_status, uint32_t* __restrict__ ex_scratch) {
     const int lane = threadIdx.x & 31;
     const int32_t r = (int32_t)(blockIdx.x * B5_SIG_WARPS + (threadIdx.x >> 5));
     if (r >= n) return;
@@ -369,6 +525,11 @@ abea_blow5_signal_kernel(const abea_b5rec_t* __restrict__ recs, int32_t n, const
             dst[j] = (float)v;
         }
         if (lane == 0) sig_status[r] = B5_OK;
+        return;
+    }
+    if (signal_method == B5_SIG_EX_ZD) { /* scratch: two words per sample of the batch, this record's at 2 * raw_off */
+        const bool ok = ex_scratch != nullptr && b5_exzd_decode_warp(p, h.sig_bytes, cnt, ex_scratch + 2 * raw_off[r], dst, lane);
+        if (lane == 0) sig_status[r] = ok ? B5_OK : B5_ERR_DATA;
         return;
     }
     const int64_t nkeys = ((int64_t)cnt + 3) / 4;

@@ -11,7 +11,7 @@
  *   abea_download                   kept separable for measurement   :910-960 (kernels), :979-1030 (D2H + unpack)
  *   abea_model_fill_log_stdv        set_model's CACHED_LOG fill      src/model.c:179
  *   abea_getevents_blow5            read_slow5_single's slow5lib     src/f5cio.c:421-470; slow5lib/src/slow5_press.c:921-1010,
- *                                   calls + event_single's first half 1118-1170; slow5.c:2840-2930
+ *                                   calls + event_single's first half 1118-1170, 1262-1842; slow5.c:2840-2930
  *   abea_getevents /                getevents (event detection) per  src/events.c:562-582, called by event_single
  *   abea_getevents_download         read + the pA conversion         src/f5c.c:692-703
  *   abea_estimate_scalings          estimate_scalings_using_mom      src/align.c:58-106, called per read by event_single
@@ -130,10 +130,10 @@ int abea_getevents_download(abea_ctx_t* ctx, abea_event_t* events, const int64_t
 /* ---- BLOW5 records decoded on the device ----
  * abea_getevents_blow5: abea_getevents for reads that are still BLOW5 records — the file's own bytes cross PCIe and
  * slow5lib's reader side runs on the GPU: record decompression (zlib inflate, slow5lib/src/slow5_press.c:921-1010),
- * record parsing (slow5.c:2840-2930), signal decompression (svb-zd, slow5_press.c:1118-1170), the widening to float
+ * record parsing (slow5.c:2840-2930), signal decompression (svb-zd, slow5_press.c:1118-1170; ex-zd, :1262-1842), the widening to float
  * and read_slow5_single's narrowing of the calibration to float (src/f5cio.c:455-461). n_samples_out (may be NULL)
  * receives each read's sample count. Everything after that is abea_getevents: the event tables stay on the device for
- * abea_getevents_download / abea_upload_batch(events == NULL). zstd records and ex-zd signals return ABEA_ERR_ARG.
+ * abea_getevents_download / abea_upload_batch(events == NULL). zstd records return ABEA_ERR_ARG.
  * abea_raw_download: the float samples of the last abea_getevents / abea_getevents_blow5, for tests of the decoders. */
 int abea_getevents_blow5(abea_ctx_t* ctx, const abea_blow5_t* records, int rna, int32_t* n_events_out,
                          int32_t* n_samples_out, abea_timing_t* timing);

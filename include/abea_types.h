@@ -119,7 +119,7 @@ typedef struct {
  *   bytes         : the records' payloads back to back (what follows each record's size field)
  *   rec_ptr/len   : first byte and stored size of record i
  *   record_method : 0 none, 1 zlib (the record-compression byte of the file header; zstd = 2 is not supported)
- *   signal_method : 0 none, 1 svb-zd (the signal-compression byte, files >= v0.2.0; ex-zd = 2 is not supported) */
+ *   signal_method : 0 none, 1 svb-zd, 2 ex-zd (the signal-compression byte, files >= v0.2.0) */
 typedef struct {
     int32_t n_reads;
     const uint8_t* bytes;

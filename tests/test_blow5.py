@@ -1,7 +1,7 @@
 """BLOW5 records decoded on the device (f5c_b200/csrc/blow5_kernels.cuh) and the int16 front door of the
-event detection. The checker is tests/blow5.py (Python's zlib + a numpy restatement of slow5lib's svb-zd) on fixtures
-written by the reference's own slow5lib (tests/golden/ecoli: a copy of test/ecoli_2kb_region/reads.blow5 — zlib, v0.1.0
-— and its first 8 records re-encoded with svb-zd signal compression by tests/golden/make_blow5_fixtures.py).
+event detection. The checker is tests/blow5.py (Python's zlib + numpy restatements of slow5lib's svb-zd and ex-zd) on
+fixtures written by the reference's own slow5lib (tests/golden/ecoli: a copy of test/ecoli_2kb_region/reads.blow5 — zlib,
+v0.1.0 — and its first 8 records re-encoded with svb-zd / ex-zd signal compression by tests/golden/make_blow5_fixtures.py).
 The CPU tests run the product kernels on the SIMT emulator; the GPU tests run all 112 records and compare the events
 with the reference's golden event tables (tests/golden/ecoli_all.json)."""
 import hashlib
@@ -61,9 +61,9 @@ def check_decode(ctx, f, idx, f_truth=None, check_events=True):
 def test_python_checker_reads_the_slow5lib_fixtures():
     f0 = blow5.Blow5(os.path.join(ECOLI, "reads.blow5"))
     assert len(f0) == 112 and f0.record_method == blow5.RECORD_ZLIB and f0.signal_method == 0
-    for name in ("ecoli8_zlib_svbzd.blow5", "ecoli8_none_svbzd.blow5"):
+    for name in ("ecoli8_zlib_svbzd.blow5", "ecoli8_none_svbzd.blow5", "ecoli8_zlib_exzd.blow5"):
         f = blow5.Blow5(os.path.join(ECOLI, name))
-        assert len(f) == 8 and f.signal_method == 1
+        assert len(f) == 8 and f.signal_method == (2 if "exzd" in name else 1)
         for i in range(8):
             a, b = f.read(i), f0.read(i)
             assert a[0] == b[0] and a[1:5] == b[1:5] and np.array_equal(a[5], b[5])
@@ -83,6 +83,61 @@ def test_emulated_svbzd_signal_decode(emu, name):
     order = np.argsort([r[1] for r in f.records])
     with AbeaContext(0, lib_path=emu) as ctx:
         check_decode(ctx, f, [int(order[0]), int(order[2])], check_events=False)
+
+
+def test_emulated_exzd_signal_decode(emu):
+    """ex-zd signal compression (slow5lib >= 1.2; slow5_press.c:1262-1842) on a file written by slow5lib itself: hundreds of
+    exceptions per read, their positions and values in streamvbyte."""
+    f = blow5.Blow5(os.path.join(ECOLI, "ecoli8_zlib_exzd.blow5"))
+    order = np.argsort([r[1] for r in f.records])
+    with AbeaContext(0, lib_path=emu) as ctx:
+        check_decode(ctx, f, [int(order[0]), int(order[2])], check_events=False)
+
+
+def exzd_records(signals, rid=b"synthetic-read"):
+    """Uncompressed BLOW5 records whose signal field is ex-zd (tests/blow5.py::ex_zd_encode, checked here against the
+    decoder that reads slow5lib's own files)."""
+    recs = []
+    for sig in signals:
+        enc = blow5.ex_zd_encode(sig)
+        assert np.array_equal(blow5.ex_zd_decode(enc), sig)
+        recs.append(np.uint16(len(rid) + 1).tobytes() + rid + b"\0" + np.uint32(0).tobytes() +
+                    np.array([8192.0, 10.0, 1400.0, 4000.0], dtype="<f8").tobytes() + np.uint64(len(enc)).tobytes() + enc + b"aux")
+    return recs
+
+
+def test_emulated_exzd_edge_cases_and_errors(emu):
+    """The branches slow5lib's real files rarely take: no exception at all, exactly one (stored inline), a common shift
+    (all samples multiples of 8), a single sample, steps that wrap int16, exceptions at the first and last position;
+    a truncated stream and one whose exception count lies must be reported."""
+    rng = np.random.default_rng(5)
+    smooth = (500 + np.cumsum(rng.integers(-20, 21, 700))).astype(np.int16)                     # no exception
+    one = smooth.copy(); one[300:] += 400                                                       # exactly one
+    shifted = ((60 + np.cumsum(rng.integers(-5, 6, 500))) * 8).astype(np.int16); shifted[100:] += 8 * 300
+    wrap = np.array([32000, -32000, 32000, 5, -5, 30000, -30000], dtype=np.int16)               # every delta an exception
+    ends = smooth[:200].copy(); ends[1:] += 900; ends[-1] -= 900
+    sigs = [smooth, one, shifted, np.array([-77], dtype=np.int16), wrap, ends]
+    recs = exzd_records(sigs)
+    rec_len = np.array([len(r) for r in recs], dtype=np.int32)
+    rec_ptr = np.zeros(len(recs), dtype=np.int64)
+    np.cumsum(rec_len[:-1].astype(np.int64), out=rec_ptr[1:])
+    payload = np.frombuffer(b"".join(recs), dtype=np.uint8).copy()
+    with AbeaContext(0, lib_path=emu) as ctx:
+        nev, ns, _ = ctx.getevents_blow5(payload, rec_ptr, rec_len, 0, 2)
+        assert [int(x) for x in ns] == [len(s) for s in sigs]
+        raw, raw_ptr = ctx.raw_download(ns)
+        for j, s_ in enumerate(sigs):
+            assert np.array_equal(raw[int(raw_ptr[j]):int(raw_ptr[j]) + len(s_)], s_.astype(np.float32)), j
+        body = bytearray(recs[1])                              # ten of the plain bytes missing; o = body.index(b"\0", 2) + 1 + 4 + 32      # the signal's length field
+        short = bytes(body[:o]) + np.uint64(len(blow5.ex_zd_encode(one)) - 10).tobytes() + bytes(body[o + 8:-13]) + b"aux"
+        with pytest.raises(AbeaError):
+            ctx.getevents_blow5(np.frombuffer(short, dtype=np.uint8).copy(), np.zeros(1, dtype=np.int64),
+                                np.array([len(short)], dtype=np.int32), 0, 2)
+        lie = bytearray(recs[0]); e0 = o + 8 + 12                              # the exception count of a stream that has none
+        lie[e0:e0 + 4] = np.uint32(3).tobytes()
+        with pytest.raises(AbeaError):
+            ctx.getevents_blow5(np.frombuffer(bytes(lie), dtype=np.uint8).copy(), np.zeros(1, dtype=np.int64),
+                                np.array([len(lie)], dtype=np.int32), 0, 2)
 
 
 def synth_records(levels, signals, rid=b"synthetic-read"):
@@ -176,7 +231,7 @@ def test_gpu_blow5_all_112_records_to_golden_events(gctx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["ecoli8_zlib_svbzd.blow5", "ecoli8_none_svbzd.blow5"])
+@pytest.mark.parametrize("name", ["ecoli8_zlib_svbzd.blow5", "ecoli8_none_svbzd.blow5", "ecoli8_zlib_exzd.blow5"])
 def test_gpu_blow5_svbzd(gctx, name):
     f = blow5.Blow5(os.path.join(ECOLI, name))
     check_decode(gctx, f, list(range(len(f))))
