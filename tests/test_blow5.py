@@ -128,7 +128,8 @@ def test_emulated_exzd_edge_cases_and_errors(emu):
         raw, raw_ptr = ctx.raw_download(ns)
         for j, s_ in enumerate(sigs):
             assert np.array_equal(raw[int(raw_ptr[j]):int(raw_ptr[j]) + len(s_)], s_.astype(np.float32)), j
-        body = bytearray(recs[1])                              # ten of the plain bytes missing; o = body.index(b"\0", 2) + 1 + 4 + 32      # the signal's length field
+        body = bytearray(recs[1])
+        o = body.index(b"\0", 2) + 1 + 4 + 32      # the signal's length field; below: ten of the plain bytes missing
         short = bytes(body[:o]) + np.uint64(len(blow5.ex_zd_encode(one)) - 10).tobytes() + bytes(body[o + 8:-13]) + b"aux"
         with pytest.raises(AbeaError):
             ctx.getevents_blow5(np.frombuffer(short, dtype=np.uint8).copy(), np.zeros(1, dtype=np.int64),
