@@ -83,6 +83,15 @@ with AbeaContext(0) as ctx:
     for j, i in enumerate(order):
         assert np.array_equal(raw[int(raw_ptr[j]):int(raw_ptr[j]) + int(ns[j])], f.read(int(i))[5].astype(np.float32))
     print("ok blow5 decode + events", int(nev.sum()))
+    fx = blow5.Blow5(os.path.join(ROOT, "tests", "golden", "ecoli", "ecoli8_zlib_exzd.blow5"))     # ex-zd signal compression
+    chunks = [fx.record_bytes(int(i)) for i in order]
+    rec_len = np.array([len(c) for c in chunks], dtype=np.int32)
+    rec_ptr = np.zeros(len(chunks), dtype=np.int64); np.cumsum(rec_len[:-1].astype(np.int64), out=rec_ptr[1:])
+    nev, ns, _ = ctx.getevents_blow5(np.frombuffer(b"".join(chunks), dtype=np.uint8).copy(), rec_ptr, rec_len, fx.record_method, fx.signal_method)
+    raw, raw_ptr = ctx.raw_download(ns)
+    for j, i in enumerate(order):
+        assert np.array_equal(raw[int(raw_ptr[j]):int(raw_ptr[j]) + int(ns[j])], f.read(int(i))[5].astype(np.float32))
+    print("ok blow5 ex-zd decode", int(ns.sum()))
     sg, seq, seq_ptr, read_len, k = synth.make_signal_batch("r9", 6, 300, 0.4, seed=12)
     _, _, nev, _ = ctx.getevents(sg["raw"].astype(np.int16), sg["raw_ptr"], sg["n_samples"], (sg["offset"], sg["range"], sg["digitisation"]), download=False)
     shell = ReadBatch(seq, seq_ptr, read_len, np.zeros(0, dtype=EVENT_DTYPE), np.zeros(6, dtype=np.int64), nev.astype(np.int32),
