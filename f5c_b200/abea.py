@@ -93,6 +93,8 @@ def _bind(path: str):
     lib.abea_getevents_blow5.argtypes = [vp, ctypes.POINTER(CBlow5), ctypes.c_int, vp, vp, ctypes.POINTER(Timing)]
     lib.abea_raw_download.argtypes = [vp, vp, vp]
     lib.abea_write_pairs.argtypes = [ctypes.c_char_p, ctypes.c_int, i32, vp, vp, vp, vp, vp]
+    lib.abea_write_resquiggle.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32,
+                                          i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.abea_estimate_scalings.argtypes = [vp, ctypes.c_int, vp, ctypes.POINTER(Timing)]
     lib.abea_scaling_stage.argtypes = [vp, i32, ctypes.POINTER(Timing)]
     lib.abea_scaling_download.argtypes = [vp, vp, vp, vp]
@@ -506,3 +508,26 @@ def write_pairs(path: str, names, aln: Alignment, flags: np.ndarray | None = Non
                               pairs.ctypes.data, pp.ctypes.data, None if fl is None else fl.ctypes.data)
     if rc != 0:
         raise AbeaError(f"abea_write_pairs failed ({rc})")
+
+
+def write_resquiggle(path: str, names, read_len, n_samples, events: np.ndarray, event_ptr, results: np.ndarray, maps: np.ndarray,
+                     map_ptr, kmer_size: int, fmt: str = "tsv", rna: bool = False, header: bool = True, append: bool = False,
+                     lib_path: str | None = None):
+    """abea_write_resquiggle: f5c resquiggle's TSV / PAF output (reference src/resquiggle.c:322-447) from the event tables
+    (start, length) and what the scaling stage left per read (flags, scalings, k-mer -> event-range map)."""
+    lib = load_library(lib_path)
+    n = len(names)
+    arr = (ctypes.c_char_p * max(n, 1))(*[s_.encode() if isinstance(s_, str) else s_ for s_ in names])
+    rl = np.ascontiguousarray(read_len, dtype=np.int32)
+    ns = np.ascontiguousarray(n_samples, dtype=np.int64)
+    ev = np.ascontiguousarray(events)
+    ep = np.ascontiguousarray(event_ptr, dtype=np.int64)
+    res = np.ascontiguousarray(results)
+    mp_ = np.ascontiguousarray(maps)
+    mptr = np.ascontiguousarray(map_ptr, dtype=np.int64)
+    rc = lib.abea_write_resquiggle(path.encode(), int(append), 1 if fmt == "paf" else 0, int(header), int(rna), int(kmer_size), n,
+                                   ctypes.cast(arr, ctypes.c_void_p), rl.ctypes.data, ns.ctypes.data, ev.ctypes.data,
+                                   ep.ctypes.data, res.ctypes.data, mp_.ctypes.data, mptr.ctypes.data)
+    if rc != 0:
+        raise AbeaError(f"abea_write_resquiggle failed ({rc})")
+

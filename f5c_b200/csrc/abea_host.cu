@@ -22,6 +22,7 @@
 #include <condition_variable>
 #include <functional>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <vector>
 #include <sched.h>
@@ -1920,6 +1921,99 @@ int abea_write_pairs(const char* path, int append, int32_t n_reads, const char* 
     if (fp != stdout) fclose(fp);
     else fflush(fp);
     return ABEA_OK;
+}
+
+/* f5c resquiggle's output_db_rsq (reference src/resquiggle.c:322-447), TSV (fmt 0) or PAF (fmt 1), from the event tables
+ * and the k-mer -> event-range maps of the scaling stage. */
+int abea_write_resquiggle(const char* path, int append, int fmt, int header, int rna, uint32_t kmer_size, int32_t n_reads,
+                          const char* const* names, const int32_t* read_len, const int64_t* n_samples,
+                          const abea_event_t* events, const int64_t* event_ptr, const abea_scaling_result_t* results,
+                          const abea_index_pair_t* maps, const int64_t* map_ptr) {
+    if (!path || n_reads < 0 || (fmt != 0 && fmt != 1)) return ABEA_ERR_ARG;
+    if (n_reads > 0 && (!names || !read_len || !n_samples || !event_ptr || !results || !maps || !map_ptr)) return ABEA_ERR_ARG;
+    FILE* fp = strcmp(path, "-") == 0 ? stdout : fopen(path, append ? "a" : "w");
+    if (!fp) return ABEA_ERR_ARG;
+    if (header && fmt == 0) fprintf(fp, "read_id\tkmer_idx\tstart_raw_idx\tend_raw_idx\n"); /* src/resquiggle.c:724-727 */
+    int rc = ABEA_OK;
+    std::vector<abea_index_pair_t> map;
+    std::string ss;
+    char num[32];
+    for (int32_t i = 0; i < n_reads && rc == ABEA_OK; i++) {
+        if (results[i].flags) continue; /* failed calibration / alignment / QC: counted, not printed */
+        const int32_t n_kmers = read_len[i] - (int32_t)kmer_size + 1;
+        if (n_kmers <= 0 || !events) { rc = ABEA_ERR_ARG; break; }
+        const abea_event_t* ev = events + event_ptr[i];
+        map.assign(maps + map_ptr[i], maps + map_ptr[i] + n_kmers);
+        if (rna) { /* :345-357 */
+            std::reverse(map.begin(), map.end());
+            for (abea_index_pair_t& m : map) std::swap(m.start, m.stop);
+        }
+        int64_t sig_start = -1, sig_start2 = -1, sig_end = -1, sig_end2 = -1, read_start = -1, read_end = -1;
+        int64_t ci = 0, mi = 0, d = 0, count_samples = 0;
+        bool first = true;
+        int matches = 0;
+        ss.clear();
+        for (int32_t j = 0; j < n_kmers; j++) {
+            const int32_t se = map[(size_t)j].start, ee = map[(size_t)j].stop;
+            if (se == -1) { /* deletion from the read */
+                sig_start = sig_end = -1;
+                if (!first) d++;
+            } else {
+                sig_start = (int64_t)ev[se].start; /* inclusive */
+                if (first) {
+                    sig_start2 = sig_start;
+                    read_start = j;
+                    ci = sig_start;
+                    first = false;
+                }
+                sig_end2 = sig_end = (int64_t)ev[ee].start + (int)ev[ee].length; /* non-inclusive */
+                read_end = j;
+                if (fmt) {
+                    if (d > 0) {
+                        snprintf(num, sizeof num, "%dD", (int)d);
+                        ss += num;
+                        d = 0;
+                    }
+                    if (j == 0) ci = sig_start;
+                    ci += (mi = sig_start - ci);
+                    if (mi) {
+                        snprintf(num, sizeof num, "%dI", (int)mi);
+                        ss += num;
+                        count_samples += mi;
+                    }
+                    ci += (mi = sig_end - sig_start);
+                    if (mi) {
+                        matches++;
+                        snprintf(num, sizeof num, "%d,", (int)mi);
+                        ss += num;
+                        count_samples += mi;
+                    }
+                }
+            }
+            if (fmt == 0) {
+                fprintf(fp, "%s\t%d\t", names[i], rna ? n_kmers - j - 1 : j);
+                if (sig_start < 0) fprintf(fp, ".\t");
+                else fprintf(fp, "%ld\t", (long)sig_start);
+                if (sig_end < 0) fprintf(fp, ".");
+                else fprintf(fp, "%ld", (long)sig_end);
+                fprintf(fp, "\n");
+                if (sig_start >= 0 && sig_end >= 0 && sig_end <= sig_start) rc = ABEA_ERR_ARG; /* the reference exits here */
+            }
+        }
+        if (fmt == 1 && rc == ABEA_OK) {
+            if (sig_start2 == -1 || sig_end2 == -1 || count_samples != sig_end2 - sig_start2) { rc = ABEA_ERR_ARG; break; } /* its asserts */
+            fprintf(fp, "%s\t%ld\t%ld\t%ld\t+\t", names[i], (long)n_samples[i], (long)sig_start2, (long)sig_end2);
+            fprintf(fp, "%s\t%d\t%ld\t%ld\t", names[i], n_kmers, (long)(rna ? n_kmers - read_start : read_start),
+                    (long)(rna ? n_kmers - 1 - read_end : read_end + 1));
+            fprintf(fp, "%d\t%d\t%d\t", matches, n_kmers, 255);
+            fprintf(fp, "sc:f:%f\t", results[0].scalings.scale); /* db->scalings->scale: the batch's first read, :442 */
+            fprintf(fp, "sh:f:%f\t", results[0].scalings.shift);
+            fprintf(fp, "ss:Z:%s\n", ss.c_str());
+        }
+    }
+    if (fp != stdout) fclose(fp);
+    else fflush(fp);
+    return rc;
 }
 
 /* ---- the ragged front door ------------------------------------------------------------------------------------ */

@@ -228,6 +228,19 @@ int abea_expand_codes(abea_ctx_t* ctx, const abea_code_word_t* d_codes, const in
 int abea_write_pairs(const char* path, int append, int32_t n_reads, const char* const* names, const int32_t* n_pairs,
                      const abea_pair_t* pairs, const int64_t* pair_ptr, const uint32_t* read_stat_flag);
 
+/* f5c resquiggle's output (src/resquiggle.c:322-447) for a batch that has been through the whole chain — event detection,
+ * alignment, abea_scaling_stage — byte for byte the text f5c prints: fmt 0 = TSV rows "read_id kmer_idx start_raw_idx
+ * end_raw_idx" (one per k-mer, "." for k-mers without events; the header line is written when header != 0), fmt 1 = PAF
+ * with the ss:Z: tag of per-base sample counts. Reads whose flags are not 0 are skipped, as the reference does. For RNA
+ * (rna != 0) the k-mer map is reversed first, as output_db_rsq does. Inputs: names, read_len, n_samples (db->sig[i]->nsample)
+ * per read; the event tables (events / event_ptr: only start and length are read); results / maps / map_ptr as
+ * abea_scaling_download returns them. The reference prints the FIRST read's scale and shift in every PAF line
+ * (db->scalings->scale, src/resquiggle.c:442-443); so does this. path "-" = stdout. Host-side formatting only. */
+int abea_write_resquiggle(const char* path, int append, int fmt, int header, int rna, uint32_t kmer_size, int32_t n_reads,
+                          const char* const* names, const int32_t* read_len, const int64_t* n_samples,
+                          const abea_event_t* events, const int64_t* event_ptr, const abea_scaling_result_t* results,
+                          const abea_index_pair_t* maps, const int64_t* map_ptr);
+
 /* Host threads abea_align_batch uses to expand the pair lists, which leave the device as path codes (the first pair of
  * a list and two bits per step: 8 bytes per 32 pairs over PCIe instead of 256) while the kernels are still running.
  * threads >= 0 sets the number (0: no path codes — the lists are written whole into a pinned caller buffer, or copied

@@ -281,6 +281,79 @@ def test_pair_dump_matches_reference_format(emu, tmp_path):
     assert open(path).read() == banded_aln_text(names, want, None)
 
 
+def resquiggle_text(names, read_len, n_samples, batch, sc, k, fmt, rna):
+    """f5c resquiggle's output (src/resquiggle.c:322-447), formatted independently in Python from the oracle's maps."""
+    out = ["read_id\tkmer_idx\tstart_raw_idx\tend_raw_idx\n"] if fmt == "tsv" else []
+    for i, nm in enumerate(names):
+        if int(sc.res["flags"][i]):
+            continue
+        ev = batch.read_events(i)
+        nk = int(read_len[i]) - k + 1
+        mp = [(int(a), int(b)) for a, b in sc.read_map(i)[:nk]]
+        if rna:
+            mp = [(b, a) for a, b in reversed(mp)]
+        first, ci, d, cnt, matches, ss = True, 0, 0, 0, 0, []
+        s2 = e2 = rs = re_ = -1
+        for j, (a, b) in enumerate(mp):
+            if a == -1:
+                st = en = -1
+                if not first:
+                    d += 1
+            else:
+                st = int(ev["start"][a])
+                if first:
+                    s2, rs, ci, first = st, j, st, False
+                en = e2 = int(ev["start"][b]) + int(ev["length"][b])
+                re_ = j
+                if fmt == "paf":
+                    if d:
+                        ss.append("%dD" % d); d = 0
+                    if j == 0:
+                        ci = st
+                    mi = st - ci; ci += mi
+                    if mi:
+                        ss.append("%dI" % mi); cnt += mi
+                    mi = en - st; ci += mi
+                    if mi:
+                        matches += 1; ss.append("%d," % mi); cnt += mi
+            if fmt == "tsv":
+                out.append("%s\t%d\t%s\t%s\n" % (nm, nk - j - 1 if rna else j, "." if st < 0 else str(st), "." if en < 0 else str(en)))
+        if fmt == "paf":
+            assert cnt == e2 - s2
+            out.append("%s\t%d\t%d\t%d\t+\t%s\t%d\t%d\t%d\t%d\t%d\t255\tsc:f:%f\tsh:f:%f\tss:Z:%s\n" % (
+                nm, int(n_samples[i]), s2, e2, nm, nk, nk - rs if rna else rs, nk - 1 - re_ if rna else re_ + 1, matches, nk,
+                float(sc.res["scalings"]["scale"][0]), float(sc.res["scalings"]["shift"][0]), "".join(ss)))
+    return "".join(out)
+
+
+@pytest.mark.parametrize("fmt", ["tsv", "paf"])
+@pytest.mark.parametrize("rna", [False, True])
+def test_resquiggle_output_matches_reference_format(emu, tmp_path, fmt, rna):
+    """abea_write_resquiggle on the oracle's chain (align -> scaling_single) of synthetic reads with skipped k-mers
+    (deletions in the ss tag / '.' rows), one read that fails QC (not printed), both formats, DNA and the RNA reversal."""
+    from f5c_b200 import synth
+    from f5c_b200.abea import write_resquiggle
+    b = synth.make_batch("r9", n_reads=6, mean_events=900, sigma=0.3, epk=1.8, seed=23, p_skip=0.08)
+    b.events["mean"][b.event_ptr[2]:b.event_ptr[2] + b.n_events[2]] += 40.0      # read 2: far off the model -> fails
+    k, m = models.load_model("r9")
+    fm = ol.full_model(m)
+    aln = ol.port_align(b, fm)
+    sc = ol.port_scaling(b, fm, aln)
+    assert int(sc.res["flags"][2]) != 0 and (sc.res["flags"] == 0).sum() >= 4
+    names = ["read-%d" % i for i in range(b.n_reads)]
+    n_samples = (b.events["start"][b.event_ptr + b.n_events - 1] + 30).astype(np.int64)
+    if rna:   # an RNA event table is reversed before the alignment (src/f5c.c:713-721): time runs backwards along it
+        for i in range(b.n_reads):
+            e = b.events[int(b.event_ptr[i]):int(b.event_ptr[i]) + int(b.n_events[i])]
+            e["start"] = (int(n_samples[i]) - e["start"].astype(np.int64) - e["length"].astype(np.int64)).astype(np.uint64)
+    path = str(tmp_path / "rsq.txt")
+    write_resquiggle(path, names, b.read_len, n_samples, b.events, b.event_ptr, sc.res, sc.maps, sc.map_ptr, k, fmt=fmt,
+                     rna=rna, lib_path=emu)
+    got = open(path).read()
+    assert got == resquiggle_text(names, b.read_len, n_samples, b, sc, k, fmt, rna)
+    assert got.count("\n") > (1000 if fmt == "tsv" else 3) and ("." in got or fmt == "paf") and ("D" in got or fmt == "tsv")
+
+
 @pytest.mark.gpu
 def test_gpu_blow5_to_banded_aln_dump(built, tmp_path):
     """tools/blow5_eventalign_dump.py: BLOW5 + FASTA -> the --print-banded-aln text, every stage on the GPU; every read's
@@ -304,3 +377,48 @@ def test_gpu_blow5_to_banded_aln_dump(built, tmp_path):
         assert hashlib.sha256(arr.tobytes()).hexdigest() == gold[name]["pairs_sha256"], name
         seen += 1
     assert seen == sum(1 for r in gold.values() if not (r["flags"] & 2))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["tsv", "paf"])
+def test_gpu_blow5_to_resquiggle(built, tmp_path, fmt):
+    """tools/blow5_resquiggle.py: BLOW5 + FASTA -> f5c resquiggle's TSV / PAF, every stage on the GPU; the rows of the six
+    shortest reads must be what the CPU chain (oracle getevents -> estimate -> align -> scaling_single) formats to."""
+    import sys
+    from f5c_b200.batch import ReadBatch, SCALINGS_DTYPE
+    out = str(tmp_path / "rsq.txt")
+    subprocess.check_call([sys.executable, os.path.join(os.path.dirname(HERE), "tools", "blow5_resquiggle.py"),
+                           os.path.join(ECOLI, "reads.blow5"), os.path.join(ECOLI, "reads.fasta"), out] + (["-c"] if fmt == "paf" else []))
+    f = blow5.Blow5(os.path.join(ECOLI, "reads.blow5"))
+    seqs = dict(blow5.read_fasta(os.path.join(ECOLI, "reads.fasta")))
+    k, m = models.load_model("r9")
+    fm = ol.full_model(m)
+    order = [int(i) for i in np.argsort([r[1] for r in f.records])[:6]]
+    recs = [f.read(i) for i in order]
+    evs = []
+    for rid, dig, off, rng, sr, sig in recs:
+        pa = ((sig.astype(np.float32) + np.float32(off)) * np.float32(np.float32(rng) / np.float32(dig))).astype(np.float32)
+        evs.append(ol.port_getevents(pa))
+    b = ReadBatch.from_reads([seqs[r[0]].encode() for r in recs], evs, np.zeros(len(recs), dtype=SCALINGS_DTYPE), k)
+    b.scalings = ol.port_estimate_scalings(b, fm)
+    aln = ol.port_align(b, fm)
+    sc = ol.port_scaling(b, fm, aln)
+    names = [r[0] for r in recs]
+    want = resquiggle_text(names, b.read_len, [len(r[5]) for r in recs], b, sc, k, fmt, False)
+    got = open(out).read()
+    if fmt == "tsv":
+        assert got.startswith("read_id\tkmer_idx\tstart_raw_idx\tend_raw_idx\n")
+        rows = {}
+        for line in got.split("\n")[1:]:
+            if line:
+                rows.setdefault(line.split("\t")[0], []).append(line)
+        for nm in names:
+            mine = [l for l in want.split("\n")[1:] if l.startswith(nm + "\t")]
+            assert rows.get(nm, []) == mine, nm
+    else:
+        lines = {l.split("\t")[0]: l for l in got.split("\n") if l}
+        for l in want.split("\n"):
+            if l:    # the sc / sh fields are the BATCH's first read's (a reference quirk): compare everything else
+                a, b_ = l.split("\t"), lines[l.split("\t")[0]].split("\t")
+                assert a[:12] == b_[:12] and a[14] == b_[14], a[0]
+
