@@ -1892,6 +1892,9 @@ __device__ __forceinline__ void abea_wide_step(abea_wide_ctx_t& cx, abea_wide_sm
             cx.kchunk_hi += 1;
             abea_wide_stage(&sm, cx.ev, cx.kpr, -1, cx.kchunk_hi, cx.E, cx.K, tid);
         }
+        /* a right move changes only the k-mer a further right move would bring in: its load is issued here, ahead of
+         * the cell; the event a down move would bring in (x_dn) is still the one loaded after the last down move */
+        cx.kp_rt = sm.kp[(cx.kb + 1 + oa) & (ABEA_WRING - 1)];
         if (cx.prev_right) abea_wide_cell<FAST>(cx.lpd_rt, A.hi, A.R, B.hi, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
         else abea_wide_cell<FAST>(cx.lpd_rt, A.hi, A.R, B.R, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
     } else {
@@ -1908,6 +1911,7 @@ __device__ __forceinline__ void abea_wide_step(abea_wide_ctx_t& cx, abea_wide_sm
             }
             abea_wide_stage(&sm, cx.ev, cx.kpr, cx.echunk_hi, -1, cx.E, cx.K, tid);
         }
+        cx.x_dn = sm.ev[(cx.eb + 1 - oa) & (ABEA_WRING - 1)]; /* likewise: only the event of a further down move changes */
         if (cx.prev_right) abea_wide_cell<FAST>(cx.lpd_dn, A.R, A.lo, B.R, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
         else abea_wide_cell<FAST>(cx.lpd_dn, A.R, A.lo, B.lo, cx.lp_step, cx.lp_stay, cx.lp_skip, Rn, fr);
     }
@@ -1960,8 +1964,6 @@ __device__ __forceinline__ void abea_wide_step(abea_wide_ctx_t& cx, abea_wide_sm
 
     /* speculative emissions of band b+1 for both moves (lanes past offset 99 read the ring at offset 99 so that they
      * never touch a chunk that is still in flight) */
-    cx.x_dn = sm.ev[(cx.eb + 1 - oa) & (ABEA_WRING - 1)];
-    cx.kp_rt = sm.kp[(cx.kb + 1 + oa) & (ABEA_WRING - 1)];
     cx.lpd_rt = (double)abea_emission_t<FAST>(cx.x_cur, cx.kp_rt);
     cx.lpd_dn = (double)abea_emission_t<FAST>(cx.x_dn, cx.kp_cur);
 
